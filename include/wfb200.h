@@ -1,0 +1,170 @@
+/*
+ * wfb200.h -- C ABI of libwfb200.so, the B200-native (sm_100a) GPU stream-operator kernels that sit
+ * underneath the WindFlow GPU operator API (Map_GPU / Filter_GPU / Reduce_GPU / Ffat_Windows_GPU and the
+ * KeyBy_Emitter_GPU grouping).
+ *
+ * The reference (ParaGroup/WindFlow) has no FFI: its GPU path is a set of C++ templates whose kernels are
+ * launched from each replica's svc(). Every entry point below replaces one such launch sequence; the
+ * reference interface it stands in for is cited as wf/<file>:<line> (relative to the reference repo).
+ * INTEGRATION.md shows the binding a WindFlow maintainer adds inside those svc() bodies.
+ *
+ * Conventions
+ *  - all functions return 0 on success, a cudaError_t value (>0) for CUDA failures, or a negative
+ *    WFB_E_* code; they never throw and never synchronise the stream unless stated;
+ *  - pointers are DEVICE pointers unless the name ends in _h; `stream` is a cudaStream_t passed as void*;
+ *  - a batch is structure-of-arrays: `tuples` (n * tuple_bytes, 16-byte aligned) and `ts` (n * uint64_t);
+ *    user functors only ever see `tuple_t &`, so this replaces wf/basic_gpu.hpp:132-140's 72-byte AoS item
+ *    without touching the operator API;
+ *  - record schemas and functors are compiled in ("programs"): the library pre-instantiates the programs
+ *    below; user code instantiates its own with WFB_DEFINE_PROGRAM from windflow_b200/csrc/wfb_kernels.cuh
+ *    and gets the same entry points for its functors.
+ */
+#ifndef WFB200_H
+#define WFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFB_ABI_VERSION 1
+
+/* negative error codes (positive values are cudaError_t) */
+#define WFB_E_BADARG    (-1)  /* null pointer, zero-size window, unknown program ... */
+#define WFB_E_NOPROG    (-2)  /* program id not registered */
+#define WFB_E_CAPACITY  (-3)  /* more distinct keys / results than the handle was created for */
+#define WFB_E_NOGPU     (-4)  /* no CUDA device: the library has NO CPU fallback */
+#define WFB_E_UNSUPPORTED (-5)
+
+/* ---- built-in programs ------------------------------------------------------------------------- */
+#define WFB_PROG_TUPLE64  0   /* bench stream of SURVEY.md 8d: wfb_tuple64_t -> wfb_result32_t            */
+#define WFB_PROG_WFTEST16 1   /* reference tests/graph_tests_gpu/graph_common_gpu.hpp:40-49 {key,value}  */
+#define WFB_PROG_WFWIN24  2   /* reference tests/win_tests_gpu/win_common_gpu.hpp:40-80 {key,id,value}   */
+
+typedef struct { uint64_t key; uint64_t id; int64_t ivalue; double fvalue; uint64_t pad[4]; } wfb_tuple64_t;
+typedef struct { uint64_t key; uint64_t id; int64_t isum; double fsum; } wfb_result32_t;
+typedef struct { uint64_t key; int64_t value; } wfb_wftest16_t;
+typedef struct { uint64_t key; uint64_t id; int64_t value; } wfb_wfwin24_t; /* tuple_t and result_t */
+
+/* Parameters of the built-in functors (a user program carries its own functor objects instead).
+ *   map_kind : 0 identity; 1 value += map_iadd, fvalue *= map_fscale   (Map_Functor_GPU "+2": iadd=2, fscale=1)
+ *   filt_kind: 0 keep all; 1 (value & 1) == 0; 2 value % filt_mod == 0 (Filter_Functor_GPU(mod)) */
+typedef struct {
+    int32_t map_kind;
+    int32_t filt_kind;
+    int64_t map_iadd;
+    double  map_fscale;
+    int64_t filt_mod;
+} wfb_functors_t;
+
+typedef struct {
+    uint32_t tuple_bytes;   /* sizeof(tuple_t) */
+    uint32_t result_bytes;  /* sizeof(result_t) of the window operators */
+    uint32_t key_bytes;     /* sizeof(key_t) (8 for all built-ins) */
+    uint32_t reserved;
+} wfb_program_info_t;
+
+/* One input batch of a multi-batch call (host-side descriptor array). */
+typedef struct {
+    const void     *tuples;     /* device, n * tuple_bytes */
+    const uint64_t *ts;         /* device, n timestamps (may be NULL for count-based windows) */
+    uint64_t        watermark;  /* Batch_GPU_t::getWatermark(id_replica), wf/batch_gpu_t.hpp:184-192 */
+    uint32_t        n;
+    uint32_t        reserved;
+} wfb_batch_t;
+
+typedef struct wfb_engine wfb_engine_t; /* per-replica scratch for the stateless / per-batch operators */
+typedef struct wfb_ffat   wfb_ffat_t;   /* per-replica state of one Ffat_Windows_GPU */
+
+/* ---- library ----------------------------------------------------------------------------------- */
+int         wfb_abi_version(void);
+const char *wfb_error_string(int code);
+int         wfb_device_count(void);                    /* 0 => every compute entry point returns WFB_E_NOGPU */
+int         wfb_program_info(int prog, wfb_program_info_t *info);
+
+/* ---- per-replica scratch ------------------------------------------------------------------------
+ * Replaces the per-replica records / Thrust allocator of wf/filter_gpu.hpp:401-470, wf/reduce_gpu.hpp:122-200,
+ * wf/keyby_emitter_gpu.hpp:519-537: tile descriptors, sort buffers, counters. Grows on demand (cudaMalloc). */
+int wfb_engine_create(wfb_engine_t **e, int prog);
+int wfb_engine_destroy(wfb_engine_t *e);
+/* launches issued by this engine so far (kernel launches only; bench.py reports it as gpu_launches) */
+uint64_t wfb_engine_launches(const wfb_engine_t *e);
+
+/* ---- Map_GPU, stateless: in-place func(tuple) over a batch --------------------------------------
+ * replaces Stateless_MAPGPU_Kernel + launch, wf/map_gpu.hpp:61-76, :357-409. */
+int wfb_map(wfb_engine_t *e, const wfb_functors_t *f, void *tuples, uint32_t n, void *stream);
+
+/* ---- Filter_GPU, stateless (optionally fused with a preceding stateless Map_GPU) ------------------
+ * out = stable compaction of { map(t) : filter(map(t)) }; *n_out_dev (device uint32) = survivors.
+ * replaces Stateless_FILTERGPU_Kernel + thrust::copy_if + D2D copy-back, wf/filter_gpu.hpp:72-88, :497-589
+ * (and, when f->map_kind != 0, the Map_GPU launch before it). in/out must not overlap unless identical
+ * (in-place compaction is allowed: tuples_out == tuples_in, ts_out == ts_in). ts_in may be NULL. */
+int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f,
+                   const void *tuples_in, const uint64_t *ts_in, uint32_t n,
+                   void *tuples_out, uint64_t *ts_out, uint32_t *n_out_dev, void *stream);
+
+/* ---- Reduce_GPU, per batch -------------------------------------------------------------------------
+ * keyed: one output item per distinct key, ascending key order, tuple = fold of the program's reduce functor
+ * over the key's items, ts = max ts. replaces Extract_Keys_Kernel + sort_by_key + reduce_by_key + D2D,
+ * wf/reduce_gpu.hpp:75-105, :226-262. */
+int wfb_reduce_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n,
+                      void *out_tuples, uint64_t *out_ts, uint32_t *n_out_dev, void *stream);
+/* un-keyed: whole batch -> one item. replaces thrust::reduce, wf/reduce_gpu.hpp:264-286. */
+int wfb_reduce_all(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n,
+                   void *out_tuple, uint64_t *out_ts, void *stream);
+
+/* ---- KeyBy_Emitter_GPU grouping (GPU->GPU) -----------------------------------------------------------
+ * start_idxs[k] = first index of the k-th distinct key (ascending key order), map_idxs[i] = next index with
+ * the same key or -1, dist_keys[k] = the key; *n_keys_dev = number of distinct keys.
+ * replaces Extract_Dests_Kernel + sort_by_key + Compute_Mapping_Kernel + unique_by_key_copy,
+ * wf/keyby_emitter_gpu.hpp:68-100, :519-583. */
+int wfb_keyby_group(wfb_engine_t *e, const void *tuples, uint32_t n,
+                    int32_t *start_idxs, int32_t *map_idxs, uint64_t *dist_keys, uint32_t *n_keys_dev,
+                    void *stream);
+
+/* ---- key -> shard partition (stands in for keyby_emitter_gpu when the pipeline spans > 1 GPU) ---------
+ * dest = key % num_shards (wf/keyby_emitter.hpp:215-217, wf/keyby_emitter_gpu.hpp:621). Stable: within a
+ * shard segment items keep arrival order. seg_off_dev[num_shards + 1] = exclusive offsets (device). */
+int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n, uint32_t num_shards,
+                     void *out_tuples, uint64_t *out_ts, uint32_t *seg_off_dev, void *stream);
+
+/* ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------
+ * Per-replica handle: owns the key table and, per key, the count, the open-pane accumulator and the FlatFAT
+ * (pane ring + internal levels). replaces Key_Descriptor / FlatFAT_GPU allocation,
+ * wf/ffat_replica_gpu.hpp:438-506, wf/flatfat_gpu.hpp:165-192.
+ *   win_type: 0 count-based (win/slide in tuples), 1 time-based (win/slide/lateness in timestamp units)
+ *   flags   : WFB_FFAT_DENSE_KEYS => keys are known to be < max_keys (slot = key, no hash probe) */
+#define WFB_FFAT_DENSE_KEYS 1u
+int wfb_ffat_create(wfb_ffat_t **h, int prog, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
+                    uint32_t max_keys, int win_type, uint64_t lateness, uint32_t flags);
+int wfb_ffat_destroy(wfb_ffat_t *h);
+uint64_t wfb_ffat_launches(const wfb_ffat_t *h);
+uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h);
+
+/* Count-based windows over `nbatches` consecutive input batches (one stream segment). Per key, items are
+ * appended in arrival order; whenever the key's count reaches the trigger (first (Nb-1)*slide+win, then every
+ * slide*Nb) Nb results result_t(key, gwid) folded over [gwid*slide, gwid*slide+win) are emitted with
+ * ts = watermark of the batch holding the triggering item. Nothing is flushed at end of stream.
+ * `pre` (may be NULL) fuses a chain of stateless Map_GPU -> Filter_GPU in front of the lift.
+ * Results are appended to out_results/out_ts (capacity out_capacity) in groups of Nb per key; the order of the
+ * groups is unspecified. *n_out_dev (device uint32) = number of results of this call.
+ * replaces Ffat_Replica_GPU::process_batch_cb + process_wins_cb and FlatFAT_GPU::add_cb/build/update/
+ * computeResults, wf/ffat_replica_gpu.hpp:734-867, wf/flatfat_gpu.hpp:226-252, :338-419. */
+int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                        void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev,
+                        void *stream);
+
+/* Number of distinct keys seen so far / error flags raised on the device (synchronises the stream). */
+int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, void *stream);
+
+/* ---- synthetic stream, generated on the device for tests and bench --------------------------
+ * key_mode: 0 i % nkeys, 1 splitmix64(i) % nkeys, 2 zipf via zipf_cdf (device, nkeys doubles) */
+int wfb_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys,
+                    const double *zipf_cdf, void *tuples, uint64_t *ts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFB200_H */

@@ -1,0 +1,167 @@
+"""CPU tests (-m "not gpu"): the oracle against the golden vectors generated from the reference's own
+wf/flatfat.hpp (tests/golden/*.npz), against the live reference pin when oracle/_ref is present, and its own
+internal consistency (tree order vs linear fold, GPU-operator semantics vs CPU-operator windows)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _stream(O, rng, n, nkeys):
+    r = np.zeros(n, dtype=O.RES)
+    r["key"] = rng.integers(0, nkeys, n)
+    r["isum"] = rng.integers(-1000, 1000, n)
+    r["fsum"] = rng.random(n)
+    return r
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cpu_ffat_matches_reference_golden(oracle, path):
+    O = oracle
+    g = np.load(path)
+    win, slide, batch = int(g["win"]), int(g["slide"]), int(g["batch"])
+    res = np.zeros(len(g["key"]), dtype=O.RES)
+    res["key"], res["isum"], res["fsum"] = g["key"], g["isum"], g["fsum"]
+    oc = O.FfatCpuOracle(win, slide)
+    outs, tss = [], []
+    for b in range(0, len(res), batch):
+        o, t = oc.process(res[b:b + batch], b)
+        outs.append(o); tss.append(t)
+    out = np.concatenate(outs); ts = np.concatenate(tss)
+    assert len(out) == len(g["out_key"]) > 0
+    assert np.array_equal(out["key"], g["out_key"]) and np.array_equal(out["id"], g["out_id"])
+    assert np.array_equal(out["isum"], g["out_isum"])
+    assert np.array_equal(out["fsum"], g["out_fsum"])  # same tree, same association: bit-exact
+    assert np.array_equal(ts, g["out_ts"])
+    eo, _ = oc.eos()
+    eo = O.sort_results(eo)
+    assert np.array_equal(eo["key"], g["eos_key"]) and np.array_equal(eo["id"], g["eos_id"])
+    assert np.array_equal(eo["isum"], g["eos_isum"]) and np.array_equal(eo["fsum"], g["eos_fsum"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+@pytest.mark.parametrize("nb", [1, 3])
+def test_gpu_operator_oracle_matches_reference_golden(oracle, path, nb):
+    """Ffat_Windows_GPU semantics (groups of Nb, no EOS flush): every emitted window equals the reference window
+    with the same (key, gwid); the emitted set is exactly the windows whose group trigger was reached."""
+    O = oracle
+    g = np.load(path)
+    win, slide, batch = int(g["win"]), int(g["slide"]), int(g["batch"])
+    res = np.zeros(len(g["key"]), dtype=O.RES)
+    res["key"], res["isum"], res["fsum"] = g["key"], g["isum"], g["fsum"]
+    go = O.FfatGpuOracle(win, slide, nb, keep_history=True)
+    outs = []
+    for b in range(0, len(res), batch):
+        o, t = go.process_batch(res[b:b + batch], b)
+        assert (t == b).all()
+        outs.append(o)
+    out = np.concatenate(outs)
+    ref = {(int(k), int(i)): (int(s), float(f)) for k, i, s, f in zip(g["out_key"], g["out_id"], g["out_isum"], g["out_fsum"])}
+    assert len(out) > 0
+    for r in out:
+        s, f = ref[(int(r["key"]), int(r["id"]))]
+        assert r["isum"] == s
+        assert abs(r["fsum"] - f) <= 1e-9 * max(1.0, abs(f))
+        lin = go.window_linear(int(r["key"]), int(r["id"]))
+        assert lin is not None and lin["isum"] == r["isum"]
+    # expected count: per key, groups fired = c < B ? 0 : 1 + (c - B) // (S*Nb)
+    B = (nb - 1) * slide + win
+    exp = 0
+    for k in np.unique(res["key"]):
+        c = int((res["key"] == k).sum())
+        exp += 0 if c < B else (1 + (c - B) // (slide * nb)) * nb
+    assert len(out) == exp
+
+
+def test_cpu_ffat_matches_live_reference(oracle):
+    O = oracle
+    if O.ref_cpu_lib() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    rng = np.random.default_rng(7)
+    for (W, S, nk) in [(4, 2, 3), (8, 8, 1), (10, 3, 5), (7, 7, 2), (5, 1, 4), (32, 8, 6), (256, 64, 3)]:
+        n = max(6000, W * nk * 6)
+        r = _stream(O, rng, n, nk)
+        oc, rc = O.FfatCpuOracle(W, S), O.RefFfatCpu(W, S)
+        for b in range(0, n, 257):
+            o, ot = oc.process(r[b:b + 257], b)
+            q, qt = rc.process(r[b:b + 257], b)
+            assert np.array_equal(ot, qt)
+            assert o.tobytes() == q.tobytes()
+        eo, _ = oc.eos(); er, _ = rc.eos()
+        assert O.sort_results(eo).tobytes() == O.sort_results(er).tobytes()
+
+
+def test_stream_generator(oracle):
+    O = oracle
+    t, ts = O.gen_tuple64(1000, 4096, O.KEY_UNIFORM, 65536)
+    assert np.array_equal(ts, np.arange(1000, 1000 + 4096, dtype=np.uint64))
+    assert np.array_equal(t["id"], ts)
+    assert (t["ivalue"] >= 0).all() and (t["ivalue"] <= 0xFFFF).all()
+    assert (t["fvalue"] >= 0).all() and (t["fvalue"] < 1).all()
+    assert (t["key"] < 65536).all() and len(np.unique(t["key"])) > 3000
+    t2, _ = O.gen_tuple64(1000, 4096, O.KEY_RR, 100)
+    assert np.array_equal(t2["key"], np.arange(1000, 1000 + 4096) % 100)
+    assert np.array_equal(t2["ivalue"], t["ivalue"])
+    t3, _ = O.gen_tuple64(0, 20000, O.KEY_ZIPF, 1000)
+    c = np.bincount(t3["key"].astype(np.int64), minlength=1000)
+    assert c[0] > c[10] > c[500]
+
+
+def test_map_filter_columns(oracle):
+    O = oracle
+    t, ts = O.gen_tuple64(0, 5000, O.KEY_UNIFORM, 64)
+    surv, sts, m = O.map_filter_tuple64(t, ts, O.MAP_ADD_SCALE, 2, 1.0000001, O.FILT_EVEN)
+    exp_iv = t["ivalue"] + 2
+    assert np.array_equal(m, (exp_iv & 1) == 0)
+    assert np.array_equal(surv["ivalue"], exp_iv[m]) and np.array_equal(sts, ts[m])
+    assert np.allclose(surv["fvalue"], (t["fvalue"] * 1.0000001)[m], rtol=0, atol=0)
+    assert np.array_equal(surv["id"], t["id"][m])  # stable: arrival order kept
+    _, _, m3 = O.map_filter_tuple64(t, ts, O.MAP_NONE, 0, 1.0, O.FILT_MOD, 3)
+    assert np.array_equal(m3, t["ivalue"] % 3 == 0)
+    neg = np.array([-4, -3, -2, -1, 0, 1, 2, 3], dtype=np.int64)
+    assert np.array_equal(O.filter_mask(neg, O.FILT_MOD, 2), [True, False, True, False, True, False, True, False])
+
+
+def test_keyby_group_and_route(oracle):
+    O = oracle
+    rng = np.random.default_rng(3)
+    keys = rng.integers(0, 37, 1000).astype(np.uint64)
+    for order in (0, 1):
+        start, mp, dk = O.keyby_group(keys, order)
+        assert len(dk) == len(np.unique(keys))
+        if order == 1:
+            assert np.array_equal(dk, np.unique(keys))
+        else:
+            _, first = np.unique(keys, return_index=True)
+            assert np.array_equal(dk, keys[np.sort(first)])
+        seen = np.zeros(len(keys), dtype=bool)
+        for k, s in zip(dk, start):
+            idx = int(s); prev = -1
+            assert idx == int(np.nonzero(keys == k)[0][0])
+            while idx != -1:
+                assert keys[idx] == k and idx > prev and not seen[idx]
+                seen[idx] = True; prev = idx; idx = int(mp[idx])
+        assert seen.all()
+    assert np.array_equal(O.route(keys, 8), keys % 8)
+    assert len(O.keyby_group(np.zeros(0, dtype=np.uint64), 1)[2]) == 0
+
+
+def test_reduce_by_key(oracle):
+    O = oracle
+    t, ts = O.gen_tuple64(0, 3000, O.KEY_UNIFORM, 50)
+    t["key"][7] = 999  # a key seen once passes through untouched
+    out, ot = O.reduce_tuple64(t, ts)
+    uk = np.unique(t["key"])
+    assert np.array_equal(out["key"], uk)
+    for r, tts in zip(out, ot):
+        sel = t["key"] == r["key"]
+        assert r["ivalue"] == t["ivalue"][sel].sum()
+        assert abs(r["fvalue"] - t["fvalue"][sel].sum()) < 1e-9
+        assert tts == ts[sel].max()
+        if sel.sum() == 1:
+            assert r["id"] == t["id"][sel][0]
+        else:
+            assert r["id"] == 0

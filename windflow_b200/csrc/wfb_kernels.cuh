@@ -1,0 +1,764 @@
+// wfb_kernels.cuh -- hand-written sm_100a kernels of the WindFlow GPU operator hot path, templated on a
+// "program" (record schema + functors, see wfb_programs.cuh).
+//
+// Kernel inventory (DESIGN.md section 4 has the roofline of each):
+//   k_tile_pass<P, MODE>   streaming tile pass: TMA bulk load of a tile of tuples into shared memory
+//                          (cp.async.bulk + mbarrier, STAGES-deep), per-tuple map / filter in registers,
+//                          block scan + decoupled look-back for the stable output offset, survivors staged in
+//                          shared memory and written with a TMA bulk store.
+//                            MODE_MAP     in-place Map_GPU                 (wf/map_gpu.hpp:61-76)
+//                            MODE_FILTER  [Map_GPU ->] Filter_GPU          (wf/filter_gpu.hpp:72-88, :555-570)
+//                            MODE_INGEST  [Map -> Filter ->] lift + key->slot for Ffat_Windows_GPU
+//                                         (wf/ffat_replica_gpu.hpp:94-121)
+//   k_radix_hist / k_radix_scan / k_radix_scatter   stable LSD radix passes over (slot, position) pairs: the
+//                          replacement of thrust::sort_by_key (wf/ffat_replica_gpu.hpp:751, keyby_emitter_gpu.hpp:547)
+//   k_slot_offsets         exclusive scan of the per-key counts of a stream segment
+//   k_ffat_update          one warp per key: ordered pane fold, FlatFAT leaf write + path update, window
+//                          queries (wf/flatfat_gpu.hpp:62-139, wf/ffat_replica_gpu.hpp:830-867)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "wfb_ptx.cuh"
+
+namespace wfb {
+
+constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pass
+constexpr int STAGES = 3;    // TMA pipeline depth (tiles in flight per CTA = STAGES-1)
+constexpr uint32_t FULL = 0xffffffffu;
+
+enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2 };
+
+// decoupled look-back tile state: [63:34] epoch, [33:32] status, [31:0] value
+constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
+__host__ __device__ __forceinline__ uint64_t pack_state(uint32_t epoch, uint64_t status, uint32_t v)
+{
+    return (static_cast<uint64_t>(epoch & 0x3fffffffu) << 34) | (status << 32) | v;
+}
+
+// one input batch as the kernels see it
+struct DevBatch {
+    const unsigned char *tuples;
+    const uint64_t *ts;
+    unsigned char *out;        // MODE_FILTER/MAP: output tuples
+    uint64_t *ts_out;          // MODE_FILTER: output timestamps (may be null)
+    uint32_t *n_out;           // MODE_FILTER: survivors of this batch (device)
+    uint64_t watermark;
+    uint32_t n;
+    uint32_t tile_begin;       // first global tile index of this batch
+};
+
+// key -> slot table (open addressing, linear probing) + per-key window state of one Ffat_Windows_GPU
+struct FfatDev {
+    // key table
+    uint64_t *ht_keys;         // capacity entries, EMPTY_KEY when free
+    uint32_t *ht_slots;        // capacity entries, INVALID_SLOT until published
+    uint32_t ht_mask;          // capacity - 1
+    uint32_t max_keys;
+    uint32_t *n_slots;         // number of keys inserted so far
+    uint32_t *err_flags;       // bit0: key table full, bit1: output capacity exceeded
+    uint32_t dense;            // 1: slot = key (keys < max_keys)
+    // per-slot state
+    uint64_t *slot_key;        // key of each slot
+    uint64_t *cnt;             // lifted results appended so far (Key_Descriptor::count)
+    unsigned char *acc;        // open-pane accumulator, result_t per slot
+    unsigned char *tree;       // FlatFAT per slot: (2*n_leaves-1) result_t, leaves first (level 0), root last
+    uint32_t *seg_cnt;         // items of the current stream segment per slot (zeroed by k_ffat_update)
+    uint32_t *seg_off;         // exclusive offsets into the sorted segment, max_keys+1
+    // window geometry (in tuples and in panes)
+    uint64_t win, slide, B;    // B = (Nb-1)*slide + win  (ffat_replica_gpu.hpp:657)
+    uint32_t nb;               // windows per trigger
+    uint32_t pane;             // pane length P = gcd(win, slide) in tuples
+    uint32_t wp, sp;           // window / slide in panes
+    uint32_t n_leaves;         // power of two >= B / P
+    uint32_t log_leaves;
+};
+constexpr uint64_t EMPTY_KEY = 0xffffffffffffffffull;
+constexpr uint32_t INVALID_SLOT = 0xffffffffu;
+
+struct TileArgs {
+    const DevBatch *batches;   // device array (nbatches entries) or null => use `one`
+    DevBatch one;
+    uint32_t nbatches;
+    uint32_t num_tiles;
+    uint64_t *tile_state;      // num_tiles words (epoch-tagged, never cleared)
+    uint32_t *ticket;          // monotonically increasing ticket counter
+    uint32_t ticket_base;      // value of *ticket when this launch starts
+    uint32_t epoch;
+    // MODE_INGEST outputs (compacted over the whole segment, arrival order)
+    unsigned char *lifted;     // result_t per surviving tuple
+    uint32_t *slots;           // slot per surviving tuple
+    uint32_t *batch_off;       // nbatches+1: compact offset of the first survivor of each batch; [nbatches]=total
+    uint32_t *n_total;         // == batch_off[nbatches]
+    FfatDev ff;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// shared-memory tile access. A tuple of C = sizeof(T)/16 16-byte chunks is read/written with its chunks
+// rotated by (idx*C/8)%C so that the 8 lanes of a quarter warp hit 8 different 16-byte bank groups
+// (stride-64B LDS.128 would otherwise be a 4-way bank conflict).
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+struct TileIO {
+    static constexpr int TB = sizeof(T);
+    static constexpr bool V16 = (TB % 16 == 0) && (TB / 16 == 1 || TB / 16 == 2 || TB / 16 == 4 || TB / 16 == 8);
+    static constexpr int C = V16 ? TB / 16 : TB / 8;
+
+    __device__ __forceinline__ static void load(const unsigned char *base, uint32_t idx, T &out)
+    {
+        if constexpr (V16) {
+            uint4 v[C];
+            const uint4 *p = reinterpret_cast<const uint4 *>(base + static_cast<size_t>(idx) * TB);
+            const uint32_t rot = (C > 1) ? ((idx * C / 8) % C) : 0;
+#pragma unroll
+            for (int j = 0; j < C; j++) v[j] = p[(j + rot) & (C - 1)];
+            // v[j] holds chunk (j+rot)%C; rotate right by rot so that v[k] holds chunk k
+#pragma unroll
+            for (int s = 1; s < C; s <<= 1) {
+                if (rot & s) {
+                    uint4 t[C];
+#pragma unroll
+                    for (int k = 0; k < C; k++) t[k] = v[(k - s) & (C - 1)];
+#pragma unroll
+                    for (int k = 0; k < C; k++) v[k] = t[k];
+                }
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(&out);
+#pragma unroll
+            for (int k = 0; k < C; k++) o[k] = v[k];
+        } else {
+            const uint64_t *p = reinterpret_cast<const uint64_t *>(base + static_cast<size_t>(idx) * TB);
+            uint64_t *o = reinterpret_cast<uint64_t *>(&out);
+#pragma unroll
+            for (int k = 0; k < C; k++) o[k] = p[k];
+        }
+    }
+
+    __device__ __forceinline__ static void store(unsigned char *base, uint32_t idx, const T &in)
+    {
+        if constexpr (V16) {
+            uint4 v[C];
+            const uint4 *src = reinterpret_cast<const uint4 *>(&in);
+#pragma unroll
+            for (int k = 0; k < C; k++) v[k] = src[k];
+            const uint32_t rot = (C > 1) ? ((idx * C / 8) % C) : 0;
+            // rotate left by rot: v'[j] = chunk (j+rot)%C, then store v'[j] at position (j+rot)%C
+#pragma unroll
+            for (int s = 1; s < C; s <<= 1) {
+                if (rot & s) {
+                    uint4 t[C];
+#pragma unroll
+                    for (int k = 0; k < C; k++) t[k] = v[(k + s) & (C - 1)];
+#pragma unroll
+                    for (int k = 0; k < C; k++) v[k] = t[k];
+                }
+            }
+            uint4 *p = reinterpret_cast<uint4 *>(base + static_cast<size_t>(idx) * TB);
+#pragma unroll
+            for (int j = 0; j < C; j++) p[(j + rot) & (C - 1)] = v[j];
+        } else {
+            uint64_t *p = reinterpret_cast<uint64_t *>(base + static_cast<size_t>(idx) * TB);
+            const uint64_t *s = reinterpret_cast<const uint64_t *>(&in);
+#pragma unroll
+            for (int k = 0; k < C; k++) p[k] = s[k];
+        }
+    }
+};
+
+// global <-> shared tile movement: TMA bulk copy when size and address allow it, else coalesced 8-byte words
+__device__ __forceinline__ bool bulk_ok(const void *g, uint32_t bytes)
+{
+    return ((reinterpret_cast<uintptr_t>(g) | bytes) & 15u) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// key -> slot lookup / insert (replaces the host unordered_map of ffat_replica_gpu.hpp:514, :783-795)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t slot_of_key(const FfatDev &ff, uint64_t key)
+{
+    if (ff.dense) {
+        if (key >= ff.max_keys) { atomicOr(ff.err_flags, 1u); return INVALID_SLOT; }
+        return static_cast<uint32_t>(key);
+    }
+    uint32_t h = static_cast<uint32_t>(mix64(key)) & ff.ht_mask;
+    for (uint32_t probe = 0; probe <= ff.ht_mask; probe++) {
+        uint64_t k = ld_relaxed_u64(&ff.ht_keys[h]);
+        if (k == EMPTY_KEY) {
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(&ff.ht_keys[h]),
+                                               static_cast<unsigned long long>(EMPTY_KEY),
+                                               static_cast<unsigned long long>(key));
+            if (old == EMPTY_KEY) { // we own the entry: allocate the slot and publish it
+                uint32_t s = atomicAdd(ff.n_slots, 1u);
+                if (s >= ff.max_keys) { atomicOr(ff.err_flags, 1u); s = INVALID_SLOT - 1; }
+                else ff.slot_key[s] = key;
+                st_release_u32(&ff.ht_slots[h], s);
+                return s >= ff.max_keys ? INVALID_SLOT : s;
+            }
+            k = old;
+        }
+        if (k == key) {
+            uint32_t s;
+            while ((s = ld_acquire_u32(&ff.ht_slots[h])) == INVALID_SLOT) { }
+            return s >= ff.max_keys ? INVALID_SLOT : s;
+        }
+        h = (h + 1) & ff.ht_mask;
+    }
+    atomicOr(ff.err_flags, 1u);
+    return INVALID_SLOT;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_tile_pass: persistent CTAs, dynamic tile tickets, STAGES-deep TMA pipeline.
+//   per tile: [thread 0] cp.async.bulk global->shared (issued STAGES-1 tiles ahead)
+//             wait mbarrier | tuple -> registers (conflict-free rotated LDS.128) | map | filter | [lift, key->slot]
+//             ballot + warp totals -> local offsets | warp 0: decoupled look-back -> tile base
+//             survivors -> shared (compacted, linear) | fence.proxy.async | [thread 0] cp.async.bulk shared->global
+// Tickets: every CTA claims STAGES-1 tickets up front and one more per processed tile, so one launch consumes
+// exactly num_tiles + gridDim.x*(STAGES-1) tickets (the host advances ticket_base by that amount).
+// ------------------------------------------------------------------------------------------------------
+template <class P, int MODE>
+struct TilePassSmem {
+    using T = typename P::tuple_t;
+    using R = typename P::result_t;
+    static constexpr uint32_t rec_bytes = (MODE == MODE_INGEST && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
+    static constexpr uint32_t stage_bytes = TILE * rec_bytes;
+    static constexpr uint32_t total = STAGES * stage_bytes + 256;
+};
+
+template <class P, int MODE>
+__global__ void __launch_bounds__(TILE) k_tile_pass(const TileArgs a, const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    using R = typename P::result_t;
+    constexpr uint32_t TB = sizeof(T);
+    constexpr uint32_t RB = sizeof(R);
+    static_assert(TB % 8 == 0 && RB % 8 == 0, "records must be multiples of 8 bytes");
+    constexpr uint32_t STAGE_BYTES = TilePassSmem<P, MODE>::stage_bytes;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *tiles = smem;                                                   // STAGES * STAGE_BYTES
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);    // STAGES mbarriers
+    uint32_t *tile_id = reinterpret_cast<uint32_t *>(full + STAGES);               // STAGES
+    uint32_t *warp_tot = tile_id + STAGES;                                         // TILE/32
+    uint32_t *bcast = warp_tot + TILE / 32;                                        // [0] = tile base
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    auto batch_of = [&](uint32_t tile, DevBatch &b) -> uint32_t {
+        if (a.batches == nullptr) { b = a.one; return 0u; }
+        uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= tile
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (a.batches[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        b = a.batches[lo];
+        return lo;
+    };
+
+    // producer (thread 0): claim the next ticket and start the TMA load of that tile into stage s
+    auto produce = [&](uint32_t s) {
+        const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        if (t >= a.num_tiles) { // nothing to load: plain arrival so that the consumers see the sentinel
+            tile_id[s] = 0x7fffffffu;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+            return;
+        }
+        DevBatch b; batch_of(t, b);
+        const uint32_t first = (t - b.tile_begin) * TILE;
+        const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
+        const unsigned char *src = b.tuples + static_cast<size_t>(first) * TB;
+        const uint32_t bytes = cnt * TB;
+        if (bulk_ok(src, bytes)) {
+            tile_id[s] = t;
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(tiles + s * STAGE_BYTES, src, bytes, &full[s]);
+        } else { // consumers fall back to coalesced word loads for this tile
+            tile_id[s] = t | 0x80000000u;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        for (int s = 0; s < STAGES - 1; s++) produce(s);
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0;; it++) {
+        const uint32_t s = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1u;
+        unsigned char *buf = tiles + s * STAGE_BYTES;
+
+        // tile_id[s] was written at least one __syncthreads ago: safe to read before the mbarrier wait, which
+        // lets the timestamp load (and the batch lookup) overlap the wait for the TMA bytes.
+        uint32_t t = tile_id[s];
+        const bool fallback = (t & 0x80000000u) != 0;
+        t &= 0x7fffffffu;
+        if (t >= a.num_tiles) break; // tickets are handed out in order: every later one is out of range too
+
+        DevBatch b;
+        const uint32_t bi = batch_of(t, b);
+        const uint32_t first = (t - b.tile_begin) * TILE;
+        const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
+        const bool active = tid < cnt;
+        uint64_t ts = 0;
+        if (MODE == MODE_FILTER && active && b.ts != nullptr) ts = b.ts[first + tid];
+
+        mbar_wait(&full[s], parity);
+
+        if (fallback) { // unaligned / odd-sized tile: coalesced 8-byte copies into the same (linear) buffer
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(b.tuples + static_cast<size_t>(first) * TB);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(buf);
+            for (uint32_t w = tid; w < cnt * (TB / 8); w += TILE) dst[w] = src[w];
+            __syncthreads();
+        }
+
+        // ---- per-tuple work in registers ---------------------------------------------------------------
+        alignas(16) T tup;
+        bool keep = false;
+        if (active) {
+            TileIO<T>::load(buf, tid, tup);
+            P::map(tup, prm);
+            keep = (MODE == MODE_MAP) ? true : P::filter(tup, prm);
+        }
+
+        uint32_t local = tid, tile_count = cnt, base = 0;
+        uint32_t slot = INVALID_SLOT;
+        if constexpr (MODE == MODE_MAP) {
+            __syncthreads(); // every thread has read its tuple: the stage can be overwritten with the results
+            if (active) TileIO<T>::store(buf, tid, tup);
+            fence_async_smem();
+            __syncthreads();
+        } else {
+            // the timestamp load must have completed before this tile publishes its count (an in-place
+            // compaction lets later tiles overwrite this tile's input once the count is visible)
+            if constexpr (MODE == MODE_FILTER) asm volatile("mov.b64 %0, %0;" : "+l"(ts));
+            // ---- stable offsets: block scan of the keep flags + decoupled look-back --------------------------
+            const uint32_t bal = __ballot_sync(FULL, keep);
+            if (lane == 0) warp_tot[warp] = __popc(bal);
+            __syncthreads(); // warp totals visible; every thread has read its tuple (stage re-usable for staging)
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = warp_tot[w]; if (w < warp) wbase += c; total += c; }
+            local = wbase + __popc(bal & lanemask_lt());
+            tile_count = total;
+
+            if (warp == 0) {
+                // look-back chain: per batch for MODE_FILTER, over the whole stream segment for MODE_INGEST
+                const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
+                uint32_t excl = 0;
+                if (t == chain_begin) {
+                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_PREFIX, tile_count));
+                } else {
+                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_AGG, tile_count));
+                    int64_t idx = static_cast<int64_t>(t) - 1;
+                    while (true) {
+                        const int64_t my = idx - lane;
+                        uint64_t w = pack_state(a.epoch, ST_PREFIX, 0); // virtual terminator below the chain start
+                        bool valid;
+                        do {
+                            valid = true;
+                            if (my >= static_cast<int64_t>(chain_begin)) {
+                                w = ld_relaxed_u64(&a.tile_state[my]);
+                                valid = ((w >> 34) == (a.epoch & 0x3fffffffu)) && (((w >> 32) & 3u) != 0);
+                            }
+                        } while (!__all_sync(FULL, valid));
+                        const uint32_t status = static_cast<uint32_t>(w >> 32) & 3u;
+                        const uint32_t pmask = __ballot_sync(FULL, status == ST_PREFIX);
+                        const uint32_t firstp = pmask ? (__ffs(pmask) - 1) : 32;
+                        uint32_t v = (lane <= firstp) ? static_cast<uint32_t>(w) : 0u;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                        excl += v;
+                        if (pmask) break;
+                        idx -= 32;
+                    }
+                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_PREFIX, excl + tile_count));
+                }
+                if (lane == 0) {
+                    bcast[0] = excl;
+                    if constexpr (MODE == MODE_FILTER) {
+                        const uint32_t last_tile = b.tile_begin + (b.n + TILE - 1) / TILE - 1;
+                        if (t == last_tile && b.n_out != nullptr) *b.n_out = excl + tile_count;
+                    } else {
+                        if (t == b.tile_begin) a.batch_off[bi] = excl;
+                        if (t == a.num_tiles - 1) { a.batch_off[a.nbatches] = excl + tile_count; *a.n_total = excl + tile_count; }
+                    }
+                }
+            }
+
+            // ---- stage the outputs in shared memory (compacted, linear layout) -----------------------------
+            if (keep) {
+                if constexpr (MODE == MODE_FILTER) {
+                    TileIO<T>::store(buf, local, tup);
+                } else {
+                    alignas(16) R res;
+                    P::lift(tup, res);
+                    slot = slot_of_key(a.ff, P::key(tup));
+                    if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                    TileIO<R>::store(buf, local, res);
+                }
+            }
+            fence_async_smem();
+            __syncthreads(); // staging complete, bcast[0] visible
+            base = bcast[0];
+        }
+
+        // ---- write out: one TMA bulk store per tile (coalesced word copies when misaligned) ---------------------
+        {
+            unsigned char *dst;
+            uint32_t bytes;
+            if constexpr (MODE == MODE_MAP) { dst = b.out + static_cast<size_t>(first) * TB; bytes = cnt * TB; }
+            else if constexpr (MODE == MODE_FILTER) { dst = b.out + static_cast<size_t>(base) * TB; bytes = tile_count * TB; }
+            else { dst = a.lifted + static_cast<size_t>(base) * RB; bytes = tile_count * RB; }
+            if (bulk_ok(dst, bytes)) {
+                if (tid == 0 && bytes) bulk_s2g(dst, buf, bytes);
+            } else {
+                uint64_t *d8 = reinterpret_cast<uint64_t *>(dst);
+                const uint64_t *s8 = reinterpret_cast<const uint64_t *>(buf);
+                for (uint32_t w = tid; w < bytes / 8; w += TILE) d8[w] = s8[w];
+            }
+            if constexpr (MODE == MODE_FILTER) { if (keep && b.ts_out != nullptr) b.ts_out[base + local] = ts; }
+            if constexpr (MODE == MODE_INGEST) { if (keep) a.slots[base + local] = slot; }
+        }
+
+        // ---- refill the pipeline. The stage refilled here is the one used by the PREVIOUS iteration: every
+        // thread has passed this iteration's barriers, so nobody still touches it with ordinary accesses, and
+        // its bulk store has finished reading once all but the newest group (committed just now, possibly
+        // empty) are done.
+        if (tid == 0) {
+            bulk_commit();
+            bulk_wait_read<1>();
+            produce((it + STAGES - 1) % STAGES);
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// record helpers (R = result_t): vectorised global load/store and warp shuffles of whole records
+// ------------------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ void ld_rec(const unsigned char *p, R &r)
+{
+    if constexpr (sizeof(R) % 16 == 0) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(p);
+        uint4 *d = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+        for (uint32_t k = 0; k < sizeof(R) / 16; k++) d[k] = s[k];
+    } else {
+        const uint64_t *s = reinterpret_cast<const uint64_t *>(p);
+        uint64_t *d = reinterpret_cast<uint64_t *>(&r);
+#pragma unroll
+        for (uint32_t k = 0; k < sizeof(R) / 8; k++) d[k] = s[k];
+    }
+}
+template <class R>
+__device__ __forceinline__ void st_rec(unsigned char *p, const R &r)
+{
+    if constexpr (sizeof(R) % 16 == 0) {
+        uint4 *d = reinterpret_cast<uint4 *>(p);
+        const uint4 *s = reinterpret_cast<const uint4 *>(&r);
+#pragma unroll
+        for (uint32_t k = 0; k < sizeof(R) / 16; k++) d[k] = s[k];
+    } else {
+        uint64_t *d = reinterpret_cast<uint64_t *>(p);
+        const uint64_t *s = reinterpret_cast<const uint64_t *>(&r);
+#pragma unroll
+        for (uint32_t k = 0; k < sizeof(R) / 8; k++) d[k] = s[k];
+    }
+}
+template <class R>
+__device__ __forceinline__ R shfl_down_rec(const R &r, uint32_t delta)
+{
+    alignas(16) R o;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&r);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+    for (uint32_t k = 0; k < sizeof(R) / 4; k++) d[k] = __shfl_down_sync(FULL, s[k], delta);
+    return o;
+}
+template <class R>
+__device__ __forceinline__ R shfl_rec(const R &r, uint32_t src)
+{
+    alignas(16) R o;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(&r);
+    uint32_t *d = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+    for (uint32_t k = 0; k < sizeof(R) / 4; k++) d[k] = __shfl_sync(FULL, s[k], src);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Stable LSD radix pass over (key32, val32) pairs, 8 bits per pass, three kernels per pass:
+//   k_radix_hist    per-tile digit histogram          H[digit * num_tiles + tile]
+//   k_radix_scan    exclusive scan of H in (digit, tile) order (single CTA)
+//   k_radix_scatter stable in-tile ranks (warp match_any, warps in index order) + scatter
+// The element count lives on the device (*n_ptr): the grid covers the capacity, tiles past n do nothing.
+// Replaces thrust::sort_by_key at wf/ffat_replica_gpu.hpp:751, wf/keyby_emitter_gpu.hpp:547,
+// wf/reduce_gpu.hpp:239 (which sorts the 72-byte items themselves; here only 8-byte pairs move).
+// ------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 2048 elements per tile
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr,
+                                                           uint32_t shift, uint32_t *__restrict__ H, uint32_t num_tiles)
+{
+    __shared__ uint32_t h[256];
+    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
+    const uint32_t n = *n_ptr;
+    h[tid] = 0;
+    __syncthreads();
+    const uint32_t start = tile * RS_TILE;
+    if (start < n) {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = start + i * RS_THREADS + tid;
+            if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    H[tid * num_tiles + tile] = h[tid];
+}
+
+// exclusive scan of `total` uint32 counters (in may alias out), one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, uint32_t *out, uint32_t total, uint32_t *sum_out)
+{
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (total + 1023) / 1024;
+    const uint32_t begin = min(tid * per, total), end = min(begin + per, total);
+    uint32_t sum = 0;
+    for (uint32_t i = begin; i < end; i++) sum += in[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += v; }
+        warp_sums[lane] = wi - w; // exclusive
+        if (lane == 31 && sum_out != nullptr) *sum_out = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - sum;
+    for (uint32_t i = begin; i < end; i++) { const uint32_t v = in[i]; out[i] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                              const uint32_t *__restrict__ n_ptr, uint32_t shift,
+                                                              const uint32_t *__restrict__ H, uint32_t num_tiles)
+{
+    __shared__ uint32_t cntw[RS_THREADS / 32][256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+    const uint32_t n = *n_ptr;
+    const uint32_t start = tile * RS_TILE;
+    if (start >= n) return;
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; w++) cntw[w][tid] = 0;
+    __syncthreads();
+    uint32_t k[RS_ITEMS], rk[RS_ITEMS];
+    // warp w owns the contiguous range [start + w*256, +256), 32 consecutive elements per round: (warp, round,
+    // lane) order == index order, so ranks are stable.
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
+        const bool valid = idx < n;
+        k[r] = valid ? keys_in[idx] : 0u;
+        const uint32_t d = valid ? ((k[r] >> shift) & 255u) : 256u;
+        const uint32_t mask = __match_any_sync(FULL, d);
+        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
+        __syncwarp();
+        if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] += __popc(mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    { // digit `tid`: exclusive prefix over the warps, on top of the tile's global base for this digit
+        uint32_t base = H[tid * num_tiles + tile];
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; w++) { const uint32_t c = cntw[w][tid]; cntw[w][tid] = base; base += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (k[r] >> shift) & 255u;
+            const uint32_t dst = cntw[warp][d] + rk[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = vals_in ? vals_in[idx] : idx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_ffat_update: one warp per key that received items in this stream segment.
+//   items of the key, in arrival order (sorted_pos[seg_off[slot] .. +seg_cnt[slot]) -> lifted[])
+//   -> ordered warp fold into the open pane (pane = gcd(win, slide) items)
+//   -> completed pane = new FlatFAT leaf (ring of n_leaves panes) + recompute of its root path
+//   -> when the key's count reaches the trigger: Nb window queries (greedy aligned-node fold, the same walk as
+//      Compute_Results_Kernel, wf/flatfat_gpu.hpp:93-139, over panes instead of tuples)
+// Window / trigger bookkeeping restates Ffat_Replica_GPU::process_wins_cb (wf/ffat_replica_gpu.hpp:830-867):
+// groups fired so far G(c) = c < B ? 0 : 1 + (c - B) / (S*Nb); next_gwid = G*Nb; trigger = B + G*S*Nb.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t level_off(uint32_t n_leaves, uint32_t level) { return 2u * n_leaves - ((2u * n_leaves) >> level); }
+
+template <class P>
+__global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const unsigned char *__restrict__ lifted,
+                                                     const uint32_t *__restrict__ sorted_pos,
+                                                     const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                     uint32_t nbatches, unsigned char *__restrict__ out_res,
+                                                     uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nslots = ff.dense ? ff.max_keys : min(*ff.n_slots, ff.max_keys);
+    const uint32_t n = ff.n_leaves, logn = ff.log_leaves;
+    const uint64_t P_ = ff.pane;
+    const uint64_t group_items = ff.slide * ff.nb;
+    const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
+
+    for (uint32_t slot = gwarp; slot < nslots; slot += nwarps) {
+        const uint32_t m = ff.seg_cnt[slot];
+        if (m == 0) continue;
+        const uint32_t off = ff.seg_off[slot];
+        uint64_t c = ff.cnt[slot];
+        const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+        unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
+        alignas(16) R acc;
+        if (c % P_ != 0) ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc); // every lane keeps a copy
+        uint64_t g = (c < ff.B) ? 0 : 1 + (c - ff.B) / group_items;
+        uint64_t trig = ff.B + g * group_items;
+
+        uint32_t j = 0;
+        while (j < m) {
+            const uint32_t room = static_cast<uint32_t>(P_ - (c % P_));
+            const uint32_t take = min(min(32u, m - j), room);
+            alignas(16) R r;
+            uint32_t p = 0;
+            if (lane < take) { p = sorted_pos[off + j + lane]; ld_rec<R>(lifted + static_cast<size_t>(p) * RB, r); }
+            // ordered fold: after the step with stride o, lane l holds items [l, l+2o) (clipped to take)
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+                const R other = shfl_down_rec<R>(r, o);
+                if (lane + o < take) P::comb(r, other, r);
+            }
+            r = shfl_rec<R>(r, 0);
+            const uint32_t last_pos = __shfl_sync(FULL, p, take - 1);
+            if (c % P_ == 0) acc = r; else P::comb(acc, r, acc);
+            c += take; j += take;
+
+            if (c % P_ == 0) { // pane complete -> leaf + root path
+                const uint32_t leaf = static_cast<uint32_t>((c / P_ - 1) & (n - 1));
+                alignas(16) R sib;
+                if (lane < logn) { // lane l fetches the sibling of the path node at level l
+                    const uint32_t idx = (leaf >> lane) ^ 1u;
+                    ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + idx) * RB, sib);
+                }
+                alignas(16) R cur = acc;
+                if (lane == 0) st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
+                for (uint32_t l = 0; l < logn; l++) {
+                    const R s = shfl_rec<R>(sib, l);
+                    alignas(16) R parent = cur; // key/id fields are don't-care in internal nodes
+                    if ((leaf >> l) & 1u) P::comb(s, cur, parent); else P::comb(cur, s, parent);
+                    cur = parent;
+                    if (lane == 0) st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                }
+                __syncwarp();
+
+                if (c == trig) { // fire Nb windows: gwid = g*Nb + i
+                    uint32_t lo = 0, hi = nbatches - 1; // batch holding the triggering item
+                    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (batch_off[mid] <= last_pos) lo = mid; else hi = mid - 1; }
+                    const uint64_t wm = batches[lo].watermark;
+                    uint32_t obase = 0;
+                    if (lane == 0) obase = atomicAdd(n_out, ff.nb);
+                    obase = __shfl_sync(FULL, obase, 0);
+                    for (uint32_t i = lane; i < ff.nb; i += 32) {
+                        const uint64_t gwid = g * ff.nb + i;
+                        alignas(16) R res = P::make_result(key, gwid);
+                        uint32_t ws = static_cast<uint32_t>((gwid * ff.sp) & (n - 1));
+                        uint32_t remaining = ff.wp;
+                        while (remaining > 0) {
+                            uint32_t range = (ws == 0) ? n : (ws & (0u - ws));
+                            const uint32_t pw = 1u << (31 - __clz(remaining));
+                            range = min(range, pw);
+                            const uint32_t level = 31 - __clz(range);
+                            alignas(16) R node;
+                            ld_rec<R>(tree + static_cast<size_t>(level_off(n, level) + (ws >> level)) * RB, node);
+                            P::comb(res, node, res);
+                            ws = (ws + range) & (n - 1);
+                            remaining -= range;
+                        }
+                        if (obase + i < out_cap) {
+                            st_rec<R>(out_res + static_cast<size_t>(obase + i) * RB, res);
+                            if (out_ts != nullptr) out_ts[obase + i] = wm;
+                        } else atomicOr(ff.err_flags, 2u);
+                    }
+                    g++; trig += group_items;
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) {
+            ff.cnt[slot] = c;
+            if (c % P_ != 0) st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
+            ff.seg_cnt[slot] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// synthetic stream of SURVEY.md 8d (integer arithmetic specified there; the tests check it bit for bit)
+// ------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void k_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys,
+                              const double *__restrict__ zipf_cdf, wfb_tuple64_t *__restrict__ out, uint64_t *__restrict__ ts)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint64_t i = start + j;
+        uint64_t key;
+        if (key_mode == 0) key = i % nkeys;
+        else if (key_mode == 1) key = splitmix64(i) % nkeys;
+        else {
+            const double u = static_cast<double>(splitmix64(i ^ 0xA5A5A5A5A5A5A5A5ull) >> 11) * (1.0 / 9007199254740992.0);
+            uint64_t lo = 0, hi = nkeys - 1;
+            while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (zipf_cdf[mid] > u) hi = mid; else lo = mid + 1; }
+            key = lo;
+        }
+        const int64_t iv = static_cast<int64_t>(splitmix64(seed ^ i) & 0xFFFFull);
+        const double fv = static_cast<double>(splitmix64(seed ^ ~i) >> 11) * (1.0 / 9007199254740992.0);
+        uint4 *o = reinterpret_cast<uint4 *>(out + j);
+        uint4 c0, c1;
+        c0.x = static_cast<uint32_t>(key); c0.y = static_cast<uint32_t>(key >> 32);
+        c0.z = static_cast<uint32_t>(i); c0.w = static_cast<uint32_t>(i >> 32);
+        const uint64_t ivb = static_cast<uint64_t>(iv);
+        const uint64_t fvb = static_cast<uint64_t>(__double_as_longlong(fv));
+        c1.x = static_cast<uint32_t>(ivb); c1.y = static_cast<uint32_t>(ivb >> 32);
+        c1.z = static_cast<uint32_t>(fvb); c1.w = static_cast<uint32_t>(fvb >> 32);
+        o[0] = c0; o[1] = c1; o[2] = make_uint4(0, 0, 0, 0); o[3] = make_uint4(0, 0, 0, 0);
+        if (ts != nullptr) ts[j] = i;
+    }
+}
+
+} // namespace wfb

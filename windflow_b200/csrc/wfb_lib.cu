@@ -1,0 +1,478 @@
+// wfb_lib.cu -- libwfb200.so: the extern "C" layer of include/wfb200.h over the kernels of wfb_kernels.cuh,
+// instantiated for the built-in programs of wfb_programs.cuh. No Thrust, no unified memory, no CPU fallback:
+// every compute entry point fails with WFB_E_NOGPU when there is no CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <new>
+#include <cuda_runtime.h>
+#include "../../include/wfb200.h"
+#include "wfb_kernels.cuh"
+#include "wfb_programs.cuh"
+
+using namespace wfb;
+
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return static_cast<int>(e__); } while (0)
+
+namespace {
+
+int g_num_sms = 0;
+
+int device_ready()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return WFB_E_NOGPU; }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return WFB_E_NOGPU;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return 0;
+}
+
+// ---- per-program launch table ------------------------------------------------------------------------------
+struct ProgramOps {
+    uint32_t tuple_bytes, result_bytes;
+    int (*tile_pass)(int mode, const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used);
+    int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
+                       const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
+                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s);
+};
+
+template <class P, int MODE>
+int launch_tile_pass(const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used)
+{
+    static int max_grid = -1;
+    constexpr uint32_t smem = TilePassSmem<P, MODE>::total;
+    if (max_grid < 0) {
+        CK(cudaFuncSetAttribute(k_tile_pass<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass<P, MODE>, TILE, smem));
+        if (per_sm < 1) per_sm = 1;
+        max_grid = per_sm * g_num_sms;
+    }
+    const uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
+    typename P::params_t prm;
+    if (params) prm = *static_cast<const typename P::params_t *>(params); else std::memset(&prm, 0, sizeof(prm));
+    k_tile_pass<P, MODE><<<grid, TILE, smem, s>>>(a, prm);
+    CK(cudaGetLastError());
+    *grid_used = grid;
+    return 0;
+}
+
+template <class P>
+int tile_pass_dispatch(int mode, const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used)
+{
+    switch (mode) {
+    case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used);
+    case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used);
+    case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used);
+    }
+    return WFB_E_BADARG;
+}
+
+template <class P>
+int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
+                         const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
+                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s)
+{
+    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class P>
+ProgramOps make_ops()
+{
+    ProgramOps o;
+    o.tuple_bytes = sizeof(typename P::tuple_t);
+    o.result_bytes = sizeof(typename P::result_t);
+    o.tile_pass = &tile_pass_dispatch<P>;
+    o.ffat_update = &ffat_update_dispatch<P>;
+    return o;
+}
+
+const ProgramOps *program(int prog)
+{
+    static const ProgramOps table[] = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>() };
+    if (prog < 0 || prog >= static_cast<int>(sizeof(table) / sizeof(table[0]))) return nullptr;
+    return &table[prog];
+}
+
+// ---- scratch shared by the tile passes: ticket counter, epoch-tagged tile states, batch descriptors -----------
+struct TileScratch {
+    uint64_t *tile_state = nullptr; uint32_t tile_cap = 0;
+    uint32_t *ticket = nullptr; uint32_t ticket_base = 0; uint32_t epoch = 0;
+    DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
+    cudaStream_t last_stream = nullptr; bool used = false; cudaEvent_t ev = nullptr;
+
+    int init()
+    {
+        CK(cudaMalloc(&ticket, sizeof(uint32_t)));
+        CK(cudaMemset(ticket, 0, sizeof(uint32_t)));
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        return 0;
+    }
+    void destroy()
+    {
+        cudaFree(tile_state); cudaFree(ticket); cudaFree(d_batches);
+        if (ev) cudaEventDestroy(ev);
+    }
+    // scratch is shared by consecutive launches: order them when the caller hops between streams
+    // (the reference launches on each batch's own stream, wf/map_gpu.hpp:399-405)
+    int enter(cudaStream_t s)
+    {
+        if (used && s != last_stream) { CK(cudaEventRecord(ev, last_stream)); CK(cudaStreamWaitEvent(s, ev, 0)); }
+        last_stream = s; used = true;
+        return 0;
+    }
+    int ensure_tiles(uint32_t num_tiles)
+    {
+        if (num_tiles <= tile_cap) return 0;
+        CK(cudaStreamSynchronize(last_stream));
+        cudaFree(tile_state);
+        tile_cap = std::max(num_tiles, 2 * tile_cap);
+        CK(cudaMalloc(&tile_state, sizeof(uint64_t) * tile_cap));
+        CK(cudaMemset(tile_state, 0, sizeof(uint64_t) * tile_cap)); // epoch 0 is never used by a launch
+        return 0;
+    }
+    int ensure_batches(uint32_t nb)
+    {
+        if (nb <= batch_cap) return 0;
+        CK(cudaStreamSynchronize(last_stream));
+        cudaFree(d_batches);
+        batch_cap = std::max(nb, 2 * batch_cap);
+        CK(cudaMalloc(&d_batches, sizeof(DevBatch) * batch_cap));
+        return 0;
+    }
+    void next_launch(TileArgs &a) { epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1; a.epoch = epoch; a.ticket = ticket; a.ticket_base = ticket_base; a.tile_state = tile_state; }
+    void launched(uint32_t num_tiles, uint32_t grid) { ticket_base += num_tiles + grid * (STAGES - 1); }
+};
+
+inline uint32_t tiles_of(uint32_t n) { return (n + TILE - 1) / TILE; }
+
+} // namespace
+
+struct wfb_engine {
+    int prog = 0;
+    const ProgramOps *ops = nullptr;
+    TileScratch ts;
+    uint64_t launches = 0;
+};
+
+struct wfb_ffat {
+    int prog = 0;
+    const ProgramOps *ops = nullptr;
+    FfatDev ff{};
+    TileScratch ts;
+    uint32_t sort_passes = 1;
+    // per-segment scratch (grown on demand)
+    uint32_t seg_cap = 0;
+    unsigned char *lifted = nullptr;
+    uint32_t *slotsA = nullptr, *slotsB = nullptr, *posA = nullptr, *posB = nullptr;
+    uint32_t *H = nullptr; uint32_t h_tiles = 0;
+    uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
+    uint32_t *n_total = nullptr;
+    uint64_t launches = 0;
+    size_t state_bytes = 0;
+    int win_type = 0;
+};
+
+extern "C" {
+
+int wfb_abi_version(void) { return WFB_ABI_VERSION; }
+
+const char *wfb_error_string(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case WFB_E_BADARG: return "wfb: bad argument";
+    case WFB_E_NOPROG: return "wfb: unknown program id";
+    case WFB_E_CAPACITY: return "wfb: capacity exceeded (keys or results)";
+    case WFB_E_NOGPU: return "wfb: no CUDA device (libwfb200 has no CPU fallback)";
+    case WFB_E_UNSUPPORTED: return "wfb: not supported";
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "wfb: unknown error";
+}
+
+int wfb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wfb_program_info(int prog, wfb_program_info_t *info)
+{
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    if (!info) return WFB_E_BADARG;
+    info->tuple_bytes = o->tuple_bytes; info->result_bytes = o->result_bytes; info->key_bytes = 8; info->reserved = 0;
+    return 0;
+}
+
+// ---- engine -------------------------------------------------------------------------------------------------
+int wfb_engine_create(wfb_engine_t **e, int prog)
+{
+    if (!e) return WFB_E_BADARG;
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    int rc = device_ready(); if (rc) return rc;
+    wfb_engine *g = new (std::nothrow) wfb_engine();
+    if (!g) return WFB_E_BADARG;
+    g->prog = prog; g->ops = o;
+    rc = g->ts.init(); if (rc) { delete g; return rc; }
+    *e = g;
+    return 0;
+}
+
+int wfb_engine_destroy(wfb_engine_t *e)
+{
+    if (!e) return 0;
+    cudaDeviceSynchronize();
+    e->ts.destroy();
+    delete e;
+    return 0;
+}
+
+uint64_t wfb_engine_launches(const wfb_engine_t *e) { return e ? e->launches : 0; }
+
+static int run_single(wfb_engine_t *e, int mode, const wfb_functors_t *f, const DevBatch &b, cudaStream_t s)
+{
+    const uint32_t num_tiles = tiles_of(b.n);
+    int rc = e->ts.enter(s); if (rc) return rc;
+    rc = e->ts.ensure_tiles(num_tiles); if (rc) return rc;
+    TileArgs a; std::memset(&a, 0, sizeof(a));
+    a.batches = nullptr; a.one = b; a.nbatches = 1; a.num_tiles = num_tiles;
+    e->ts.next_launch(a);
+    uint32_t grid = 0;
+    rc = e->ops->tile_pass(mode, a, f, num_tiles, s, &grid); if (rc) return rc;
+    e->ts.launched(num_tiles, grid);
+    e->launches++;
+    return 0;
+}
+
+int wfb_map(wfb_engine_t *e, const wfb_functors_t *f, void *tuples, uint32_t n, void *stream)
+{
+    if (!e || !f || (!tuples && n)) return WFB_E_BADARG;
+    if (n == 0) return 0;
+    DevBatch b; std::memset(&b, 0, sizeof(b));
+    b.tuples = static_cast<const unsigned char *>(tuples); b.out = static_cast<unsigned char *>(tuples); b.n = n;
+    return run_single(e, MODE_MAP, f, b, static_cast<cudaStream_t>(stream));
+}
+
+int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f, const void *tuples_in, const uint64_t *ts_in, uint32_t n,
+                   void *tuples_out, uint64_t *ts_out, uint32_t *n_out_dev, void *stream)
+{
+    if (!e || !f || !n_out_dev || (n && (!tuples_in || !tuples_out))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    DevBatch b; std::memset(&b, 0, sizeof(b));
+    b.tuples = static_cast<const unsigned char *>(tuples_in); b.ts = ts_in;
+    b.out = static_cast<unsigned char *>(tuples_out); b.ts_out = ts_in ? ts_out : nullptr; b.n_out = n_out_dev; b.n = n;
+    return run_single(e, MODE_FILTER, f, b, s);
+}
+
+int wfb_reduce_by_key(wfb_engine_t *, const void *, const uint64_t *, uint32_t, void *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
+int wfb_reduce_all(wfb_engine_t *, const void *, const uint64_t *, uint32_t, void *, uint64_t *, void *) { return WFB_E_UNSUPPORTED; }
+int wfb_keyby_group(wfb_engine_t *, const void *, uint32_t, int32_t *, int32_t *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
+int wfb_shard_by_key(wfb_engine_t *, const void *, const uint64_t *, uint32_t, uint32_t, void *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
+
+// ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------------
+static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
+                    uint32_t max_keys, int win_type, uint64_t lateness, uint32_t flags)
+{
+    (void) lateness;
+    if (!hh || win == 0 || slide == 0 || wins_per_batch == 0 || max_keys == 0) return WFB_E_BADARG;
+    if (win_type != 0) return WFB_E_UNSUPPORTED; // time-based windows: see DESIGN.md (next)
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    int rc = device_ready(); if (rc) return rc;
+    wfb_ffat *h = new (std::nothrow) wfb_ffat();
+    if (!h) return WFB_E_BADARG;
+    h->prog = prog; h->ops = o; h->win_type = win_type;
+    rc = h->ts.init(); if (rc) { delete h; return rc; }
+    FfatDev &ff = h->ff;
+    ff.win = win; ff.slide = slide; ff.nb = wins_per_batch;
+    ff.B = static_cast<uint64_t>(wins_per_batch - 1) * slide + win;
+    const uint64_t pane = gcd_u64(win, slide);
+    const uint64_t bp = ff.B / pane;
+    if (pane > 0xffffffffull || bp > (1ull << 30)) { delete h; return WFB_E_BADARG; }
+    ff.pane = static_cast<uint32_t>(pane); ff.wp = static_cast<uint32_t>(win / pane); ff.sp = static_cast<uint32_t>(slide / pane);
+    uint32_t n = 1, lg = 0; while (n < bp) { n <<= 1; lg++; }
+    ff.n_leaves = n; ff.log_leaves = lg;
+    ff.max_keys = max_keys; ff.dense = (flags & WFB_FFAT_DENSE_KEYS) ? 1u : 0u;
+    uint32_t cap = 1; while (cap < 2ull * max_keys) cap <<= 1;
+    ff.ht_mask = cap - 1;
+    const size_t RB = o->result_bytes;
+    const size_t tree_bytes = static_cast<size_t>(max_keys) * (2ull * n - 1) * RB;
+    size_t total = 0;
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)); if (e_ != cudaSuccess) { wfb_ffat_destroy(h); return static_cast<int>(e_); } total += (bytes); } while (0)
+    if (!ff.dense) {
+        ALLOC(ff.ht_keys, sizeof(uint64_t) * cap);
+        ALLOC(ff.ht_slots, sizeof(uint32_t) * cap);
+        CK(cudaMemset(ff.ht_keys, 0xff, sizeof(uint64_t) * cap));
+        CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
+    }
+    ALLOC(ff.n_slots, sizeof(uint32_t) * 2);
+    ff.err_flags = ff.n_slots + 1;
+    CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 2));
+    ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
+    ALLOC(ff.cnt, sizeof(uint64_t) * max_keys);
+    CK(cudaMemset(ff.cnt, 0, sizeof(uint64_t) * max_keys));
+    ALLOC(ff.acc, RB * max_keys);
+    CK(cudaMemset(ff.acc, 0, RB * max_keys));
+    ALLOC(ff.tree, tree_bytes);
+    CK(cudaMemset(ff.tree, 0, tree_bytes));
+    ALLOC(ff.seg_cnt, sizeof(uint32_t) * max_keys);
+    CK(cudaMemset(ff.seg_cnt, 0, sizeof(uint32_t) * max_keys));
+    ALLOC(ff.seg_off, sizeof(uint32_t) * (static_cast<size_t>(max_keys) + 1));
+    ALLOC(h->n_total, sizeof(uint32_t));
+#undef ALLOC
+    uint32_t bits = 0; while ((1ull << bits) < max_keys) bits++;
+    h->sort_passes = std::max(1u, (bits + 7) / 8);
+    h->state_bytes = total;
+    *hh = h;
+    return 0;
+}
+
+int wfb_ffat_destroy(wfb_ffat_t *h)
+{
+    if (!h) return 0;
+    cudaDeviceSynchronize();
+    FfatDev &ff = h->ff;
+    cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
+    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off);
+    cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
+    cudaFree(h->H); cudaFree(h->batch_off); cudaFree(h->n_total);
+    h->ts.destroy();
+    delete h;
+    return 0;
+}
+
+uint64_t wfb_ffat_launches(const wfb_ffat_t *h) { return h ? h->launches : 0; }
+uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes : 0; }
+
+static int ffat_ensure_segment(wfb_ffat *h, uint32_t total, uint32_t nbatches, cudaStream_t s)
+{
+    if (total > h->seg_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB); cudaFree(h->H);
+        h->seg_cap = std::max(total, 2 * h->seg_cap);
+        CK(cudaMalloc(&h->lifted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
+        CK(cudaMalloc(&h->slotsA, sizeof(uint32_t) * h->seg_cap));
+        CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->seg_cap));
+        CK(cudaMalloc(&h->posA, sizeof(uint32_t) * h->seg_cap));
+        CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->seg_cap));
+        h->h_tiles = (h->seg_cap + RS_TILE - 1) / RS_TILE;
+        CK(cudaMalloc(&h->H, sizeof(uint32_t) * 256 * h->h_tiles));
+    }
+    if (nbatches + 1 > h->batch_off_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(h->batch_off);
+        h->batch_off_cap = std::max(nbatches + 1, 2 * h->batch_off_cap);
+        CK(cudaMalloc(&h->batch_off, sizeof(uint32_t) * h->batch_off_cap));
+    }
+    return 0;
+}
+
+int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                        void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
+{
+    if (!h || !n_out_dev || (nbatches && !batches_h) || (out_capacity && !out_results)) return WFB_E_BADARG;
+    if (h->win_type != 0) return WFB_E_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = h->ts.enter(s); if (rc) return rc;
+    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+
+    std::vector<DevBatch> hb; // empty batches trigger nothing: only the non-empty ones reach the device
+    hb.reserve(nbatches);
+    uint64_t total = 0; uint32_t tiles = 0;
+    for (uint32_t i = 0; i < nbatches; i++) {
+        if (batches_h[i].n == 0) continue;
+        if (!batches_h[i].tuples) return WFB_E_BADARG;
+        DevBatch b; std::memset(&b, 0, sizeof(b));
+        b.tuples = static_cast<const unsigned char *>(batches_h[i].tuples); b.ts = batches_h[i].ts;
+        b.watermark = batches_h[i].watermark; b.n = batches_h[i].n; b.tile_begin = tiles;
+        tiles += tiles_of(b.n); total += b.n;
+        hb.push_back(b);
+    }
+    if (total == 0) return 0;
+    nbatches = static_cast<uint32_t>(hb.size());
+    if (total > 0x7fffffffull) return WFB_E_BADARG;
+    rc = ffat_ensure_segment(h, static_cast<uint32_t>(total), nbatches, s); if (rc) return rc;
+    rc = h->ts.ensure_tiles(tiles); if (rc) return rc;
+    rc = h->ts.ensure_batches(nbatches); if (rc) return rc;
+    CK(cudaMemcpyAsync(h->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+
+    // 1. streaming pass: [map -> filter ->] lift, key -> slot, stable compaction over the whole segment
+    TileArgs a; std::memset(&a, 0, sizeof(a));
+    a.batches = h->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
+    a.lifted = h->lifted; a.slots = h->slotsA; a.batch_off = h->batch_off; a.n_total = h->n_total; a.ff = h->ff;
+    h->ts.next_launch(a);
+    uint32_t grid = 0;
+    rc = h->ops->tile_pass(MODE_INGEST, a, pre, tiles, s, &grid); if (rc) return rc;
+    h->ts.launched(tiles, grid);
+    h->launches++;
+
+    // 2. per-key offsets of the segment
+    k_scan_u32<<<1, 1024, 0, s>>>(h->ff.seg_cnt, h->ff.seg_off, h->ff.max_keys, h->ff.seg_off + h->ff.max_keys);
+    CK(cudaGetLastError());
+    h->launches++;
+
+    // 3. stable sort of (slot, position) by slot: LSD radix, 8 bits per pass
+    const uint32_t st = (static_cast<uint32_t>(total) + RS_TILE - 1) / RS_TILE;
+    const uint32_t *kin = h->slotsA, *vin = nullptr;
+    uint32_t *kout = h->slotsB, *vout = h->posB;
+    for (uint32_t p = 0; p < h->sort_passes; p++) {
+        k_radix_hist<<<st, RS_THREADS, 0, s>>>(kin, h->n_total, 8 * p, h->H, st);
+        k_scan_u32<<<1, 1024, 0, s>>>(h->H, h->H, 256 * st, nullptr);
+        k_radix_scatter<<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, h->n_total, 8 * p, h->H, st);
+        CK(cudaGetLastError());
+        h->launches += 3;
+        kin = kout; vin = vout;
+        if (kout == h->slotsB) { kout = h->slotsA; vout = h->posA; } else { kout = h->slotsB; vout = h->posB; }
+    }
+    const uint32_t *sorted_pos = vin;
+
+    // 4. one warp per key: pane fold, FlatFAT update, window queries
+    const uint32_t warps_needed = h->ff.max_keys;
+    uint32_t ugrid = std::min((warps_needed + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u);
+    ugrid = std::max(ugrid, 1u);
+    rc = h->ops->ffat_update(h->ff, h->lifted, sorted_pos, h->batch_off, h->ts.d_batches, nbatches,
+                             static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s);
+    if (rc) return rc;
+    h->launches++;
+    return 0;
+}
+
+int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, void *stream)
+{
+    if (!h) return WFB_E_BADARG;
+    uint32_t v[2] = {0, 0};
+    CK(cudaMemcpyAsync(v, h->ff.n_slots, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (n_keys_h) *n_keys_h = v[0];
+    if (err_flags_h) *err_flags_h = v[1];
+    return 0;
+}
+
+int wfb_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys, const double *zipf_cdf,
+                    void *tuples, uint64_t *ts, void *stream)
+{
+    int rc = device_ready(); if (rc) return rc;
+    if ((n && !tuples) || nkeys == 0 || (key_mode == 2 && !zipf_cdf)) return WFB_E_BADARG;
+    if (n == 0) return 0;
+    const uint32_t grid = std::min((n + 255) / 256, static_cast<uint32_t>(g_num_sms) * 16u);
+    k_gen_tuple64<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(seed, start, n, key_mode, nkeys, zipf_cdf,
+                                                                       static_cast<wfb_tuple64_t *>(tuples), ts);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

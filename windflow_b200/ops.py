@@ -1,0 +1,241 @@
+"""Host-side handles over the C ABI (include/wfb200.h), used by tests/, bench.py and __graft_entry__.smoke().
+
+PyTorch is only plumbing here: device memory (uint8 / int64 tensors), streams and torch.distributed. Every
+compute call goes through libwfb200.so; nothing in this module computes on the CPU.
+
+Naming follows the reference operators: Map_GPU (wf/map_gpu.hpp), Filter_GPU (wf/filter_gpu.hpp), Reduce_GPU
+(wf/reduce_gpu.hpp), Ffat_Windows_GPU (wf/ffat_windows_gpu.hpp), KeyBy_Emitter_GPU (wf/keyby_emitter_gpu.hpp).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Batch as CBatch
+from ._lib import Functors, check
+
+PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24 = 0, 1, 2
+
+TUPLE64 = np.dtype([("key", "<u8"), ("id", "<u8"), ("ivalue", "<i8"), ("fvalue", "<f8"), ("pad", "<u8", (4,))])
+RESULT32 = np.dtype([("key", "<u8"), ("id", "<u8"), ("isum", "<i8"), ("fsum", "<f8")])
+WFTEST16 = np.dtype([("key", "<u8"), ("value", "<i8")])
+WFWIN24 = np.dtype([("key", "<u8"), ("id", "<u8"), ("value", "<i8")])
+
+TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24}
+RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24}
+
+KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
+SEED = 0x5EED5EED
+
+
+def functors(map_kind=0, iadd=0, fscale=1.0, filt_kind=0, mod=1):
+    return Functors(map_kind, filt_kind, iadd, fscale, mod)
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def to_device(arr, device="cuda"):
+    """numpy (structured) array -> flat uint8 CUDA tensor holding the same bytes."""
+    a = np.ascontiguousarray(arr)
+    return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(device)
+
+
+def to_host(t, dtype, n=None):
+    """uint8 CUDA tensor -> numpy array of `dtype` (first n records)."""
+    a = t.cpu().numpy().view(dtype)
+    return a if n is None else a[:n]
+
+
+def ts_to_device(ts, device="cuda"):
+    return torch.from_numpy(np.ascontiguousarray(ts, dtype=np.uint64).view(np.int64).copy()).to(device)
+
+
+def ts_to_host(t, n=None):
+    a = t.cpu().numpy().view(np.uint64)
+    return a if n is None else a[:n]
+
+
+class DeviceBatch:
+    """Batch_GPU_t stand-in (wf/batch_gpu_t.hpp:50-243), structure-of-arrays: `tuples` (uint8, n*tuple_bytes) and
+    `ts` (int64 holding uint64 bits), the number of meaningful items `n` and the batch watermark."""
+
+    def __init__(self, tuples, ts, n, watermark=0):
+        self.tuples, self.ts, self.n, self.watermark = tuples, ts, int(n), int(watermark)
+
+    @staticmethod
+    def from_host(arr, ts=None, watermark=None, device="cuda"):
+        t = to_device(arr, device)
+        d = ts_to_device(ts, device) if ts is not None else None
+        wm = int(ts[0]) if (watermark is None and ts is not None and len(ts)) else int(watermark or 0)
+        return DeviceBatch(t, d, len(arr), wm)
+
+
+class Engine:
+    """Per-replica scratch + the stateless / per-batch operators of one program."""
+
+    def __init__(self, prog=PROG_TUPLE64):
+        self.L = _lib.lib()
+        if self.L.wfb_device_count() <= 0:
+            raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
+        self.prog = prog
+        self.h = C.c_void_p()
+        check(self.L.wfb_engine_create(C.byref(self.h), prog), "wfb_engine_create")
+        info = _lib.ProgramInfo()
+        check(self.L.wfb_program_info(prog, C.byref(info)), "wfb_program_info")
+        self.tuple_bytes, self.result_bytes = info.tuple_bytes, info.result_bytes
+
+    def close(self):
+        if self.h:
+            self.L.wfb_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.L.wfb_engine_launches(self.h))
+
+    # Map_GPU (stateless), in place
+    def map(self, batch, f, stream=None):
+        check(self.L.wfb_map(self.h, C.byref(f), _ptr(batch.tuples), batch.n, _stream_ptr(stream)), "wfb_map")
+        return batch
+
+    # [Map_GPU ->] Filter_GPU (stateless): returns (out batch, n_out device tensor). out may alias in.
+    def map_filter(self, batch, f, out=None, n_out=None, stream=None):
+        if out is None:
+            out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts) if batch.ts is not None else None,
+                              batch.n, batch.watermark)
+        if n_out is None:
+            n_out = torch.zeros(1, dtype=torch.int32, device=batch.tuples.device)
+        check(self.L.wfb_map_filter(self.h, C.byref(f), _ptr(batch.tuples), _ptr(batch.ts), batch.n,
+                                    _ptr(out.tuples), _ptr(out.ts), _ptr(n_out), _stream_ptr(stream)), "wfb_map_filter")
+        return out, n_out
+
+    def reduce_by_key(self, batch, out=None, n_out=None, stream=None):
+        if out is None:
+            out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts), batch.n, batch.watermark)
+        if n_out is None:
+            n_out = torch.zeros(1, dtype=torch.int32, device=batch.tuples.device)
+        check(self.L.wfb_reduce_by_key(self.h, _ptr(batch.tuples), _ptr(batch.ts), batch.n, _ptr(out.tuples), _ptr(out.ts),
+                                       _ptr(n_out), _stream_ptr(stream)), "wfb_reduce_by_key")
+        return out, n_out
+
+    def reduce_all(self, batch, stream=None):
+        out_t = torch.empty(self.tuple_bytes, dtype=torch.uint8, device=batch.tuples.device)
+        out_ts = torch.zeros(1, dtype=torch.int64, device=batch.tuples.device)
+        check(self.L.wfb_reduce_all(self.h, _ptr(batch.tuples), _ptr(batch.ts), batch.n, _ptr(out_t), _ptr(out_ts),
+                                    _stream_ptr(stream)), "wfb_reduce_all")
+        return out_t, out_ts
+
+    def keyby_group(self, batch, stream=None):
+        dev = batch.tuples.device
+        start = torch.empty(max(1, batch.n), dtype=torch.int32, device=dev)
+        mp = torch.empty(max(1, batch.n), dtype=torch.int32, device=dev)
+        dk = torch.empty(max(1, batch.n), dtype=torch.int64, device=dev)
+        nk = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(self.L.wfb_keyby_group(self.h, _ptr(batch.tuples), batch.n, _ptr(start), _ptr(mp), _ptr(dk), _ptr(nk),
+                                     _stream_ptr(stream)), "wfb_keyby_group")
+        return start, mp, dk, nk
+
+    def shard_by_key(self, batch, num_shards, stream=None):
+        dev = batch.tuples.device
+        out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts) if batch.ts is not None else None,
+                          batch.n, batch.watermark)
+        seg = torch.zeros(num_shards + 1, dtype=torch.int32, device=dev)
+        check(self.L.wfb_shard_by_key(self.h, _ptr(batch.tuples), _ptr(batch.ts), batch.n, num_shards, _ptr(out.tuples),
+                                      _ptr(out.ts), _ptr(seg), _stream_ptr(stream)), "wfb_shard_by_key")
+        return out, seg
+
+
+class FfatWindowsGPU:
+    """Ffat_Windows_GPU replica state (wf/ffat_windows_gpu.hpp, wf/ffat_replica_gpu.hpp): count-based windows
+    `withCBWindows(win, slide)`, `withNumWinPerBatch(nb)`."""
+
+    def __init__(self, prog, win, slide, nb, max_keys, dense_keys=False, win_type=0, lateness=0):
+        self.L = _lib.lib()
+        if self.L.wfb_device_count() <= 0:
+            raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
+        self.prog, self.win, self.slide, self.nb = prog, win, slide, nb
+        self.h = C.c_void_p()
+        check(self.L.wfb_ffat_create(C.byref(self.h), prog, win, slide, nb, max_keys, win_type, lateness,
+                                     1 if dense_keys else 0), "wfb_ffat_create")
+        self.res_dtype = RESULT_DTYPE[prog]
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.L.wfb_ffat_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.L.wfb_ffat_launches(self.h))
+
+    @property
+    def state_bytes(self):
+        return int(self.L.wfb_ffat_state_bytes(self.h))
+
+    def max_results(self, n_items):
+        """Upper bound on the results one call over n_items input items can produce."""
+        return (n_items // max(1, self.slide * self.nb) + 65536) * self.nb
+
+    def process(self, batches, pre=None, out=None, out_ts=None, n_out=None, stream=None):
+        """One stream segment (list of DeviceBatch). Returns (out uint8 tensor, out_ts int64 tensor, n_out tensor)."""
+        dev = batches[0].tuples.device
+        total = sum(b.n for b in batches)
+        if out is None:
+            cap = self.max_results(total)
+            out = torch.empty(cap * self.res_dtype.itemsize, dtype=torch.uint8, device=dev)
+            out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
+        cap = out.numel() // self.res_dtype.itemsize
+        if n_out is None:
+            n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        arr = (CBatch * len(batches))()
+        for i, b in enumerate(batches):
+            arr[i].tuples = b.tuples.data_ptr()
+            arr[i].ts = b.ts.data_ptr() if b.ts is not None else None
+            arr[i].watermark = b.watermark
+            arr[i].n = b.n
+        check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
+                                         _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
+              "wfb_ffat_process_cb")
+        return out, out_ts, n_out
+
+    def results_to_host(self, out, out_ts, n_out):
+        n = int(n_out.item())
+        return to_host(out, self.res_dtype)[:n].copy(), ts_to_host(out_ts)[:n].copy()
+
+    def stats(self, stream=None):
+        nk, ef = C.c_uint32(0), C.c_uint32(0)
+        check(self.L.wfb_ffat_stats(self.h, C.byref(nk), C.byref(ef), _stream_ptr(stream)), "wfb_ffat_stats")
+        return nk.value, ef.value
+
+
+def gen_tuple64(start, n, key_mode=KEY_UNIFORM, nkeys=65536, seed=SEED, zipf_cdf=None, device="cuda", stream=None,
+                tuples=None, ts=None):
+    """Device-side generator of the synthetic stream of SURVEY.md 8d."""
+    L = _lib.lib()
+    if tuples is None:
+        tuples = torch.empty(n * 64, dtype=torch.uint8, device=device)
+        ts = torch.empty(n, dtype=torch.int64, device=device)
+    check(L.wfb_gen_tuple64(seed, start, n, key_mode, nkeys, _ptr(zipf_cdf), _ptr(tuples), _ptr(ts), _stream_ptr(stream)),
+          "wfb_gen_tuple64")
+    return DeviceBatch(tuples, ts, n, start)
