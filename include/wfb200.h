@@ -156,6 +156,12 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev,
                         void *stream);
 
+/* Per-phase device timing of wfb_ffat_process_cb calls (CUDA events recorded on the launching stream).
+ * enable != 0 starts recording (up to 512 calls); the call returns, for the calls recorded since the last query,
+ * ms_h[0] = streaming ingest pass, ms_h[1] = key offsets + radix sort, ms_h[2] = window update, ms_h[3] = whole
+ * call, and *calls_h = number of calls summed. Synchronises on the last recorded event. */
+int wfb_ffat_timing(wfb_ffat_t *h, int enable, float *ms_h, uint32_t *calls_h);
+
 /* Number of distinct keys seen so far / error flags raised on the device (synchronises the stream). */
 int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, void *stream);
 

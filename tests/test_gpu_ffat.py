@@ -183,7 +183,7 @@ def test_ffat_wfwin24_reference_functors(wfb, oracle):
     _check(O, got, gts, np.concatenate(exp), np.concatenate(ets), res_is32=False)
 
 
-@pytest.mark.parametrize("geom", [(64, 16, 5), (4096, 64, 1), (4096, 64, 65), (16, 4, 4)])
+@pytest.mark.parametrize("geom", [(64, 16, 5), (4096, 64, 1), (4096, 64, 65), (16, 4, 5)])
 def test_reference_flatfat_gpu_on_this_box(wfb, oracle, geom):
     """The reference's own FlatFAT_GPU (wf/flatfat_gpu.hpp compiled for sm_100a into oracle/_ref) run on this GPU:
     pins the oracle's restatement of K12-K14 and our kernels against the reference itself (power-of-two B)."""

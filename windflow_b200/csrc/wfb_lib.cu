@@ -178,6 +178,16 @@ struct wfb_ffat {
     uint64_t launches = 0;
     size_t state_bytes = 0;
     int win_type = 0;
+    // optional per-phase timing (wfb_ffat_timing)
+    bool timing = false;
+    std::vector<cudaEvent_t> tev; // 4 events per recorded call
+    uint32_t tev_used = 0;        // recorded calls since the last query
+    static constexpr uint32_t TEV_MAX = 512;
+    void mark(int which, cudaStream_t s)
+    {
+        if (!timing || tev_used >= TEV_MAX) return;
+        cudaEventRecord(tev[tev_used * 4 + which], s);
+    }
 };
 
 extern "C" {
@@ -350,6 +360,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off);
     cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
     cudaFree(h->H); cudaFree(h->batch_off); cudaFree(h->n_total);
+    for (auto &e : h->tev) cudaEventDestroy(e);
     h->ts.destroy();
     delete h;
     return 0;
@@ -410,6 +421,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     rc = h->ts.ensure_batches(nbatches); if (rc) return rc;
     CK(cudaMemcpyAsync(h->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
 
+    h->mark(0, s);
     // 1. streaming pass: [map -> filter ->] lift, key -> slot, stable compaction over the whole segment
     TileArgs a; std::memset(&a, 0, sizeof(a));
     a.batches = h->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
@@ -420,6 +432,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     h->ts.launched(tiles, grid);
     h->launches++;
 
+    h->mark(1, s);
     // 2. per-key offsets of the segment
     k_scan_u32<<<1, 1024, 0, s>>>(h->ff.seg_cnt, h->ff.seg_off, h->ff.max_keys, h->ff.seg_off + h->ff.max_keys);
     CK(cudaGetLastError());
@@ -440,6 +453,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     }
     const uint32_t *sorted_pos = vin;
 
+    h->mark(2, s);
     // 4. one warp per key: pane fold, FlatFAT update, window queries
     const uint32_t warps_needed = h->ff.max_keys;
     uint32_t ugrid = std::min((warps_needed + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u);
@@ -448,6 +462,35 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
                              static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s);
     if (rc) return rc;
     h->launches++;
+    h->mark(3, s);
+    if (h->timing && h->tev_used < wfb_ffat::TEV_MAX) h->tev_used++;
+    return 0;
+}
+
+int wfb_ffat_timing(wfb_ffat_t *h, int enable, float *ms_h, uint32_t *calls_h)
+{
+    if (!h) return WFB_E_BADARG;
+    float acc[4] = {0, 0, 0, 0};
+    if (h->tev_used) {
+        CK(cudaEventSynchronize(h->tev[(h->tev_used - 1) * 4 + 3]));
+        for (uint32_t i = 0; i < h->tev_used; i++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEvent_t *e = &h->tev[i * 4];
+            CK(cudaEventElapsedTime(&a, e[0], e[1]));
+            CK(cudaEventElapsedTime(&b, e[1], e[2]));
+            CK(cudaEventElapsedTime(&c, e[2], e[3]));
+            CK(cudaEventElapsedTime(&d, e[0], e[3]));
+            acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += d;
+        }
+    }
+    if (ms_h) for (int i = 0; i < 4; i++) ms_h[i] = acc[i];
+    if (calls_h) *calls_h = h->tev_used;
+    h->tev_used = 0;
+    if (enable && h->tev.empty()) {
+        h->tev.resize(wfb_ffat::TEV_MAX * 4);
+        for (auto &e : h->tev) CK(cudaEventCreate(&e));
+    }
+    h->timing = enable != 0;
     return 0;
 }
 

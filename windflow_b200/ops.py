@@ -223,6 +223,13 @@ class FfatWindowsGPU:
         n = int(n_out.item())
         return to_host(out, self.res_dtype)[:n].copy(), ts_to_host(out_ts)[:n].copy()
 
+    def timing(self, enable=True):
+        """(ingest_ms, sort_ms, update_ms, total_ms, calls) summed over the calls recorded since the last query."""
+        ms = (C.c_float * 4)()
+        calls = C.c_uint32(0)
+        check(self.L.wfb_ffat_timing(self.h, 1 if enable else 0, ms, C.byref(calls)), "wfb_ffat_timing")
+        return ms[0], ms[1], ms[2], ms[3], calls.value
+
     def stats(self, stream=None):
         nk, ef = C.c_uint32(0), C.c_uint32(0)
         check(self.L.wfb_ffat_stats(self.h, C.byref(nk), C.byref(ef), _stream_ptr(stream)), "wfb_ffat_stats")
