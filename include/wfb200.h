@@ -92,6 +92,10 @@ int wfb_engine_destroy(wfb_engine_t *e);
 /* launches issued by this engine so far (kernel launches only; bench.py reports it as gpu_launches) */
 uint64_t wfb_engine_launches(const wfb_engine_t *e);
 
+/* number of significant low bits of key_t for the per-batch keyed operators below (default 64): the stable LSD
+ * radix sort that replaces thrust::sort_by_key runs ceil(bits/8) passes. */
+int wfb_engine_set_key_bits(wfb_engine_t *e, uint32_t bits);
+
 /* ---- Map_GPU, stateless: in-place func(tuple) over a batch --------------------------------------
  * replaces Stateless_MAPGPU_Kernel + launch, wf/map_gpu.hpp:61-76, :357-409. */
 int wfb_map(wfb_engine_t *e, const wfb_functors_t *f, void *tuples, uint32_t n, void *stream);

@@ -70,9 +70,11 @@ def lib():
         L.wfo_ffat_cpu_process.restype = _u64
         L.wfo_ffat_cpu_eos.argtypes = [_vp, _vp, _vp, _u64]
         L.wfo_ffat_cpu_eos.restype = _u64
-        L.wfo_cpu_pipeline_run.argtypes = [_vp, _vp, _u64, C.c_int, _i64, _f64, C.c_int, _i64, _u64, _u64,
-                                           _u32, _u32, _u64, _vp]
-        L.wfo_cpu_pipeline_run.restype = _u64
+        L.wfo_cpu_pipe_create.argtypes = [C.c_int, _i64, _f64, C.c_int, _i64, _u64, _u64, _u32, _u32]
+        L.wfo_cpu_pipe_create.restype = _vp
+        L.wfo_cpu_pipe_destroy.argtypes = [_vp]
+        L.wfo_cpu_pipe_run.argtypes = [_vp, _vp, _vp, _u64, _u64, _vp]
+        L.wfo_cpu_pipe_run.restype = _u64
         _lib = L
     return _lib
 
@@ -244,12 +246,36 @@ class FfatCpuOracle:
         self.close()
 
 
-def cpu_pipeline_run(tuples, ts, map_kind, ia, fa, filt_kind, im, win, slide, shard, nshards, batch):
-    """Reference CPU path Map -> Filter -> Ffat_Windows(CB) on one key shard; returns (n_windows, checksum)."""
-    cs = C.c_int64(0)
-    n = lib().wfo_cpu_pipeline_run(_p(tuples), _p(ts), len(tuples), map_kind, ia, fa, filt_kind, im, win, slide,
-                                   shard, nshards, batch, C.byref(cs))
-    return n, cs.value
+class CpuPipe:
+    """Reference CPU path Map -> Filter -> Ffat_Windows(CB) on one key shard (one replica == one thread).
+    kind "port": the oracle's restatement (wf_oracle.c); kind "reference": the reference's own wf/flatfat.hpp under
+    the restated replica loop (oracle/_ref/libwfref_flatfat.so)."""
+
+    def __init__(self, kind, map_kind, ia, fa, filt_kind, im, win, slide, shard, nshards):
+        self.kind = kind
+        if kind == "reference":
+            self.L = ref_cpu_lib()
+            self.L.wfref_cpu_pipe_create.argtypes = [C.c_int, _i64, _f64, C.c_int, _i64, _u64, _u64, _u32, _u32]
+            self.L.wfref_cpu_pipe_create.restype = _vp
+            self.L.wfref_cpu_pipe_destroy.argtypes = [_vp]
+            self.L.wfref_cpu_pipe_run.argtypes = [_vp, _vp, _vp, _u64, _u64, _vp]
+            self.L.wfref_cpu_pipe_run.restype = _u64
+            self._run, self._destroy = self.L.wfref_cpu_pipe_run, self.L.wfref_cpu_pipe_destroy
+            self.h = self.L.wfref_cpu_pipe_create(map_kind, ia, fa, filt_kind, im, win, slide, shard, nshards)
+        else:
+            self.L = lib()
+            self._run, self._destroy = self.L.wfo_cpu_pipe_run, self.L.wfo_cpu_pipe_destroy
+            self.h = self.L.wfo_cpu_pipe_create(map_kind, ia, fa, filt_kind, im, win, slide, shard, nshards)
+        self.checksum = C.c_int64(0)
+        self.windows = 0
+
+    def run(self, tuples, ts, batch):
+        self.windows += self._run(self.h, _p(tuples), _p(ts), len(tuples), batch, C.byref(self.checksum))
+
+    def close(self):
+        if self.h:
+            self._destroy(self.h)
+            self.h = None
 
 
 # ---------------------------------------------------------------------------------------------------

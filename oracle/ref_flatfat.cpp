@@ -114,6 +114,54 @@ uint64_t wfref_ffat_cpu_eos(void *hh, res_t *out, uint64_t *out_ts, uint64_t out
     return nout;
 }
 
+/* CPU baseline pipe over the REFERENCE FlatFAT: restated Map (wf/map.hpp:174-190) -> Filter (wf/filter.hpp:184-205)
+ * loops in front of the reference wf::FlatFAT driven as FFAT_Replica::process_input_cb does, on one key shard
+ * (key % nshards == shard, wf/keyby_emitter.hpp:215-217). Tuple layout = the 64-byte bench tuple of SURVEY 8d. */
+struct tuple64_t { uint64_t key, id; int64_t ivalue; double fvalue; uint64_t pad[4]; };
+struct RefPipe
+{
+    RefFfatCpu ffat;
+    int map_kind, filt_kind; int64_t ia, im; double fa; uint32_t shard, nshards;
+    std::vector<res_t> lift, out; std::vector<uint64_t> ots;
+    RefPipe(uint64_t w, uint64_t s): ffat(w, s) {}
+};
+
+void *wfref_cpu_pipe_create(int map_kind, int64_t ia, double fa, int filt_kind, int64_t im,
+                            uint64_t win, uint64_t slide, uint32_t shard, uint32_t nshards)
+{
+    RefPipe *p = new RefPipe(win, slide);
+    p->map_kind = map_kind; p->ia = ia; p->fa = fa; p->filt_kind = filt_kind; p->im = im; p->shard = shard; p->nshards = nshards;
+    return p;
+}
+void wfref_cpu_pipe_destroy(void *pp) { delete reinterpret_cast<RefPipe *>(pp); }
+
+uint64_t wfref_ffat_cpu_process(void *hh, const res_t *res, uint64_t n, uint64_t wm, res_t *out, uint64_t *out_ts, uint64_t out_cap);
+
+uint64_t wfref_cpu_pipe_run(void *pp, const tuple64_t *tuples, const uint64_t *ts, uint64_t n, uint64_t batch, int64_t *checksum)
+{
+    RefPipe *p = reinterpret_cast<RefPipe *>(pp);
+    if (p->lift.size() < batch) { p->lift.resize(batch); p->out.resize(batch + 16); p->ots.resize(batch + 16); }
+    uint64_t nwin = 0; int64_t cs = 0;
+    for (uint64_t off = 0; off < n; off += batch) {
+        uint64_t m = (n - off < batch) ? (n - off) : batch, nl = 0;
+        for (uint64_t i = 0; i < m; i++) {
+            const tuple64_t &src = tuples[off + i];
+            if (src.key % p->nshards != p->shard) continue;
+            tuple64_t t = src;
+            if (p->map_kind == 1) { t.ivalue += p->ia; t.fvalue *= p->fa; }
+            bool keep = p->filt_kind == 0 ? true : (p->filt_kind == 1 ? ((t.ivalue & 1) == 0) : ((t.ivalue % p->im) == 0));
+            if (!keep) continue;
+            res_t r(t.key, 0); r.isum = t.ivalue; r.fsum = t.fvalue;
+            p->lift[nl++] = r;
+        }
+        uint64_t k = wfref_ffat_cpu_process(&p->ffat, p->lift.data(), nl, ts[off], p->out.data(), p->ots.data(), batch + 16);
+        for (uint64_t i = 0; i < k && i < batch + 16; i++) cs += p->out[i].isum;
+        nwin += k;
+    }
+    *checksum += cs;
+    return nwin;
+}
+
 /* Raw FlatFAT access for unit-level pinning: one tree, scripted insert/remove/getResult. */
 void *wfref_fat_create(uint64_t key, uint64_t n)
 {

@@ -626,42 +626,62 @@ uint64_t wfo_ffat_cpu_eos(wfo_ffat_cpu_t *h, wfo_res_t *out, uint64_t *out_ts, u
 
 /* ------------------------------------------------------------------------------------------------
  * CPU baseline driver: the reference's CPU Map -> Filter -> Ffat_Windows(CB) path (map.hpp:174-190,
- * filter.hpp:184-205, ffat_replica.hpp:215-278) over a pre-generated tuple64 sample, on ONE key shard
+ * filter.hpp:184-205, ffat_replica.hpp:215-278) over pre-generated tuple64 buffers, on ONE key shard
  * (BASELINE.json config 1 shape). `shard`/`nshards` select keys with key % nshards == shard (keyby routing,
- * keyby_emitter.hpp:215-217), so `nshards` threads each running this function mirror parallelism = nshards.
- * The watermark of each batch of `batch` tuples is its first timestamp. Returns the number of
- * windows; *checksum accumulates isum of every window.
+ * keyby_emitter.hpp:215-217), so `nshards` threads each owning one pipe mirror parallelism = nshards.
+ * The watermark of each batch of `batch` tuples is its first timestamp. State persists across
+ * wfo_cpu_pipe_run calls (a stream fed buffer by buffer). Returns the number of windows of the call;
+ * *checksum accumulates isum of every window.
  * ---------------------------------------------------------------------------------------------- */
-uint64_t wfo_cpu_pipeline_run(const wfo_tuple64_t *tuples, const uint64_t *ts, uint64_t n,
-                              int map_kind, int64_t ia, double fa, int filt_kind, int64_t im,
-                              uint64_t win, uint64_t slide, uint32_t shard, uint32_t nshards,
-                              uint64_t batch, int64_t *checksum)
+typedef struct {
+    wfo_ffat_cpu_t *ffat;
+    int map_kind, filt_kind; int64_t ia, im; double fa;
+    uint32_t shard, nshards;
+    wfo_res_t *lift, *out; uint64_t *ots; uint64_t cap;
+} wfo_cpu_pipe_t;
+
+wfo_cpu_pipe_t *wfo_cpu_pipe_create(int map_kind, int64_t ia, double fa, int filt_kind, int64_t im,
+                                    uint64_t win, uint64_t slide, uint32_t shard, uint32_t nshards)
 {
-    wfo_ffat_cpu_t *h = wfo_ffat_cpu_create(win, slide);
-    wfo_res_t *lift = (wfo_res_t *)malloc(sizeof(wfo_res_t) * batch);
-    uint64_t ocap = batch + 16;
-    wfo_res_t *out = (wfo_res_t *)malloc(sizeof(wfo_res_t) * ocap);
-    uint64_t *ots = (uint64_t *)malloc(sizeof(uint64_t) * ocap);
+    wfo_cpu_pipe_t *p = (wfo_cpu_pipe_t *)calloc(1, sizeof(*p));
+    p->ffat = wfo_ffat_cpu_create(win, slide);
+    p->map_kind = map_kind; p->ia = ia; p->fa = fa; p->filt_kind = filt_kind; p->im = im;
+    p->shard = shard; p->nshards = nshards;
+    return p;
+}
+
+void wfo_cpu_pipe_destroy(wfo_cpu_pipe_t *p)
+{
+    wfo_ffat_cpu_destroy(p->ffat); free(p->lift); free(p->out); free(p->ots); free(p);
+}
+
+uint64_t wfo_cpu_pipe_run(wfo_cpu_pipe_t *p, const wfo_tuple64_t *tuples, const uint64_t *ts, uint64_t n,
+                          uint64_t batch, int64_t *checksum)
+{
+    if (p->cap < batch) {
+        p->cap = batch;
+        p->lift = (wfo_res_t *)realloc(p->lift, sizeof(wfo_res_t) * batch);
+        p->out = (wfo_res_t *)realloc(p->out, sizeof(wfo_res_t) * (batch + 16));
+        p->ots = (uint64_t *)realloc(p->ots, sizeof(uint64_t) * (batch + 16));
+    }
     uint64_t nwin = 0; int64_t cs = 0;
     for (uint64_t off = 0; off < n; off += batch) {
         uint64_t m = (n - off < batch) ? (n - off) : batch;
         uint64_t nl = 0;
         for (uint64_t i = 0; i < m; i++) {
             const wfo_tuple64_t *src = &tuples[off + i];
-            if (src->key % nshards != shard) continue;
+            if (src->key % p->nshards != p->shard) continue;
             wfo_tuple64_t t = *src;
-            if (map_kind == 1) { t.ivalue += ia; t.fvalue *= fa; }
-            int keep = filt_kind == 0 ? 1 : (filt_kind == 1 ? ((t.ivalue & 1) == 0) : ((t.ivalue % im) == 0));
+            if (p->map_kind == 1) { t.ivalue += p->ia; t.fvalue *= p->fa; }
+            int keep = p->filt_kind == 0 ? 1 : (p->filt_kind == 1 ? ((t.ivalue & 1) == 0) : ((t.ivalue % p->im) == 0));
             if (!keep) continue;
-            lift[nl].key = t.key; lift[nl].id = 0; lift[nl].isum = t.ivalue; lift[nl].fsum = t.fvalue; nl++;
+            p->lift[nl].key = t.key; p->lift[nl].id = 0; p->lift[nl].isum = t.ivalue; p->lift[nl].fsum = t.fvalue; nl++;
         }
-        uint64_t k = wfo_ffat_cpu_process(h, lift, nl, ts[off], out, ots, ocap);
-        for (uint64_t i = 0; i < k && i < ocap; i++) cs += out[i].isum;
+        uint64_t k = wfo_ffat_cpu_process(p->ffat, p->lift, nl, ts[off], p->out, p->ots, batch + 16);
+        for (uint64_t i = 0; i < k && i < batch + 16; i++) cs += p->out[i].isum;
         nwin += k;
     }
-    *checksum = cs;
-    free(lift); free(out); free(ots);
-    wfo_ffat_cpu_destroy(h);
+    *checksum += cs;
     return nwin;
 }
 

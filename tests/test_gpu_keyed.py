@@ -1,0 +1,131 @@
+"""GPU parity tests (-m gpu): Reduce_GPU (keyed / un-keyed), KeyBy_Emitter_GPU grouping and the key -> shard
+partition through the C ABI against the oracle. Integer results, indices and order are bit-exact; floating-point
+sums within 1e-6 relative (thrust's association is implementation-defined)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SIZES = [1, 2, 33, 255, 2048, 2049, 65536, 100001]
+
+
+def _batch(O, n, nkeys, mode=None, start=0):
+    t, ts = O.gen_tuple64(start, n, O.KEY_UNIFORM if mode is None else mode, nkeys)
+    t["pad"] = np.arange(n * 4, dtype=np.uint64).reshape(n, 4)
+    return t, ts
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("nkeys", [1, 7, 5000])
+def test_keyby_group(wfb, oracle, n, nkeys):
+    import torch
+    O, ops = oracle, wfb
+    t, ts = _batch(O, n, nkeys)
+    t["key"] = t["key"] * 0x9E3779B97F4A7C15 % (1 << 40)  # scattered 40-bit keys
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    eng.set_key_bits(40)
+    start, mp, dk, nk = eng.keyby_group(ops.DeviceBatch.from_host(t, ts))
+    torch.cuda.synchronize()
+    es, em, ek = O.keyby_group(t["key"], 1)  # GPU->GPU path: ascending key order (keyby_emitter_gpu.hpp:547-564)
+    k = int(nk.item())
+    assert k == len(ek)
+    assert np.array_equal(dk.cpu().numpy().view(np.uint64)[:k], ek)
+    assert np.array_equal(start.cpu().numpy()[:k], es)
+    assert np.array_equal(mp.cpu().numpy()[:n], em)
+
+
+def test_keyby_group_full_64bit_keys(wfb, oracle):
+    import torch
+    O, ops = oracle, wfb
+    n = 30000
+    t, ts = _batch(O, n, 300)
+    t["key"] = (t["key"] + 1) * np.uint64(0xD6E8FEB86659FD93)  # wraps: uses all 64 bits
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    start, mp, dk, nk = eng.keyby_group(ops.DeviceBatch.from_host(t, ts))
+    torch.cuda.synchronize()
+    es, em, ek = O.keyby_group(t["key"], 1)
+    k = int(nk.item())
+    assert k == len(ek) and np.array_equal(dk.cpu().numpy().view(np.uint64)[:k], ek)
+    assert np.array_equal(start.cpu().numpy()[:k], es) and np.array_equal(mp.cpu().numpy()[:n], em)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("dist", ["uniform50", "zipf1m", "single"])
+def test_reduce_by_key(wfb, oracle, n, dist):
+    import torch
+    O, ops = oracle, wfb
+    if dist == "uniform50":
+        t, ts = _batch(O, n, 50)
+    elif dist == "zipf1m":
+        t, ts = _batch(O, n, 1000000, O.KEY_ZIPF)   # BASELINE config 3: 1M keys, Zipf 0.8
+    else:
+        t, ts = _batch(O, n, 1)
+    ts = (ts * 7919) % 100003  # non-monotone timestamps: ts of the result = max over the key
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    eng.set_key_bits(20)
+    out, n_out = eng.reduce_by_key(ops.DeviceBatch.from_host(t, ts))
+    torch.cuda.synchronize()
+    exp, ets = O.reduce_tuple64(t, ts)
+    k = int(n_out.item())
+    assert k == len(exp)
+    got = ops.to_host(out.tuples, ops.TUPLE64)[:k]
+    assert np.array_equal(got["key"], exp["key"])            # ascending key order
+    assert np.array_equal(got["ivalue"], exp["ivalue"])
+    assert np.allclose(got["fvalue"], exp["fvalue"], rtol=1e-6, atol=0)
+    assert np.array_equal(got["id"], exp["id"]) and np.array_equal(got["pad"], exp["pad"])  # singletons pass through
+    assert np.array_equal(ops.ts_to_host(out.ts)[:k], ets)
+
+
+@pytest.mark.parametrize("n", [1, 100, 1024, 65536, 77777])
+def test_reduce_all(wfb, oracle, n):
+    import torch
+    O, ops = oracle, wfb
+    t, ts = _batch(O, n, 100)
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    out_t, out_ts = eng.reduce_all(ops.DeviceBatch.from_host(t, ts))
+    torch.cuda.synchronize()
+    r = ops.to_host(out_t, ops.TUPLE64)[0]
+    # thrust::reduce(init = default item): key of the init item (0), sums over the batch, ts = max (reduce_gpu.hpp:264-273)
+    assert r["key"] == 0 and r["id"] == 0
+    assert r["ivalue"] == t["ivalue"].sum()
+    assert abs(r["fvalue"] - t["fvalue"].sum()) <= 1e-6 * abs(t["fvalue"].sum())
+    assert int(ops.ts_to_host(out_ts)[0]) == int(ts.max())
+
+
+def test_reduce_reference_test_functor(wfb, oracle):
+    """Reduce_Functor_GPU of tests/graph_tests_gpu/graph_common_gpu.hpp:268-279 on {key, value} tuples."""
+    import torch
+    O, ops = oracle, wfb
+    rng = np.random.default_rng(4)
+    n = 20000
+    t = np.zeros(n, dtype=ops.WFTEST16)
+    t["key"] = rng.integers(0, 9, n)
+    t["value"] = rng.integers(-100, 100, n)
+    ts = np.arange(n, dtype=np.uint64)
+    eng = ops.Engine(ops.PROG_WFTEST16)
+    eng.set_key_bits(8)
+    out, n_out = eng.reduce_by_key(ops.DeviceBatch.from_host(t, ts))
+    torch.cuda.synchronize()
+    k = int(n_out.item())
+    got = ops.to_host(out.tuples, ops.WFTEST16)[:k]
+    uk = np.unique(t["key"])
+    assert np.array_equal(got["key"], uk)
+    assert np.array_equal(got["value"], [t["value"][t["key"] == x].sum() for x in uk])
+    assert np.array_equal(ops.ts_to_host(out.ts)[:k], [ts[t["key"] == x].max() for x in uk])
+
+
+@pytest.mark.parametrize("n", [1, 257, 65536, 100001])
+@pytest.mark.parametrize("shards", [1, 2, 4, 8])
+def test_shard_by_key(wfb, oracle, n, shards):
+    import torch
+    O, ops = oracle, wfb
+    t, ts = _batch(O, n, 65536)
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    out, seg = eng.shard_by_key(ops.DeviceBatch.from_host(t, ts), shards)
+    torch.cuda.synchronize()
+    dest = O.route(t["key"], shards)          # key % num_dests (keyby_emitter.hpp:215-217)
+    order = np.argsort(dest, kind="stable")   # stable: arrival order inside a shard
+    got = ops.to_host(out.tuples, ops.TUPLE64)
+    assert got.tobytes() == t[order].tobytes()
+    assert np.array_equal(ops.ts_to_host(out.ts), ts[order])
+    off = seg.cpu().numpy()
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(np.bincount(dest, minlength=shards))]))

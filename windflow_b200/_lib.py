@@ -40,6 +40,7 @@ SYMBOLS = {
     "wfb_engine_create": (C.c_int, [C.POINTER(vp), C.c_int]),
     "wfb_engine_destroy": (C.c_int, [vp]),
     "wfb_engine_launches": (u64, [vp]),
+    "wfb_engine_set_key_bits": (C.c_int, [vp, u32]),
     "wfb_map": (C.c_int, [vp, C.POINTER(Functors), vp, u32, vp]),
     "wfb_map_filter": (C.c_int, [vp, C.POINTER(Functors), vp, vp, u32, vp, vp, vp, vp]),
     "wfb_reduce_by_key": (C.c_int, [vp, vp, vp, u32, vp, vp, vp, vp]),

@@ -509,12 +509,13 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 2048 elements per tile
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr,
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
                                                            uint32_t shift, uint32_t *__restrict__ H, uint32_t num_tiles)
 {
     __shared__ uint32_t h[256];
     const uint32_t tid = threadIdx.x, tile = blockIdx.x;
-    const uint32_t n = *n_ptr;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
     h[tid] = 0;
     __syncthreads();
     const uint32_t start = tile * RS_TILE;
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t *__res
 #pragma unroll
         for (int i = 0; i < RS_ITEMS; i++) {
             const uint32_t idx = start + i * RS_THREADS + tid;
-            if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+            if (idx < n) atomicAdd(&h[static_cast<uint32_t>(keys[idx] >> shift) & 255u], 1u);
         }
     }
     __syncthreads();
@@ -555,28 +556,30 @@ __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, uint32_t 
     for (uint32_t i = begin; i < end; i++) { const uint32_t v = in[i]; out[i] = run; run += v; }
 }
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                                                              uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                                                              const uint32_t *__restrict__ n_ptr, uint32_t shift,
+template <class K>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                              K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                              const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t shift,
                                                               const uint32_t *__restrict__ H, uint32_t num_tiles)
 {
     __shared__ uint32_t cntw[RS_THREADS / 32][256];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
-    const uint32_t n = *n_ptr;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
     const uint32_t start = tile * RS_TILE;
     if (start >= n) return;
 #pragma unroll
     for (int w = 0; w < RS_THREADS / 32; w++) cntw[w][tid] = 0;
     __syncthreads();
-    uint32_t k[RS_ITEMS], rk[RS_ITEMS];
+    K k[RS_ITEMS];
+    uint32_t rk[RS_ITEMS];
     // warp w owns the contiguous range [start + w*256, +256), 32 consecutive elements per round: (warp, round,
     // lane) order == index order, so ranks are stable.
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
         const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
         const bool valid = idx < n;
-        k[r] = valid ? keys_in[idx] : 0u;
-        const uint32_t d = valid ? ((k[r] >> shift) & 255u) : 256u;
+        k[r] = valid ? keys_in[idx] : K(0);
+        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & 255u) : 256u;
         const uint32_t mask = __match_any_sync(FULL, d);
         rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
         __syncwarp();
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t *__
     for (int r = 0; r < RS_ITEMS; r++) {
         const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
         if (idx < n) {
-            const uint32_t d = (k[r] >> shift) & 255u;
+            const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & 255u;
             const uint32_t dst = cntw[warp][d] + rk[r];
             keys_out[dst] = k[r];
             vals_out[dst] = vals_in ? vals_in[idx] : idx;
@@ -718,6 +721,165 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
             if (c % P_ != 0) st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
             ff.seg_cnt[slot] = 0;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Per-batch keyed operators built on the sort: KeyBy_Emitter_GPU grouping, Reduce_GPU, key -> shard partition
+// ------------------------------------------------------------------------------------------------------
+// keys[i] = key_extr(tuple_i)   (Extract_Keys_Kernel wf/reduce_gpu.hpp:75-86, Extract_Dests_Kernel wf/keyby_emitter_gpu.hpp:68-81)
+template <class P>
+__global__ void k_extract_keys(const unsigned char *__restrict__ tuples, uint32_t n, uint64_t *__restrict__ keys,
+                               uint32_t *__restrict__ dest, uint32_t num_shards)
+{
+    using T = typename P::tuple_t;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const T *t = reinterpret_cast<const T *>(tuples + static_cast<size_t>(i) * sizeof(T));
+        const uint64_t k = P::key(*t);
+        if (keys) keys[i] = k;
+        if (dest) dest[i] = static_cast<uint32_t>(k % num_shards); // wf/keyby_emitter.hpp:215-217
+    }
+}
+
+// head[i] = 1 when sorted position i starts a new key; map_idxs links equal neighbours
+// (Compute_Mapping_Kernel, wf/keyby_emitter_gpu.hpp:84-100)
+__global__ void k_seg_heads(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, uint32_t n,
+                            uint32_t *__restrict__ head, int32_t *__restrict__ map_idxs)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        head[i] = (i == 0 || skeys[i] != skeys[i - 1]) ? 1u : 0u;
+        if (map_idxs) map_idxs[sidx[i]] = (i + 1 < n && skeys[i] == skeys[i + 1]) ? static_cast<int32_t>(sidx[i + 1]) : -1;
+    }
+}
+
+// after the exclusive scan of head[] (seg[i] = index of the segment sorted position i belongs to, for heads):
+// start_idxs[k] / dist_keys[k] of the k-th distinct key (unique_by_key_copy, wf/keyby_emitter_gpu.hpp:559-564),
+// seg_begin[k] = first sorted position of segment k (used by the reduce), *n_keys = number of segments
+__global__ void k_seg_finish(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, const uint32_t *__restrict__ head_scan,
+                             uint32_t n, int32_t *__restrict__ start_idxs, uint64_t *__restrict__ dist_keys,
+                             uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ n_keys)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool is_head = (i == 0 || skeys[i] != skeys[i - 1]);
+        if (is_head) {
+            const uint32_t k = head_scan[i];
+            if (start_idxs) start_idxs[k] = static_cast<int32_t>(sidx[i]);
+            if (dist_keys) dist_keys[k] = skeys[i];
+            if (seg_begin) seg_begin[k] = i;
+        }
+        if (i == n - 1) {
+            const uint32_t total = head_scan[i] + (is_head ? 1u : 0u); // exclusive scan value + own flag
+            if (n_keys) *n_keys = total;
+            if (seg_begin) seg_begin[total] = n;
+        }
+    }
+}
+
+// Reduce_GPU keyed: one warp per distinct key folds the key's items in arrival order with P::reduce, ts = max
+// (thrust_reduce_func_gpu_t, wf/reduce_gpu.hpp:88-105; reduce_by_key :245-252). Output k = k-th smallest key.
+template <class P>
+__global__ void __launch_bounds__(256) k_reduce_segments(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts,
+                                                         const uint32_t *__restrict__ sidx, const uint32_t *__restrict__ seg_begin,
+                                                         const uint32_t *__restrict__ n_keys, unsigned char *__restrict__ out_tuples,
+                                                         uint64_t *__restrict__ out_ts)
+{
+    using T = typename P::tuple_t;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nk = *n_keys;
+    for (uint32_t k = gwarp; k < nk; k += nwarps) {
+        const uint32_t b = seg_begin[k], e = seg_begin[k + 1];
+        alignas(16) T acc; uint64_t mts = 0; bool have = false;
+        for (uint32_t j = b; j < e; j += 32) {
+            const uint32_t take = min(32u, e - j);
+            alignas(16) T t; uint64_t tt = 0;
+            if (lane < take) {
+                const uint32_t i = sidx[j + lane];
+                ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), t);
+                tt = ts ? ts[i] : 0;
+            }
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+                const T other = shfl_down_rec<T>(t, o);
+                const uint64_t ots = __shfl_down_sync(FULL, tt, o);
+                if (lane + o < take) { t = P::reduce(t, other); tt = tt < ots ? ots : tt; }
+            }
+            t = shfl_rec<T>(t, 0); tt = __shfl_sync(FULL, tt, 0);
+            if (!have) { acc = t; mts = tt; have = true; }
+            else { acc = P::reduce(acc, t); mts = mts < tt ? tt : mts; }
+        }
+        if (lane == 0) {
+            st_rec<T>(out_tuples + static_cast<size_t>(k) * sizeof(T), acc);
+            if (out_ts) out_ts[k] = mts;
+        }
+    }
+}
+
+// Reduce_GPU un-keyed: the whole batch folded into one item, starting from a default-constructed item
+// (thrust::reduce with init = batch_item_gpu_t<tuple_t>(), wf/reduce_gpu.hpp:264-273). One CTA of 1024 threads.
+template <class P>
+__global__ void __launch_bounds__(1024) k_reduce_all(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts, uint32_t n,
+                                                     unsigned char *__restrict__ out_tuple, uint64_t *__restrict__ out_ts)
+{
+    using T = typename P::tuple_t;
+    __shared__ __align__(16) unsigned char sm[32 * sizeof(T)];
+    __shared__ uint64_t smts[32];
+    __shared__ uint32_t smhave[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // thread t folds the contiguous chunk [t*per, (t+1)*per): order preserved
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = min(tid * per, n), e = min(b + per, n);
+    alignas(16) T acc; uint64_t mts = 0; bool have = false;
+    for (uint32_t i = b; i < e; i++) {
+        alignas(16) T t; ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), t);
+        const uint64_t tt = ts ? ts[i] : 0;
+        if (!have) { acc = t; mts = tt; have = true; } else { acc = P::reduce(acc, t); mts = mts < tt ? tt : mts; }
+    }
+    // ordered combine across lanes, then across warps (a lane/warp without items is skipped)
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+        const T other = shfl_down_rec<T>(acc, o);
+        const uint64_t ots = __shfl_down_sync(FULL, mts, o);
+        const bool ohave = __shfl_down_sync(FULL, have ? 1u : 0u, o) != 0;
+        if (lane + o < 32 && ohave) {
+            if (have) { acc = P::reduce(acc, other); mts = mts < ots ? ots : mts; } else { acc = other; mts = ots; have = true; }
+        }
+    }
+    if (lane == 0) { st_rec<T>(sm + warp * sizeof(T), acc); smts[warp] = mts; smhave[warp] = have ? 1u : 0u; }
+    __syncthreads();
+    if (tid == 0) {
+        T init{};                 // default-constructed tuple, timestamp 0
+        alignas(16) T r = init; uint64_t rts = 0;
+        for (uint32_t w = 0; w < 32; w++) if (smhave[w]) {
+            alignas(16) T t; ld_rec<T>(sm + w * sizeof(T), t);
+            r = P::reduce(r, t); rts = rts < smts[w] ? smts[w] : rts;
+        }
+        st_rec<T>(out_tuple, r);
+        if (out_ts) *out_ts = rts;
+    }
+}
+
+// payload gather after a stable partition: out[j] = in[perm[j]] (tuples and timestamps)
+template <class P>
+__global__ void k_gather_tuples(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts, const uint32_t *__restrict__ perm,
+                                uint32_t n, unsigned char *__restrict__ out_tuples, uint64_t *__restrict__ out_ts)
+{
+    using T = typename P::tuple_t;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = perm[j];
+        alignas(16) T t; ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), t);
+        st_rec<T>(out_tuples + static_cast<size_t>(j) * sizeof(T), t);
+        if (ts && out_ts) out_ts[j] = ts[i];
+    }
+}
+
+// seg_off[d] for d in [0, num_shards]: first sorted position whose destination is >= d (sorted dest array)
+__global__ void k_shard_offsets(const uint32_t *__restrict__ sdest, uint32_t n, uint32_t num_shards, uint32_t *__restrict__ seg_off)
+{
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d <= num_shards; d += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n; // lower_bound(sdest, d)
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sdest[mid] < d) lo = mid + 1; else hi = mid; }
+        seg_off[d] = lo;
     }
 }
 

@@ -39,6 +39,12 @@ struct ProgramOps {
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
                        uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s);
+    int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s);
+    int (*reduce_segments)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
+                           const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s);
+    int (*reduce_all)(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s);
+    int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
+                  uint64_t *out_ts, cudaStream_t s);
 };
 
 template <class P, int MODE>
@@ -83,6 +89,39 @@ int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const u
     return 0;
 }
 
+inline uint32_t grid_for(uint32_t n, uint32_t per_block) { return std::max(1u, std::min((n + per_block - 1) / per_block, static_cast<uint32_t>(g_num_sms) * 16u)); }
+
+template <class P>
+int extract_keys_dispatch(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s)
+{
+    k_extract_keys<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, n, keys, dest, num_shards);
+    CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
+                             const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s)
+{
+    k_reduce_segments<P><<<grid_for(n, 8), 256, 0, s>>>(tuples, ts, sidx, seg_begin, n_keys, out_tuples, out_ts);
+    CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int reduce_all_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s)
+{
+    k_reduce_all<P><<<1, 1024, 0, s>>>(tuples, ts, n, out_tuple, out_ts);
+    CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int gather_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
+                    uint64_t *out_ts, cudaStream_t s)
+{
+    k_gather_tuples<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, ts, perm, n, out_tuples, out_ts);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <class P>
 ProgramOps make_ops()
 {
@@ -91,6 +130,10 @@ ProgramOps make_ops()
     o.result_bytes = sizeof(typename P::result_t);
     o.tile_pass = &tile_pass_dispatch<P>;
     o.ffat_update = &ffat_update_dispatch<P>;
+    o.extract_keys = &extract_keys_dispatch<P>;
+    o.reduce_segments = &reduce_segments_dispatch<P>;
+    o.reduce_all = &reduce_all_dispatch<P>;
+    o.gather = &gather_dispatch<P>;
     return o;
 }
 
@@ -160,6 +203,53 @@ struct wfb_engine {
     const ProgramOps *ops = nullptr;
     TileScratch ts;
     uint64_t launches = 0;
+    // scratch of the per-batch keyed operators (sort buffers), grown on demand
+    uint32_t key_bits = 64;
+    uint32_t cap = 0;
+    uint64_t *keysA = nullptr, *keysB = nullptr;
+    uint32_t *idxA = nullptr, *idxB = nullptr, *destA = nullptr, *destB = nullptr;
+    uint32_t *head = nullptr, *seg_begin = nullptr, *H = nullptr;
+    uint32_t h_tiles = 0;
+
+    int ensure_sort(uint32_t n, cudaStream_t s)
+    {
+        if (n <= cap) return 0;
+        CK(cudaStreamSynchronize(s));
+        cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
+        cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+        cap = std::max(n, 2 * cap);
+        CK(cudaMalloc(&keysA, sizeof(uint64_t) * cap)); CK(cudaMalloc(&keysB, sizeof(uint64_t) * cap));
+        CK(cudaMalloc(&idxA, sizeof(uint32_t) * cap)); CK(cudaMalloc(&idxB, sizeof(uint32_t) * cap));
+        CK(cudaMalloc(&destA, sizeof(uint32_t) * cap)); CK(cudaMalloc(&destB, sizeof(uint32_t) * cap));
+        CK(cudaMalloc(&head, sizeof(uint32_t) * cap)); CK(cudaMalloc(&seg_begin, sizeof(uint32_t) * (static_cast<size_t>(cap) + 1)));
+        h_tiles = (cap + RS_TILE - 1) / RS_TILE;
+        CK(cudaMalloc(&H, sizeof(uint32_t) * 256 * h_tiles));
+        return 0;
+    }
+    // stable LSD radix sort of (keysA[i], i) by key over `bits` bits; returns the buffers holding the result
+    int sort64(uint32_t n, cudaStream_t s, const uint64_t **skeys, const uint32_t **sidx)
+    {
+        const uint32_t st = (n + RS_TILE - 1) / RS_TILE;
+        const uint32_t passes = std::max(1u, (key_bits + 7) / 8);
+        const uint64_t *kin = keysA; const uint32_t *vin = nullptr;
+        uint64_t *kout = keysB; uint32_t *vout = idxB;
+        for (uint32_t p = 0; p < passes; p++) {
+            k_radix_hist<uint64_t><<<st, RS_THREADS, 0, s>>>(kin, nullptr, n, 8 * p, H, st);
+            k_scan_u32<<<1, 1024, 0, s>>>(H, H, 256 * st, nullptr);
+            k_radix_scatter<uint64_t><<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, nullptr, n, 8 * p, H, st);
+            CK(cudaGetLastError());
+            launches += 3;
+            kin = kout; vin = vout;
+            if (kout == keysB) { kout = keysA; vout = idxA; } else { kout = keysB; vout = idxB; }
+        }
+        *skeys = kin; *sidx = vin;
+        return 0;
+    }
+    void free_sort()
+    {
+        cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
+        cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+    }
 };
 
 struct wfb_ffat {
@@ -244,6 +334,7 @@ int wfb_engine_destroy(wfb_engine_t *e)
     if (!e) return 0;
     cudaDeviceSynchronize();
     e->ts.destroy();
+    e->free_sort();
     delete e;
     return 0;
 }
@@ -286,10 +377,90 @@ int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f, const void *tuples_
     return run_single(e, MODE_FILTER, f, b, s);
 }
 
-int wfb_reduce_by_key(wfb_engine_t *, const void *, const uint64_t *, uint32_t, void *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
-int wfb_reduce_all(wfb_engine_t *, const void *, const uint64_t *, uint32_t, void *, uint64_t *, void *) { return WFB_E_UNSUPPORTED; }
-int wfb_keyby_group(wfb_engine_t *, const void *, uint32_t, int32_t *, int32_t *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
-int wfb_shard_by_key(wfb_engine_t *, const void *, const uint64_t *, uint32_t, uint32_t, void *, uint64_t *, uint32_t *, void *) { return WFB_E_UNSUPPORTED; }
+int wfb_engine_set_key_bits(wfb_engine_t *e, uint32_t bits)
+{
+    if (!e || bits == 0 || bits > 64) return WFB_E_BADARG;
+    e->key_bits = bits;
+    return 0;
+}
+
+// sort the batch's (key, index) pairs and derive the key segments; shared by reduce_by_key and keyby_group
+static int keyed_prepare(wfb_engine_t *e, const void *tuples, uint32_t n, int32_t *map_idxs, int32_t *start_idxs, uint64_t *dist_keys,
+                         uint32_t *n_keys_dev, cudaStream_t s, const uint32_t **sidx_out)
+{
+    int rc = e->ts.enter(s); if (rc) return rc;
+    rc = e->ensure_sort(n, s); if (rc) return rc;
+    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, e->keysA, nullptr, 1, s); if (rc) return rc;
+    e->launches++;
+    const uint64_t *skeys; const uint32_t *sidx;
+    rc = e->sort64(n, s, &skeys, &sidx); if (rc) return rc;
+    const uint32_t g = grid_for(n, 256);
+    k_seg_heads<<<g, 256, 0, s>>>(skeys, sidx, n, e->head, map_idxs);
+    k_scan_u32<<<1, 1024, 0, s>>>(e->head, e->head, n, nullptr);
+    k_seg_finish<<<g, 256, 0, s>>>(skeys, sidx, e->head, n, start_idxs, dist_keys, e->seg_begin, n_keys_dev);
+    CK(cudaGetLastError());
+    e->launches += 3;
+    *sidx_out = sidx;
+    return 0;
+}
+
+int wfb_reduce_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n,
+                      void *out_tuples, uint64_t *out_ts, uint32_t *n_out_dev, void *stream)
+{
+    if (!e || !n_out_dev || (n && (!tuples || !out_tuples))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    const uint32_t *sidx;
+    int rc = keyed_prepare(e, tuples, n, nullptr, nullptr, nullptr, n_out_dev, s, &sidx); if (rc) return rc;
+    rc = e->ops->reduce_segments(static_cast<const unsigned char *>(tuples), ts, sidx, e->seg_begin, n_out_dev,
+                                 static_cast<unsigned char *>(out_tuples), ts ? out_ts : nullptr, n, s);
+    if (rc) return rc;
+    e->launches++;
+    return 0;
+}
+
+int wfb_reduce_all(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n, void *out_tuple, uint64_t *out_ts, void *stream)
+{
+    if (!e || !out_tuple || (n && !tuples)) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = e->ts.enter(s); if (rc) return rc;
+    rc = e->ops->reduce_all(static_cast<const unsigned char *>(tuples), ts, n, static_cast<unsigned char *>(out_tuple), out_ts, s);
+    if (rc) return rc;
+    e->launches++;
+    return 0;
+}
+
+int wfb_keyby_group(wfb_engine_t *e, const void *tuples, uint32_t n, int32_t *start_idxs, int32_t *map_idxs, uint64_t *dist_keys,
+                    uint32_t *n_keys_dev, void *stream)
+{
+    if (!e || !n_keys_dev || (n && (!tuples || !start_idxs || !map_idxs || !dist_keys))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) { CK(cudaMemsetAsync(n_keys_dev, 0, sizeof(uint32_t), s)); return 0; }
+    const uint32_t *sidx;
+    return keyed_prepare(e, tuples, n, map_idxs, start_idxs, dist_keys, n_keys_dev, s, &sidx);
+}
+
+int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n, uint32_t num_shards,
+                     void *out_tuples, uint64_t *out_ts, uint32_t *seg_off_dev, void *stream)
+{
+    if (!e || !seg_off_dev || num_shards == 0 || num_shards > 256 || (n && (!tuples || !out_tuples))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) { CK(cudaMemsetAsync(seg_off_dev, 0, sizeof(uint32_t) * (num_shards + 1), s)); return 0; }
+    int rc = e->ts.enter(s); if (rc) return rc;
+    rc = e->ensure_sort(n, s); if (rc) return rc;
+    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, nullptr, e->destA, num_shards, s); if (rc) return rc;
+    const uint32_t st = (n + RS_TILE - 1) / RS_TILE;
+    k_radix_hist<uint32_t><<<st, RS_THREADS, 0, s>>>(e->destA, nullptr, n, 0, e->H, st);
+    k_scan_u32<<<1, 1024, 0, s>>>(e->H, e->H, 256 * st, nullptr);
+    k_radix_scatter<uint32_t><<<st, RS_THREADS, 0, s>>>(e->destA, nullptr, e->destB, e->idxB, nullptr, n, 0, e->H, st);
+    k_shard_offsets<<<1, 288, 0, s>>>(e->destB, n, num_shards, seg_off_dev);
+    CK(cudaGetLastError());
+    rc = e->ops->gather(static_cast<const unsigned char *>(tuples), ts, e->idxB, n, static_cast<unsigned char *>(out_tuples),
+                        ts ? out_ts : nullptr, s);
+    if (rc) return rc;
+    e->launches += 6;
+    return 0;
+}
 
 // ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------------
 static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
@@ -443,9 +614,9 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     const uint32_t *kin = h->slotsA, *vin = nullptr;
     uint32_t *kout = h->slotsB, *vout = h->posB;
     for (uint32_t p = 0; p < h->sort_passes; p++) {
-        k_radix_hist<<<st, RS_THREADS, 0, s>>>(kin, h->n_total, 8 * p, h->H, st);
+        k_radix_hist<uint32_t><<<st, RS_THREADS, 0, s>>>(kin, h->n_total, 0, 8 * p, h->H, st);
         k_scan_u32<<<1, 1024, 0, s>>>(h->H, h->H, 256 * st, nullptr);
-        k_radix_scatter<<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, h->n_total, 8 * p, h->H, st);
+        k_radix_scatter<uint32_t><<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, h->n_total, 0, 8 * p, h->H, st);
         CK(cudaGetLastError());
         h->launches += 3;
         kin = kout; vin = vout;

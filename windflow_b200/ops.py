@@ -107,6 +107,9 @@ class Engine:
     def launches(self):
         return int(self.L.wfb_engine_launches(self.h))
 
+    def set_key_bits(self, bits):
+        check(self.L.wfb_engine_set_key_bits(self.h, bits), "wfb_engine_set_key_bits")
+
     # Map_GPU (stateless), in place
     def map(self, batch, f, stream=None):
         check(self.L.wfb_map(self.h, C.byref(f), _ptr(batch.tuples), batch.n, _stream_ptr(stream)), "wfb_map")
