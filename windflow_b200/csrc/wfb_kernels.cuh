@@ -606,6 +606,152 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restric
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Onesweep-style stable LSD radix pass (8-bit digits): ONE kernel per pass.
+//   k_radix_ghist     digit histograms of every pass in one read of the keys   ghist[pass][256]
+//   k_onesweep_pass   per tile (dynamic ticket order): stable in-tile ranks (warp match_any, warps in index order),
+//                     per-digit decoupled look-back over the earlier tiles (thread d owns digit d, epoch-tagged
+//                     64-bit state words), keys/values regrouped by digit in shared memory and written coalesced.
+// ctl layout (uint32): [pass][256] histograms, then [pass] ticket counters; the host clears it once per sort.
+// ------------------------------------------------------------------------------------------------------
+constexpr int OS_THREADS = 256;
+constexpr int OS_MAX_PASSES = 8;
+// elements per thread: 16 for 32-bit keys (4096 per tile), 8 for 64-bit keys (2048 per tile) -- static smem <= 48 KB
+template <class K> struct OsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8; static constexpr int TILE_ELEMS = OS_THREADS * ITEMS; };
+
+template <class K>
+__global__ void __launch_bounds__(256) k_radix_ghist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                                     uint32_t passes, uint32_t *__restrict__ ctl)
+{
+    __shared__ uint32_t h[OS_MAX_PASSES * 256];
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
+    for (uint32_t i = threadIdx.x; i < passes * 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const K k = keys[i];
+        for (uint32_t p = 0; p < passes; p++) atomicAdd(&h[p * 256 + (static_cast<uint32_t>(k >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < passes * 256; i += blockDim.x) if (h[i]) atomicAdd(&ctl[i], h[i]);
+}
+
+template <class K>
+__global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                              K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                              const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t pass,
+                                                              uint32_t passes, uint32_t *__restrict__ ctl,
+                                                              uint64_t *__restrict__ tile_state, uint32_t epoch)
+{
+    __shared__ uint32_t cntw[OS_THREADS / 32][256]; // per-warp digit counts -> exclusive offsets over the warps
+    __shared__ uint32_t dig_off[256];               // exclusive offset of each digit inside the tile
+    __shared__ uint32_t bin_base[256];              // global position of the tile's first element of each digit
+    __shared__ uint32_t wsum[OS_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    constexpr int OS_ITEMS = OsCfg<K>::ITEMS;
+    constexpr int OS_TILE = OsCfg<K>::TILE_ELEMS;
+    __shared__ K skeys[OS_TILE];
+    __shared__ uint32_t svals[OS_TILE];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
+    const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
+    const uint32_t shift = 8 * pass;
+    if (tid == 0) s_tile = atomicAdd(&ctl[passes * 256 + pass], 1u);
+#pragma unroll
+    for (int w = 0; w < OS_THREADS / 32; w++) cntw[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= num_tiles) return;
+    const uint32_t start = tile * OS_TILE;
+
+    // ---- stable in-tile ranks: warp w owns [start + w*512, +512), 32 consecutive elements per round ------------
+    K k[OS_ITEMS];
+    uint32_t rk[OS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OS_ITEMS) + r * 32 + lane;
+        const bool valid = idx < n;
+        k[r] = valid ? keys_in[idx] : K(0);
+        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & 255u) : 256u;
+        const uint32_t mask = __match_any_sync(FULL, d);
+        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
+        __syncwarp();
+        if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] += __popc(mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- digit `tid`: tile total, exclusive offsets over warps, publish, look back -----------------------------------
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < OS_THREADS / 32; w++) { const uint32_t c = cntw[w][tid]; cntw[w][tid] = total; total += c; }
+    uint64_t *my_state = tile_state + static_cast<size_t>(tile) * 256 + tid;
+    st_relaxed_u64(my_state, pack_state(epoch, tile == 0 ? ST_PREFIX : ST_AGG, total));
+    // global base of digit tid = exclusive scan of the pass histogram over the digits
+    const uint32_t gcount = ctl[pass * 256 + tid];
+    uint32_t incl = gcount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    // exclusive offset of the digit inside the tile (same scan over `total`)
+    uint32_t tincl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, tincl, o); if (lane >= o) tincl += v; }
+    __shared__ uint32_t twsum[OS_THREADS / 32];
+    if (lane == 31) twsum[warp] = tincl;
+    __syncthreads();
+    uint32_t gbase = incl - gcount, tbase = tincl - total;
+#pragma unroll
+    for (uint32_t w = 0; w < OS_THREADS / 32; w++) if (w < warp) { gbase += wsum[w]; tbase += twsum[w]; }
+    uint32_t excl = 0;
+    if (tile > 0) {
+        int64_t t2 = static_cast<int64_t>(tile) - 1;
+        while (true) {
+            const uint64_t w = ld_relaxed_u64(tile_state + static_cast<size_t>(t2) * 256 + tid);
+            if ((w >> 34) != (epoch & 0x3fffffffu) || ((w >> 32) & 3u) == 0) continue; // not published yet
+            excl += static_cast<uint32_t>(w);
+            if (((w >> 32) & 3u) == ST_PREFIX) break;
+            t2--;
+        }
+        st_relaxed_u64(my_state, pack_state(epoch, ST_PREFIX, excl + total));
+    }
+    dig_off[tid] = tbase;
+    bin_base[tid] = gbase + excl;
+    __syncthreads();
+
+    // ---- regroup by digit in shared memory, then coalesced writes ---------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OS_ITEMS) + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & 255u;
+            const uint32_t lp = dig_off[d] + cntw[warp][d] + rk[r];
+            skeys[lp] = k[r];
+            svals[lp] = vals_in ? vals_in[idx] : idx;
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = min(static_cast<uint32_t>(OS_TILE), n - start);
+    for (uint32_t i = tid; i < cnt; i += OS_THREADS) {
+        const K kk = skeys[i];
+        const uint32_t d = static_cast<uint32_t>(kk >> shift) & 255u;
+        const uint32_t dst = bin_base[d] + (i - dig_off[d]);
+        keys_out[dst] = kk;
+        vals_out[dst] = svals[i];
+    }
+}
+
+// seg_off[slot] = first sorted position of each key present in the segment (its length is seg_cnt[slot])
+__global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const uint32_t *__restrict__ n_ptr, uint32_t max_keys,
+                             uint32_t *__restrict__ seg_off)
+{
+    const uint32_t n = *n_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = sorted_slots[i];
+        if (s < max_keys && (i == 0 || sorted_slots[i - 1] != s)) seg_off[s] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_ffat_update: one warp per key that received items in this stream segment.
 //   items of the key, in arrival order (sorted_pos[seg_off[slot] .. +seg_cnt[slot]) -> lifted[])
 //   -> ordered warp fold into the open pane (pane = gcd(win, slide) items)

@@ -196,6 +196,55 @@ struct TileScratch {
 
 inline uint32_t tiles_of(uint32_t n) { return (n + TILE - 1) / TILE; }
 
+// scratch + launcher of the onesweep radix sort (one per engine / window handle)
+struct RadixSorter {
+    uint32_t *ctl = nullptr;        // [passes][256] histograms + [passes] tickets
+    uint64_t *state = nullptr;      // [tiles][256] look-back words
+    uint32_t state_tiles = 0;
+    uint32_t epoch = 0;
+    uint64_t launches = 0;
+
+    int ensure(uint32_t cap_elems, uint32_t min_tile, cudaStream_t s)
+    {
+        if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * (OS_MAX_PASSES * 256 + OS_MAX_PASSES)));
+        const uint32_t tiles = (cap_elems + min_tile - 1) / min_tile;
+        if (tiles > state_tiles) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(state);
+            state_tiles = tiles;
+            CK(cudaMalloc(&state, sizeof(uint64_t) * 256 * state_tiles));
+            CK(cudaMemset(state, 0, sizeof(uint64_t) * 256 * state_tiles));
+        }
+        return 0;
+    }
+    void destroy() { cudaFree(ctl); cudaFree(state); }
+
+    // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
+    template <class K>
+    int sort(K *kA, K *kB, uint32_t *vA, uint32_t *vB, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t passes,
+             cudaStream_t s, const K **skeys, const uint32_t **svals)
+    {
+        constexpr uint32_t TE = OsCfg<K>::TILE_ELEMS;
+        int rc = ensure(cap, TE, s); if (rc) return rc;
+        passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
+        CK(cudaMemsetAsync(ctl, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
+        const uint32_t tiles = std::max(1u, (cap + TE - 1) / TE);
+        k_radix_ghist<K><<<std::min(tiles, static_cast<uint32_t>(g_num_sms) * 4u), 256, 0, s>>>(kA, n_ptr, n_host, passes, ctl);
+        const K *kin = kA; const uint32_t *vin = nullptr;
+        K *kout = kB; uint32_t *vout = vB;
+        for (uint32_t p = 0; p < passes; p++) {
+            epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1;
+            k_onesweep_pass<K><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch);
+            kin = kout; vin = vout;
+            if (kout == kB) { kout = kA; vout = vA; } else { kout = kB; vout = vB; }
+        }
+        CK(cudaGetLastError());
+        launches += 1 + passes;
+        *skeys = kin; *svals = vin;
+        return 0;
+    }
+};
+
 } // namespace
 
 struct wfb_engine {
@@ -210,6 +259,7 @@ struct wfb_engine {
     uint32_t *idxA = nullptr, *idxB = nullptr, *destA = nullptr, *destB = nullptr;
     uint32_t *head = nullptr, *seg_begin = nullptr, *H = nullptr;
     uint32_t h_tiles = 0;
+    RadixSorter sorter;
 
     int ensure_sort(uint32_t n, cudaStream_t s)
     {
@@ -226,29 +276,19 @@ struct wfb_engine {
         CK(cudaMalloc(&H, sizeof(uint32_t) * 256 * h_tiles));
         return 0;
     }
-    // stable LSD radix sort of (keysA[i], i) by key over `bits` bits; returns the buffers holding the result
+    // stable LSD radix sort of (keysA[i], i) by key over `key_bits` bits; returns the buffers holding the result
     int sort64(uint32_t n, cudaStream_t s, const uint64_t **skeys, const uint32_t **sidx)
     {
-        const uint32_t st = (n + RS_TILE - 1) / RS_TILE;
-        const uint32_t passes = std::max(1u, (key_bits + 7) / 8);
-        const uint64_t *kin = keysA; const uint32_t *vin = nullptr;
-        uint64_t *kout = keysB; uint32_t *vout = idxB;
-        for (uint32_t p = 0; p < passes; p++) {
-            k_radix_hist<uint64_t><<<st, RS_THREADS, 0, s>>>(kin, nullptr, n, 8 * p, H, st);
-            k_scan_u32<<<1, 1024, 0, s>>>(H, H, 256 * st, nullptr);
-            k_radix_scatter<uint64_t><<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, nullptr, n, 8 * p, H, st);
-            CK(cudaGetLastError());
-            launches += 3;
-            kin = kout; vin = vout;
-            if (kout == keysB) { kout = keysA; vout = idxA; } else { kout = keysB; vout = idxB; }
-        }
-        *skeys = kin; *sidx = vin;
-        return 0;
+        const uint64_t before = sorter.launches;
+        int rc = sorter.sort<uint64_t>(keysA, keysB, idxA, idxB, nullptr, n, n, (key_bits + 7) / 8, s, skeys, sidx);
+        launches += sorter.launches - before;
+        return rc;
     }
     void free_sort()
     {
         cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
         cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+        sorter.destroy();
     }
 };
 
@@ -262,7 +302,7 @@ struct wfb_ffat {
     uint32_t seg_cap = 0;
     unsigned char *lifted = nullptr;
     uint32_t *slotsA = nullptr, *slotsB = nullptr, *posA = nullptr, *posB = nullptr;
-    uint32_t *H = nullptr; uint32_t h_tiles = 0;
+    RadixSorter sorter;
     uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
     uint32_t *n_total = nullptr;
     uint64_t launches = 0;
@@ -449,16 +489,15 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
     int rc = e->ts.enter(s); if (rc) return rc;
     rc = e->ensure_sort(n, s); if (rc) return rc;
     rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, nullptr, e->destA, num_shards, s); if (rc) return rc;
-    const uint32_t st = (n + RS_TILE - 1) / RS_TILE;
-    k_radix_hist<uint32_t><<<st, RS_THREADS, 0, s>>>(e->destA, nullptr, n, 0, e->H, st);
-    k_scan_u32<<<1, 1024, 0, s>>>(e->H, e->H, 256 * st, nullptr);
-    k_radix_scatter<uint32_t><<<st, RS_THREADS, 0, s>>>(e->destA, nullptr, e->destB, e->idxB, nullptr, n, 0, e->H, st);
-    k_shard_offsets<<<1, 288, 0, s>>>(e->destB, n, num_shards, seg_off_dev);
+    const uint32_t *sdest, *perm;
+    const uint64_t before = e->sorter.launches;
+    rc = e->sorter.sort<uint32_t>(e->destA, e->destB, e->idxA, e->idxB, nullptr, n, n, 1, s, &sdest, &perm); if (rc) return rc;
+    k_shard_offsets<<<1, 288, 0, s>>>(sdest, n, num_shards, seg_off_dev);
     CK(cudaGetLastError());
-    rc = e->ops->gather(static_cast<const unsigned char *>(tuples), ts, e->idxB, n, static_cast<unsigned char *>(out_tuples),
+    rc = e->ops->gather(static_cast<const unsigned char *>(tuples), ts, perm, n, static_cast<unsigned char *>(out_tuples),
                         ts ? out_ts : nullptr, s);
     if (rc) return rc;
-    e->launches += 6;
+    e->launches += 3 + (e->sorter.launches - before);
     return 0;
 }
 
@@ -530,7 +569,8 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
     cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off);
     cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
-    cudaFree(h->H); cudaFree(h->batch_off); cudaFree(h->n_total);
+    h->sorter.destroy();
+    cudaFree(h->batch_off); cudaFree(h->n_total);
     for (auto &e : h->tev) cudaEventDestroy(e);
     h->ts.destroy();
     delete h;
@@ -544,15 +584,13 @@ static int ffat_ensure_segment(wfb_ffat *h, uint32_t total, uint32_t nbatches, c
 {
     if (total > h->seg_cap) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB); cudaFree(h->H);
+        cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
         h->seg_cap = std::max(total, 2 * h->seg_cap);
         CK(cudaMalloc(&h->lifted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
         CK(cudaMalloc(&h->slotsA, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->posA, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->seg_cap));
-        h->h_tiles = (h->seg_cap + RS_TILE - 1) / RS_TILE;
-        CK(cudaMalloc(&h->H, sizeof(uint32_t) * 256 * h->h_tiles));
     }
     if (nbatches + 1 > h->batch_off_cap) {
         CK(cudaStreamSynchronize(s));
@@ -604,25 +642,20 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     h->launches++;
 
     h->mark(1, s);
-    // 2. per-key offsets of the segment
-    k_scan_u32<<<1, 1024, 0, s>>>(h->ff.seg_cnt, h->ff.seg_off, h->ff.max_keys, h->ff.seg_off + h->ff.max_keys);
+    // 2. stable sort of (slot, arrival position) by slot: onesweep radix, 8 bits per pass
+    const uint32_t *sorted_slots, *sorted_pos;
+    {
+        const uint64_t before = h->sorter.launches;
+        rc = h->sorter.sort<uint32_t>(h->slotsA, h->slotsB, h->posA, h->posB, h->n_total, 0, static_cast<uint32_t>(total),
+                                      h->sort_passes, s, &sorted_slots, &sorted_pos);
+        if (rc) return rc;
+        h->launches += h->sorter.launches - before;
+    }
+    // 3. first sorted position of every key present in the segment
+    k_seg_starts<<<std::min((static_cast<uint32_t>(total) + 255u) / 256u, static_cast<uint32_t>(g_num_sms) * 8u), 256, 0, s>>>(
+        sorted_slots, h->n_total, h->ff.max_keys, h->ff.seg_off);
     CK(cudaGetLastError());
     h->launches++;
-
-    // 3. stable sort of (slot, position) by slot: LSD radix, 8 bits per pass
-    const uint32_t st = (static_cast<uint32_t>(total) + RS_TILE - 1) / RS_TILE;
-    const uint32_t *kin = h->slotsA, *vin = nullptr;
-    uint32_t *kout = h->slotsB, *vout = h->posB;
-    for (uint32_t p = 0; p < h->sort_passes; p++) {
-        k_radix_hist<uint32_t><<<st, RS_THREADS, 0, s>>>(kin, h->n_total, 0, 8 * p, h->H, st);
-        k_scan_u32<<<1, 1024, 0, s>>>(h->H, h->H, 256 * st, nullptr);
-        k_radix_scatter<uint32_t><<<st, RS_THREADS, 0, s>>>(kin, vin, kout, vout, h->n_total, 0, 8 * p, h->H, st);
-        CK(cudaGetLastError());
-        h->launches += 3;
-        kin = kout; vin = vout;
-        if (kout == h->slotsB) { kout = h->slotsA; vout = h->posA; } else { kout = h->slotsB; vout = h->posB; }
-    }
-    const uint32_t *sorted_pos = vin;
 
     h->mark(2, s);
     // 4. one warp per key: pane fold, FlatFAT update, window queries
