@@ -17,13 +17,14 @@
 //                          queries (wf/flatfat_gpu.hpp:62-139, wf/ffat_replica_gpu.hpp:830-867)
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "wfb_ptx.cuh"
 
 namespace wfb {
 
 constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pass
-constexpr int STAGES = 3;    // TMA pipeline depth (tiles in flight per CTA = STAGES-1)
+constexpr int STAGES = 4;    // TMA ring depth per CTA
 constexpr uint32_t FULL = 0xffffffffu;
 
 enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2 };
@@ -84,6 +85,8 @@ struct TileArgs {
     uint32_t *ticket;          // monotonically increasing ticket counter
     uint32_t ticket_base;      // value of *ticket when this launch starts
     uint32_t epoch;
+    uint64_t tmap_base;        // global address the 2-D tensor map starts at (rows of 64 bytes)
+    uint32_t use_tmap;         // 1: `tmap` is valid for this launch
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
     unsigned char *lifted;     // result_t per surviving tuple
     uint32_t *slots;           // slot per surviving tuple
@@ -213,150 +216,232 @@ __device__ __forceinline__ uint32_t slot_of_key(const FfatDev &ff, uint64_t key)
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_tile_pass: persistent CTAs, dynamic tile tickets, STAGES-deep TMA pipeline.
-//   per tile: [thread 0] cp.async.bulk global->shared (issued STAGES-1 tiles ahead)
-//             wait mbarrier | tuple -> registers (conflict-free rotated LDS.128) | map | filter | [lift, key->slot]
-//             ballot + warp totals -> local offsets | warp 0: decoupled look-back -> tile base
-//             survivors -> shared (compacted, linear) | fence.proxy.async | [thread 0] cp.async.bulk shared->global
-// Tickets: every CTA claims STAGES-1 tickets up front and one more per processed tile, so one launch consumes
-// exactly num_tiles + gridDim.x*(STAGES-1) tickets (the host advances ticket_base by that amount).
+// k_tile_pass: persistent, warp-specialised CTAs (10 warps), dynamic tile tickets, STAGES-deep TMA ring.
+//   warp 0      PRODUCER  (one lane): wait empty[s] | claim ticket | find the batch | TMA load of the tile:
+//                         cp.async.bulk.tensor.2d with SWIZZLE_64B for full tiles of 64-byte tuples (bank-conflict
+//                         free LDS.128 without register shuffling), cp.async.bulk (linear) otherwise; timestamps of
+//                         the tile ride on the same mbarrier.
+//   warps 1..8  CONSUMERS (one tuple per thread): wait full[s] | tuple -> registers | map | filter | [lift,
+//                         key->slot, per-key count] | ballot + warp totals -> local offsets (one named barrier) |
+//                         survivors -> shared (compacted, linear) | publish the tile count (look-back AGGREGATE) |
+//                         arrive staged[s] and move on to the next tile.
+//   warp 9      EPILOGUE: wait staged[s] | decoupled look-back -> tile base, publish PREFIX | one TMA bulk store of
+//                         the compacted records, coalesced stores of the staged slots / timestamps | wait for the
+//                         store to have read shared memory | arrive empty[s].
+// Tickets: every CTA claims one ticket per processed tile plus the failing one, so a launch consumes exactly
+// num_tiles + gridDim.x tickets (the host advances ticket_base by that amount).
 // ------------------------------------------------------------------------------------------------------
+constexpr uint32_t TP_THREADS = TILE + 64;         // producer warp + 8 consumer warps + epilogue warp
+constexpr uint32_t TILE_SENTINEL = 0x7fffffffu;
+enum { TF_SWZ = 1u, TF_FALLBACK = 2u, TF_TS_SMEM = 4u };
+
+struct StageMeta {
+    uint32_t tile, batch, first, cnt, flags, count; // count: survivors (written by the consumers)
+    uint32_t pad[2];
+};
+
 template <class P, int MODE>
 struct TilePassSmem {
     using T = typename P::tuple_t;
     using R = typename P::result_t;
     static constexpr uint32_t rec_bytes = (MODE == MODE_INGEST && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
-    static constexpr uint32_t stage_bytes = TILE * rec_bytes;
-    static constexpr uint32_t total = STAGES * stage_bytes + 256;
+    static constexpr uint32_t tile_bytes = (TILE * rec_bytes + 1023u) & ~1023u; // swizzled stages need 512-B alignment
+    static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : TILE * 16u; // slots | ts in + ts out
+    static constexpr uint32_t stage_bytes = tile_bytes + aux_bytes;
+    static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 512 /*barriers, meta, scan*/;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int32_t c0, int32_t c1, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TILE) : "memory"); }
+
 template <class P, int MODE>
-__global__ void __launch_bounds__(TILE) k_tile_pass(const TileArgs a, const typename P::params_t prm)
+__global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant__ CUtensorMap tmap, const TileArgs a,
+                                                          const typename P::params_t prm)
 {
     using T = typename P::tuple_t;
     using R = typename P::result_t;
+    using SM = TilePassSmem<P, MODE>;
     constexpr uint32_t TB = sizeof(T);
     constexpr uint32_t RB = sizeof(R);
     static_assert(TB % 8 == 0 && RB % 8 == 0, "records must be multiples of 8 bytes");
-    constexpr uint32_t STAGE_BYTES = TilePassSmem<P, MODE>::stage_bytes;
+    constexpr bool CAN_SWZ = (TB == 64);
 
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *tiles = smem;                                                   // STAGES * STAGE_BYTES
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);    // STAGES mbarriers
-    uint32_t *tile_id = reinterpret_cast<uint32_t *>(full + STAGES);               // STAGES
-    uint32_t *warp_tot = tile_id + STAGES;                                         // TILE/32
-    uint32_t *bcast = warp_tot + TILE / 32;                                        // [0] = tile base
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char *ctl = smem + STAGES * SM::stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ctl);          // STAGES  producer -> consumers (tx)
+    uint64_t *staged = full + STAGES;                            // STAGES  consumers -> epilogue
+    uint64_t *empty = staged + STAGES;                           // STAGES  epilogue -> producer
+    StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);  // STAGES
+    uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 (double-buffered by iteration parity)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    auto batch_of = [&](uint32_t tile, DevBatch &b) -> uint32_t {
-        if (a.batches == nullptr) { b = a.one; return 0u; }
-        uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= tile
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (a.batches[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
-        }
-        b = a.batches[lo];
-        return lo;
-    };
-
-    // producer (thread 0): claim the next ticket and start the TMA load of that tile into stage s
-    auto produce = [&](uint32_t s) {
-        const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
-        if (t >= a.num_tiles) { // nothing to load: plain arrival so that the consumers see the sentinel
-            tile_id[s] = 0x7fffffffu;
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-            return;
-        }
-        DevBatch b; batch_of(t, b);
-        const uint32_t first = (t - b.tile_begin) * TILE;
-        const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
-        const unsigned char *src = b.tuples + static_cast<size_t>(first) * TB;
-        const uint32_t bytes = cnt * TB;
-        if (bulk_ok(src, bytes)) {
-            tile_id[s] = t;
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(tiles + s * STAGE_BYTES, src, bytes, &full[s]);
-        } else { // consumers fall back to coalesced word loads for this tile
-            tile_id[s] = t | 0x80000000u;
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-        }
-    };
+    auto stage_buf = [&](uint32_t s) { return smem + s * SM::stage_bytes; };
+    auto stage_aux = [&](uint32_t s) { return smem + s * SM::stage_bytes + SM::tile_bytes; };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&staged[s], TILE / 32); mbar_init(&empty[s], 1); }
         mbar_fence_init();
-        for (int s = 0; s < STAGES - 1; s++) produce(s);
     }
     __syncthreads();
 
-    for (uint32_t it = 0;; it++) {
-        const uint32_t s = it % STAGES;
-        const uint32_t parity = (it / STAGES) & 1u;
-        unsigned char *buf = tiles + s * STAGE_BYTES;
-
-        // tile_id[s] was written at least one __syncthreads ago: safe to read before the mbarrier wait, which
-        // lets the timestamp load (and the batch lookup) overlap the wait for the TMA bytes.
-        uint32_t t = tile_id[s];
-        const bool fallback = (t & 0x80000000u) != 0;
-        t &= 0x7fffffffu;
-        if (t >= a.num_tiles) break; // tickets are handed out in order: every later one is out of range too
-
-        DevBatch b;
-        const uint32_t bi = batch_of(t, b);
-        const uint32_t first = (t - b.tile_begin) * TILE;
-        const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
-        const bool active = tid < cnt;
-        uint64_t ts = 0;
-        if (MODE == MODE_FILTER && active && b.ts != nullptr) ts = b.ts[first + tid];
-
-        mbar_wait(&full[s], parity);
-
-        if (fallback) { // unaligned / odd-sized tile: coalesced 8-byte copies into the same (linear) buffer
-            const uint64_t *src = reinterpret_cast<const uint64_t *>(b.tuples + static_cast<size_t>(first) * TB);
-            uint64_t *dst = reinterpret_cast<uint64_t *>(buf);
-            for (uint32_t w = tid; w < cnt * (TB / 8); w += TILE) dst[w] = src[w];
-            __syncthreads();
+    if (warp == 0) {
+        // ================================= PRODUCER =================================
+        if (lane == 0) {
+            for (uint32_t it = 0;; it++) {
+                const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
+                mbar_wait(&empty[s], par ^ 1u); // a fresh barrier passes the wait on parity 1
+                const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                StageMeta &m = meta[s];
+                if (t >= a.num_tiles) { m.tile = TILE_SENTINEL; mbar_arrive(&full[s]); break; }
+                DevBatch b; uint32_t bi = 0;
+                if (a.batches == nullptr) b = a.one;
+                else {
+                    uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= t
+                    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (a.batches[mid].tile_begin <= t) lo = mid; else hi = mid - 1; }
+                    bi = lo; b = a.batches[lo];
+                }
+                const uint32_t first = (t - b.tile_begin) * TILE;
+                const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
+                const unsigned char *src = b.tuples + static_cast<size_t>(first) * TB;
+                uint32_t flags = 0, tx = 0;
+                const uint64_t off = reinterpret_cast<uint64_t>(src) - a.tmap_base;
+                if (CAN_SWZ && a.use_tmap && cnt == TILE && (off & 63u) == 0 && (off >> 6) < 0x7fffff00ull) flags = TF_SWZ;
+                else if (!bulk_ok(src, cnt * TB)) flags = TF_FALLBACK;
+                if (!(flags & TF_FALLBACK)) tx += cnt * TB;
+                const uint64_t *tsp = (MODE == MODE_FILTER && b.ts != nullptr) ? b.ts + first : nullptr;
+                if (tsp != nullptr && bulk_ok(tsp, cnt * 8u)) { flags |= TF_TS_SMEM; tx += cnt * 8u; }
+                m.tile = t; m.batch = bi; m.first = first; m.cnt = cnt; m.flags = flags;
+                if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
+                if (flags & TF_SWZ) tma_load_2d(stage_buf(s), &tmap, 0, static_cast<int32_t>(off >> 6), &full[s]);
+                else if (!(flags & TF_FALLBACK)) bulk_g2s(stage_buf(s), src, cnt * TB, &full[s]);
+                if (flags & TF_TS_SMEM) bulk_g2s(stage_aux(s), tsp, cnt * 8u, &full[s]);
+            }
         }
-
-        // ---- per-tuple work in registers ---------------------------------------------------------------
-        alignas(16) T tup;
-        bool keep = false;
-        if (active) {
-            TileIO<T>::load(buf, tid, tup);
-            P::map(tup, prm);
-            keep = (MODE == MODE_MAP) ? true : P::filter(tup, prm);
-        }
-
-        uint32_t local = tid, tile_count = cnt, base = 0;
-        uint32_t slot = INVALID_SLOT;
-        if constexpr (MODE == MODE_MAP) {
-            __syncthreads(); // every thread has read its tuple: the stage can be overwritten with the results
-            if (active) TileIO<T>::store(buf, tid, tup);
-            fence_async_smem();
-            __syncthreads();
-        } else {
-            // the timestamp load must have completed before this tile publishes its count (an in-place
-            // compaction lets later tiles overwrite this tile's input once the count is visible)
-            if constexpr (MODE == MODE_FILTER) asm volatile("mov.b64 %0, %0;" : "+l"(ts));
-            // ---- stable offsets: block scan of the keep flags + decoupled look-back --------------------------
-            const uint32_t bal = __ballot_sync(FULL, keep);
-            if (lane == 0) warp_tot[warp] = __popc(bal);
-            __syncthreads(); // warp totals visible; every thread has read its tuple (stage re-usable for staging)
-            uint32_t wbase = 0, total = 0;
+    } else if (warp <= TILE / 32) {
+        // ================================= CONSUMERS =================================
+        const uint32_t ctid = tid - 32, cwarp = warp - 1;
+        for (uint32_t it = 0;; it++) {
+            const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
+            unsigned char *buf = stage_buf(s);
+            mbar_wait(&full[s], par);
+            const StageMeta m = meta[s];
+            if (m.tile == TILE_SENTINEL) { // pass the end-of-work marker on to the epilogue warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&staged[s]);
+                break;
+            }
+            DevBatch b;
+            if (a.batches == nullptr) b = a.one; else b = a.batches[m.batch];
+            const uint32_t cnt = m.cnt;
+            const bool active = ctid < cnt;
+            if (m.flags & TF_FALLBACK) { // unaligned / odd-sized tile: coalesced 8-byte copies into the linear buffer
+                const uint64_t *src = reinterpret_cast<const uint64_t *>(b.tuples + static_cast<size_t>(m.first) * TB);
+                uint64_t *dst = reinterpret_cast<uint64_t *>(buf);
+                for (uint32_t w = ctid; w < cnt * (TB / 8); w += TILE) dst[w] = src[w];
+                consumer_bar();
+            }
+            // ---- per-tuple work in registers ---------------------------------------------------------------
+            alignas(16) T tup;
+            uint64_t ts = 0;
+            bool keep = false;
+            if (active) {
+                if constexpr (CAN_SWZ) {
+                    if (m.flags & TF_SWZ) { // SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+                        const uint4 *p = reinterpret_cast<const uint4 *>(buf + static_cast<size_t>(ctid) * 64);
+                        const uint32_t x = (ctid >> 1) & 3u;
+                        uint4 *o = reinterpret_cast<uint4 *>(&tup);
 #pragma unroll
-            for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = warp_tot[w]; if (w < warp) wbase += c; total += c; }
-            local = wbase + __popc(bal & lanemask_lt());
-            tile_count = total;
-
-            if (warp == 0) {
-                // look-back chain: per batch for MODE_FILTER, over the whole stream segment for MODE_INGEST
+                        for (uint32_t jj = 0; jj < 4; jj++) o[jj] = p[jj ^ x];
+                    } else TileIO<T>::load(buf, ctid, tup);
+                } else TileIO<T>::load(buf, ctid, tup);
+                if constexpr (MODE == MODE_FILTER) {
+                    if (b.ts != nullptr)
+                        ts = (m.flags & TF_TS_SMEM) ? reinterpret_cast<const uint64_t *>(stage_aux(s))[ctid] : b.ts[m.first + ctid];
+                }
+                P::map(tup, prm);
+                keep = (MODE == MODE_MAP) ? true : P::filter(tup, prm);
+            }
+            uint32_t slot = INVALID_SLOT;
+            alignas(16) R res;
+            if constexpr (MODE == MODE_INGEST) {
+                if (keep) {
+                    P::lift(tup, res);
+                    slot = slot_of_key(a.ff, P::key(tup));
+                    if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                }
+            }
+            if constexpr (MODE == MODE_MAP) {
+                consumer_bar(); // every consumer has read its tuple: overwrite the stage with the results
+                if (active) {
+                    if constexpr (CAN_SWZ) {
+                        if (m.flags & TF_SWZ) {
+                            uint4 *p = reinterpret_cast<uint4 *>(buf + static_cast<size_t>(ctid) * 64);
+                            const uint32_t x = (ctid >> 1) & 3u;
+                            const uint4 *o = reinterpret_cast<const uint4 *>(&tup);
+#pragma unroll
+                            for (uint32_t jj = 0; jj < 4; jj++) p[jj ^ x] = o[jj];
+                        } else TileIO<T>::store(buf, ctid, tup);
+                    } else TileIO<T>::store(buf, ctid, tup);
+                }
+                if (ctid == 0) meta[s].count = cnt;
+            } else {
+                // ---- stable local offsets: ballot + warp totals (double-buffered), ONE named barrier ------------
+                const uint32_t bal = __ballot_sync(FULL, keep);
+                uint32_t *wt = warp_tot + (it & 1u) * (TILE / 32);
+                if (lane == 0) wt[cwarp] = __popc(bal);
+                consumer_bar(); // totals visible; every consumer has read its tuple (stage re-usable for staging)
+                uint32_t wbase = 0, total = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = wt[w]; if (w < cwarp) wbase += c; total += c; }
+                const uint32_t local = wbase + __popc(bal & lanemask_lt());
+                if (ctid == 0) { // publish the aggregate right away so that other CTAs' look-backs never wait for us
+                    meta[s].count = total;
+                    const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
+                    if (m.tile != chain_begin) st_relaxed_u64(&a.tile_state[m.tile], pack_state(a.epoch, ST_AGG, total));
+                }
+                if (keep) {
+                    if constexpr (MODE == MODE_FILTER) {
+                        TileIO<T>::store(buf, local, tup);
+                        if (b.ts_out != nullptr) reinterpret_cast<uint64_t *>(stage_aux(s) + TILE * 8)[local] = ts;
+                    } else {
+                        TileIO<R>::store(buf, local, res);
+                        reinterpret_cast<uint32_t *>(stage_aux(s))[local] = slot;
+                    }
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&staged[s]);
+        }
+    } else {
+        // ================================= EPILOGUE =================================
+        for (uint32_t it = 0;; it++) {
+            const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
+            unsigned char *buf = stage_buf(s);
+            mbar_wait(&staged[s], par);
+            const StageMeta m = meta[s];
+            if (m.tile == TILE_SENTINEL) break;
+            DevBatch b;
+            if (a.batches == nullptr) b = a.one; else b = a.batches[m.batch];
+            const uint32_t t = m.tile, tile_count = m.count;
+            uint32_t excl = 0;
+            if constexpr (MODE != MODE_MAP) {
                 const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
-                uint32_t excl = 0;
-                if (t == chain_begin) {
-                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_PREFIX, tile_count));
-                } else {
-                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_AGG, tile_count));
+                if (t != chain_begin) {
                     int64_t idx = static_cast<int64_t>(t) - 1;
                     while (true) {
                         const int64_t my = idx - lane;
@@ -379,68 +464,53 @@ __global__ void __launch_bounds__(TILE) k_tile_pass(const TileArgs a, const type
                         if (pmask) break;
                         idx -= 32;
                     }
-                    if (lane == 0) st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_PREFIX, excl + tile_count));
                 }
                 if (lane == 0) {
-                    bcast[0] = excl;
+                    st_relaxed_u64(&a.tile_state[t], pack_state(a.epoch, ST_PREFIX, excl + tile_count));
                     if constexpr (MODE == MODE_FILTER) {
                         const uint32_t last_tile = b.tile_begin + (b.n + TILE - 1) / TILE - 1;
                         if (t == last_tile && b.n_out != nullptr) *b.n_out = excl + tile_count;
                     } else {
-                        if (t == b.tile_begin) a.batch_off[bi] = excl;
+                        if (t == b.tile_begin) a.batch_off[m.batch] = excl;
                         if (t == a.num_tiles - 1) { a.batch_off[a.nbatches] = excl + tile_count; *a.n_total = excl + tile_count; }
                     }
                 }
             }
-
-            // ---- stage the outputs in shared memory (compacted, linear layout) -----------------------------
-            if (keep) {
-                if constexpr (MODE == MODE_FILTER) {
-                    TileIO<T>::store(buf, local, tup);
-                } else {
-                    alignas(16) R res;
-                    P::lift(tup, res);
-                    slot = slot_of_key(a.ff, P::key(tup));
-                    if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
-                    TileIO<R>::store(buf, local, res);
-                }
-            }
-            fence_async_smem();
-            __syncthreads(); // staging complete, bcast[0] visible
-            base = bcast[0];
-        }
-
-        // ---- write out: one TMA bulk store per tile (coalesced word copies when misaligned) ---------------------
-        {
+            // ---- write out ---------------------------------------------------------------------------------------
             unsigned char *dst;
             uint32_t bytes;
-            if constexpr (MODE == MODE_MAP) { dst = b.out + static_cast<size_t>(first) * TB; bytes = cnt * TB; }
-            else if constexpr (MODE == MODE_FILTER) { dst = b.out + static_cast<size_t>(base) * TB; bytes = tile_count * TB; }
-            else { dst = a.lifted + static_cast<size_t>(base) * RB; bytes = tile_count * RB; }
-            if (bulk_ok(dst, bytes)) {
-                if (tid == 0 && bytes) bulk_s2g(dst, buf, bytes);
+            if constexpr (MODE == MODE_MAP) { dst = b.out + static_cast<size_t>(m.first) * TB; bytes = m.cnt * TB; }
+            else if constexpr (MODE == MODE_FILTER) { dst = b.out + static_cast<size_t>(excl) * TB; bytes = tile_count * TB; }
+            else { dst = a.lifted + static_cast<size_t>(excl) * RB; bytes = tile_count * RB; }
+            if (MODE == MODE_MAP && (m.flags & TF_SWZ)) {
+                if (lane == 0) tma_store_2d(&tmap, 0, static_cast<int32_t>((reinterpret_cast<uint64_t>(dst) - a.tmap_base) >> 6), buf);
+            } else if (bulk_ok(dst, bytes)) {
+                if (lane == 0 && bytes) bulk_s2g(dst, buf, bytes);
             } else {
                 uint64_t *d8 = reinterpret_cast<uint64_t *>(dst);
                 const uint64_t *s8 = reinterpret_cast<const uint64_t *>(buf);
-                for (uint32_t w = tid; w < bytes / 8; w += TILE) d8[w] = s8[w];
+                for (uint32_t w = lane; w < bytes / 8; w += 32) d8[w] = s8[w];
             }
-            if constexpr (MODE == MODE_FILTER) { if (keep && b.ts_out != nullptr) b.ts_out[base + local] = ts; }
-            if constexpr (MODE == MODE_INGEST) { if (keep) a.slots[base + local] = slot; }
+            if constexpr (MODE == MODE_FILTER) {
+                if (b.ts_out != nullptr) {
+                    const uint64_t *sts = reinterpret_cast<const uint64_t *>(stage_aux(s) + TILE * 8);
+                    for (uint32_t i = lane; i < tile_count; i += 32) b.ts_out[excl + i] = sts[i];
+                }
+            }
+            if constexpr (MODE == MODE_INGEST) {
+                const uint32_t *ssl = reinterpret_cast<const uint32_t *>(stage_aux(s));
+                for (uint32_t i = lane; i < tile_count; i += 32) a.slots[excl + i] = ssl[i];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                bulk_commit();
+                bulk_wait_read<0>();   // the store has finished READING shared memory: the stage can be refilled
+                mbar_arrive(&empty[s]);
+            }
         }
-
-        // ---- refill the pipeline. The stage refilled here is the one used by the PREVIOUS iteration: every
-        // thread has passed this iteration's barriers, so nobody still touches it with ordinary accesses, and
-        // its bulk store has finished reading once all but the newest group (committed just now, possibly
-        // empty) are done.
-        if (tid == 0) {
-            bulk_commit();
-            bulk_wait_read<1>();
-            produce((it + STAGES - 1) % STAGES);
-        }
+        if (lane == 0) bulk_wait_all<0>();
     }
-    if (tid == 0) bulk_wait_all<0>();
 }
-
 
 // ------------------------------------------------------------------------------------------------------
 // record helpers (R = result_t): vectorised global load/store and warp shuffles of whole records

@@ -7,6 +7,7 @@
 #include <vector>
 #include <algorithm>
 #include <new>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/wfb200.h"
 #include "wfb_kernels.cuh"
@@ -19,6 +20,41 @@ using namespace wfb;
 namespace {
 
 int g_num_sms = 0;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D view [rows][64 bytes] of a span of device memory holding 64-byte tuples, box = one tile, SWIZZLE_64B
+bool make_tuple_tmap(CUtensorMap *m, uint64_t base, uint64_t end)
+{
+    std::memset(m, 0, sizeof(*m));
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc || (base & 63u) || end <= base) return false;
+    const uint64_t rows = (end - base) / 64;
+    if (rows == 0 || rows > 0xffffffffull) return false;
+    cuuint64_t gdim[2] = {64, rows};
+    cuuint64_t gstr[1] = {64};
+    cuuint32_t box[2] = {64, TILE};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, reinterpret_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int device_ready()
 {
@@ -35,7 +71,8 @@ int device_ready()
 // ---- per-program launch table ------------------------------------------------------------------------------
 struct ProgramOps {
     uint32_t tuple_bytes, result_bytes;
-    int (*tile_pass)(int mode, const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used);
+    int (*tile_pass)(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                     uint64_t span_begin, uint64_t span_end);
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
                        uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s);
@@ -48,33 +85,39 @@ struct ProgramOps {
 };
 
 template <class P, int MODE>
-int launch_tile_pass(const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used)
+int launch_tile_pass(TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                     uint64_t span_begin, uint64_t span_end)
 {
     static int max_grid = -1;
     constexpr uint32_t smem = TilePassSmem<P, MODE>::total;
     if (max_grid < 0) {
         CK(cudaFuncSetAttribute(k_tile_pass<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass<P, MODE>, TILE, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass<P, MODE>, TP_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
         max_grid = per_sm * g_num_sms;
     }
     const uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
     typename P::params_t prm;
     if (params) prm = *static_cast<const typename P::params_t *>(params); else std::memset(&prm, 0, sizeof(prm));
-    k_tile_pass<P, MODE><<<grid, TILE, smem, s>>>(a, prm);
+    alignas(64) CUtensorMap tmap;
+    a.use_tmap = 0; a.tmap_base = span_begin;
+    if (sizeof(typename P::tuple_t) == 64 && make_tuple_tmap(&tmap, span_begin, span_end)) a.use_tmap = 1;
+    else std::memset(&tmap, 0, sizeof(tmap));
+    k_tile_pass<P, MODE><<<grid, TP_THREADS, smem, s>>>(tmap, a, prm);
     CK(cudaGetLastError());
     *grid_used = grid;
     return 0;
 }
 
 template <class P>
-int tile_pass_dispatch(int mode, const TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used)
+int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                       uint64_t span_begin, uint64_t span_end)
 {
     switch (mode) {
-    case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used);
-    case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used);
-    case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used);
+    case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
     }
     return WFB_E_BADARG;
 }
@@ -191,7 +234,7 @@ struct TileScratch {
         return 0;
     }
     void next_launch(TileArgs &a) { epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1; a.epoch = epoch; a.ticket = ticket; a.ticket_base = ticket_base; a.tile_state = tile_state; }
-    void launched(uint32_t num_tiles, uint32_t grid) { ticket_base += num_tiles + grid * (STAGES - 1); }
+    void launched(uint32_t num_tiles, uint32_t grid) { ticket_base += num_tiles + grid; } // one failing claim per CTA
 };
 
 inline uint32_t tiles_of(uint32_t n) { return (n + TILE - 1) / TILE; }
@@ -390,7 +433,8 @@ static int run_single(wfb_engine_t *e, int mode, const wfb_functors_t *f, const 
     a.batches = nullptr; a.one = b; a.nbatches = 1; a.num_tiles = num_tiles;
     e->ts.next_launch(a);
     uint32_t grid = 0;
-    rc = e->ops->tile_pass(mode, a, f, num_tiles, s, &grid); if (rc) return rc;
+    const uint64_t sb = reinterpret_cast<uint64_t>(b.tuples);
+    rc = e->ops->tile_pass(mode, a, f, num_tiles, s, &grid, sb, sb + static_cast<uint64_t>(b.n) * e->ops->tuple_bytes); if (rc) return rc;
     e->ts.launched(num_tiles, grid);
     e->launches++;
     return 0;
@@ -613,6 +657,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     std::vector<DevBatch> hb; // empty batches trigger nothing: only the non-empty ones reach the device
     hb.reserve(nbatches);
     uint64_t total = 0; uint32_t tiles = 0;
+    uint64_t span_begin = ~0ull, span_end = 0; // address span of the segment's tuples (for the 2-D tensor map)
     for (uint32_t i = 0; i < nbatches; i++) {
         if (batches_h[i].n == 0) continue;
         if (!batches_h[i].tuples) return WFB_E_BADARG;
@@ -620,6 +665,8 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         b.tuples = static_cast<const unsigned char *>(batches_h[i].tuples); b.ts = batches_h[i].ts;
         b.watermark = batches_h[i].watermark; b.n = batches_h[i].n; b.tile_begin = tiles;
         tiles += tiles_of(b.n); total += b.n;
+        const uint64_t p0 = reinterpret_cast<uint64_t>(b.tuples);
+        span_begin = std::min(span_begin, p0); span_end = std::max(span_end, p0 + static_cast<uint64_t>(b.n) * h->ops->tuple_bytes);
         hb.push_back(b);
     }
     if (total == 0) return 0;
@@ -637,7 +684,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     a.lifted = h->lifted; a.slots = h->slotsA; a.batch_off = h->batch_off; a.n_total = h->n_total; a.ff = h->ff;
     h->ts.next_launch(a);
     uint32_t grid = 0;
-    rc = h->ops->tile_pass(MODE_INGEST, a, pre, tiles, s, &grid); if (rc) return rc;
+    rc = h->ops->tile_pass(MODE_INGEST, a, pre, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
     h->launches++;
 
