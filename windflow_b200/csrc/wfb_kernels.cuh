@@ -48,6 +48,9 @@ struct DevBatch {
     uint32_t tile_begin;       // first global tile index of this batch
 };
 
+// one fired window group whose Nb window queries are evaluated after the update kernel
+struct Trigger { uint64_t key; uint64_t g; uint32_t slot; uint32_t last_pos; uint32_t obase; uint32_t pad; };
+
 // key -> slot table (open addressing, linear probing) + per-key window state of one Ffat_Windows_GPU
 struct FfatDev {
     // key table
@@ -65,6 +68,9 @@ struct FfatDev {
     unsigned char *tree;       // FlatFAT per slot: (2*n_leaves-1) result_t, leaves first (level 0), root last
     uint32_t *seg_cnt;         // items of the current stream segment per slot (zeroed by k_ffat_update)
     uint32_t *seg_off;         // exclusive offsets into the sorted segment, max_keys+1
+    struct Trigger *trig;      // deferred window groups of the current segment (evaluated by k_ffat_windows)
+    uint32_t *n_trig;          // number of deferred groups
+    uint32_t trig_cap;
     // window geometry (in tuples and in panes)
     uint64_t win, slide, B;    // B = (Nb-1)*slide + win  (ffat_replica_gpu.hpp:657)
     uint32_t nb;               // windows per trigger
@@ -471,6 +477,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                         const uint32_t last_tile = b.tile_begin + (b.n + TILE - 1) / TILE - 1;
                         if (t == last_tile && b.n_out != nullptr) *b.n_out = excl + tile_count;
                     } else {
+                        if (t == 0) *a.ff.n_trig = 0; // deferred window groups of this segment (k_ffat_update runs later)
                         if (t == b.tile_begin) a.batch_off[m.batch] = excl;
                         if (t == a.num_tiles - 1) { a.batch_off[a.nbatches] = excl + tile_count; *a.n_total = excl + tile_count; }
                     }
@@ -685,8 +692,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restric
 // ------------------------------------------------------------------------------------------------------
 constexpr int OS_THREADS = 256;
 constexpr int OS_MAX_PASSES = 8;
-// elements per thread: 16 for 32-bit keys (4096 per tile), 8 for 64-bit keys (2048 per tile) -- static smem <= 48 KB
-template <class K> struct OsCfg { static constexpr int ITEMS = sizeof(K) == 4 ? 16 : 8; static constexpr int TILE_ELEMS = OS_THREADS * ITEMS; };
+// elements per thread (ITEMS): <= 16 for 32-bit keys, <= 8 for 64-bit keys (static smem <= 48 KB)
+template <class K> struct OsCfg { static constexpr int MAX_ITEMS = sizeof(K) == 4 ? 16 : 8; };
 
 template <class K>
 __global__ void __launch_bounds__(256) k_radix_ghist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
@@ -704,7 +711,7 @@ __global__ void __launch_bounds__(256) k_radix_ghist(const K *__restrict__ keys,
     for (uint32_t i = threadIdx.x; i < passes * 256; i += blockDim.x) if (h[i]) atomicAdd(&ctl[i], h[i]);
 }
 
-template <class K>
+template <class K, int OS_ITEMS>
 __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                               K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                               const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t pass,
@@ -716,8 +723,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
     __shared__ uint32_t bin_base[256];              // global position of the tile's first element of each digit
     __shared__ uint32_t wsum[OS_THREADS / 32];
     __shared__ uint32_t s_tile;
-    constexpr int OS_ITEMS = OsCfg<K>::ITEMS;
-    constexpr int OS_TILE = OsCfg<K>::TILE_ELEMS;
+    constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
     __shared__ K skeys[OS_TILE];
     __shared__ uint32_t svals[OS_TILE];
 
@@ -833,6 +839,64 @@ __global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const ui
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t level_off(uint32_t n_leaves, uint32_t level) { return 2u * n_leaves - ((2u * n_leaves) >> level); }
 
+// watermark of the batch that holds compact position `pos` (batch_off has nbatches+1 ascending entries)
+__device__ __forceinline__ uint64_t batch_watermark(const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                    uint32_t nbatches, uint32_t pos)
+{
+    uint32_t lo = 0, hi = nbatches - 1;
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (batch_off[mid] <= pos) lo = mid; else hi = mid - 1; }
+    return batches[lo].watermark;
+}
+
+// one window: result_t(key, gwid) folded left to right over the largest aligned FlatFAT nodes covering panes
+// [gwid*sp, gwid*sp + wp) of the key's ring (the walk of Compute_Results_Kernel, wf/flatfat_gpu.hpp:109-136)
+template <class P>
+__device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsigned char *tree, uint64_t key, uint64_t gwid, uint64_t wm,
+                                                 uint32_t opos, unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts,
+                                                 uint32_t out_cap)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    const uint32_t n = ff.n_leaves;
+    alignas(16) R res = P::make_result(key, gwid);
+    uint32_t ws = static_cast<uint32_t>((gwid * ff.sp) & (n - 1));
+    uint32_t remaining = ff.wp;
+    while (remaining > 0) {
+        uint32_t range = (ws == 0) ? n : (ws & (0u - ws));
+        const uint32_t pw = 1u << (31 - __clz(remaining));
+        range = min(range, pw);
+        const uint32_t level = 31 - __clz(range);
+        alignas(16) R node;
+        ld_rec<R>(tree + static_cast<size_t>(level_off(n, level) + (ws >> level)) * RB, node);
+        P::comb(res, node, res);
+        ws = (ws + range) & (n - 1);
+        remaining -= range;
+    }
+    if (opos < out_cap) {
+        st_rec<R>(out_res + static_cast<size_t>(opos) * RB, res);
+        if (out_ts != nullptr) out_ts[opos] = wm;
+    } else atomicOr(ff.err_flags, 2u);
+}
+
+// deferred window groups: one thread per window
+template <class P>
+__global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const uint32_t *__restrict__ batch_off,
+                                                      const DevBatch *__restrict__ batches, uint32_t nbatches,
+                                                      unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts, uint32_t out_cap)
+{
+    using R = typename P::result_t;
+    const uint32_t nt = min(*ff.n_trig, ff.trig_cap);
+    const uint64_t total = static_cast<uint64_t>(nt) * ff.nb;
+    const size_t tree_stride = static_cast<size_t>(2 * ff.n_leaves - 1) * sizeof(R);
+    for (uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; w < total; w += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t ti = static_cast<uint32_t>(w / ff.nb), i = static_cast<uint32_t>(w % ff.nb);
+        const Trigger tr = ff.trig[ti];
+        const uint64_t wm = batch_watermark(batch_off, batches, nbatches, tr.last_pos);
+        ffat_eval_window<P>(ff, ff.tree + static_cast<size_t>(tr.slot) * tree_stride, tr.key, tr.g * ff.nb + i, wm, tr.obase + i,
+                            out_res, out_ts, out_cap);
+    }
+}
+
 template <class P>
 __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const unsigned char *__restrict__ lifted,
                                                      const uint32_t *__restrict__ sorted_pos,
@@ -900,32 +964,24 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                 __syncwarp();
 
                 if (c == trig) { // fire Nb windows: gwid = g*Nb + i
-                    uint32_t lo = 0, hi = nbatches - 1; // batch holding the triggering item
-                    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (batch_off[mid] <= last_pos) lo = mid; else hi = mid - 1; }
-                    const uint64_t wm = batches[lo].watermark;
                     uint32_t obase = 0;
                     if (lane == 0) obase = atomicAdd(n_out, ff.nb);
                     obase = __shfl_sync(FULL, obase, 0);
-                    for (uint32_t i = lane; i < ff.nb; i += 32) {
-                        const uint64_t gwid = g * ff.nb + i;
-                        alignas(16) R res = P::make_result(key, gwid);
-                        uint32_t ws = static_cast<uint32_t>((gwid * ff.sp) & (n - 1));
-                        uint32_t remaining = ff.wp;
-                        while (remaining > 0) {
-                            uint32_t range = (ws == 0) ? n : (ws & (0u - ws));
-                            const uint32_t pw = 1u << (31 - __clz(remaining));
-                            range = min(range, pw);
-                            const uint32_t level = 31 - __clz(range);
-                            alignas(16) R node;
-                            ld_rec<R>(tree + static_cast<size_t>(level_off(n, level) + (ws >> level)) * RB, node);
-                            P::comb(res, node, res);
-                            ws = (ws + range) & (n - 1);
-                            remaining -= range;
-                        }
-                        if (obase + i < out_cap) {
-                            st_rec<R>(out_res + static_cast<size_t>(obase + i) * RB, res);
-                            if (out_ts != nullptr) out_ts[obase + i] = wm;
-                        } else atomicOr(ff.err_flags, 2u);
+                    // No further pane of this key can complete in this segment => the tree stays as it is now and the
+                    // queries can run later, thread-per-window, in k_ffat_windows; otherwise evaluate them here.
+                    bool deferred = (m - j) < P_;
+                    if (deferred) {
+                        uint32_t ti = 0;
+                        if (lane == 0) ti = atomicAdd(ff.n_trig, 1u);
+                        ti = __shfl_sync(FULL, ti, 0);
+                        if (ti < ff.trig_cap) {
+                            if (lane == 0) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
+                        } else deferred = false;
+                    }
+                    if (!deferred) {
+                        const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
+                        for (uint32_t i = lane; i < ff.nb; i += 32)
+                            ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap);
                     }
                     g++; trig += group_items;
                     __syncwarp();

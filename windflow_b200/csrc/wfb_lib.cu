@@ -76,6 +76,8 @@ struct ProgramOps {
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
                        uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s);
+    int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
+                        unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s);
     int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s);
     int (*reduce_segments)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
                            const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s);
@@ -132,6 +134,15 @@ int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const u
     return 0;
 }
 
+template <class P>
+int ffat_windows_dispatch(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
+                          unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s)
+{
+    k_ffat_windows<P><<<grid, 256, 0, s>>>(ff, batch_off, batches, nbatches, out_res, out_ts, out_cap);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 inline uint32_t grid_for(uint32_t n, uint32_t per_block) { return std::max(1u, std::min((n + per_block - 1) / per_block, static_cast<uint32_t>(g_num_sms) * 16u)); }
 
 template <class P>
@@ -173,6 +184,7 @@ ProgramOps make_ops()
     o.result_bytes = sizeof(typename P::result_t);
     o.tile_pass = &tile_pass_dispatch<P>;
     o.ffat_update = &ffat_update_dispatch<P>;
+    o.ffat_windows = &ffat_windows_dispatch<P>;
     o.extract_keys = &extract_keys_dispatch<P>;
     o.reduce_segments = &reduce_segments_dispatch<P>;
     o.reduce_all = &reduce_all_dispatch<P>;
@@ -263,12 +275,26 @@ struct RadixSorter {
     void destroy() { cudaFree(ctl); cudaFree(state); }
 
     // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
+    template <class K, int ITEMS>
+    void launch_pass(uint32_t tiles, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host,
+                     uint32_t p, uint32_t passes, cudaStream_t s)
+    {
+        k_onesweep_pass<K, ITEMS><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch);
+    }
+
     template <class K>
     int sort(K *kA, K *kB, uint32_t *vA, uint32_t *vB, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t passes,
              cudaStream_t s, const K **skeys, const uint32_t **svals)
     {
-        constexpr uint32_t TE = OsCfg<K>::TILE_ELEMS;
-        int rc = ensure(cap, TE, s); if (rc) return rc;
+        static int items = 0; // elements per thread of a pass (tuning knob: WFB_OS_ITEMS = 4, 8 or 16)
+        if (items == 0) {
+            const char *e = std::getenv("WFB_OS_ITEMS");
+            items = e ? std::atoi(e) : 8;
+            if (items != 4 && items != 8 && items != 16) items = 8;
+            if (items > OsCfg<K>::MAX_ITEMS) items = OsCfg<K>::MAX_ITEMS;
+        }
+        const uint32_t TE = OS_THREADS * static_cast<uint32_t>(items);
+        int rc = ensure(cap, OS_THREADS * 4, s); if (rc) return rc;
         passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
         CK(cudaMemsetAsync(ctl, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
         const uint32_t tiles = std::max(1u, (cap + TE - 1) / TE);
@@ -277,7 +303,9 @@ struct RadixSorter {
         K *kout = kB; uint32_t *vout = vB;
         for (uint32_t p = 0; p < passes; p++) {
             epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1;
-            k_onesweep_pass<K><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch);
+            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
+            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
+            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
             kin = kout; vin = vout;
             if (kout == kB) { kout = kA; vout = vA; } else { kout = kB; vout = vB; }
         }
@@ -583,9 +611,10 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         CK(cudaMemset(ff.ht_keys, 0xff, sizeof(uint64_t) * cap));
         CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
     }
-    ALLOC(ff.n_slots, sizeof(uint32_t) * 2);
+    ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
     ff.err_flags = ff.n_slots + 1;
-    CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 2));
+    ff.n_trig = ff.n_slots + 2;
+    CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
     ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
     ALLOC(ff.cnt, sizeof(uint64_t) * max_keys);
     CK(cudaMemset(ff.cnt, 0, sizeof(uint64_t) * max_keys));
@@ -611,7 +640,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaDeviceSynchronize();
     FfatDev &ff = h->ff;
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
-    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off);
+    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off); cudaFree(ff.trig);
     cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
     h->sorter.destroy();
     cudaFree(h->batch_off); cudaFree(h->n_total);
@@ -635,6 +664,10 @@ static int ffat_ensure_segment(wfb_ffat *h, uint32_t total, uint32_t nbatches, c
         CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->posA, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->seg_cap));
+        cudaFree(h->ff.trig);
+        const uint64_t per_group = std::max<uint64_t>(1, h->ff.slide * h->ff.nb);
+        h->ff.trig_cap = static_cast<uint32_t>(std::min<uint64_t>(h->seg_cap / per_group + h->ff.max_keys + 1, 0x7fffffffull));
+        CK(cudaMalloc(&h->ff.trig, sizeof(Trigger) * h->ff.trig_cap));
     }
     if (nbatches + 1 > h->batch_off_cap) {
         CK(cudaStreamSynchronize(s));
@@ -711,6 +744,11 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     ugrid = std::max(ugrid, 1u);
     rc = h->ops->ffat_update(h->ff, h->lifted, sorted_pos, h->batch_off, h->ts.d_batches, nbatches,
                              static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s);
+    if (rc) return rc;
+    h->launches++;
+    // 5. deferred window groups: one thread per window
+    rc = h->ops->ffat_windows(h->ff, h->batch_off, h->ts.d_batches, nbatches, static_cast<unsigned char *>(out_results), out_ts,
+                              out_capacity, static_cast<uint32_t>(g_num_sms) * 4u, s);
     if (rc) return rc;
     h->launches++;
     h->mark(3, s);
