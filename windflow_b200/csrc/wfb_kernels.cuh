@@ -716,7 +716,9 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
                                                               K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                               const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t pass,
                                                               uint32_t passes, uint32_t *__restrict__ ctl,
-                                                              uint64_t *__restrict__ tile_state, uint32_t epoch)
+                                                              uint64_t *__restrict__ tile_state, uint32_t epoch,
+                                                              const unsigned char *__restrict__ payload_in,
+                                                              unsigned char *__restrict__ payload_out, uint32_t payload_bytes)
 {
     __shared__ uint32_t cntw[OS_THREADS / 32][256]; // per-warp digit counts -> exclusive offsets over the warps
     __shared__ uint32_t dig_off[256];               // exclusive offset of each digit inside the tile
@@ -812,7 +814,19 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
         const uint32_t d = static_cast<uint32_t>(kk >> shift) & 255u;
         const uint32_t dst = bin_base[d] + (i - dig_off[d]);
         keys_out[dst] = kk;
-        vals_out[dst] = svals[i];
+        const uint32_t v = svals[i];
+        vals_out[dst] = v;
+        if (payload_out != nullptr) { // the last pass also moves the records: out[dst] = in[value]
+            if ((payload_bytes & 15u) == 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(payload_in + static_cast<size_t>(v) * payload_bytes);
+                uint4 *dstp = reinterpret_cast<uint4 *>(payload_out + static_cast<size_t>(dst) * payload_bytes);
+                for (uint32_t q = 0; q < payload_bytes / 16; q++) dstp[q] = src[q];
+            } else {
+                const uint64_t *src = reinterpret_cast<const uint64_t *>(payload_in + static_cast<size_t>(v) * payload_bytes);
+                uint64_t *dstp = reinterpret_cast<uint64_t *>(payload_out + static_cast<size_t>(dst) * payload_bytes);
+                for (uint32_t q = 0; q < payload_bytes / 8; q++) dstp[q] = src[q];
+            }
+        }
     }
 }
 
@@ -829,7 +843,8 @@ __global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const ui
 
 // ------------------------------------------------------------------------------------------------------
 // k_ffat_update: one warp per key that received items in this stream segment.
-//   items of the key, in arrival order (sorted_pos[seg_off[slot] .. +seg_cnt[slot]) -> lifted[])
+//   items of the key, in arrival order: lifted[sorted_pos[seg_off[slot] .. +seg_cnt[slot])] (gather = 1), or, when the last
+//   sort pass also moved the records (gather = 0), lifted[seg_off[slot] .. +seg_cnt[slot])
 //   -> ordered warp fold into the open pane (pane = gcd(win, slide) items)
 //   -> completed pane = new FlatFAT leaf (ring of n_leaves panes) + recompute of its root path
 //   -> when the key's count reaches the trigger: Nb window queries (greedy aligned-node fold, the same walk as
@@ -902,7 +917,8 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                                                      const uint32_t *__restrict__ sorted_pos,
                                                      const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
                                                      uint32_t nbatches, unsigned char *__restrict__ out_res,
-                                                     uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out)
+                                                     uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
+                                                     uint32_t gather)
 {
     using R = typename P::result_t;
     constexpr uint32_t RB = sizeof(R);
@@ -926,14 +942,21 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
         if (c % P_ != 0) ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc); // every lane keeps a copy
         uint64_t g = (c < ff.B) ? 0 : 1 + (c - ff.B) / group_items;
         uint64_t trig = ff.B + g * group_items;
+        if (!gather) { // pull the key's (contiguous) records towards L2 before the chunk loop needs them
+            const unsigned char *seg = lifted + static_cast<size_t>(off) * RB;
+            const uint32_t lines = (m * RB + 127u) / 128u;
+            for (uint32_t l = lane; l < lines && l < 128u; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(seg + static_cast<size_t>(l) * 128u));
+        }
 
         uint32_t j = 0;
         while (j < m) {
             const uint32_t room = static_cast<uint32_t>(P_ - (c % P_));
             const uint32_t take = min(min(32u, m - j), room);
             alignas(16) R r;
-            uint32_t p = 0;
-            if (lane < take) { p = sorted_pos[off + j + lane]; ld_rec<R>(lifted + static_cast<size_t>(p) * RB, r); }
+            if (lane < take) {
+                const uint32_t p = gather ? sorted_pos[off + j + lane] : (off + j + lane);
+                ld_rec<R>(lifted + static_cast<size_t>(p) * RB, r);
+            }
             // ordered fold: after the step with stride o, lane l holds items [l, l+2o) (clipped to take)
 #pragma unroll
             for (uint32_t o = 1; o < 32; o <<= 1) {
@@ -941,7 +964,6 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                 if (lane + o < take) P::comb(r, other, r);
             }
             r = shfl_rec<R>(r, 0);
-            const uint32_t last_pos = __shfl_sync(FULL, p, take - 1);
             if (c % P_ == 0) acc = r; else P::comb(acc, r, acc);
             c += take; j += take;
 
@@ -964,6 +986,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                 __syncwarp();
 
                 if (c == trig) { // fire Nb windows: gwid = g*Nb + i
+                    const uint32_t last_pos = sorted_pos[off + j - 1]; // arrival position of the triggering item
                     uint32_t obase = 0;
                     if (lane == 0) obase = atomicAdd(n_out, ff.nb);
                     obase = __shfl_sync(FULL, obase, 0);

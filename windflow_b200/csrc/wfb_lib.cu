@@ -75,7 +75,7 @@ struct ProgramOps {
                      uint64_t span_begin, uint64_t span_end);
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s);
+                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather);
     int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
                         unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s);
     int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s);
@@ -127,9 +127,9 @@ int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_
 template <class P>
 int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                          const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s)
+                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather)
 {
-    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out);
+    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather);
     CK(cudaGetLastError());
     return 0;
 }
@@ -277,14 +277,16 @@ struct RadixSorter {
     // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
     template <class K, int ITEMS>
     void launch_pass(uint32_t tiles, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host,
-                     uint32_t p, uint32_t passes, cudaStream_t s)
+                     uint32_t p, uint32_t passes, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes)
     {
-        k_onesweep_pass<K, ITEMS><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch);
+        k_onesweep_pass<K, ITEMS><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch,
+                                                               pin, pout, pbytes);
     }
 
     template <class K>
     int sort(K *kA, K *kB, uint32_t *vA, uint32_t *vB, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t passes,
-             cudaStream_t s, const K **skeys, const uint32_t **svals)
+             cudaStream_t s, const K **skeys, const uint32_t **svals,
+             const unsigned char *payload_in = nullptr, unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0)
     {
         static int items = 0; // elements per thread of a pass (tuning knob: WFB_OS_ITEMS = 4, 8 or 16)
         if (items == 0) {
@@ -303,9 +305,12 @@ struct RadixSorter {
         K *kout = kB; uint32_t *vout = vB;
         for (uint32_t p = 0; p < passes; p++) {
             epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1;
-            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
-            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
-            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s);
+            const bool last = (p + 1 == passes);
+            const unsigned char *pin = last ? payload_in : nullptr;
+            unsigned char *pout = last ? payload_out : nullptr;
+            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
+            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
+            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
             kin = kout; vin = vout;
             if (kout == kB) { kout = kA; vout = vA; } else { kout = kB; vout = vB; }
         }
@@ -371,7 +376,7 @@ struct wfb_ffat {
     uint32_t sort_passes = 1;
     // per-segment scratch (grown on demand)
     uint32_t seg_cap = 0;
-    unsigned char *lifted = nullptr;
+    unsigned char *lifted = nullptr, *lifted_sorted = nullptr;
     uint32_t *slotsA = nullptr, *slotsB = nullptr, *posA = nullptr, *posB = nullptr;
     RadixSorter sorter;
     uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
@@ -379,6 +384,7 @@ struct wfb_ffat {
     uint64_t launches = 0;
     size_t state_bytes = 0;
     int win_type = 0;
+    bool move_payload = false;    // tuning knob WFB_SORT_PAYLOAD=1: the last sort pass also moves the lifted records
     // optional per-phase timing (wfb_ffat_timing)
     bool timing = false;
     std::vector<cudaEvent_t> tev; // 4 events per recorded call
@@ -588,6 +594,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     wfb_ffat *h = new (std::nothrow) wfb_ffat();
     if (!h) return WFB_E_BADARG;
     h->prog = prog; h->ops = o; h->win_type = win_type;
+    { const char *e = std::getenv("WFB_SORT_PAYLOAD"); h->move_payload = e && std::atoi(e) != 0; }
     rc = h->ts.init(); if (rc) { delete h; return rc; }
     FfatDev &ff = h->ff;
     ff.win = win; ff.slide = slide; ff.nb = wins_per_batch;
@@ -641,7 +648,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     FfatDev &ff = h->ff;
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
     cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off); cudaFree(ff.trig);
-    cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
+    cudaFree(h->lifted); cudaFree(h->lifted_sorted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
     h->sorter.destroy();
     cudaFree(h->batch_off); cudaFree(h->n_total);
     for (auto &e : h->tev) cudaEventDestroy(e);
@@ -657,9 +664,10 @@ static int ffat_ensure_segment(wfb_ffat *h, uint32_t total, uint32_t nbatches, c
 {
     if (total > h->seg_cap) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(h->lifted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
+        cudaFree(h->lifted); cudaFree(h->lifted_sorted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
         h->seg_cap = std::max(total, 2 * h->seg_cap);
         CK(cudaMalloc(&h->lifted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
+        CK(cudaMalloc(&h->lifted_sorted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
         CK(cudaMalloc(&h->slotsA, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->seg_cap));
         CK(cudaMalloc(&h->posA, sizeof(uint32_t) * h->seg_cap));
@@ -727,7 +735,8 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     {
         const uint64_t before = h->sorter.launches;
         rc = h->sorter.sort<uint32_t>(h->slotsA, h->slotsB, h->posA, h->posB, h->n_total, 0, static_cast<uint32_t>(total),
-                                      h->sort_passes, s, &sorted_slots, &sorted_pos);
+                                      h->sort_passes, s, &sorted_slots, &sorted_pos, h->move_payload ? h->lifted : nullptr,
+                                      h->move_payload ? h->lifted_sorted : nullptr, h->ops->result_bytes);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
     }
@@ -742,8 +751,9 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     const uint32_t warps_needed = h->ff.max_keys;
     uint32_t ugrid = std::min((warps_needed + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u);
     ugrid = std::max(ugrid, 1u);
-    rc = h->ops->ffat_update(h->ff, h->lifted, sorted_pos, h->batch_off, h->ts.d_batches, nbatches,
-                             static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s);
+    rc = h->ops->ffat_update(h->ff, h->move_payload ? h->lifted_sorted : h->lifted, sorted_pos, h->batch_off, h->ts.d_batches, nbatches,
+                             static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s,
+                             h->move_payload ? 0u : 1u);
     if (rc) return rc;
     h->launches++;
     // 5. deferred window groups: one thread per window
