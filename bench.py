@@ -223,7 +223,8 @@ def run_ours(args):
                                      watermark=start + i * BATCH) for i in range(bps)])
     torch.cuda.synchronize()
 
-    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=nkeys_local, dense_keys=True)
+    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=nkeys_local, dense_keys=True,
+                            pipelined=not args.no_pipeline)
     cap = ff.max_results(seg_tuples)
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
     out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -298,6 +299,7 @@ def run_ours(args):
                        "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0", "selectivity": SIGMA,
                        "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
                        "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
+                       "pipelined": not args.no_pipeline,
                        "parallelism": f"keyby{world}"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -404,6 +406,7 @@ def main():
     ap.add_argument("--nb", type=int, default=65, help="withNumWinPerBatch")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-pipeline", action="store_true", help="results of a segment returned by the same call (no overlap)")
     ap.add_argument("--prime-steps", type=int, default=-1, help="override state priming (ncu runs); default: steady state")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

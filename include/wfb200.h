@@ -141,6 +141,11 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
  *   win_type: 0 count-based (win/slide in tuples), 1 time-based (win/slide/lateness in timestamp units)
  *   flags   : WFB_FFAT_DENSE_KEYS => keys are known to be < max_keys (slot = key, no hash probe) */
 #define WFB_FFAT_DENSE_KEYS 1u
+/*   WFB_FFAT_PIPELINED  => results are delivered one call late: wfb_ffat_process_cb(segment k) returns the results of
+ *                          segment k-1 (none on the first call) while sort + update of segment k run on an internal stream and
+ *                          overlap the ingest pass of segment k+1; wfb_ffat_flush returns the last segment's results. The
+ *                          set of results over the whole stream is identical to the non-pipelined mode. */
+#define WFB_FFAT_PIPELINED 2u
 int wfb_ffat_create(wfb_ffat_t **h, int prog, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
                     uint32_t max_keys, int win_type, uint64_t lateness, uint32_t flags);
 int wfb_ffat_destroy(wfb_ffat_t *h);
@@ -159,6 +164,9 @@ uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h);
 int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev,
                         void *stream);
+
+/* Pipelined handles only: deliver the results of the last segment (a no-op with *n_out_dev = 0 otherwise). */
+int wfb_ffat_flush(wfb_ffat_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);
 
 /* Per-phase device timing of wfb_ffat_process_cb calls (CUDA events recorded on the launching stream).
  * enable != 0 starts recording (up to 512 calls); the call returns, for the calls recorded since the last query,

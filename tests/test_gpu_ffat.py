@@ -14,13 +14,24 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 
 
 def _run_gpu(ops, ff, batches, pre=None, group=1):
+    """Feeds the batches `group` at a time; a pipelined handle hands results over one call late (+ flush at the end)."""
     import torch
     got, gts = [], []
     for i in range(0, len(batches), group):
         out, out_ts, n_out = ff.process(batches[i:i + group], pre=pre)
         torch.cuda.synchronize()
         r, t = ff.results_to_host(out, out_ts, n_out)
+        if ff.pipelined and i == 0:
+            assert len(r) == 0
         got.append(r); gts.append(t)
+    if ff.pipelined:
+        out, out_ts, n_out = ff.flush(device=batches[0].tuples.device)
+        torch.cuda.synchronize()
+        r, t = ff.results_to_host(out, out_ts, n_out)
+        got.append(r); gts.append(t)
+        out, out_ts, n_out = ff.flush(device=batches[0].tuples.device)  # nothing left
+        torch.cuda.synchronize()
+        assert int(n_out.item()) == 0
     return np.concatenate(got), np.concatenate(gts)
 
 
@@ -52,12 +63,13 @@ CASES = [  # win, slide, nb, nkeys, n, batch, group(batches per call), dense
 ]
 
 
+@pytest.mark.parametrize("pipelined", [False, True], ids=["direct", "pipelined"])
 @pytest.mark.parametrize("case", CASES, ids=[f"w{c[0]}_s{c[1]}_nb{c[2]}_k{c[3]}" for c in CASES])
-def test_ffat_cb_vs_oracle(wfb, oracle, case):
+def test_ffat_cb_vs_oracle(wfb, oracle, case, pipelined):
     O, ops = oracle, wfb
     win, slide, nb, nkeys, n, batch, group, dense = case
     t, ts = O.gen_tuple64(0, n, O.KEY_UNIFORM, nkeys)
-    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, win, slide, nb, max_keys=max(nkeys, 8), dense_keys=dense)
+    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, win, slide, nb, max_keys=max(nkeys, 8), dense_keys=dense, pipelined=pipelined)
     go = O.FfatGpuOracle(win, slide, nb)
     batches, exp, ets = [], [], []
     for b in range(0, n, batch):
@@ -108,7 +120,7 @@ def test_ffat_ragged_and_empty_batches(wfb, oracle):
     rng = np.random.default_rng(11)
     sizes = [0, 1, 5, 0, 300, 1, 2, 1023, 0, 77, 4096, 3, 0, 0, 9]
     t, ts = O.gen_tuple64(0, sum(sizes), O.KEY_UNIFORM, nkeys)
-    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, win, slide, nb, max_keys=8)
+    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, win, slide, nb, max_keys=8, pipelined=True)
     go = O.FfatGpuOracle(win, slide, nb)
     batches, exp, ets, off = [], [], [], 0
     for k, sz in enumerate(sizes):

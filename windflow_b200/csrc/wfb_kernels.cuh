@@ -93,6 +93,7 @@ struct TileArgs {
     uint32_t epoch;
     uint64_t tmap_base;        // global address the 2-D tensor map starts at (rows of 64 bytes)
     uint32_t use_tmap;         // 1: `tmap` is valid for this launch
+    uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
     unsigned char *lifted;     // result_t per surviving tuple
     uint32_t *slots;           // slot per surviving tuple
@@ -1176,6 +1177,22 @@ __global__ void k_shard_offsets(const uint32_t *__restrict__ sdest, uint32_t n, 
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sdest[mid] < d) lo = mid + 1; else hi = mid; }
         seg_off[d] = lo;
     }
+}
+
+// pipelined window operator: hand the results of a finished segment over to the caller's buffers
+__global__ void k_copy_results(const unsigned char *__restrict__ src, const uint64_t *__restrict__ src_ts, const uint32_t *__restrict__ src_n,
+                               uint32_t rec_bytes, unsigned char *__restrict__ dst, uint64_t *__restrict__ dst_ts, uint32_t dst_cap,
+                               uint32_t *__restrict__ n_out, uint32_t *__restrict__ err_flags)
+{
+    const uint32_t n = *src_n;
+    const uint32_t m = min(n, dst_cap);
+    const uint64_t words = static_cast<uint64_t>(m) * (rec_bytes / 8);
+    const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src);
+    uint64_t *d8 = reinterpret_cast<uint64_t *>(dst);
+    const uint64_t gtid = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x, gsz = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t w = gtid; w < words; w += gsz) d8[w] = s8[w];
+    if (dst_ts != nullptr) for (uint64_t i = gtid; i < m; i += gsz) dst_ts[i] = src_ts[i];
+    if (gtid == 0) { *n_out = m; if (n > dst_cap) atomicOr(err_flags, 2u); }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -99,7 +99,8 @@ int launch_tile_pass(TileArgs &a, const void *params, uint32_t want_grid, cudaSt
         if (per_sm < 1) per_sm = 1;
         max_grid = per_sm * g_num_sms;
     }
-    const uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
+    uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
+    if (a.max_ctas_per_sm) grid = std::max(1u, std::min(grid, a.max_ctas_per_sm * static_cast<uint32_t>(g_num_sms)));
     typename P::params_t prm;
     if (params) prm = *static_cast<const typename P::params_t *>(params); else std::memset(&prm, 0, sizeof(prm));
     alignas(64) CUtensorMap tmap;
@@ -368,22 +369,48 @@ struct wfb_engine {
     }
 };
 
+// per-segment scratch of one Ffat_Windows_GPU; two sets when the handle is pipelined (the ingest pass of segment k+1
+// overlaps sort + update of segment k)
+struct SegScratch {
+    uint32_t cap = 0;                     // capacity in records
+    unsigned char *lifted = nullptr, *lifted_sorted = nullptr;
+    uint32_t *slotsA = nullptr, *slotsB = nullptr, *posA = nullptr, *posB = nullptr;
+    uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
+    DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
+    uint32_t *n_total = nullptr;
+    uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
+    Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
+    // pipelined mode: results of the segment wait here until the next call / flush delivers them
+    unsigned char *res = nullptr; uint64_t *res_ts = nullptr; uint32_t *res_n = nullptr; uint32_t res_cap = 0;
+    cudaEvent_t ev_ingest = nullptr, ev_done = nullptr;
+    bool pending = false;
+    uint32_t nbatches = 0, total = 0;
+
+    void destroy()
+    {
+        cudaFree(lifted); cudaFree(lifted_sorted); cudaFree(slotsA); cudaFree(slotsB); cudaFree(posA); cudaFree(posB);
+        cudaFree(batch_off); cudaFree(d_batches); cudaFree(n_total); cudaFree(seg_cnt); cudaFree(trig);
+        cudaFree(res); cudaFree(res_ts); // n_trig and res_n live inside the n_total allocation
+        if (ev_ingest) cudaEventDestroy(ev_ingest);
+        if (ev_done) cudaEventDestroy(ev_done);
+    }
+};
+
 struct wfb_ffat {
     int prog = 0;
     const ProgramOps *ops = nullptr;
     FfatDev ff{};
     TileScratch ts;
     uint32_t sort_passes = 1;
-    // per-segment scratch (grown on demand)
-    uint32_t seg_cap = 0;
-    unsigned char *lifted = nullptr, *lifted_sorted = nullptr;
-    uint32_t *slotsA = nullptr, *slotsB = nullptr, *posA = nullptr, *posB = nullptr;
+    SegScratch seg[2];
     RadixSorter sorter;
-    uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
-    uint32_t *n_total = nullptr;
+    bool pipelined = false;
+    uint64_t call_no = 0;
+    cudaStream_t s2 = nullptr;            // pipelined mode: sort + update + window queries run here
     uint64_t launches = 0;
     size_t state_bytes = 0;
     int win_type = 0;
+    uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
     bool move_payload = false;    // tuning knob WFB_SORT_PAYLOAD=1: the last sort pass also moves the lifted records
     // optional per-phase timing (wfb_ffat_timing)
     bool timing = false;
@@ -620,7 +647,6 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     }
     ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
     ff.err_flags = ff.n_slots + 1;
-    ff.n_trig = ff.n_slots + 2;
     CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
     ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
     ALLOC(ff.cnt, sizeof(uint64_t) * max_keys);
@@ -629,10 +655,23 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     CK(cudaMemset(ff.acc, 0, RB * max_keys));
     ALLOC(ff.tree, tree_bytes);
     CK(cudaMemset(ff.tree, 0, tree_bytes));
-    ALLOC(ff.seg_cnt, sizeof(uint32_t) * max_keys);
-    CK(cudaMemset(ff.seg_cnt, 0, sizeof(uint32_t) * max_keys));
     ALLOC(ff.seg_off, sizeof(uint32_t) * (static_cast<size_t>(max_keys) + 1));
-    ALLOC(h->n_total, sizeof(uint32_t));
+    h->pipelined = (flags & WFB_FFAT_PIPELINED) != 0;
+    for (int p = 0; p < (h->pipelined ? 2 : 1); p++) {
+        SegScratch &g = h->seg[p];
+        ALLOC(g.seg_cnt, sizeof(uint32_t) * max_keys);
+        CK(cudaMemset(g.seg_cnt, 0, sizeof(uint32_t) * max_keys));
+        ALLOC(g.n_total, sizeof(uint32_t) * 4);
+        CK(cudaMemset(g.n_total, 0, sizeof(uint32_t) * 4));
+        g.n_trig = g.n_total + 1; g.res_n = nullptr;
+        CK(cudaEventCreateWithFlags(&g.ev_ingest, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming));
+    }
+    if (h->pipelined) {
+        CK(cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking));
+        const char *e = std::getenv("WFB_INGEST_CTAS_PER_SM");
+        h->ingest_ctas_per_sm = e ? static_cast<uint32_t>(std::atoi(e)) : 2u;
+    }
 #undef ALLOC
     uint32_t bits = 0; while ((1ull << bits) < max_keys) bits++;
     h->sort_passes = std::max(1u, (bits + 7) / 8);
@@ -647,42 +686,93 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaDeviceSynchronize();
     FfatDev &ff = h->ff;
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
-    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_cnt); cudaFree(ff.seg_off); cudaFree(ff.trig);
-    cudaFree(h->lifted); cudaFree(h->lifted_sorted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
+    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off);
+    for (int p = 0; p < 2; p++) h->seg[p].destroy();
     h->sorter.destroy();
-    cudaFree(h->batch_off); cudaFree(h->n_total);
+    if (h->s2) cudaStreamDestroy(h->s2);
     for (auto &e : h->tev) cudaEventDestroy(e);
     h->ts.destroy();
     delete h;
+    cudaGetLastError();
     return 0;
 }
 
 uint64_t wfb_ffat_launches(const wfb_ffat_t *h) { return h ? h->launches : 0; }
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes : 0; }
 
-static int ffat_ensure_segment(wfb_ffat *h, uint32_t total, uint32_t nbatches, cudaStream_t s)
+static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint32_t nbatches, cudaStream_t s)
 {
-    if (total > h->seg_cap) {
+    if (total > g.cap) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(h->lifted); cudaFree(h->lifted_sorted); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posA); cudaFree(h->posB);
-        h->seg_cap = std::max(total, 2 * h->seg_cap);
-        CK(cudaMalloc(&h->lifted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
-        CK(cudaMalloc(&h->lifted_sorted, static_cast<size_t>(h->seg_cap) * h->ops->result_bytes));
-        CK(cudaMalloc(&h->slotsA, sizeof(uint32_t) * h->seg_cap));
-        CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->seg_cap));
-        CK(cudaMalloc(&h->posA, sizeof(uint32_t) * h->seg_cap));
-        CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->seg_cap));
-        cudaFree(h->ff.trig);
+        if (h->s2) CK(cudaStreamSynchronize(h->s2));
+        cudaFree(g.lifted); cudaFree(g.lifted_sorted); cudaFree(g.slotsA); cudaFree(g.slotsB); cudaFree(g.posA); cudaFree(g.posB);
+        cudaFree(g.trig); cudaFree(g.res); cudaFree(g.res_ts);
+        g.cap = std::max(total, 2 * g.cap);
+        const size_t RB = h->ops->result_bytes;
+        CK(cudaMalloc(&g.lifted, static_cast<size_t>(g.cap) * RB));
+        if (h->move_payload) CK(cudaMalloc(&g.lifted_sorted, static_cast<size_t>(g.cap) * RB));
+        CK(cudaMalloc(&g.slotsA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.slotsB, sizeof(uint32_t) * g.cap));
+        CK(cudaMalloc(&g.posA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.posB, sizeof(uint32_t) * g.cap));
         const uint64_t per_group = std::max<uint64_t>(1, h->ff.slide * h->ff.nb);
-        h->ff.trig_cap = static_cast<uint32_t>(std::min<uint64_t>(h->seg_cap / per_group + h->ff.max_keys + 1, 0x7fffffffull));
-        CK(cudaMalloc(&h->ff.trig, sizeof(Trigger) * h->ff.trig_cap));
+        g.trig_cap = static_cast<uint32_t>(std::min<uint64_t>(g.cap / per_group + h->ff.max_keys + 1, 0x7fffffffull));
+        CK(cudaMalloc(&g.trig, sizeof(Trigger) * g.trig_cap));
+        if (h->pipelined) { // every group that can fire in one segment: trig_cap groups of Nb results
+            g.res_cap = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(g.trig_cap) * h->ff.nb, 0x7fffffffull));
+            CK(cudaMalloc(&g.res, static_cast<size_t>(g.res_cap) * RB));
+            CK(cudaMalloc(&g.res_ts, sizeof(uint64_t) * g.res_cap));
+            g.res_n = g.n_total + 2;
+        }
     }
-    if (nbatches + 1 > h->batch_off_cap) {
+    if (nbatches + 1 > g.batch_off_cap) {
         CK(cudaStreamSynchronize(s));
-        cudaFree(h->batch_off);
-        h->batch_off_cap = std::max(nbatches + 1, 2 * h->batch_off_cap);
-        CK(cudaMalloc(&h->batch_off, sizeof(uint32_t) * h->batch_off_cap));
+        if (h->s2) CK(cudaStreamSynchronize(h->s2));
+        cudaFree(g.batch_off); cudaFree(g.d_batches);
+        g.batch_off_cap = std::max(nbatches + 1, 2 * g.batch_off_cap);
+        CK(cudaMalloc(&g.batch_off, sizeof(uint32_t) * g.batch_off_cap));
+        CK(cudaMalloc(&g.d_batches, sizeof(DevBatch) * g.batch_off_cap));
     }
+    return 0;
+}
+
+// sort + update + deferred window queries of the segment held in `g`, results to (out, out_ts, n_out)
+static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsigned char *out, uint64_t *out_ts, uint32_t out_cap,
+                             uint32_t *n_out, cudaStream_t s)
+{
+    // stable sort of (slot, arrival position) by slot: onesweep radix, 8 bits per pass
+    const uint32_t *sorted_slots, *sorted_pos;
+    const uint64_t before = h->sorter.launches;
+    int rc = h->sorter.sort<uint32_t>(g.slotsA, g.slotsB, g.posA, g.posB, g.n_total, 0, g.total, h->sort_passes, s, &sorted_slots,
+                                      &sorted_pos, h->move_payload ? g.lifted : nullptr, h->move_payload ? g.lifted_sorted : nullptr,
+                                      h->ops->result_bytes);
+    if (rc) return rc;
+    h->launches += h->sorter.launches - before;
+    // first sorted position of every key present in the segment
+    k_seg_starts<<<std::min((g.total + 255u) / 256u, static_cast<uint32_t>(g_num_sms) * 8u), 256, 0, s>>>(sorted_slots, g.n_total,
+                                                                                                         ff.max_keys, ff.seg_off);
+    CK(cudaGetLastError());
+    h->launches++;
+    h->mark(2, s);
+    // one warp per key: pane fold, FlatFAT update; then one thread per fired window
+    uint32_t ugrid = std::max(1u, std::min((ff.max_keys + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u));
+    rc = h->ops->ffat_update(ff, h->move_payload ? g.lifted_sorted : g.lifted, sorted_pos, g.batch_off, g.d_batches, g.nbatches,
+                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u);
+    if (rc) return rc;
+    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s);
+    if (rc) return rc;
+    h->launches += 2;
+    return 0;
+}
+
+// pipelined mode: hand the finished results of the segment in `g` to the caller (stream-ordered on s)
+static int ffat_deliver(wfb_ffat *h, SegScratch &g, unsigned char *out, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s)
+{
+    if (!g.pending) { CK(cudaMemsetAsync(n_out, 0, sizeof(uint32_t), s)); return 0; }
+    CK(cudaStreamWaitEvent(s, g.ev_done, 0));
+    k_copy_results<<<static_cast<uint32_t>(g_num_sms) * 2u, 256, 0, s>>>(g.res, g.res_ts, g.res_n, h->ops->result_bytes, out, out_ts,
+                                                                          out_cap, n_out, h->ff.err_flags);
+    CK(cudaGetLastError());
+    h->launches++;
+    g.pending = false;
     return 0;
 }
 
@@ -693,7 +783,10 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     if (h->win_type != 0) return WFB_E_UNSUPPORTED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = h->ts.enter(s); if (rc) return rc;
-    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+    unsigned char *out = static_cast<unsigned char *>(out_results);
+    const uint32_t par = h->pipelined ? static_cast<uint32_t>(h->call_no & 1u) : 0u;
+    SegScratch &g = h->seg[par];
+    SegScratch &prev = h->seg[h->pipelined ? (par ^ 1u) : 0u];
 
     std::vector<DevBatch> hb; // empty batches trigger nothing: only the non-empty ones reach the device
     hb.reserve(nbatches);
@@ -710,60 +803,64 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         span_begin = std::min(span_begin, p0); span_end = std::max(span_end, p0 + static_cast<uint64_t>(b.n) * h->ops->tuple_bytes);
         hb.push_back(b);
     }
-    if (total == 0) return 0;
-    nbatches = static_cast<uint32_t>(hb.size());
     if (total > 0x7fffffffull) return WFB_E_BADARG;
-    rc = ffat_ensure_segment(h, static_cast<uint32_t>(total), nbatches, s); if (rc) return rc;
+    if (total == 0) { // nothing to ingest: (pipelined) still deliver what is pending
+        if (h->pipelined) return ffat_deliver(h, prev, out, out_ts, out_capacity, n_out_dev, s);
+        CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+        return 0;
+    }
+    nbatches = static_cast<uint32_t>(hb.size());
+    rc = ffat_ensure_segment(h, g, static_cast<uint32_t>(total), nbatches, s); if (rc) return rc;
     rc = h->ts.ensure_tiles(tiles); if (rc) return rc;
-    rc = h->ts.ensure_batches(nbatches); if (rc) return rc;
-    CK(cudaMemcpyAsync(h->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(g.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    g.nbatches = nbatches; g.total = static_cast<uint32_t>(total);
+
+    FfatDev ff = h->ff; // this call's view of the state: per-segment buffers of parity `par`
+    ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap;
 
     h->mark(0, s);
     // 1. streaming pass: [map -> filter ->] lift, key -> slot, stable compaction over the whole segment
     TileArgs a; std::memset(&a, 0, sizeof(a));
-    a.batches = h->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
-    a.lifted = h->lifted; a.slots = h->slotsA; a.batch_off = h->batch_off; a.n_total = h->n_total; a.ff = h->ff;
+    a.batches = g.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
+    a.lifted = g.lifted; a.slots = g.slotsA; a.batch_off = g.batch_off; a.n_total = g.n_total; a.ff = ff;
     h->ts.next_launch(a);
+    a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     uint32_t grid = 0;
     rc = h->ops->tile_pass(MODE_INGEST, a, pre, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
     h->launches++;
-
     h->mark(1, s);
-    // 2. stable sort of (slot, arrival position) by slot: onesweep radix, 8 bits per pass
-    const uint32_t *sorted_slots, *sorted_pos;
-    {
-        const uint64_t before = h->sorter.launches;
-        rc = h->sorter.sort<uint32_t>(h->slotsA, h->slotsB, h->posA, h->posB, h->n_total, 0, static_cast<uint32_t>(total),
-                                      h->sort_passes, s, &sorted_slots, &sorted_pos, h->move_payload ? h->lifted : nullptr,
-                                      h->move_payload ? h->lifted_sorted : nullptr, h->ops->result_bytes);
-        if (rc) return rc;
-        h->launches += h->sorter.launches - before;
-    }
-    // 3. first sorted position of every key present in the segment
-    k_seg_starts<<<std::min((static_cast<uint32_t>(total) + 255u) / 256u, static_cast<uint32_t>(g_num_sms) * 8u), 256, 0, s>>>(
-        sorted_slots, h->n_total, h->ff.max_keys, h->ff.seg_off);
-    CK(cudaGetLastError());
-    h->launches++;
 
-    h->mark(2, s);
-    // 4. one warp per key: pane fold, FlatFAT update, window queries
-    const uint32_t warps_needed = h->ff.max_keys;
-    uint32_t ugrid = std::min((warps_needed + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u);
-    ugrid = std::max(ugrid, 1u);
-    rc = h->ops->ffat_update(h->ff, h->move_payload ? h->lifted_sorted : h->lifted, sorted_pos, h->batch_off, h->ts.d_batches, nbatches,
-                             static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, ugrid, s,
-                             h->move_payload ? 0u : 1u);
-    if (rc) return rc;
-    h->launches++;
-    // 5. deferred window groups: one thread per window
-    rc = h->ops->ffat_windows(h->ff, h->batch_off, h->ts.d_batches, nbatches, static_cast<unsigned char *>(out_results), out_ts,
-                              out_capacity, static_cast<uint32_t>(g_num_sms) * 4u, s);
-    if (rc) return rc;
-    h->launches++;
-    h->mark(3, s);
+    if (!h->pipelined) {
+        CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+        rc = ffat_window_phase(h, g, ff, out, out_ts, out_capacity, n_out_dev, s); if (rc) return rc;
+        h->mark(3, s);
+    } else {
+        // the ingest pass of this segment is queued: now hand over the previous segment's results, then start this
+        // segment's sort + update on the internal stream, where it overlaps the NEXT call's ingest pass
+        CK(cudaEventRecord(g.ev_ingest, s));
+        rc = ffat_deliver(h, prev, out, out_ts, out_capacity, n_out_dev, s); if (rc) return rc;
+        CK(cudaStreamWaitEvent(h->s2, g.ev_ingest, 0));
+        CK(cudaMemsetAsync(g.res_n, 0, sizeof(uint32_t), h->s2));
+        rc = ffat_window_phase(h, g, ff, g.res, g.res_ts, g.res_cap, g.res_n, h->s2); if (rc) return rc;
+        h->mark(3, h->s2);
+        CK(cudaEventRecord(g.ev_done, h->s2));
+        g.pending = true;
+    }
     if (h->timing && h->tev_used < wfb_ffat::TEV_MAX) h->tev_used++;
+    h->call_no++;
     return 0;
+}
+
+int wfb_ffat_flush(wfb_ffat_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
+{
+    if (!h || !n_out_dev || (out_capacity && !out_results)) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!h->pipelined) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    int rc = h->ts.enter(s); if (rc) return rc;
+    // at most one segment is pending: the one of the last call
+    SegScratch &last = h->seg[(h->call_no + 1) & 1u];
+    return ffat_deliver(h, last, static_cast<unsigned char *>(out_results), out_ts, out_capacity, n_out_dev, s);
 }
 
 int wfb_ffat_timing(wfb_ffat_t *h, int enable, float *ms_h, uint32_t *calls_h)
@@ -797,6 +894,7 @@ int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, voi
 {
     if (!h) return WFB_E_BADARG;
     uint32_t v[2] = {0, 0};
+    if (h->s2) CK(cudaStreamSynchronize(h->s2));
     CK(cudaMemcpyAsync(v, h->ff.n_slots, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (n_keys_h) *n_keys_h = v[0];

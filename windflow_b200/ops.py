@@ -166,14 +166,15 @@ class FfatWindowsGPU:
     """Ffat_Windows_GPU replica state (wf/ffat_windows_gpu.hpp, wf/ffat_replica_gpu.hpp): count-based windows
     `withCBWindows(win, slide)`, `withNumWinPerBatch(nb)`."""
 
-    def __init__(self, prog, win, slide, nb, max_keys, dense_keys=False, win_type=0, lateness=0):
+    def __init__(self, prog, win, slide, nb, max_keys, dense_keys=False, win_type=0, lateness=0, pipelined=False):
         self.L = _lib.lib()
         if self.L.wfb_device_count() <= 0:
             raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
         self.prog, self.win, self.slide, self.nb = prog, win, slide, nb
         self.h = C.c_void_p()
+        self.pipelined = pipelined
         check(self.L.wfb_ffat_create(C.byref(self.h), prog, win, slide, nb, max_keys, win_type, lateness,
-                                     1 if dense_keys else 0), "wfb_ffat_create")
+                                     (1 if dense_keys else 0) | (2 if pipelined else 0)), "wfb_ffat_create")
         self.res_dtype = RESULT_DTYPE[prog]
         self._keep = None
 
@@ -220,6 +221,18 @@ class FfatWindowsGPU:
         check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                          _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
               "wfb_ffat_process_cb")
+        return out, out_ts, n_out
+
+    def flush(self, out=None, out_ts=None, n_out=None, stream=None, device="cuda"):
+        """Pipelined handles: the results of the last segment (count 0 otherwise)."""
+        if out is None:
+            cap = self.max_results(1 << 22)
+            out = torch.empty(cap * self.res_dtype.itemsize, dtype=torch.uint8, device=device)
+            out_ts = torch.empty(cap, dtype=torch.int64, device=device)
+        if n_out is None:
+            n_out = torch.zeros(1, dtype=torch.int32, device=out.device)
+        cap = out.numel() // self.res_dtype.itemsize
+        check(self.L.wfb_ffat_flush(self.h, _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)), "wfb_ffat_flush")
         return out, out_ts, n_out
 
     def results_to_host(self, out, out_ts, n_out):
