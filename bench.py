@@ -209,32 +209,47 @@ def run_ours(args):
     nb = args.nb
     B = (nb - 1) * SLIDE + WIN
     f = ops.functors(**MAP, **FILT)
-
-    # N > 1: keys shard by key % N (keyby routing); rank r generates and processes the tuples of its own key shard
-    # (round-1 multi-GPU arm = independent key shards, no exchange step yet).
-    nkeys_local = NKEYS // world
+    pipelined = not args.no_pipeline
 
     # ---- input ring, resident in HBM (larger than L2: ring * seg_tuples * 64 B) ---------------------------------
-    segs = []
+    # N = 1: one fused call per segment. N > 1: rank r owns the K batches [r*K, (r+1)*K) of every
+    # global step, Map->Filter, partition by key % N, NCCL all-to-all, windows on the rank's key shard.
+    from windflow_b200 import multigpu
+    segs_whole, segs = [], []
     for r in range(ring):
-        start = (rank * ring + r) * seg_tuples
-        b = ops.gen_tuple64(start, seg_tuples, ops.KEY_UNIFORM, nkeys_local)
+        start = multigpu.owner_span(r, rank, world, seg_tuples)[0]
+        b = ops.gen_tuple64(start, seg_tuples, ops.KEY_UNIFORM, NKEYS)
+        b.watermark = start
+        segs_whole.append(b)
         segs.append([ops.DeviceBatch(b.tuples[i * BATCH * 64:(i + 1) * BATCH * 64], b.ts[i * BATCH:(i + 1) * BATCH], BATCH,
                                      watermark=start + i * BATCH) for i in range(bps)])
     torch.cuda.synchronize()
 
-    ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=nkeys_local, dense_keys=True,
-                            pipelined=not args.no_pipeline)
-    cap = ff.max_results(seg_tuples)
+    if world == 1:
+        ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=NKEYS, dense_keys=True, pipelined=pipelined)
+        pipe = None
+    else:
+        pipe = multigpu.KeyShardedPipeline(ops, ops.PROG_TUPLE64, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=pipelined)
+        ff = pipe.ff
+    cap = ff.max_results(seg_tuples * (2 if world > 1 else 1))
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
     out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    def process_device_segment(whole, batches):
+        if pipe is None:
+            ff.process(batches, pre=f, out=out, out_ts=out_ts, n_out=n_out)
+        else:
+            pipe.step(whole, out, out_ts, n_out)
+
     def step(i):
-        ff.process(segs[i % ring], pre=f, out=out, out_ts=out_ts, n_out=n_out)
+        process_device_segment(segs_whole[i % ring], segs[i % ring])
+
+    def launches_now():
+        return ff.launches + (pipe.eng.launches if pipe is not None else 0)
 
     # ---- prime the window state (untimed setup): every key past its first trigger --------------------------------
-    prime = int(np.ceil(B * nkeys_local / SIGMA / seg_tuples)) + 2
+    prime = int(np.ceil(B * NKEYS / SIGMA / (seg_tuples * world))) + 2
     if args.prime_steps >= 0:
         prime = args.prime_steps  # profiling runs only: the timed steps are then NOT steady state
     for i in range(prime):
@@ -253,7 +268,7 @@ def run_ours(args):
 
     # ---- timed region: K steps, device-resident inputs ------------------------------------------------------------
     ff.timing(True)
-    launches0 = ff.launches
+    launches0 = launches_now()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -266,7 +281,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    launches = ff.launches - launches0
+    launches = launches_now() - launches0
     ing_ms, sort_ms, upd_ms, tot_ms, calls = ff.timing(False)
     err = ff.stats()[1]
     if err:
@@ -278,7 +293,7 @@ def run_ours(args):
     value = world * args.steps * seg_tuples / (ms_max * 1e-3)
 
     # ---- e2e: the same call with HOST (pinned) buffers, copies inside the timed region ------------------------------
-    e2e = run_e2e(torch, ops, ff, f, segs, seg_tuples, bps, dev, args, world, out, out_ts, n_out)
+    e2e = run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev, args, world, out, n_out)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -294,13 +309,13 @@ def run_ours(args):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i64+f64", "data": "synthetic",
             "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES,
-                       "batches_per_step": bps, "tuples_per_step_per_gpu": seg_tuples, "keys": NKEYS, "keys_per_gpu": nkeys_local,
+                       "batches_per_step": bps, "tuples_per_step_per_gpu": seg_tuples, "keys": NKEYS, "keys_per_gpu": NKEYS // world,
                        "key_dist": "uniform", "win": WIN, "slide": SLIDE, "wins_per_batch": nb,
                        "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0", "selectivity": SIGMA,
                        "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
                        "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
                        "pipelined": not args.no_pipeline,
-                       "parallelism": f"keyby{world}"},
+                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (Map->Filter->shard_by_key->NCCL all-to-all->Ffat)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
@@ -321,20 +336,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(torch, ops, ff, f, segs, seg_tuples, bps, dev, args, world, out, out_ts, n_out):
-    """Same operator call, inputs start in pinned host memory every step; result count + results come back."""
+def run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev, args, world, out, n_out):
+    """Same operator call(s), inputs start in pinned host memory every step; result count + results come back."""
     import torch.distributed as dist
     steps = max(2, min(args.steps, args.e2e_steps))
     nbuf = 2
     host_t = [torch.empty(seg_tuples * 64, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
     host_ts = [torch.empty(seg_tuples, dtype=torch.int64).pin_memory() for _ in range(nbuf)]
-    for k in range(nbuf):
-        base = segs[k % len(segs)][0]
-        # segment k's device bytes are contiguous (generated in one piece): copy them out once, untimed
-        whole_t = torch.cat([b.tuples for b in segs[k % len(segs)]])
-        whole_ts = torch.cat([b.ts for b in segs[k % len(segs)]])
-        host_t[k].copy_(whole_t); host_ts[k].copy_(whole_ts)
-        del whole_t, whole_ts, base
+    for k in range(nbuf):  # the segments' bytes are copied out to the host once, untimed
+        host_t[k].copy_(segs_whole[k % len(segs_whole)].tuples); host_ts[k].copy_(segs_whole[k % len(segs_whole)].ts)
     dev_t = [torch.empty(seg_tuples * 64, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dev_ts = [torch.empty(seg_tuples, dtype=torch.int64, device=dev) for _ in range(nbuf)]
     host_n = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -344,7 +354,7 @@ def run_e2e(torch, ops, ff, f, segs, seg_tuples, bps, dev, args, world, out, out
     main = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(nbuf)]
     freed = [torch.cuda.Event() for _ in range(nbuf)]
-    wm0 = segs[0][0].watermark
+    wm0 = segs_whole[0].watermark
 
     def h2d(k):
         with torch.cuda.stream(copy_stream):
@@ -355,9 +365,11 @@ def run_e2e(torch, ops, ff, f, segs, seg_tuples, bps, dev, args, world, out, out
 
     def compute(k, step_idx):
         main.wait_event(ready[k])
+        wm = wm0 + step_idx * seg_tuples
+        whole = ops.DeviceBatch(dev_t[k], dev_ts[k], seg_tuples, wm)
         batches = [ops.DeviceBatch(dev_t[k][i * BATCH * 64:(i + 1) * BATCH * 64], dev_ts[k][i * BATCH:(i + 1) * BATCH], BATCH,
-                                   watermark=wm0 + step_idx * seg_tuples + i * BATCH) for i in range(bps)]
-        ff.process(batches, pre=f, out=out, out_ts=out_ts, n_out=n_out)
+                                   watermark=wm + i * BATCH) for i in range(bps)]
+        process_device_segment(whole, batches)
         freed[k].record(main)
         host_n.copy_(n_out, non_blocking=True)
 
@@ -391,7 +403,7 @@ def run_e2e(torch, ops, ff, f, segs, seg_tuples, bps, dev, args, world, out, out
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     val = world * steps * seg_tuples / (float(t_ms.item()) * 1e-3)
     return {"value": val, "unit": "tuples/s", "h2d_bytes_per_step": seg_tuples * 72, "d2h_bytes_per_step": d2h_bytes // steps,
-            "steps": steps, "note": "pinned host segment -> H2D (double-buffered on a copy stream) -> one wfb_ffat_process_cb call "
+            "steps": steps, "note": "pinned host segment -> H2D (double-buffered on a copy stream) -> the operator call(s) "
                                     "-> D2H of the result count and the window results"}
 
 

@@ -1,0 +1,74 @@
+"""CPU test (-m "not gpu") of the multi-GPU host logic with the gloo backend, world size 2: segment ownership, the
+count + segment all-to-all, source-rank-order concatenation. The per-rank compute is done by the ORACLE here (this is
+a test of the exchange plumbing); the merged windows must equal the single-operator oracle on the whole stream."""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys, pickle
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, os.environ["WFB_ROOT"])
+    from oracle import oracle as O
+    from windflow_b200 import multigpu as M
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    win, slide, nb, nkeys, seg_tuples, steps = 16, 4, 2, 37, 3000, 6
+    go = O.FfatGpuOracle(win, slide, nb)
+    mine = []
+    for t in range(steps):
+        first, last = M.owner_span(t, rank, world, seg_tuples)
+        tup, ts = O.gen_tuple64(first, last - first, O.KEY_UNIFORM, nkeys)
+        surv, sts, _ = O.map_filter_tuple64(tup, ts, 1, 2, 1.0000001, 1)
+        dest = O.route(surv["key"], world)
+        order = np.argsort(dest, kind="stable")
+        part = np.ascontiguousarray(surv[order])
+        counts = np.bincount(dest, minlength=world)
+        send = torch.from_numpy(part.view(np.uint8).reshape(-1).copy())
+        rc, rw = M.exchange_counts(torch.tensor(counts.tolist(), dtype=torch.int64), int(ts[0]))
+        assert rw.tolist() == [M.owner_span(t, s, world, seg_tuples)[0] for s in range(world)]
+        recv, offs = M.exchange_segments(send, counts.tolist(), rc.tolist(), 64)
+        for s in range(world):
+            chunk = recv[offs[s] * 64:offs[s + 1] * 64].numpy().view(O.TUPLE64)
+            assert (chunk["key"] % world == rank).all()
+            assert (np.diff(chunk["id"].astype(np.int64)) > 0).all()        # arrival order kept inside a chunk
+            r, _ = go.process_batch(O.lift_tuple64(chunk), int(rw[s]))
+            mine.append(r)
+    mine = np.concatenate(mine) if mine else np.zeros(0, dtype=O.RES)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine.tobytes())
+    if rank == 0:
+        got = np.concatenate([np.frombuffer(b, dtype=O.RES) for b in gathered])
+        # single operator over the whole stream, same segments in global order
+        ref = O.FfatGpuOracle(win, slide, nb)
+        exp = []
+        for t in range(steps):
+            for s in range(world):
+                first, last = M.owner_span(t, s, world, seg_tuples)
+                tup, ts = O.gen_tuple64(first, last - first, O.KEY_UNIFORM, nkeys)
+                surv, _, _ = O.map_filter_tuple64(tup, ts, 1, 2, 1.0000001, 1)
+                r, _ = ref.process_batch(O.lift_tuple64(surv), int(ts[0]))
+                exp.append(r)
+        exp = O.sort_results(np.concatenate(exp)); got = O.sort_results(got)
+        assert len(got) == len(exp) > 0, (len(got), len(exp))
+        assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["id"], exp["id"])
+        assert np.array_equal(got["isum"], exp["isum"]) and np.allclose(got["fsum"], exp["fsum"], rtol=1e-9)
+        print("MULTI_OK", len(got))
+    dist.destroy_process_group()
+''')
+
+
+def test_keyby_sharded_exchange_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, WFB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() % 400)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "MULTI_OK" in out.stdout

@@ -152,10 +152,11 @@ class Engine:
                                      _stream_ptr(stream)), "wfb_keyby_group")
         return start, mp, dk, nk
 
-    def shard_by_key(self, batch, num_shards, stream=None):
+    def shard_by_key(self, batch, num_shards, out=None, stream=None):
         dev = batch.tuples.device
-        out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts) if batch.ts is not None else None,
-                          batch.n, batch.watermark)
+        if out is None:
+            out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts) if batch.ts is not None else None,
+                              batch.n, batch.watermark)
         seg = torch.zeros(num_shards + 1, dtype=torch.int32, device=dev)
         check(self.L.wfb_shard_by_key(self.h, _ptr(batch.tuples), _ptr(batch.ts), batch.n, num_shards, _ptr(out.tuples),
                                       _ptr(out.ts), _ptr(seg), _stream_ptr(stream)), "wfb_shard_by_key")
