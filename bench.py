@@ -229,7 +229,7 @@ def run_ours(args):
         ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=NKEYS, dense_keys=True, pipelined=pipelined)
         pipe = None
     else:
-        pipe = multigpu.KeyShardedPipeline(ops, ops.PROG_TUPLE64, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=pipelined)
+        pipe = multigpu.KeyShardedPipeline(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=pipelined)
         ff = pipe.ff
     cap = ff.max_results(seg_tuples * (2 if world > 1 else 1))
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
@@ -240,7 +240,7 @@ def run_ours(args):
         if pipe is None:
             ff.process(batches, pre=f, out=out, out_ts=out_ts, n_out=n_out)
         else:
-            pipe.step(whole, out, out_ts, n_out)
+            pipe.step(batches, whole.watermark, out, out_ts, n_out)
 
     def step(i):
         process_device_segment(segs_whole[i % ring], segs[i % ring])
@@ -315,7 +315,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
                        "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
                        "pipelined": not args.no_pipeline,
-                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (Map->Filter->shard_by_key->NCCL all-to-all->Ffat)")},
+                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (fused Map->Filter->lift->shard | NCCL all-to-all of 32-B results | Ffat on the key shard)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,

@@ -42,6 +42,7 @@ extern "C" {
 #define WFB_PROG_TUPLE64  0   /* bench stream of SURVEY.md 8d: wfb_tuple64_t -> wfb_result32_t            */
 #define WFB_PROG_WFTEST16 1   /* reference tests/graph_tests_gpu/graph_common_gpu.hpp:40-49 {key,value}  */
 #define WFB_PROG_WFWIN24  2   /* reference tests/win_tests_gpu/win_common_gpu.hpp:40-80 {key,id,value}   */
+#define WFB_PROG_LIFTED32 3   /* already-lifted wfb_result32_t records (destination side of the multi-GPU keyby) */
 
 typedef struct { uint64_t key; uint64_t id; int64_t ivalue; double fvalue; uint64_t pad[4]; } wfb_tuple64_t;
 typedef struct { uint64_t key; uint64_t id; int64_t isum; double fsum; } wfb_result32_t;
@@ -133,6 +134,13 @@ int wfb_keyby_group(wfb_engine_t *e, const void *tuples, uint32_t n,
  * shard segment items keep arrival order. seg_off_dev[num_shards + 1] = exclusive offsets (device). */
 int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n, uint32_t num_shards,
                      void *out_tuples, uint64_t *out_ts, uint32_t *seg_off_dev, void *stream);
+
+/* Fused source side of the multi-GPU keyby: [Map_GPU -> Filter_GPU ->] lift of `nbatches` batches and stable partition
+ * of the lifted results by key % num_shards (num_shards <= 8) in ONE pass. Shard d's records land, in arrival order, at
+ * out_regions + d * region_capacity * result_bytes; counts_dev[d] = records of shard d, counts_dev[8] != 0 => a region
+ * overflowed (records beyond region_capacity are dropped). counts_dev must hold 9 uint32. */
+int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
+                   void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream);
 
 /* ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------
  * Per-replica handle: owns the key table and, per key, the count, the open-pane accumulator and the FlatFAT

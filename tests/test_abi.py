@@ -37,6 +37,7 @@ def test_version_and_errors(L):
     assert L.wfb_program_info(0, C.byref(info)) == 0 and (info.tuple_bytes, info.result_bytes) == (64, 32)
     assert L.wfb_program_info(1, C.byref(info)) == 0 and (info.tuple_bytes, info.result_bytes) == (16, 24)
     assert L.wfb_program_info(2, C.byref(info)) == 0 and (info.tuple_bytes, info.result_bytes) == (24, 24)
+    assert L.wfb_program_info(3, C.byref(info)) == 0 and (info.tuple_bytes, info.result_bytes) == (32, 32)
     assert L.wfb_program_info(99, C.byref(info)) == -2
 
 

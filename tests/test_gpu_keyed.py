@@ -129,3 +129,75 @@ def test_shard_by_key(wfb, oracle, n, shards):
     assert np.array_equal(ops.ts_to_host(out.ts), ts[order])
     off = seg.cpu().numpy()
     assert np.array_equal(off, np.concatenate([[0], np.cumsum(np.bincount(dest, minlength=shards))]))
+
+
+@pytest.mark.parametrize("shards", [1, 2, 3, 8])
+@pytest.mark.parametrize("sizes", [[1], [255, 257, 0, 1000], [65536, 65536, 4097]])
+def test_shard_lift_fused(wfb, oracle, shards, sizes):
+    """Fused Map -> Filter -> lift -> stable partition by key % n == the operators applied one after the other."""
+    import torch
+    O, ops = oracle, wfb
+    n = sum(sizes)
+    t, ts = _batch(O, n, 5000)
+    f = ops.functors(map_kind=1, iadd=2, fscale=1.0000001, filt_kind=1)
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    batches, off = [], 0
+    for sz in sizes:
+        if sz:
+            batches.append(ops.DeviceBatch.from_host(t[off:off + sz], ts[off:off + sz]))
+        else:
+            batches.append(ops.DeviceBatch(torch.empty(0, dtype=torch.uint8, device="cuda"), None, 0))
+        off += sz
+    cap = n
+    regions = torch.zeros(shards * cap * 32, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(9, dtype=torch.int32, device="cuda")
+    eng.shard_lift(batches, f, shards, regions, cap, counts)
+    torch.cuda.synchronize()
+    surv, _, _ = O.map_filter_tuple64(t, ts, 1, 2, 1.0000001, 1)
+    lifted = O.lift_tuple64(surv)
+    dest = O.route(surv["key"], shards)
+    c = counts.cpu().numpy()
+    assert c[8] == 0
+    got = ops.to_host(regions, ops.RESULT32).reshape(shards, cap)
+    for d in range(shards):
+        exp = lifted[dest == d]
+        assert c[d] == len(exp)
+        assert got[d][:c[d]].tobytes() == exp.tobytes()
+
+
+def test_key_sharded_pipeline_world1_nccl(wfb, oracle):
+    """The multi-GPU pipeline object on a world of one rank (NCCL): shard_lift -> all-to-all -> lifted-record window
+    operator must equal the oracle windows of the fused single-GPU path."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from windflow_b200 import multigpu
+    O, ops = oracle, wfb
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    win, slide, nb, nkeys, n, batch = 64, 16, 2, 40, 60000, 4096
+    t, ts = O.gen_tuple64(0, n, O.KEY_UNIFORM, nkeys)
+    f = ops.functors(map_kind=1, iadd=2, fscale=1.0000001, filt_kind=1)
+    pipe = multigpu.KeyShardedPipeline(ops, f, win, slide, nb, 64, 0, 1, torch.device("cuda", 0), pipelined=True)
+    go = O.FfatGpuOracle(win, slide, nb)
+    cap = pipe.ff.max_results(n)
+    out = torch.empty(cap * 32, dtype=torch.uint8, device="cuda"); out_ts = torch.empty(cap, dtype=torch.int64, device="cuda")
+    n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got, exp = [], []
+    step = 3 * batch
+    for s0 in range(0, n, step):
+        bs = [ops.DeviceBatch.from_host(t[b:b + batch], ts[b:b + batch]) for b in range(s0, min(n, s0 + step), batch)]
+        pipe.step(bs, int(ts[s0]), out, out_ts, n_out)
+        torch.cuda.synchronize()
+        got.append(pipe.ff.results_to_host(out, out_ts, n_out)[0])
+        surv, _, _ = O.map_filter_tuple64(t[s0:s0 + step], ts[s0:s0 + step], 1, 2, 1.0000001, 1)
+        exp.append(go.process_batch(O.lift_tuple64(surv), int(ts[s0]))[0])
+    o, ots, no = pipe.ff.flush()
+    torch.cuda.synchronize()
+    got.append(pipe.ff.results_to_host(o, ots, no)[0])
+    g = O.sort_results(np.concatenate(got)); e = O.sort_results(np.concatenate(exp))
+    assert len(g) == len(e) > 0
+    assert np.array_equal(g["key"], e["key"]) and np.array_equal(g["id"], e["id"]) and np.array_equal(g["isum"], e["isum"])
+    assert np.allclose(g["fsum"], e["fsum"], rtol=1e-6, atol=0)
+    dist.destroy_process_group()

@@ -47,6 +47,7 @@ SYMBOLS = {
     "wfb_reduce_all": (C.c_int, [vp, vp, vp, u32, vp, vp, vp]),
     "wfb_keyby_group": (C.c_int, [vp, vp, u32, vp, vp, vp, vp, vp]),
     "wfb_shard_by_key": (C.c_int, [vp, vp, vp, u32, u32, vp, vp, vp, vp]),
+    "wfb_shard_lift": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), u32, u32, vp, u32, vp, vp]),
     "wfb_ffat_create": (C.c_int, [C.POINTER(vp), C.c_int, u64, u64, u32, u32, C.c_int, u64, u32]),
     "wfb_ffat_destroy": (C.c_int, [vp]),
     "wfb_ffat_launches": (u64, [vp]),

@@ -8,6 +8,7 @@
 //                          shared memory and written with a TMA bulk store.
 //                            MODE_MAP     in-place Map_GPU                 (wf/map_gpu.hpp:61-76)
 //                            MODE_FILTER  [Map_GPU ->] Filter_GPU          (wf/filter_gpu.hpp:72-88, :555-570)
+//                            MODE_SHARD   [Map -> Filter ->] lift + stable partition by key % n (multi-GPU keyby)
 //                            MODE_INGEST  [Map -> Filter ->] lift + key->slot for Ffat_Windows_GPU
 //                                         (wf/ffat_replica_gpu.hpp:94-121)
 //   k_radix_hist / k_radix_scan / k_radix_scatter   stable LSD radix passes over (slot, position) pairs: the
@@ -27,7 +28,8 @@ constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pas
 constexpr int STAGES = 4;    // TMA ring depth per CTA
 constexpr uint32_t FULL = 0xffffffffu;
 
-enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2 };
+enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2, MODE_SHARD = 3 };
+constexpr uint32_t MAX_SHARDS = 8;
 
 // decoupled look-back tile state: [63:34] epoch, [33:32] status, [31:0] value
 constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
@@ -94,6 +96,9 @@ struct TileArgs {
     uint64_t tmap_base;        // global address the 2-D tensor map starts at (rows of 64 bytes)
     uint32_t use_tmap;         // 1: `tmap` is valid for this launch
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
+    // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
+    uint32_t nshards, region_cap;
+    uint32_t *shard_counts;    // nshards totals (device)
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
     unsigned char *lifted;     // result_t per surviving tuple
     uint32_t *slots;           // slot per surviving tuple
@@ -245,17 +250,18 @@ enum { TF_SWZ = 1u, TF_FALLBACK = 2u, TF_TS_SMEM = 4u };
 struct StageMeta {
     uint32_t tile, batch, first, cnt, flags, count; // count: survivors (written by the consumers)
     uint32_t pad[2];
+    uint32_t bcount[MAX_SHARDS];                    // MODE_SHARD: survivors per destination shard
 };
 
 template <class P, int MODE>
 struct TilePassSmem {
     using T = typename P::tuple_t;
     using R = typename P::result_t;
-    static constexpr uint32_t rec_bytes = (MODE == MODE_INGEST && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
+    static constexpr uint32_t rec_bytes = ((MODE == MODE_INGEST || MODE == MODE_SHARD) && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
     static constexpr uint32_t tile_bytes = (TILE * rec_bytes + 1023u) & ~1023u; // swizzled stages need 512-B alignment
-    static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : TILE * 16u; // slots | ts in + ts out
+    static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : (MODE == MODE_FILTER ? TILE * 16u : 0u); // slots | ts in + ts out
     static constexpr uint32_t stage_bytes = tile_bytes + aux_bytes;
-    static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 512 /*barriers, meta, scan*/;
+    static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, meta, scan*/;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     uint64_t *staged = full + STAGES;                            // STAGES  consumers -> epilogue
     uint64_t *empty = staged + STAGES;                           // STAGES  epilogue -> producer
     StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);  // STAGES
-    uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 (double-buffered by iteration parity)
+    uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 [x MAX_SHARDS] (double-buffered by iteration parity)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto stage_buf = [&](uint32_t s) { return smem + s * SM::stage_bytes; };
@@ -391,7 +397,33 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
                 }
             }
-            if constexpr (MODE == MODE_MAP) {
+            if constexpr (MODE == MODE_SHARD) {
+                // ---- stable partition by destination shard: one ballot per shard, ONE named barrier --------------------
+                uint32_t dest = 0, myrank = 0;
+                if (keep) { P::lift(tup, res); dest = static_cast<uint32_t>(P::key(tup) % a.nshards); }
+                uint32_t *wt = warp_tot + (it & 1u) * ((TILE / 32) * MAX_SHARDS);
+                for (uint32_t sh = 0; sh < a.nshards; sh++) {
+                    const uint32_t bal = __ballot_sync(FULL, keep && dest == sh);
+                    if (lane == 0) wt[cwarp * MAX_SHARDS + sh] = __popc(bal);
+                    if (keep && dest == sh) myrank = __popc(bal & lanemask_lt());
+                }
+                consumer_bar();
+                uint32_t local = myrank, all = 0;
+                for (uint32_t sh = 0; sh < a.nshards; sh++) {
+                    uint32_t tot = 0, before = 0;
+#pragma unroll
+                    for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = wt[w * MAX_SHARDS + sh]; if (w < cwarp) before += c; tot += c; }
+                    if (sh < dest) local += tot;            // shards are laid out one after the other inside the tile
+                    else if (sh == dest) local += before;
+                    all += tot;
+                    if (ctid == sh) { // consumer thread `sh` publishes shard sh's aggregate of this tile
+                        meta[s].bcount[sh] = tot;
+                        if (m.tile != 0) st_relaxed_u64(&a.tile_state[static_cast<size_t>(m.tile) * MAX_SHARDS + sh], pack_state(a.epoch, ST_AGG, tot));
+                    }
+                }
+                if (ctid == 0) meta[s].count = all;
+                if (keep) TileIO<R>::store(buf, local, res);
+            } else if constexpr (MODE == MODE_MAP) {
                 consumer_bar(); // every consumer has read its tuple: overwrite the stage with the results
                 if (active) {
                     if constexpr (CAN_SWZ) {
@@ -446,6 +478,46 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if (a.batches == nullptr) b = a.one; else b = a.batches[m.batch];
             const uint32_t t = m.tile, tile_count = m.count;
             uint32_t excl = 0;
+            if constexpr (MODE == MODE_SHARD) {
+                // lane sh < nshards owns shard sh: its own look-back chain, its own contiguous run of the staged tile
+                const uint32_t mycnt = (lane < a.nshards) ? m.bcount[lane] : 0u;
+                uint32_t mybase = mycnt; // exclusive prefix of the shard counts = offset of the shard's run in the stage
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, mybase, o); if (lane >= static_cast<uint32_t>(o)) mybase += v; }
+                mybase -= mycnt;
+                if (lane < a.nshards) {
+                    if (t != 0) {
+                        int64_t my = static_cast<int64_t>(t) - 1;
+                        while (true) {
+                            const uint64_t w = ld_relaxed_u64(&a.tile_state[static_cast<size_t>(my) * MAX_SHARDS + lane]);
+                            if ((w >> 34) != (a.epoch & 0x3fffffffu) || ((w >> 32) & 3u) == 0) continue; // not published yet
+                            excl += static_cast<uint32_t>(w);
+                            if (((w >> 32) & 3u) == ST_PREFIX) break;
+                            my--;
+                        }
+                    }
+                    st_relaxed_u64(&a.tile_state[static_cast<size_t>(t) * MAX_SHARDS + lane], pack_state(a.epoch, ST_PREFIX, excl + mycnt));
+                    if (t == a.num_tiles - 1) a.shard_counts[lane] = excl + mycnt;
+                    if (excl + mycnt > a.region_cap) atomicOr(a.ff.err_flags ? a.ff.err_flags : a.shard_counts + MAX_SHARDS, 2u);
+                }
+                __syncwarp();
+                for (uint32_t sh = 0; sh < a.nshards; sh++) {
+                    const uint32_t c = __shfl_sync(FULL, mycnt, sh), bs = __shfl_sync(FULL, mybase, sh), ex = __shfl_sync(FULL, excl, sh);
+                    if (c == 0 || ex + c > a.region_cap) continue;
+                    unsigned char *dsts = a.lifted + (static_cast<size_t>(sh) * a.region_cap + ex) * RB;
+                    const unsigned char *srcs = buf + static_cast<size_t>(bs) * RB;
+                    const uint32_t nbytes = c * RB;
+                    if (bulk_ok(dsts, nbytes) && (reinterpret_cast<uintptr_t>(srcs) & 15u) == 0) { if (lane == 0) bulk_s2g(dsts, srcs, nbytes); }
+                    else {
+                        uint64_t *d8 = reinterpret_cast<uint64_t *>(dsts);
+                        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(srcs);
+                        for (uint32_t w = lane; w < nbytes / 8; w += 32) d8[w] = s8[w];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); mbar_arrive(&empty[s]); }
+                continue;
+            }
             if constexpr (MODE != MODE_MAP) {
                 const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
                 if (t != chain_begin) {

@@ -121,6 +121,7 @@ int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_
     case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used, span_begin, span_end);
     case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used, span_begin, span_end);
     case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_SHARD: return launch_tile_pass<P, MODE_SHARD>(a, params, want_grid, s, grid_used, span_begin, span_end);
     }
     return WFB_E_BADARG;
 }
@@ -195,7 +196,7 @@ ProgramOps make_ops()
 
 const ProgramOps *program(int prog)
 {
-    static const ProgramOps table[] = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>() };
+    static const ProgramOps table[] = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() };
     if (prog < 0 || prog >= static_cast<int>(sizeof(table) / sizeof(table[0]))) return nullptr;
     return &table[prog];
 }
@@ -603,6 +604,43 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
                         ts ? out_ts : nullptr, s);
     if (rc) return rc;
     e->launches += 3 + (e->sorter.launches - before);
+    return 0;
+}
+
+int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
+                   void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream)
+{
+    if (!e || !counts_dev || !out_regions || num_shards == 0 || num_shards > MAX_SHARDS || (nbatches && !batches_h)) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = e->ts.enter(s); if (rc) return rc;
+    CK(cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * (MAX_SHARDS + 1), s));
+    std::vector<DevBatch> hb; hb.reserve(nbatches);
+    uint64_t total = 0; uint32_t tiles = 0; uint64_t span_begin = ~0ull, span_end = 0;
+    for (uint32_t i = 0; i < nbatches; i++) {
+        if (batches_h[i].n == 0) continue;
+        if (!batches_h[i].tuples) return WFB_E_BADARG;
+        DevBatch b; std::memset(&b, 0, sizeof(b));
+        b.tuples = static_cast<const unsigned char *>(batches_h[i].tuples); b.watermark = batches_h[i].watermark;
+        b.n = batches_h[i].n; b.tile_begin = tiles;
+        tiles += tiles_of(b.n); total += b.n;
+        const uint64_t p0 = reinterpret_cast<uint64_t>(b.tuples);
+        span_begin = std::min(span_begin, p0); span_end = std::max(span_end, p0 + static_cast<uint64_t>(b.n) * e->ops->tuple_bytes);
+        hb.push_back(b);
+    }
+    if (total == 0) return 0;
+    if (total > 0x7fffffffull) return WFB_E_BADARG;
+    nbatches = static_cast<uint32_t>(hb.size());
+    rc = e->ts.ensure_tiles(tiles * MAX_SHARDS); if (rc) return rc;
+    rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
+    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    TileArgs a; std::memset(&a, 0, sizeof(a));
+    a.batches = e->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
+    a.lifted = static_cast<unsigned char *>(out_regions); a.nshards = num_shards; a.region_cap = region_capacity; a.shard_counts = counts_dev;
+    e->ts.next_launch(a);
+    uint32_t grid = 0;
+    rc = e->ops->tile_pass(MODE_SHARD, a, pre, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+    e->ts.launched(tiles, grid);
+    e->launches++;
     return 0;
 }
 

@@ -112,4 +112,25 @@ struct ProgWfWin24 {
     }
 };
 
+// ---- program 3: already-lifted bench records (multi-GPU keyby: the source GPU ran Map -> Filter -> lift and shipped
+// 32-byte results; the destination GPU only looks up the key slot and runs the window operator) -----------------
+struct ProgLifted32 {
+    using tuple_t = wfb_result32_t;
+    using result_t = wfb_result32_t;
+    using key_t = uint64_t;
+    using params_t = wfb_functors_t;
+    static constexpr int id = WFB_PROG_LIFTED32;
+
+    __host__ __device__ static void map(tuple_t &, const params_t &) {}
+    __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
+    __host__ __device__ static key_t key(const tuple_t &t) { return t.key; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r) { r = t; }
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out) { ProgTuple64::comb(a, b, out); }
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid) { return ProgTuple64::make_result(k, gwid); }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b)
+    {
+        tuple_t r; r.key = a.key; r.id = 0; r.isum = a.isum + b.isum; r.fsum = a.fsum + b.fsum; return r;
+    }
+};
+
 } // namespace wfb

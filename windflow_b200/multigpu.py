@@ -48,41 +48,57 @@ def exchange_segments(send_buf, send_counts_h, recv_counts_h, item_bytes, recv_b
     return recv_buf, offs
 
 
-class KeyShardedPipeline:
-    """Map_GPU -> Filter_GPU -> (keyby across GPUs) -> Ffat_Windows_GPU on this rank's key shard."""
+def exchange_regions(regions, region_cap, send_counts_h, recv_counts_h, item_bytes, recv_buf=None):
+    """All-to-all of the shard regions written by wfb_shard_lift (region d starts at d*region_cap items). Returns
+    (recv_buf, offsets): chunk s came from source rank s, in its arrival order."""
+    world = len(send_counts_h)
+    n_recv = int(sum(recv_counts_h))
+    if recv_buf is None or recv_buf.numel() < max(1, n_recv) * item_bytes:
+        recv_buf = torch.empty(max(1, n_recv) * item_bytes, dtype=torch.uint8, device=regions.device)
+    offs = [0]
+    for c in recv_counts_h:
+        offs.append(offs[-1] + int(c))
+    ins = [regions[d * region_cap * item_bytes:(d * region_cap + int(send_counts_h[d])) * item_bytes] for d in range(world)]
+    outs = [recv_buf[offs[s] * item_bytes:offs[s + 1] * item_bytes] for s in range(world)]
+    dist.all_to_all(outs, ins)
+    return recv_buf, offs
 
-    def __init__(self, ops, prog, functors, win, slide, nb, max_keys, rank, world, device, pipelined=True):
+
+class KeyShardedPipeline:
+    """Map_GPU -> Filter_GPU -> (keyby across GPUs) -> Ffat_Windows_GPU on this rank's key shard.
+
+    Source side: ONE fused pass (wfb_shard_lift): map, filter, lift and the stable partition of the 32-byte lifted
+    results by key % world. Exchange: sizes + watermarks in one small all-to-all, then the records (NCCL, NVLink).
+    Destination side: the window operator instantiated for already-lifted records (WFB_PROG_LIFTED32)."""
+
+    def __init__(self, ops, functors, win, slide, nb, max_keys, rank, world, device, pipelined=True):
         self.ops, self.f, self.rank, self.world, self.dev = ops, functors, rank, world, device
-        self.eng = ops.Engine(prog)
-        self.ff = ops.FfatWindowsGPU(prog, win, slide, nb, max_keys=max_keys, dense_keys=True, pipelined=pipelined)
-        self.tb = self.eng.tuple_bytes
-        self.filt = self.part = self.recv = None
-        self.n_f = torch.zeros(1, dtype=torch.int32, device=device)
-        self.launches_extra = 0
+        self.eng = ops.Engine(ops.PROG_TUPLE64)
+        self.ff = ops.FfatWindowsGPU(ops.PROG_LIFTED32, win, slide, nb, max_keys=max_keys, dense_keys=True, pipelined=pipelined)
+        self.rb = self.eng.result_bytes
+        self.regions = self.recv = None
+        self.region_cap = 0
+        self.counts = torch.zeros(9, dtype=torch.int32, device=device)
 
     def _ensure(self, n):
-        if self.filt is None or self.filt.numel() < n * self.tb:
-            self.filt = torch.empty(n * self.tb, dtype=torch.uint8, device=self.dev)
-            self.part = torch.empty(n * self.tb, dtype=torch.uint8, device=self.dev)
+        if self.region_cap < n:
+            self.region_cap = n  # worst case: every item of the segment survives and goes to one shard
+            self.regions = torch.empty(self.world * n * self.rb, dtype=torch.uint8, device=self.dev)
 
-    def step(self, seg, out, out_ts, n_out):
-        """seg: one DeviceBatch holding this rank's K batches back to back. Results of the window operator go to out."""
+    def step(self, batches, watermark, out, out_ts, n_out):
+        """batches: this rank's K batches of the global step. Results of the window operator go to out."""
         ops = self.ops
-        self._ensure(seg.n)
-        fb = ops.DeviceBatch(self.filt, None, seg.n, seg.watermark)
-        inb = ops.DeviceBatch(seg.tuples, None, seg.n, seg.watermark)
-        self.eng.map_filter(inb, self.f, out=fb, n_out=self.n_f)                   # fused Map -> Filter over the segment
-        n = int(self.n_f.item())
-        fb.n = n
-        pb = ops.DeviceBatch(self.part, None, n, seg.watermark)
-        _, seg_off = self.eng.shard_by_key(fb, self.world, out=pb)                  # stable partition by key % world
-        off_h = seg_off.cpu().tolist()
-        send_counts_h = [off_h[d + 1] - off_h[d] for d in range(self.world)]
+        self._ensure(sum(b.n for b in batches))
+        self.eng.shard_lift(batches, self.f, self.world, self.regions, self.region_cap, self.counts)
+        cnt_h = self.counts.cpu().tolist()                         # the only host sync of the source side
+        if cnt_h[8]:
+            raise RuntimeError("wfb_shard_lift: shard region overflow")
+        send_counts_h = cnt_h[:self.world]
         send_counts = torch.tensor(send_counts_h, dtype=torch.int64, device=self.dev)
-        rc, rw = exchange_counts(send_counts, seg.watermark)
+        rc, rw = exchange_counts(send_counts, watermark)
         recv_counts_h, wms = rc.cpu().tolist(), rw.cpu().tolist()
-        self.recv, offs = exchange_segments(self.part, send_counts_h, recv_counts_h, self.tb, self.recv)
-        batches = [ops.DeviceBatch(self.recv[offs[s] * self.tb:offs[s + 1] * self.tb], None, offs[s + 1] - offs[s], wms[s])
-                   for s in range(self.world)]
-        self.ff.process(batches, pre=None, out=out, out_ts=out_ts, n_out=n_out)
+        self.recv, offs = exchange_regions(self.regions, self.region_cap, send_counts_h, recv_counts_h, self.rb, self.recv)
+        chunks = [ops.DeviceBatch(self.recv[offs[s] * self.rb:offs[s + 1] * self.rb], None, offs[s + 1] - offs[s], wms[s])
+                  for s in range(self.world)]
+        self.ff.process(chunks, pre=None, out=out, out_ts=out_ts, n_out=n_out)
         return sum(recv_counts_h)

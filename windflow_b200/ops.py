@@ -15,15 +15,15 @@ from . import _lib
 from ._lib import Batch as CBatch
 from ._lib import Functors, check
 
-PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24 = 0, 1, 2
+PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32 = 0, 1, 2, 3
 
 TUPLE64 = np.dtype([("key", "<u8"), ("id", "<u8"), ("ivalue", "<i8"), ("fvalue", "<f8"), ("pad", "<u8", (4,))])
 RESULT32 = np.dtype([("key", "<u8"), ("id", "<u8"), ("isum", "<i8"), ("fsum", "<f8")])
 WFTEST16 = np.dtype([("key", "<u8"), ("value", "<i8")])
 WFWIN24 = np.dtype([("key", "<u8"), ("id", "<u8"), ("value", "<i8")])
 
-TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24}
-RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24}
+TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
+RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
 
 KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
 SEED = 0x5EED5EED
@@ -152,6 +152,14 @@ class Engine:
                                      _stream_ptr(stream)), "wfb_keyby_group")
         return start, mp, dk, nk
 
+    def shard_lift(self, batches, pre, num_shards, regions, region_capacity, counts, stream=None):
+        """Fused [Map -> Filter ->] lift + stable partition by key % num_shards (source side of the multi-GPU keyby).
+        regions: uint8 tensor of num_shards * region_capacity * result_bytes; counts: int32 tensor of 9."""
+        arr = _cbatches(batches)
+        check(self.L.wfb_shard_lift(self.h, C.byref(pre) if pre is not None else None, arr, len(batches), num_shards,
+                                    _ptr(regions), region_capacity, _ptr(counts), _stream_ptr(stream)), "wfb_shard_lift")
+        return counts
+
     def shard_by_key(self, batch, num_shards, out=None, stream=None):
         dev = batch.tuples.device
         if out is None:
@@ -161,6 +169,16 @@ class Engine:
         check(self.L.wfb_shard_by_key(self.h, _ptr(batch.tuples), _ptr(batch.ts), batch.n, num_shards, _ptr(out.tuples),
                                       _ptr(out.ts), _ptr(seg), _stream_ptr(stream)), "wfb_shard_by_key")
         return out, seg
+
+
+def _cbatches(batches):
+    arr = (CBatch * len(batches))()
+    for i, b in enumerate(batches):
+        arr[i].tuples = b.tuples.data_ptr()
+        arr[i].ts = b.ts.data_ptr() if b.ts is not None else None
+        arr[i].watermark = b.watermark
+        arr[i].n = b.n
+    return arr
 
 
 class FfatWindowsGPU:
