@@ -30,6 +30,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 
 enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2, MODE_SHARD = 3 };
 constexpr uint32_t MAX_SHARDS = 8;
+constexpr uint32_t SHARD_STATE_WORDS = 2 + MAX_SHARDS; // per tile: 2 packed aggregate words + one prefix word per shard
 
 // decoupled look-back tile state: [63:34] epoch, [33:32] status, [31:0] value
 constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 }
                 consumer_bar();
                 uint32_t local = myrank, all = 0;
+                uint64_t pk0 = 0, pk1 = 0; // tile counts of shards 0-3 / 4-7, 10 bits each (a tile holds <= 256 items)
                 for (uint32_t sh = 0; sh < a.nshards; sh++) {
                     uint32_t tot = 0, before = 0;
 #pragma unroll
@@ -416,10 +418,14 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     if (sh < dest) local += tot;            // shards are laid out one after the other inside the tile
                     else if (sh == dest) local += before;
                     all += tot;
-                    if (ctid == sh) { // consumer thread `sh` publishes shard sh's aggregate of this tile
-                        meta[s].bcount[sh] = tot;
-                        if (m.tile != 0) st_relaxed_u64(&a.tile_state[static_cast<size_t>(m.tile) * MAX_SHARDS + sh], pack_state(a.epoch, ST_AGG, tot));
-                    }
+                    if (sh < 4) pk0 |= static_cast<uint64_t>(tot) << (10 * sh); else pk1 |= static_cast<uint64_t>(tot) << (10 * (sh - 4));
+                    if (ctid == sh) meta[s].bcount[sh] = tot;
+                }
+                if (ctid == 0 && m.tile != 0) { // publish the aggregates at once: [epoch 22 | status 2 | 4 x 10-bit counts]
+                    uint64_t *st = a.tile_state + static_cast<size_t>(m.tile) * SHARD_STATE_WORDS;
+                    const uint64_t tag = (static_cast<uint64_t>(a.epoch & 0x3fffffu) << 42) | (ST_AGG << 40);
+                    st_relaxed_u64(st + 0, tag | pk0);
+                    st_relaxed_u64(st + 1, tag | pk1);
                 }
                 if (ctid == 0) meta[s].count = all;
                 if (keep) TileIO<R>::store(buf, local, res);
@@ -479,26 +485,63 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             const uint32_t t = m.tile, tile_count = m.count;
             uint32_t excl = 0;
             if constexpr (MODE == MODE_SHARD) {
-                // lane sh < nshards owns shard sh: its own look-back chain, its own contiguous run of the staged tile
+                // One warp-wide decoupled look-back resolves ALL shards: lane l inspects tile t-1-l (then t-33-l ...), whose
+                // state is 2 packed AGGREGATE words (all shards' tile counts) + one PREFIX word per shard.
                 const uint32_t mycnt = (lane < a.nshards) ? m.bcount[lane] : 0u;
                 uint32_t mybase = mycnt; // exclusive prefix of the shard counts = offset of the shard's run in the stage
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, mybase, o); if (lane >= static_cast<uint32_t>(o)) mybase += v; }
                 mybase -= mycnt;
-                if (lane < a.nshards) {
-                    if (t != 0) {
-                        int64_t my = static_cast<int64_t>(t) - 1;
-                        while (true) {
-                            const uint64_t w = ld_relaxed_u64(&a.tile_state[static_cast<size_t>(my) * MAX_SHARDS + lane]);
-                            if ((w >> 34) != (a.epoch & 0x3fffffffu) || ((w >> 32) & 3u) == 0) continue; // not published yet
-                            excl += static_cast<uint32_t>(w);
-                            if (((w >> 32) & 3u) == ST_PREFIX) break;
-                            my--;
+                uint32_t sums[MAX_SHARDS];
+#pragma unroll
+                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) sums[sh] = 0;
+                if (t != 0) {
+                    const uint64_t etag = static_cast<uint64_t>(a.epoch & 0x3fffffu);
+                    uint32_t done = 0;
+                    const uint32_t full_mask = (1u << a.nshards) - 1u;
+                    int64_t idx = static_cast<int64_t>(t) - 1;
+                    while (done != full_mask) {
+                        const int64_t my = idx - lane;
+                        uint64_t a0 = 0, a1 = 0, pre[MAX_SHARDS];
+                        if (my >= 0) {
+                            const uint64_t *st = a.tile_state + static_cast<size_t>(my) * SHARD_STATE_WORDS;
+#pragma unroll
+                            for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) pre[sh] = (sh < a.nshards) ? ld_relaxed_u64(st + 2 + sh) : 0;
+                            if (my != 0) { // tile 0 never publishes aggregates (its prefixes are its counts)
+                                do { a0 = ld_relaxed_u64(st + 0); } while ((a0 >> 42) != etag || ((a0 >> 40) & 3u) != ST_AGG);
+                                do { a1 = ld_relaxed_u64(st + 1); } while ((a1 >> 42) != etag || ((a1 >> 40) & 3u) != ST_AGG);
+                            } else {
+#pragma unroll
+                                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++)
+                                    if (sh < a.nshards) while ((pre[sh] >> 34) != (a.epoch & 0x3fffffffu) || ((pre[sh] >> 32) & 3u) != ST_PREFIX) pre[sh] = ld_relaxed_u64(st + 2 + sh);
+                            }
                         }
+#pragma unroll
+                        for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) {
+                            if (sh >= a.nshards || (done >> sh) & 1u) continue;
+                            bool isP; uint32_t val;
+                            if (my < 0) { isP = true; val = 0; }
+                            else {
+                                isP = ((pre[sh] >> 34) == (a.epoch & 0x3fffffffu)) && (((pre[sh] >> 32) & 3u) == ST_PREFIX);
+                                val = isP ? static_cast<uint32_t>(pre[sh]) : static_cast<uint32_t>(((sh < 4 ? a0 : a1) >> (10 * (sh & 3))) & 1023u);
+                            }
+                            const uint32_t pmask = __ballot_sync(FULL, isP);
+                            const uint32_t firstp = pmask ? (__ffs(pmask) - 1) : 32;
+                            uint32_t v = (lane <= firstp) ? val : 0u;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                            sums[sh] += v;
+                            if (pmask) done |= 1u << sh;
+                        }
+                        idx -= 32;
                     }
-                    st_relaxed_u64(&a.tile_state[static_cast<size_t>(t) * MAX_SHARDS + lane], pack_state(a.epoch, ST_PREFIX, excl + mycnt));
+                }
+#pragma unroll
+                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) if (lane == sh) excl = sums[sh];
+                if (lane < a.nshards) {
+                    st_relaxed_u64(a.tile_state + static_cast<size_t>(t) * SHARD_STATE_WORDS + 2 + lane, pack_state(a.epoch, ST_PREFIX, excl + mycnt));
                     if (t == a.num_tiles - 1) a.shard_counts[lane] = excl + mycnt;
-                    if (excl + mycnt > a.region_cap) atomicOr(a.ff.err_flags ? a.ff.err_flags : a.shard_counts + MAX_SHARDS, 2u);
+                    if (excl + mycnt > a.region_cap) atomicOr(a.shard_counts + MAX_SHARDS, 2u);
                 }
                 __syncwarp();
                 for (uint32_t sh = 0; sh < a.nshards; sh++) {

@@ -630,7 +630,7 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
     if (total == 0) return 0;
     if (total > 0x7fffffffull) return WFB_E_BADARG;
     nbatches = static_cast<uint32_t>(hb.size());
-    rc = e->ts.ensure_tiles(tiles * MAX_SHARDS); if (rc) return rc;
+    rc = e->ts.ensure_tiles(tiles * SHARD_STATE_WORDS); if (rc) return rc;
     rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
     CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
     TileArgs a; std::memset(&a, 0, sizeof(a));
