@@ -84,6 +84,11 @@ int         wfb_abi_version(void);
 const char *wfb_error_string(int code);
 int         wfb_device_count(void);                    /* 0 => every compute entry point returns WFB_E_NOGPU */
 int         wfb_program_info(int prog, wfb_program_info_t *info);
+/* Adds an application-defined program (record schema + functors compiled in the application's own .cu): `ops` is the
+ * launch table built by wfb::register_program<P>() of windflow_b200/csrc/wfb_launch.cuh. Returns the new program id
+ * (>= 4) or a negative error. For such programs every `const wfb_functors_t *` parameter below points to the program's
+ * own params_t (its functor objects) instead. */
+int         wfb_program_register(const void *ops, size_t ops_bytes);
 
 /* ---- per-replica scratch ------------------------------------------------------------------------
  * Replaces the per-replica records / Thrust allocator of wf/filter_gpu.hpp:401-470, wf/reduce_gpu.hpp:122-200,
@@ -92,6 +97,9 @@ int wfb_engine_create(wfb_engine_t **e, int prog);
 int wfb_engine_destroy(wfb_engine_t *e);
 /* launches issued by this engine so far (kernel launches only; bench.py reports it as gpu_launches) */
 uint64_t wfb_engine_launches(const wfb_engine_t *e);
+/* The program's params_t (functor objects) used by the calls that take no functor argument (key extraction, reduce).
+ * Built-in programs need none; for a registered program pass its params_t (bytes must equal sizeof(params_t)). */
+int wfb_engine_set_params(wfb_engine_t *e, const void *params, size_t bytes);
 
 /* number of significant low bits of key_t for the per-batch keyed operators below (default 64): the stable LSD
  * radix sort that replaces thrust::sort_by_key runs ceil(bits/8) passes. */
@@ -158,6 +166,8 @@ int wfb_ffat_create(wfb_ffat_t **h, int prog, uint64_t win, uint64_t slide, uint
                     uint32_t max_keys, int win_type, uint64_t lateness, uint32_t flags);
 int wfb_ffat_destroy(wfb_ffat_t *h);
 uint64_t wfb_ffat_launches(const wfb_ffat_t *h);
+/* params_t of a registered program used by the key extractor, lift and combine (see wfb_engine_set_params). */
+int wfb_ffat_set_params(wfb_ffat_t *h, const void *params, size_t bytes);
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h);
 
 /* Count-based windows over `nbatches` consecutive input batches (one stream segment). Per key, items are

@@ -1,0 +1,116 @@
+// Application-level test of the WindFlow builder API over libwfb200 (include/wf/windflow_gpu.hpp), written like the
+// reference's own GPU tests (tests/graph_tests_gpu/test_graph_gpu_1.cpp, tests/win_tests_gpu/test_win_fat_gpu_tb.cpp):
+// same tuple / result structs and functors (graph_common_gpu.hpp, win_common_gpu.hpp), a Sink accumulating a global sum,
+// and -- since the stream is deterministic (value = i per key) -- a closed-form expected value instead of run-to-run
+// invariance. Prints FACADE_OK on success.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <optional>
+#include <wf/windflow_gpu.hpp>
+
+using namespace wf;
+
+struct tuple_t { // tests/win_tests_gpu/win_common_gpu.hpp:40-58
+    size_t key; uint64_t id; int64_t value;
+    __host__ __device__ tuple_t(): key(0), id(0), value(0) {}
+    __host__ __device__ tuple_t(size_t k, uint64_t i): key(k), id(i), value(0) {}
+};
+struct result_t { // :61-80
+    size_t key; uint64_t id; int64_t value;
+    __host__ __device__ result_t(): key(0), id(0), value(0) {}
+    __host__ __device__ result_t(size_t k, uint64_t i): key(k), id(i), value(0) {}
+};
+
+struct Source_Positive_Functor { // :100-116 (timestamps increase by 1 here instead of a random gap)
+    size_t len, keys;
+    void operator()(Source_Shipper<tuple_t> &shipper)
+    {
+        uint64_t next_ts = 0;
+        for (size_t i = 1; i <= len; i++)
+            for (size_t k = 0; k < keys; k++) {
+                tuple_t t(k, 0); t.value = static_cast<int64_t>(i);
+                shipper.pushWithTimestamp(t, next_ts); shipper.setNextWatermark(next_ts); next_ts++;
+            }
+    }
+};
+struct Map_Functor_GPU { __host__ __device__ void operator()(tuple_t &t) { t.value = t.value + 2; } };              // :221-229
+struct Filter_Functor_GPU { int mod; __host__ __device__ bool operator()(tuple_t &t) { return t.value % mod == 0; } }; // graph_common_gpu.hpp:198-215
+struct Lift_Functor_GPU { __host__ __device__ void operator()(const tuple_t &t, result_t &r) { r.value = t.value; } }; // :295-303
+struct Comb_Functor_GPU { __host__ __device__ void operator()(const result_t &a, const result_t &b, result_t &o) { o.value = a.value + b.value; } }; // :306-314
+struct Key_Functor { __host__ __device__ size_t operator()(const tuple_t &t) { return t.key; } };
+struct Reduce_Functor_GPU { // graph_common_gpu.hpp:268-279
+    __host__ __device__ tuple_t operator()(const tuple_t &a, const tuple_t &b) { tuple_t r; r.key = a.key; r.value = a.value + b.value; return r; }
+};
+
+static std::atomic<long> global_sum{0};
+static std::atomic<long> received{0};
+struct Sink_Functor {
+    void operator()(std::optional<result_t> &out) { if (out) { global_sum += out->value; received++; } }
+};
+struct Sink_Functor_T {
+    void operator()(std::optional<tuple_t> &out) { if (out) { global_sum += out->value; received++; } }
+};
+
+static void check(const char *what, long got, long exp)
+{
+    if (got != exp) { std::printf("FAILED %s: got %ld expected %ld\n", what, got, exp); std::exit(1); }
+    std::printf("%s OK (%ld)\n", what, got);
+}
+
+int main()
+{
+    const size_t len = 3000, keys = 7, batch = 1000;
+    // ---- test 1: Source -> Map_GPU -> Filter_GPU -> Sink (test_graph_gpu_1 shape) -------------------------------------
+    {
+        global_sum = 0; received = 0;
+        PipeGraph graph("test_graph_gpu", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withParallelism(1).withOutputBatchSize(batch).build());
+        mp.chain(MapGPU_Builder(Map_Functor_GPU()).withName("mapgpu1").withParallelism(2).build());
+        mp.chain(FilterGPU_Builder(Filter_Functor_GPU{3}).withName("filtergpu1").build());
+        mp.chain(MapGPU_Builder(Map_Functor_GPU()).withName("mapgpu2").build());
+        mp.chain_sink(Sink_Builder(Sink_Functor_T()).withName("sink").build());
+        graph.run();
+        long exp = 0, cnt = 0;
+        for (size_t i = 1; i <= len; i++) if ((i + 2) % 3 == 0) { exp += static_cast<long>(i + 4) * keys; cnt += keys; }
+        check("map-filter-map sum", global_sum, exp); check("map-filter-map count", received, cnt);
+    }
+    // ---- test 2: Source -> Map_GPU -> Ffat_Windows_GPU (CB, keyed) -> Sink ------------------------------------------------
+    {
+        global_sum = 0; received = 0;
+        const uint64_t win = 64, slide = 16; const size_t nwb = 3;
+        PipeGraph graph("test_win_fat_gpu_cb", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(batch).build());
+        mp.chain(MapGPU_Builder(Map_Functor_GPU()).withName("mapgpu").build());
+        mp.add(Ffat_WindowsGPU_Builder(Lift_Functor_GPU(), Comb_Functor_GPU()).withName("ffat_agg").withKeyBy(Key_Functor())
+                   .withCBWindows(win, slide).withNumWinPerBatch(nwb).withMaxKeys(16).build());
+        mp.chain_sink(Sink_Builder(Sink_Functor()).withName("sink").build());
+        graph.run();
+        // per key: items value = i + 2; groups fired = 1 + (len - B) / (slide*nwb), B = (nwb-1)*slide + win
+        const uint64_t B = (nwb - 1) * slide + win;
+        const uint64_t groups = 1 + (len - B) / (slide * nwb);
+        long exp = 0;
+        for (uint64_t g = 0; g < groups * nwb; g++) { const long a = g * slide + 1 + 2, b = g * slide + win + 2; exp += (a + b) * static_cast<long>(win) / 2; }
+        check("ffat cb windows sum", global_sum, exp * static_cast<long>(keys));
+        check("ffat cb windows count", received, static_cast<long>(groups * nwb * keys));
+    }
+    // ---- test 3: Source -> Reduce_GPU (keyed) -> Sink (test_graph_gpu_4 shape) -----------------------------------------------
+    {
+        global_sum = 0; received = 0;
+        PipeGraph graph("test_reduce_gpu", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(batch).build());
+        mp.chain(ReduceGPU_Builder(Reduce_Functor_GPU()).withName("reducegpu").withKeyBy(Key_Functor()).build());
+        mp.chain_sink(Sink_Builder(Sink_Functor_T()).withName("sink").build());
+        graph.run();
+        long exp = 0;
+        for (size_t i = 1; i <= len; i++) exp += static_cast<long>(i) * keys; // a reduce only regroups the values
+        check("reduce_by_key sum", global_sum, exp);
+        const long nb = (len * keys + batch - 1) / batch;
+        check("reduce_by_key items", received, nb * static_cast<long>(keys)); // every batch holds all 7 keys
+    }
+    std::printf("FACADE_OK\n");
+    return 0;
+}

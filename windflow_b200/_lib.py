@@ -36,10 +36,13 @@ SYMBOLS = {
     "wfb_abi_version": (C.c_int, []),
     "wfb_error_string": (C.c_char_p, [C.c_int]),
     "wfb_device_count": (C.c_int, []),
+    "wfb_program_register": (C.c_int, [vp, C.c_size_t]),
     "wfb_program_info": (C.c_int, [C.c_int, C.POINTER(ProgramInfo)]),
     "wfb_engine_create": (C.c_int, [C.POINTER(vp), C.c_int]),
     "wfb_engine_destroy": (C.c_int, [vp]),
     "wfb_engine_launches": (u64, [vp]),
+    "wfb_engine_set_params": (C.c_int, [vp, vp, C.c_size_t]),
+    "wfb_ffat_set_params": (C.c_int, [vp, vp, C.c_size_t]),
     "wfb_engine_set_key_bits": (C.c_int, [vp, u32]),
     "wfb_map": (C.c_int, [vp, C.POINTER(Functors), vp, u32, vp]),
     "wfb_map_filter": (C.c_int, [vp, C.POINTER(Functors), vp, vp, u32, vp, vp, vp, vp]),

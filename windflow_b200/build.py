@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwfb200.so")
 SOURCES = ["wfb_lib.cu"]
-HEADERS = ["wfb_kernels.cuh", "wfb_programs.cuh", "wfb_ptx.cuh", os.path.join("..", "..", "include", "wfb200.h")]
+HEADERS = ["wfb_kernels.cuh", "wfb_launch.cuh", "wfb_programs.cuh", "wfb_ptx.cuh", os.path.join("..", "..", "include", "wfb200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

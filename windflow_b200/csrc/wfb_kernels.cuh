@@ -393,15 +393,15 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             alignas(16) R res;
             if constexpr (MODE == MODE_INGEST) {
                 if (keep) {
-                    P::lift(tup, res);
-                    slot = slot_of_key(a.ff, P::key(tup));
+                    P::lift(tup, res, prm);
+                    slot = slot_of_key(a.ff, P::key(tup, prm));
                     if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
                 }
             }
             if constexpr (MODE == MODE_SHARD) {
                 // ---- stable partition by destination shard: one ballot per shard, ONE named barrier --------------------
                 uint32_t dest = 0, myrank = 0;
-                if (keep) { P::lift(tup, res); dest = static_cast<uint32_t>(P::key(tup) % a.nshards); }
+                if (keep) { P::lift(tup, res, prm); dest = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); }
                 uint32_t *wt = warp_tot + (it & 1u) * ((TILE / 32) * MAX_SHARDS);
                 for (uint32_t sh = 0; sh < a.nshards; sh++) {
                     const uint32_t bal = __ballot_sync(FULL, keep && dest == sh);
@@ -984,12 +984,12 @@ __device__ __forceinline__ uint64_t batch_watermark(const uint32_t *__restrict__
 template <class P>
 __device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsigned char *tree, uint64_t key, uint64_t gwid, uint64_t wm,
                                                  uint32_t opos, unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts,
-                                                 uint32_t out_cap)
+                                                 uint32_t out_cap, const typename P::params_t &prm)
 {
     using R = typename P::result_t;
     constexpr uint32_t RB = sizeof(R);
     const uint32_t n = ff.n_leaves;
-    alignas(16) R res = P::make_result(key, gwid);
+    alignas(16) R res = P::make_result(key, gwid, prm);
     uint32_t ws = static_cast<uint32_t>((gwid * ff.sp) & (n - 1));
     uint32_t remaining = ff.wp;
     while (remaining > 0) {
@@ -999,7 +999,7 @@ __device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsign
         const uint32_t level = 31 - __clz(range);
         alignas(16) R node;
         ld_rec<R>(tree + static_cast<size_t>(level_off(n, level) + (ws >> level)) * RB, node);
-        P::comb(res, node, res);
+        P::comb(res, node, res, prm);
         ws = (ws + range) & (n - 1);
         remaining -= range;
     }
@@ -1013,7 +1013,8 @@ __device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsign
 template <class P>
 __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const uint32_t *__restrict__ batch_off,
                                                       const DevBatch *__restrict__ batches, uint32_t nbatches,
-                                                      unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts, uint32_t out_cap)
+                                                      unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts, uint32_t out_cap,
+                                                      const typename P::params_t prm)
 {
     using R = typename P::result_t;
     const uint32_t nt = min(*ff.n_trig, ff.trig_cap);
@@ -1024,7 +1025,7 @@ __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const ui
         const Trigger tr = ff.trig[ti];
         const uint64_t wm = batch_watermark(batch_off, batches, nbatches, tr.last_pos);
         ffat_eval_window<P>(ff, ff.tree + static_cast<size_t>(tr.slot) * tree_stride, tr.key, tr.g * ff.nb + i, wm, tr.obase + i,
-                            out_res, out_ts, out_cap);
+                            out_res, out_ts, out_cap, prm);
     }
 }
 
@@ -1034,7 +1035,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                                                      const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
                                                      uint32_t nbatches, unsigned char *__restrict__ out_res,
                                                      uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
-                                                     uint32_t gather)
+                                                     uint32_t gather, const typename P::params_t prm)
 {
     using R = typename P::result_t;
     constexpr uint32_t RB = sizeof(R);
@@ -1077,10 +1078,10 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
 #pragma unroll
             for (uint32_t o = 1; o < 32; o <<= 1) {
                 const R other = shfl_down_rec<R>(r, o);
-                if (lane + o < take) P::comb(r, other, r);
+                if (lane + o < take) P::comb(r, other, r, prm);
             }
             r = shfl_rec<R>(r, 0);
-            if (c % P_ == 0) acc = r; else P::comb(acc, r, acc);
+            if (c % P_ == 0) acc = r; else P::comb(acc, r, acc, prm);
             c += take; j += take;
 
             if (c % P_ == 0) { // pane complete -> leaf + root path
@@ -1095,7 +1096,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                 for (uint32_t l = 0; l < logn; l++) {
                     const R s = shfl_rec<R>(sib, l);
                     alignas(16) R parent = cur; // key/id fields are don't-care in internal nodes
-                    if ((leaf >> l) & 1u) P::comb(s, cur, parent); else P::comb(cur, s, parent);
+                    if ((leaf >> l) & 1u) P::comb(s, cur, parent, prm); else P::comb(cur, s, parent, prm);
                     cur = parent;
                     if (lane == 0) st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
                 }
@@ -1120,7 +1121,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                     if (!deferred) {
                         const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
                         for (uint32_t i = lane; i < ff.nb; i += 32)
-                            ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap);
+                            ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap, prm);
                     }
                     g++; trig += group_items;
                     __syncwarp();
@@ -1141,12 +1142,12 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
 // keys[i] = key_extr(tuple_i)   (Extract_Keys_Kernel wf/reduce_gpu.hpp:75-86, Extract_Dests_Kernel wf/keyby_emitter_gpu.hpp:68-81)
 template <class P>
 __global__ void k_extract_keys(const unsigned char *__restrict__ tuples, uint32_t n, uint64_t *__restrict__ keys,
-                               uint32_t *__restrict__ dest, uint32_t num_shards)
+                               uint32_t *__restrict__ dest, uint32_t num_shards, const typename P::params_t prm)
 {
     using T = typename P::tuple_t;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const T *t = reinterpret_cast<const T *>(tuples + static_cast<size_t>(i) * sizeof(T));
-        const uint64_t k = P::key(*t);
+        const uint64_t k = P::key(*t, prm);
         if (keys) keys[i] = k;
         if (dest) dest[i] = static_cast<uint32_t>(k % num_shards); // wf/keyby_emitter.hpp:215-217
     }
@@ -1192,7 +1193,7 @@ template <class P>
 __global__ void __launch_bounds__(256) k_reduce_segments(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts,
                                                          const uint32_t *__restrict__ sidx, const uint32_t *__restrict__ seg_begin,
                                                          const uint32_t *__restrict__ n_keys, unsigned char *__restrict__ out_tuples,
-                                                         uint64_t *__restrict__ out_ts)
+                                                         uint64_t *__restrict__ out_ts, const typename P::params_t prm)
 {
     using T = typename P::tuple_t;
     const uint32_t lane = threadIdx.x & 31;
@@ -1213,11 +1214,11 @@ __global__ void __launch_bounds__(256) k_reduce_segments(const unsigned char *__
             for (uint32_t o = 1; o < 32; o <<= 1) {
                 const T other = shfl_down_rec<T>(t, o);
                 const uint64_t ots = __shfl_down_sync(FULL, tt, o);
-                if (lane + o < take) { t = P::reduce(t, other); tt = tt < ots ? ots : tt; }
+                if (lane + o < take) { t = P::reduce(t, other, prm); tt = tt < ots ? ots : tt; }
             }
             t = shfl_rec<T>(t, 0); tt = __shfl_sync(FULL, tt, 0);
             if (!have) { acc = t; mts = tt; have = true; }
-            else { acc = P::reduce(acc, t); mts = mts < tt ? tt : mts; }
+            else { acc = P::reduce(acc, t, prm); mts = mts < tt ? tt : mts; }
         }
         if (lane == 0) {
             st_rec<T>(out_tuples + static_cast<size_t>(k) * sizeof(T), acc);
@@ -1230,7 +1231,8 @@ __global__ void __launch_bounds__(256) k_reduce_segments(const unsigned char *__
 // (thrust::reduce with init = batch_item_gpu_t<tuple_t>(), wf/reduce_gpu.hpp:264-273). One CTA of 1024 threads.
 template <class P>
 __global__ void __launch_bounds__(1024) k_reduce_all(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts, uint32_t n,
-                                                     unsigned char *__restrict__ out_tuple, uint64_t *__restrict__ out_ts)
+                                                     unsigned char *__restrict__ out_tuple, uint64_t *__restrict__ out_ts,
+                                                     const typename P::params_t prm)
 {
     using T = typename P::tuple_t;
     __shared__ __align__(16) unsigned char sm[32 * sizeof(T)];
@@ -1244,7 +1246,7 @@ __global__ void __launch_bounds__(1024) k_reduce_all(const unsigned char *__rest
     for (uint32_t i = b; i < e; i++) {
         alignas(16) T t; ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), t);
         const uint64_t tt = ts ? ts[i] : 0;
-        if (!have) { acc = t; mts = tt; have = true; } else { acc = P::reduce(acc, t); mts = mts < tt ? tt : mts; }
+        if (!have) { acc = t; mts = tt; have = true; } else { acc = P::reduce(acc, t, prm); mts = mts < tt ? tt : mts; }
     }
     // ordered combine across lanes, then across warps (a lane/warp without items is skipped)
 #pragma unroll
@@ -1253,7 +1255,7 @@ __global__ void __launch_bounds__(1024) k_reduce_all(const unsigned char *__rest
         const uint64_t ots = __shfl_down_sync(FULL, mts, o);
         const bool ohave = __shfl_down_sync(FULL, have ? 1u : 0u, o) != 0;
         if (lane + o < 32 && ohave) {
-            if (have) { acc = P::reduce(acc, other); mts = mts < ots ? ots : mts; } else { acc = other; mts = ots; have = true; }
+            if (have) { acc = P::reduce(acc, other, prm); mts = mts < ots ? ots : mts; } else { acc = other; mts = ots; have = true; }
         }
     }
     if (lane == 0) { st_rec<T>(sm + warp * sizeof(T), acc); smts[warp] = mts; smhave[warp] = have ? 1u : 0u; }
@@ -1263,7 +1265,7 @@ __global__ void __launch_bounds__(1024) k_reduce_all(const unsigned char *__rest
         alignas(16) T r = init; uint64_t rts = 0;
         for (uint32_t w = 0; w < 32; w++) if (smhave[w]) {
             alignas(16) T t; ld_rec<T>(sm + w * sizeof(T), t);
-            r = P::reduce(r, t); rts = rts < smts[w] ? smts[w] : rts;
+            r = P::reduce(r, t, prm); rts = rts < smts[w] ? smts[w] : rts;
         }
         st_rec<T>(out_tuple, r);
         if (out_ts) *out_ts = rts;

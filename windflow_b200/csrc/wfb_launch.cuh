@@ -1,0 +1,210 @@
+// wfb_launch.cuh -- host-side launchers of the kernels of wfb_kernels.cuh for ONE program, and the table of function
+// pointers (ProgramOps) through which libwfb200's C ABI reaches them. libwfb200.so instantiates it for the built-in
+// programs; an application instantiates it for its own functors with wfb::register_program<MyProgram>() (see
+// INTEGRATION.md section 3) and then uses the same C ABI with the returned program id.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/wfb200.h"
+#include "wfb_kernels.cuh"
+
+#define WFB_CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return static_cast<int>(e__); } while (0)
+
+namespace wfb {
+
+inline int num_sms()
+{
+    static int n = 0;
+    if (n == 0) { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D view [rows][64 bytes] of a span of device memory holding 64-byte tuples, box = one tile, SWIZZLE_64B
+inline bool make_tuple_tmap(CUtensorMap *m, uint64_t base, uint64_t end)
+{
+    std::memset(m, 0, sizeof(*m));
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc || (base & 63u) || end <= base) return false;
+    const uint64_t rows = (end - base) / 64;
+    if (rows == 0 || rows > 0xffffffffull) return false;
+    cuuint64_t gdim[2] = {64, rows};
+    cuuint64_t gstr[1] = {64};
+    cuuint32_t box[2] = {64, TILE};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, reinterpret_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- per-program launch table ------------------------------------------------------------------------------
+struct ProgramOps {
+    uint32_t tuple_bytes, result_bytes, params_bytes, reserved;
+    int (*tile_pass)(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                     uint64_t span_begin, uint64_t span_end);
+    int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
+                       const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
+                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params);
+    int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
+                        unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params);
+    int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s,
+                        const void *params);
+    int (*reduce_segments)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
+                           const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s, const void *params);
+    int (*reduce_all)(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s,
+                      const void *params);
+    int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
+                  uint64_t *out_ts, cudaStream_t s);
+};
+
+template <class P>
+inline typename P::params_t load_params(const void *params)
+{
+    typename P::params_t prm;
+    if (params) std::memcpy(&prm, params, sizeof(prm)); else std::memset(&prm, 0, sizeof(prm));
+    return prm;
+}
+
+template <class P, int MODE>
+int launch_tile_pass(TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                     uint64_t span_begin, uint64_t span_end)
+{
+    static int max_grid = -1;
+    constexpr uint32_t smem = TilePassSmem<P, MODE>::total;
+    if (max_grid < 0) {
+        WFB_CK(cudaFuncSetAttribute(k_tile_pass<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0;
+        WFB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass<P, MODE>, TP_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        max_grid = per_sm * wfb::num_sms();
+    }
+    uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
+    if (a.max_ctas_per_sm) grid = std::max(1u, std::min(grid, a.max_ctas_per_sm * static_cast<uint32_t>(wfb::num_sms())));
+    const typename P::params_t prm = load_params<P>(params);
+    alignas(64) CUtensorMap tmap;
+    a.use_tmap = 0; a.tmap_base = span_begin;
+    if (sizeof(typename P::tuple_t) == 64 && make_tuple_tmap(&tmap, span_begin, span_end)) a.use_tmap = 1;
+    else std::memset(&tmap, 0, sizeof(tmap));
+    k_tile_pass<P, MODE><<<grid, TP_THREADS, smem, s>>>(tmap, a, prm);
+    WFB_CK(cudaGetLastError());
+    *grid_used = grid;
+    return 0;
+}
+
+template <class P>
+int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                       uint64_t span_begin, uint64_t span_end)
+{
+    switch (mode) {
+    case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    case MODE_SHARD: return launch_tile_pass<P, MODE_SHARD>(a, params, want_grid, s, grid_used, span_begin, span_end);
+    }
+    return WFB_E_BADARG;
+}
+
+template <class P>
+int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
+                         const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
+                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params)
+{
+    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather,
+                                          load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
+template <class P>
+int ffat_windows_dispatch(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
+                          unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params)
+{
+    k_ffat_windows<P><<<grid, 256, 0, s>>>(ff, batch_off, batches, nbatches, out_res, out_ts, out_cap, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
+inline uint32_t grid_for(uint32_t n, uint32_t per_block) { return std::max(1u, std::min((n + per_block - 1) / per_block, static_cast<uint32_t>(wfb::num_sms()) * 16u)); }
+
+template <class P>
+int extract_keys_dispatch(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s,
+                          const void *params)
+{
+    k_extract_keys<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, n, keys, dest, num_shards, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
+                             const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s,
+                             const void *params)
+{
+    k_reduce_segments<P><<<grid_for(n, 8), 256, 0, s>>>(tuples, ts, sidx, seg_begin, n_keys, out_tuples, out_ts, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int reduce_all_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s,
+                        const void *params)
+{
+    k_reduce_all<P><<<1, 1024, 0, s>>>(tuples, ts, n, out_tuple, out_ts, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int gather_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
+                    uint64_t *out_ts, cudaStream_t s)
+{
+    k_gather_tuples<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, ts, perm, n, out_tuples, out_ts);
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
+template <class P>
+ProgramOps make_ops()
+{
+    ProgramOps o;
+    o.tuple_bytes = sizeof(typename P::tuple_t);
+    o.result_bytes = sizeof(typename P::result_t);
+    o.params_bytes = sizeof(typename P::params_t); o.reserved = 0;
+    o.tile_pass = &tile_pass_dispatch<P>;
+    o.ffat_update = &ffat_update_dispatch<P>;
+    o.ffat_windows = &ffat_windows_dispatch<P>;
+    o.extract_keys = &extract_keys_dispatch<P>;
+    o.reduce_segments = &reduce_segments_dispatch<P>;
+    o.reduce_all = &reduce_all_dispatch<P>;
+    o.gather = &gather_dispatch<P>;
+    return o;
+}
+
+
+// registers the launch table of program P with libwfb200 and returns its program id (>= 4), or a negative error
+template <class P>
+int register_program()
+{
+    static int id = -1;
+    if (id < 0) { const ProgramOps o = make_ops<P>(); id = wfb_program_register(&o, sizeof(o)); }
+    return id;
+}
+
+} // namespace wfb

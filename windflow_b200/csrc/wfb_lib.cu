@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include "../../include/wfb200.h"
 #include "wfb_kernels.cuh"
+#include "wfb_launch.cuh"
 #include "wfb_programs.cuh"
 
 using namespace wfb;
@@ -20,41 +21,6 @@ using namespace wfb;
 namespace {
 
 int g_num_sms = 0;
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_encode_tiled()
-{
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-        cudaGetLastError();
-    }
-    return fn;
-}
-
-// 2-D view [rows][64 bytes] of a span of device memory holding 64-byte tuples, box = one tile, SWIZZLE_64B
-bool make_tuple_tmap(CUtensorMap *m, uint64_t base, uint64_t end)
-{
-    std::memset(m, 0, sizeof(*m));
-    PFN_encodeTiled enc = get_encode_tiled();
-    if (!enc || (base & 63u) || end <= base) return false;
-    const uint64_t rows = (end - base) / 64;
-    if (rows == 0 || rows > 0xffffffffull) return false;
-    cuuint64_t gdim[2] = {64, rows};
-    cuuint64_t gstr[1] = {64};
-    cuuint32_t box[2] = {64, TILE};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, reinterpret_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 int device_ready()
 {
@@ -68,137 +34,17 @@ int device_ready()
     return 0;
 }
 
-// ---- per-program launch table ------------------------------------------------------------------------------
-struct ProgramOps {
-    uint32_t tuple_bytes, result_bytes;
-    int (*tile_pass)(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
-                     uint64_t span_begin, uint64_t span_end);
-    int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
-                       const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather);
-    int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
-                        unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s);
-    int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s);
-    int (*reduce_segments)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
-                           const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s);
-    int (*reduce_all)(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s);
-    int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
-                  uint64_t *out_ts, cudaStream_t s);
-};
-
-template <class P, int MODE>
-int launch_tile_pass(TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
-                     uint64_t span_begin, uint64_t span_end)
+std::vector<ProgramOps> &registry()
 {
-    static int max_grid = -1;
-    constexpr uint32_t smem = TilePassSmem<P, MODE>::total;
-    if (max_grid < 0) {
-        CK(cudaFuncSetAttribute(k_tile_pass<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_pass<P, MODE>, TP_THREADS, smem));
-        if (per_sm < 1) per_sm = 1;
-        max_grid = per_sm * g_num_sms;
-    }
-    uint32_t grid = std::max(1u, std::min(want_grid, static_cast<uint32_t>(max_grid)));
-    if (a.max_ctas_per_sm) grid = std::max(1u, std::min(grid, a.max_ctas_per_sm * static_cast<uint32_t>(g_num_sms)));
-    typename P::params_t prm;
-    if (params) prm = *static_cast<const typename P::params_t *>(params); else std::memset(&prm, 0, sizeof(prm));
-    alignas(64) CUtensorMap tmap;
-    a.use_tmap = 0; a.tmap_base = span_begin;
-    if (sizeof(typename P::tuple_t) == 64 && make_tuple_tmap(&tmap, span_begin, span_end)) a.use_tmap = 1;
-    else std::memset(&tmap, 0, sizeof(tmap));
-    k_tile_pass<P, MODE><<<grid, TP_THREADS, smem, s>>>(tmap, a, prm);
-    CK(cudaGetLastError());
-    *grid_used = grid;
-    return 0;
-}
-
-template <class P>
-int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
-                       uint64_t span_begin, uint64_t span_end)
-{
-    switch (mode) {
-    case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used, span_begin, span_end);
-    case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used, span_begin, span_end);
-    case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
-    case MODE_SHARD: return launch_tile_pass<P, MODE_SHARD>(a, params, want_grid, s, grid_used, span_begin, span_end);
-    }
-    return WFB_E_BADARG;
-}
-
-template <class P>
-int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
-                         const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather)
-{
-    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather);
-    CK(cudaGetLastError());
-    return 0;
-}
-
-template <class P>
-int ffat_windows_dispatch(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
-                          unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s)
-{
-    k_ffat_windows<P><<<grid, 256, 0, s>>>(ff, batch_off, batches, nbatches, out_res, out_ts, out_cap);
-    CK(cudaGetLastError());
-    return 0;
-}
-
-inline uint32_t grid_for(uint32_t n, uint32_t per_block) { return std::max(1u, std::min((n + per_block - 1) / per_block, static_cast<uint32_t>(g_num_sms) * 16u)); }
-
-template <class P>
-int extract_keys_dispatch(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s)
-{
-    k_extract_keys<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, n, keys, dest, num_shards);
-    CK(cudaGetLastError());
-    return 0;
-}
-template <class P>
-int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *sidx, const uint32_t *seg_begin,
-                             const uint32_t *n_keys, unsigned char *out_tuples, uint64_t *out_ts, uint32_t n, cudaStream_t s)
-{
-    k_reduce_segments<P><<<grid_for(n, 8), 256, 0, s>>>(tuples, ts, sidx, seg_begin, n_keys, out_tuples, out_ts);
-    CK(cudaGetLastError());
-    return 0;
-}
-template <class P>
-int reduce_all_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s)
-{
-    k_reduce_all<P><<<1, 1024, 0, s>>>(tuples, ts, n, out_tuple, out_ts);
-    CK(cudaGetLastError());
-    return 0;
-}
-template <class P>
-int gather_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
-                    uint64_t *out_ts, cudaStream_t s)
-{
-    k_gather_tuples<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, ts, perm, n, out_tuples, out_ts);
-    CK(cudaGetLastError());
-    return 0;
-}
-
-template <class P>
-ProgramOps make_ops()
-{
-    ProgramOps o;
-    o.tuple_bytes = sizeof(typename P::tuple_t);
-    o.result_bytes = sizeof(typename P::result_t);
-    o.tile_pass = &tile_pass_dispatch<P>;
-    o.ffat_update = &ffat_update_dispatch<P>;
-    o.ffat_windows = &ffat_windows_dispatch<P>;
-    o.extract_keys = &extract_keys_dispatch<P>;
-    o.reduce_segments = &reduce_segments_dispatch<P>;
-    o.reduce_all = &reduce_all_dispatch<P>;
-    o.gather = &gather_dispatch<P>;
-    return o;
+    static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() }; table.reserve(4096); }
+    return table;
 }
 
 const ProgramOps *program(int prog)
 {
-    static const ProgramOps table[] = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() };
-    if (prog < 0 || prog >= static_cast<int>(sizeof(table) / sizeof(table[0]))) return nullptr;
-    return &table[prog];
+    std::vector<ProgramOps> &t = registry();
+    if (prog < 0 || prog >= static_cast<int>(t.size())) return nullptr;
+    return &t[prog];
 }
 
 // ---- scratch shared by the tile passes: ticket counter, epoch-tagged tile states, batch descriptors -----------
@@ -328,6 +174,8 @@ struct RadixSorter {
 struct wfb_engine {
     int prog = 0;
     const ProgramOps *ops = nullptr;
+    std::vector<unsigned char> params; // the program's params_t used by key / reduce (zeros unless wfb_engine_set_params)
+    const void *pp() const { return params.empty() ? nullptr : params.data(); }
     TileScratch ts;
     uint64_t launches = 0;
     // scratch of the per-batch keyed operators (sort buffers), grown on demand
@@ -400,6 +248,8 @@ struct SegScratch {
 struct wfb_ffat {
     int prog = 0;
     const ProgramOps *ops = nullptr;
+    std::vector<unsigned char> params; // the program's params_t used by key / lift / comb (zeros unless wfb_ffat_set_params)
+    const void *pp() const { return params.empty() ? nullptr : params.data(); }
     FfatDev ff{};
     TileScratch ts;
     uint32_t sort_passes = 1;
@@ -450,6 +300,16 @@ int wfb_device_count(void)
     return n;
 }
 
+int wfb_program_register(const void *ops, size_t ops_bytes)
+{
+    if (!ops || ops_bytes != sizeof(ProgramOps)) return WFB_E_BADARG;
+    std::vector<ProgramOps> &t = registry();
+    if (t.size() >= 4096) return WFB_E_CAPACITY;
+    t.reserve(4096); // handles keep pointers into the table: never reallocate it
+    t.push_back(*static_cast<const ProgramOps *>(ops));
+    return static_cast<int>(t.size()) - 1;
+}
+
 int wfb_program_info(int prog, wfb_program_info_t *info)
 {
     const ProgramOps *o = program(prog);
@@ -485,6 +345,13 @@ int wfb_engine_destroy(wfb_engine_t *e)
 }
 
 uint64_t wfb_engine_launches(const wfb_engine_t *e) { return e ? e->launches : 0; }
+
+int wfb_engine_set_params(wfb_engine_t *e, const void *params, size_t bytes)
+{
+    if (!e || !params || bytes != e->ops->params_bytes) return WFB_E_BADARG;
+    e->params.assign(static_cast<const unsigned char *>(params), static_cast<const unsigned char *>(params) + bytes);
+    return 0;
+}
 
 static int run_single(wfb_engine_t *e, int mode, const wfb_functors_t *f, const DevBatch &b, cudaStream_t s)
 {
@@ -536,7 +403,7 @@ static int keyed_prepare(wfb_engine_t *e, const void *tuples, uint32_t n, int32_
 {
     int rc = e->ts.enter(s); if (rc) return rc;
     rc = e->ensure_sort(n, s); if (rc) return rc;
-    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, e->keysA, nullptr, 1, s); if (rc) return rc;
+    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, e->keysA, nullptr, 1, s, e->pp()); if (rc) return rc;
     e->launches++;
     const uint64_t *skeys; const uint32_t *sidx;
     rc = e->sort64(n, s, &skeys, &sidx); if (rc) return rc;
@@ -559,7 +426,7 @@ int wfb_reduce_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, u
     const uint32_t *sidx;
     int rc = keyed_prepare(e, tuples, n, nullptr, nullptr, nullptr, n_out_dev, s, &sidx); if (rc) return rc;
     rc = e->ops->reduce_segments(static_cast<const unsigned char *>(tuples), ts, sidx, e->seg_begin, n_out_dev,
-                                 static_cast<unsigned char *>(out_tuples), ts ? out_ts : nullptr, n, s);
+                                 static_cast<unsigned char *>(out_tuples), ts ? out_ts : nullptr, n, s, e->pp());
     if (rc) return rc;
     e->launches++;
     return 0;
@@ -570,7 +437,7 @@ int wfb_reduce_all(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint
     if (!e || !out_tuple || (n && !tuples)) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = e->ts.enter(s); if (rc) return rc;
-    rc = e->ops->reduce_all(static_cast<const unsigned char *>(tuples), ts, n, static_cast<unsigned char *>(out_tuple), out_ts, s);
+    rc = e->ops->reduce_all(static_cast<const unsigned char *>(tuples), ts, n, static_cast<unsigned char *>(out_tuple), out_ts, s, e->pp());
     if (rc) return rc;
     e->launches++;
     return 0;
@@ -594,7 +461,7 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
     if (n == 0) { CK(cudaMemsetAsync(seg_off_dev, 0, sizeof(uint32_t) * (num_shards + 1), s)); return 0; }
     int rc = e->ts.enter(s); if (rc) return rc;
     rc = e->ensure_sort(n, s); if (rc) return rc;
-    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, nullptr, e->destA, num_shards, s); if (rc) return rc;
+    rc = e->ops->extract_keys(static_cast<const unsigned char *>(tuples), n, nullptr, e->destA, num_shards, s, e->pp()); if (rc) return rc;
     const uint32_t *sdest, *perm;
     const uint64_t before = e->sorter.launches;
     rc = e->sorter.sort<uint32_t>(e->destA, e->destB, e->idxA, e->idxB, nullptr, n, n, 1, s, &sdest, &perm); if (rc) return rc;
@@ -638,7 +505,7 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
     a.lifted = static_cast<unsigned char *>(out_regions); a.nshards = num_shards; a.region_cap = region_capacity; a.shard_counts = counts_dev;
     e->ts.next_launch(a);
     uint32_t grid = 0;
-    rc = e->ops->tile_pass(MODE_SHARD, a, pre, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+    rc = e->ops->tile_pass(MODE_SHARD, a, pre ? static_cast<const void *>(pre) : e->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     e->ts.launched(tiles, grid);
     e->launches++;
     return 0;
@@ -736,6 +603,13 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
 }
 
 uint64_t wfb_ffat_launches(const wfb_ffat_t *h) { return h ? h->launches : 0; }
+
+int wfb_ffat_set_params(wfb_ffat_t *h, const void *params, size_t bytes)
+{
+    if (!h || !params || bytes != h->ops->params_bytes) return WFB_E_BADARG;
+    h->params.assign(static_cast<const unsigned char *>(params), static_cast<const unsigned char *>(params) + bytes);
+    return 0;
+}
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes : 0; }
 
 static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint32_t nbatches, cudaStream_t s)
@@ -793,9 +667,9 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
     // one warp per key: pane fold, FlatFAT update; then one thread per fired window
     uint32_t ugrid = std::max(1u, std::min((ff.max_keys + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u));
     rc = h->ops->ffat_update(ff, h->move_payload ? g.lifted_sorted : g.lifted, sorted_pos, g.batch_off, g.d_batches, g.nbatches,
-                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u);
+                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u, h->pp());
     if (rc) return rc;
-    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s);
+    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp());
     if (rc) return rc;
     h->launches += 2;
     return 0;
@@ -864,7 +738,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     h->ts.next_launch(a);
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     uint32_t grid = 0;
-    rc = h->ops->tile_pass(MODE_INGEST, a, pre, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+    rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
     h->launches++;
     h->mark(1, s);

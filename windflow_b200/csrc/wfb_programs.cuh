@@ -4,11 +4,12 @@
 //   tuple_t, result_t, key_t (uint64_t), params_t (functor objects / parameters, passed by value to kernels)
 //   map(tuple_t&, params)            Map_GPU functor      __host__ __device__ void(tuple_t &)           (API:50-52)
 //   filter(tuple_t&, params)->bool   Filter_GPU functor   __host__ __device__ bool(tuple_t &)           (API:34-36)
-//   key(const tuple_t&)->key_t       key extractor        __host__ __device__ key_t(const tuple_t &)    (API:213)
-//   lift(const tuple_t&, result_t&)  FFAT lift            (API:150-151)
-//   comb(a, b, out)                  FFAT combine (associative; must tolerate out aliasing a)  (API:153-154)
-//   make_result(key, gwid)           result_t(key, gwid) constructor (wf/basic_gpu.hpp:236-247)
-//   reduce(t1, t2)->tuple_t          Reduce_GPU functor   (API:78-79)
+//   key(const tuple_t&, params)->key_t       key extractor    __host__ __device__ key_t(const tuple_t &)    (API:213)
+//   lift(const tuple_t&, result_t&, params)  FFAT lift        (API:150-151)
+//   comb(a, b, out, params)                  FFAT combine (associative; must tolerate out aliasing a)  (API:153-154)
+//   make_result(key, gwid, params)           result_t(key, gwid) constructor (wf/basic_gpu.hpp:236-247)
+//   reduce(t1, t2, params)->tuple_t          Reduce_GPU functor   (API:78-79)
+// (every function receives the program's params_t, i.e. the functor objects, which the kernels carry by value)
 // User code writes the same struct around its own functors and instantiates the kernels with
 // WFB_DEFINE_PROGRAM (wfb_kernels.cuh); see INTEGRATION.md.
 #pragma once
@@ -35,21 +36,21 @@ struct ProgTuple64 {
         if (p.filt_kind == 2) return (t.ivalue % p.filt_mod) == 0;
         return true;
     }
-    __host__ __device__ static key_t key(const tuple_t &t) { return t.key; }
-    __host__ __device__ static void lift(const tuple_t &t, result_t &r)
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &) { return t.key; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &)
     {
         r.key = t.key; r.id = 0; r.isum = t.ivalue; r.fsum = t.fvalue;
     }
-    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out)
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &)
     {
         int64_t is = a.isum + b.isum; double fs = a.fsum + b.fsum;
         out.isum = is; out.fsum = fs;
     }
-    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid)
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &)
     {
         result_t r; r.key = k; r.id = gwid; r.isum = 0; r.fsum = 0.0; return r;
     }
-    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b)
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.ivalue = a.ivalue + b.ivalue; r.fvalue = a.fvalue + b.fvalue;
         r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0; return r;
@@ -74,11 +75,11 @@ struct ProgWfTest16 {
         if (p.filt_kind == 2) return (t.value % p.filt_mod) == 0;
         return true;
     }
-    __host__ __device__ static key_t key(const tuple_t &t) { return t.key; }
-    __host__ __device__ static void lift(const tuple_t &t, result_t &r) { r.key = t.key; r.id = 0; r.value = t.value; }
-    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out) { out.value = a.value + b.value; }
-    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
-    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b) // Reduce_Functor_GPU :268-279
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &) { return t.key; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r.key = t.key; r.id = 0; r.value = t.value; }
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &) { out.value = a.value + b.value; }
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &) // Reduce_Functor_GPU :268-279
     {
         tuple_t r; r.key = a.key; r.value = a.value + b.value; return r;
     }
@@ -102,11 +103,11 @@ struct ProgWfWin24 {
         if (p.filt_kind == 2) return (t.value % p.filt_mod) == 0;
         return true;
     }
-    __host__ __device__ static key_t key(const tuple_t &t) { return t.key; }
-    __host__ __device__ static void lift(const tuple_t &t, result_t &r) { r.key = t.key; r.id = 0; r.value = t.value; } // :295-303
-    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out) { out.value = a.value + b.value; } // :306-314
-    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
-    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b)
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &) { return t.key; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r.key = t.key; r.id = 0; r.value = t.value; } // :295-303
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &) { out.value = a.value + b.value; } // :306-314
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.value = a.value + b.value; return r;
     }
@@ -123,11 +124,11 @@ struct ProgLifted32 {
 
     __host__ __device__ static void map(tuple_t &, const params_t &) {}
     __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
-    __host__ __device__ static key_t key(const tuple_t &t) { return t.key; }
-    __host__ __device__ static void lift(const tuple_t &t, result_t &r) { r = t; }
-    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out) { ProgTuple64::comb(a, b, out); }
-    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid) { return ProgTuple64::make_result(k, gwid); }
-    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b)
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &) { return t.key; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r = t; }
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &p) { ProgTuple64::comb(a, b, out, p); }
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &p) { return ProgTuple64::make_result(k, gwid, p); }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.isum = a.isum + b.isum; r.fsum = a.fsum + b.fsum; return r;
     }
