@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K *__restrict__
 }
 
 // exclusive scan of `total` uint32 counters (in may alias out), one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, uint32_t *out, uint32_t total, uint32_t *sum_out)
+static __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, uint32_t *out, uint32_t total, uint32_t *sum_out)
 {
     __shared__ uint32_t warp_sums[32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
 }
 
 // seg_off[slot] = first sorted position of each key present in the segment (its length is seg_cnt[slot])
-__global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const uint32_t *__restrict__ n_ptr, uint32_t max_keys,
+static __global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const uint32_t *__restrict__ n_ptr, uint32_t max_keys,
                              uint32_t *__restrict__ seg_off)
 {
     const uint32_t n = *n_ptr;
@@ -1155,7 +1155,7 @@ __global__ void k_extract_keys(const unsigned char *__restrict__ tuples, uint32_
 
 // head[i] = 1 when sorted position i starts a new key; map_idxs links equal neighbours
 // (Compute_Mapping_Kernel, wf/keyby_emitter_gpu.hpp:84-100)
-__global__ void k_seg_heads(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, uint32_t n,
+static __global__ void k_seg_heads(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, uint32_t n,
                             uint32_t *__restrict__ head, int32_t *__restrict__ map_idxs)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1167,7 +1167,7 @@ __global__ void k_seg_heads(const uint64_t *__restrict__ skeys, const uint32_t *
 // after the exclusive scan of head[] (seg[i] = index of the segment sorted position i belongs to, for heads):
 // start_idxs[k] / dist_keys[k] of the k-th distinct key (unique_by_key_copy, wf/keyby_emitter_gpu.hpp:559-564),
 // seg_begin[k] = first sorted position of segment k (used by the reduce), *n_keys = number of segments
-__global__ void k_seg_finish(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, const uint32_t *__restrict__ head_scan,
+static __global__ void k_seg_finish(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx, const uint32_t *__restrict__ head_scan,
                              uint32_t n, int32_t *__restrict__ start_idxs, uint64_t *__restrict__ dist_keys,
                              uint32_t *__restrict__ seg_begin, uint32_t *__restrict__ n_keys)
 {
@@ -1287,7 +1287,7 @@ __global__ void k_gather_tuples(const unsigned char *__restrict__ tuples, const 
 }
 
 // seg_off[d] for d in [0, num_shards]: first sorted position whose destination is >= d (sorted dest array)
-__global__ void k_shard_offsets(const uint32_t *__restrict__ sdest, uint32_t n, uint32_t num_shards, uint32_t *__restrict__ seg_off)
+static __global__ void k_shard_offsets(const uint32_t *__restrict__ sdest, uint32_t n, uint32_t num_shards, uint32_t *__restrict__ seg_off)
 {
     for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d <= num_shards; d += gridDim.x * blockDim.x) {
         uint32_t lo = 0, hi = n; // lower_bound(sdest, d)
@@ -1297,7 +1297,7 @@ __global__ void k_shard_offsets(const uint32_t *__restrict__ sdest, uint32_t n, 
 }
 
 // pipelined window operator: hand the results of a finished segment over to the caller's buffers
-__global__ void k_copy_results(const unsigned char *__restrict__ src, const uint64_t *__restrict__ src_ts, const uint32_t *__restrict__ src_n,
+static __global__ void k_copy_results(const unsigned char *__restrict__ src, const uint64_t *__restrict__ src_ts, const uint32_t *__restrict__ src_n,
                                uint32_t rec_bytes, unsigned char *__restrict__ dst, uint64_t *__restrict__ dst_ts, uint32_t dst_cap,
                                uint32_t *__restrict__ n_out, uint32_t *__restrict__ err_flags)
 {
@@ -1323,7 +1323,7 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
     return x ^ (x >> 31);
 }
 
-__global__ void k_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys,
+static __global__ void k_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys,
                               const double *__restrict__ zipf_cdf, wfb_tuple64_t *__restrict__ out, uint64_t *__restrict__ ts)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
