@@ -74,6 +74,9 @@ struct FfatDev {
     struct Trigger *trig;      // deferred window groups of the current segment (evaluated by k_ffat_windows)
     uint32_t *n_trig;          // number of deferred groups
     uint32_t trig_cap;
+    uint32_t *heavy;           // slots with more than light_max items in the segment (handled warp-per-key)
+    uint32_t *n_heavy;
+    uint32_t light_max;
     // window geometry (in tuples and in panes)
     uint64_t win, slide, B;    // B = (Nb-1)*slide + win  (ffat_replica_gpu.hpp:657)
     uint32_t nb;               // windows per trigger
@@ -100,6 +103,8 @@ struct TileArgs {
     // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
     uint32_t nshards, region_cap;
     uint32_t *shard_counts;    // nshards totals (device)
+    // MODE_INGEST: digit histograms of the slot sort that follows (RadixSorter ctl), accumulated per CTA in shared memory
+    uint32_t *sort_ctl; uint32_t sort_passes;
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
     unsigned char *lifted;     // result_t per surviving tuple
     uint32_t *slots;           // slot per surviving tuple
@@ -262,7 +267,8 @@ struct TilePassSmem {
     static constexpr uint32_t tile_bytes = (TILE * rec_bytes + 1023u) & ~1023u; // swizzled stages need 512-B alignment
     static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : (MODE == MODE_FILTER ? TILE * 16u : 0u); // slots | ts in + ts out
     static constexpr uint32_t stage_bytes = tile_bytes + aux_bytes;
-    static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, meta, scan*/;
+    static constexpr uint32_t hist_bytes = (MODE == MODE_INGEST) ? 4u * 256u * 4u : 0u; // up to 4 sort passes
+    static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, meta, scan*/ + hist_bytes;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     uint64_t *empty = staged + STAGES;                           // STAGES  epilogue -> producer
     StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);  // STAGES
     uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 [x MAX_SHARDS] (double-buffered by iteration parity)
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(ctl + 1024);      // MODE_INGEST: [pass][256] digit counts of this CTA
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto stage_buf = [&](uint32_t s) { return smem + s * SM::stage_bytes; };
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&staged[s], TILE / 32); mbar_init(&empty[s], 1); }
         mbar_fence_init();
     }
+    if constexpr (MODE == MODE_INGEST) { for (uint32_t i = tid; i < 4u * 256u; i += TP_THREADS) s_hist[i] = 0; }
     __syncthreads();
 
     if (warp == 0) {
@@ -356,6 +364,12 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if (m.tile == TILE_SENTINEL) { // pass the end-of-work marker on to the epilogue warp
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&staged[s]);
+                if constexpr (MODE == MODE_INGEST) {
+                    if (a.sort_ctl != nullptr) { // every consumer is done counting: add this CTA's digit counts to the global ones
+                        consumer_bar();
+                        for (uint32_t i = ctid; i < a.sort_passes * 256u; i += TILE) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&a.sort_ctl[i], c); }
+                    }
+                }
                 break;
             }
             DevBatch b;
@@ -396,6 +410,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     P::lift(tup, res, prm);
                     slot = slot_of_key(a.ff, P::key(tup, prm));
                     if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                    if (a.sort_ctl != nullptr) // digit counts for the radix passes over the slots (invalid slots sort last)
+                        for (uint32_t ps = 0; ps < a.sort_passes; ps++) atomicAdd(&s_hist[ps * 256 + ((slot >> (8 * ps)) & 255u)], 1u);
                 }
             }
             if constexpr (MODE == MODE_SHARD) {
@@ -593,7 +609,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                         const uint32_t last_tile = b.tile_begin + (b.n + TILE - 1) / TILE - 1;
                         if (t == last_tile && b.n_out != nullptr) *b.n_out = excl + tile_count;
                     } else {
-                        if (t == 0) *a.ff.n_trig = 0; // deferred window groups of this segment (k_ffat_update runs later)
+                        if (t == 0) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists filled by the update kernels
                         if (t == b.tile_begin) a.batch_off[m.batch] = excl;
                         if (t == a.num_tiles - 1) { a.batch_off[a.nbatches] = excl + tile_count; *a.n_total = excl + tile_count; }
                     }
@@ -834,7 +850,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
                                                               uint32_t passes, uint32_t *__restrict__ ctl,
                                                               uint64_t *__restrict__ tile_state, uint32_t epoch,
                                                               const unsigned char *__restrict__ payload_in,
-                                                              unsigned char *__restrict__ payload_out, uint32_t payload_bytes)
+                                                              unsigned char *__restrict__ payload_out, uint32_t payload_bytes,
+                                                              uint32_t *__restrict__ seg_first, uint32_t seg_first_n)
 {
     __shared__ uint32_t cntw[OS_THREADS / 32][256]; // per-warp digit counts -> exclusive offsets over the warps
     __shared__ uint32_t dig_off[256];               // exclusive offset of each digit inside the tile
@@ -897,14 +914,22 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
 #pragma unroll
     for (uint32_t w = 0; w < OS_THREADS / 32; w++) if (w < warp) { gbase += wsum[w]; tbase += twsum[w]; }
     uint32_t excl = 0;
-    if (tile > 0) {
+    if (tile > 0) { // thread d walks digit d's chain back, 8 independent loads per step
         int64_t t2 = static_cast<int64_t>(tile) - 1;
-        while (true) {
-            const uint64_t w = ld_relaxed_u64(tile_state + static_cast<size_t>(t2) * 256 + tid);
-            if ((w >> 34) != (epoch & 0x3fffffffu) || ((w >> 32) & 3u) == 0) continue; // not published yet
-            excl += static_cast<uint32_t>(w);
-            if (((w >> 32) & 3u) == ST_PREFIX) break;
-            t2--;
+        bool found = false;
+        while (!found) {
+            uint64_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) w[q] = (t2 - q >= 0) ? ld_relaxed_u64(tile_state + static_cast<size_t>(t2 - q) * 256 + tid) : 0ull;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (found || t2 - q < 0) continue;
+                if ((w[q] >> 34) != (epoch & 0x3fffffffu) || ((w[q] >> 32) & 3u) == 0) { t2 -= q; goto next_round; } // not published yet: retry from here
+                excl += static_cast<uint32_t>(w[q]);
+                if (((w[q] >> 32) & 3u) == ST_PREFIX) found = true;
+            }
+            t2 -= 8;
+        next_round:;
         }
         st_relaxed_u64(my_state, pack_state(epoch, ST_PREFIX, excl + total));
     }
@@ -932,6 +957,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
         keys_out[dst] = kk;
         const uint32_t v = svals[i];
         vals_out[dst] = v;
+        // last pass of the window operator's sort: first sorted position of every key (entries start at 0xffffffff)
+        if (seg_first != nullptr && static_cast<uint64_t>(kk) < seg_first_n) atomicMin(&seg_first[static_cast<uint32_t>(kk)], dst);
         if (payload_out != nullptr) { // the last pass also moves the records: out[dst] = in[value]
             if ((payload_bytes & 15u) == 0) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(payload_in + static_cast<size_t>(v) * payload_bytes);
@@ -954,6 +981,121 @@ static __global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, c
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t s = sorted_slots[i];
         if (s < max_keys && (i == 0 || sorted_slots[i - 1] != s)) seg_off[s] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_ffat_update_lanes: ONE THREAD per key for the (usual) keys with few items in the segment: 65 536 keys are 65 536
+// independent, short sequential folds -- enough parallelism to hide the latency of the dependent loads that bound the
+// warp-per-key kernel. Each thread walks its key's items in arrival order (4 loads in flight), folds them into the open
+// pane; a completed pane is written as a FlatFAT leaf and its root path recomputed in a warp-converged step (all lanes
+// leave the item loop together when any of them completes a pane), fired groups go to the deferred window list.
+// Keys with more than ff.light_max items are put on the heavy list for k_ffat_update (warp per key).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t level_off(uint32_t n_leaves, uint32_t level);
+__device__ __forceinline__ uint64_t batch_watermark(const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                    uint32_t nbatches, uint32_t pos);
+template <class P>
+__device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsigned char *tree, uint64_t key, uint64_t gwid, uint64_t wm,
+                                                 uint32_t opos, unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts,
+                                                 uint32_t out_cap, const typename P::params_t &prm);
+
+template <class P>
+__global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, const unsigned char *__restrict__ lifted,
+                                                           const uint32_t *__restrict__ sorted_pos,
+                                                           const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                           uint32_t nbatches, unsigned char *__restrict__ out_res,
+                                                           uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
+                                                           uint32_t gather, const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    constexpr uint32_t U = 4; // item loads in flight per thread
+    const uint32_t nslots = ff.dense ? ff.max_keys : min(*ff.n_slots, ff.max_keys);
+    const uint32_t n = ff.n_leaves, logn = ff.log_leaves;
+    const uint64_t P_ = ff.pane;
+    const uint64_t group_items = ff.slide * ff.nb;
+    const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
+
+    for (uint32_t base = blockIdx.x * blockDim.x; base < nslots; base += gridDim.x * blockDim.x) { // block-uniform
+        const uint32_t slot = base + threadIdx.x;
+        uint32_t m = (slot < nslots) ? ff.seg_cnt[slot] : 0u;
+        if (m > ff.light_max) { // heavy key: k_ffat_update takes it (its seg_cnt stays for that kernel)
+            const uint32_t hi = atomicAdd(ff.n_heavy, 1u);
+            if (hi < ff.max_keys) ff.heavy[hi] = slot;
+            m = 0;
+        }
+        const bool act = m > 0;
+        uint32_t off = 0; uint64_t c = 0, key = 0, g = 0, trig = 0;
+        alignas(16) R acc;
+        unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
+        if (act) {
+            off = ff.seg_off[slot]; c = ff.cnt[slot];
+            key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+            if (c % P_ != 0) ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
+            g = (c < ff.B) ? 0 : 1 + (c - ff.B) / group_items;
+            trig = ff.B + g * group_items;
+        }
+        uint32_t j = 0;
+        while (__any_sync(FULL, act && j < m)) {
+            // ---- phase 1: fold items until the open pane completes (or the key runs out of items) -------------------
+            bool completed = false;
+            while (act && j < m && !completed) {
+                uint32_t p[U];
+                alignas(16) R it[U];
+                const uint32_t k = min(U, m - j);
+#pragma unroll
+                for (uint32_t q = 0; q < U; q++) if (q < k) p[q] = gather ? sorted_pos[off + j + q] : (off + j + q);
+#pragma unroll
+                for (uint32_t q = 0; q < U; q++) if (q < k) ld_rec<R>(lifted + static_cast<size_t>(p[q]) * RB, it[q]);
+#pragma unroll
+                for (uint32_t q = 0; q < U; q++) {
+                    if (q < k && !completed) {
+                        if (c % P_ == 0) acc = it[q]; else P::comb(acc, it[q], acc, prm);
+                        c++; j++;
+                        completed = (c % P_ == 0);
+                    }
+                }
+            }
+            // ---- phase 2 (warp-converged): new leaf, root path, fired groups -----------------------------------------------
+            if (completed) {
+                const uint32_t leaf = static_cast<uint32_t>((c / P_ - 1) & (n - 1));
+                for (uint32_t l = 0; l < logn; l++) // siblings towards L2 first: the sequential walk below then hits
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB));
+                alignas(16) R cur = acc;
+                st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
+                for (uint32_t l = 0; l < logn; l++) {
+                    alignas(16) R s;
+                    ld_rec<R>(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB, s);
+                    alignas(16) R parent = cur;
+                    if ((leaf >> l) & 1u) P::comb(s, cur, parent, prm); else P::comb(cur, s, parent, prm);
+                    cur = parent;
+                    st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                }
+                if (c == trig) {
+                    const uint32_t last_pos = sorted_pos[off + j - 1]; // arrival position of the triggering item
+                    const uint32_t obase = atomicAdd(n_out, ff.nb);
+                    bool deferred = (m - j) < P_; // no further pane of this key can complete in this segment
+                    if (deferred) {
+                        const uint32_t ti = atomicAdd(ff.n_trig, 1u);
+                        if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
+                        else deferred = false;
+                    }
+                    if (!deferred) {
+                        const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
+                        for (uint32_t i = 0; i < ff.nb; i++)
+                            ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap, prm);
+                    }
+                    g++; trig += group_items;
+                }
+            }
+        }
+        if (act) {
+            ff.cnt[slot] = c;
+            if (c % P_ != 0) st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
+            ff.seg_cnt[slot] = 0;
+            ff.seg_off[slot] = 0xffffffffu; // the next segment's sort records the key's first position with atomicMin
+        }
     }
 }
 
@@ -1035,7 +1177,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                                                      const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
                                                      uint32_t nbatches, unsigned char *__restrict__ out_res,
                                                      uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
-                                                     uint32_t gather, const typename P::params_t prm)
+                                                     uint32_t gather, const typename P::params_t prm, uint32_t use_heavy_list)
 {
     using R = typename P::result_t;
     constexpr uint32_t RB = sizeof(R);
@@ -1048,7 +1190,10 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
     const uint64_t group_items = ff.slide * ff.nb;
     const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
 
-    for (uint32_t slot = gwarp; slot < nslots; slot += nwarps) {
+    // use_heavy_list = 1: only the keys k_ffat_update_lanes put on the heavy list; 0: every key of the segment
+    const uint32_t nwork = use_heavy_list ? min(*ff.n_heavy, ff.max_keys) : nslots;
+    for (uint32_t wi = gwarp; wi < nwork; wi += nwarps) {
+        const uint32_t slot = use_heavy_list ? ff.heavy[wi] : wi;
         const uint32_t m = ff.seg_cnt[slot];
         if (m == 0) continue;
         const uint32_t off = ff.seg_off[slot];
@@ -1132,6 +1277,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
             ff.cnt[slot] = c;
             if (c % P_ != 0) st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
             ff.seg_cnt[slot] = 0;
+            ff.seg_off[slot] = 0xffffffffu;
         }
     }
 }

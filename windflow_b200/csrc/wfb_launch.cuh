@@ -64,7 +64,7 @@ struct ProgramOps {
                      uint64_t span_begin, uint64_t span_end);
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params);
+                       uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params, uint32_t lanes_grid);
     int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
                         unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params);
     int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s,
@@ -127,10 +127,18 @@ int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_
 template <class P>
 int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                          const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
-                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params)
+                         uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params,
+                         uint32_t lanes_grid)
 {
-    k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather,
-                                          load_params<P>(params));
+    const typename P::params_t prm = load_params<P>(params);
+    if (lanes_grid) { // thread-per-key pass for the light keys, then warp-per-key only for the heavy list it produced
+        k_ffat_update_lanes<P><<<lanes_grid, 128, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out,
+                                                           gather, prm);
+        k_ffat_update<P><<<std::max(1u, std::min(grid, static_cast<uint32_t>(wfb::num_sms()) * 2u)), 256, 0, s>>>(
+            ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather, prm, 1u);
+    } else {
+        k_ffat_update<P><<<grid, 256, 0, s>>>(ff, lifted, sorted_pos, batch_off, batches, nbatches, out_res, out_ts, out_cap, n_out, gather, prm, 0u);
+    }
     WFB_CK(cudaGetLastError());
     return 0;
 }

@@ -125,17 +125,33 @@ struct RadixSorter {
     // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
     template <class K, int ITEMS>
     void launch_pass(uint32_t tiles, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host,
-                     uint32_t p, uint32_t passes, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes)
+                     uint32_t p, uint32_t passes, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
+                     uint32_t *seg_first, uint32_t seg_first_n)
     {
         k_onesweep_pass<K, ITEMS><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch,
-                                                               pin, pout, pbytes);
+                                                               pin, pout, pbytes, seg_first, seg_first_n);
+    }
+
+    // clears the histograms / tickets of the next sort; call it BEFORE a producer that fills the histograms itself
+    static constexpr size_t CTL_WORDS = OS_MAX_PASSES * 256 + OS_MAX_PASSES;
+    static int prepare(uint32_t *ctl_buf, uint32_t passes, cudaStream_t s)
+    {
+        passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
+        WFB_CK(cudaMemsetAsync(ctl_buf, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
+        return 0;
     }
 
     template <class K>
     int sort(K *kA, K *kB, uint32_t *vA, uint32_t *vB, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t passes,
              cudaStream_t s, const K **skeys, const uint32_t **svals,
-             const unsigned char *payload_in = nullptr, unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0)
+             const unsigned char *payload_in = nullptr, unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0,
+             uint32_t *ready_ctl = nullptr, uint32_t *seg_first = nullptr, uint32_t seg_first_n = 0)
     {
+        // ready_ctl != nullptr: histograms already accumulated there by the producer of the keys (after prepare())
+        uint32_t *const own_ctl = ctl;
+        const bool hist_ready = ready_ctl != nullptr;
+        if (hist_ready) ctl = ready_ctl;
+        struct Restore { uint32_t *&c; uint32_t *v; ~Restore() { c = v; } } restore{ctl, own_ctl};
         static int items = 0; // elements per thread of a pass (tuning knob: WFB_OS_ITEMS = 4, 8 or 16)
         if (items == 0) {
             const char *e = std::getenv("WFB_OS_ITEMS");
@@ -146,9 +162,12 @@ struct RadixSorter {
         const uint32_t TE = OS_THREADS * static_cast<uint32_t>(items);
         int rc = ensure(cap, OS_THREADS * 4, s); if (rc) return rc;
         passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
-        CK(cudaMemsetAsync(ctl, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
         const uint32_t tiles = std::max(1u, (cap + TE - 1) / TE);
-        k_radix_ghist<K><<<std::min(tiles, static_cast<uint32_t>(g_num_sms) * 4u), 256, 0, s>>>(kA, n_ptr, n_host, passes, ctl);
+        if (!hist_ready) {
+            CK(cudaMemsetAsync(ctl, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
+            k_radix_ghist<K><<<std::min(tiles, static_cast<uint32_t>(g_num_sms) * 4u), 256, 0, s>>>(kA, n_ptr, n_host, passes, ctl);
+            launches++;
+        }
         const K *kin = kA; const uint32_t *vin = nullptr;
         K *kout = kB; uint32_t *vout = vB;
         for (uint32_t p = 0; p < passes; p++) {
@@ -156,14 +175,15 @@ struct RadixSorter {
             const bool last = (p + 1 == passes);
             const unsigned char *pin = last ? payload_in : nullptr;
             unsigned char *pout = last ? payload_out : nullptr;
-            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
-            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
-            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes);
+            uint32_t *sf = last ? seg_first : nullptr;
+            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
+            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
+            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
             kin = kout; vin = vout;
             if (kout == kB) { kout = kA; vout = vA; } else { kout = kB; vout = vB; }
         }
         CK(cudaGetLastError());
-        launches += 1 + passes;
+        launches += passes;
         *skeys = kin; *svals = vin;
         return 0;
     }
@@ -229,16 +249,18 @@ struct SegScratch {
     uint32_t *n_total = nullptr;
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
+    uint32_t *n_heavy = nullptr;
+    uint32_t *sort_ctl = nullptr;         // digit histograms + tickets of this segment's slot sort
     // pipelined mode: results of the segment wait here until the next call / flush delivers them
     unsigned char *res = nullptr; uint64_t *res_ts = nullptr; uint32_t *res_n = nullptr; uint32_t res_cap = 0;
     cudaEvent_t ev_ingest = nullptr, ev_done = nullptr;
-    bool pending = false;
+    bool pending = false, hist_ready = false;
     uint32_t nbatches = 0, total = 0;
 
     void destroy()
     {
         cudaFree(lifted); cudaFree(lifted_sorted); cudaFree(slotsA); cudaFree(slotsB); cudaFree(posA); cudaFree(posB);
-        cudaFree(batch_off); cudaFree(d_batches); cudaFree(n_total); cudaFree(seg_cnt); cudaFree(trig);
+        cudaFree(batch_off); cudaFree(d_batches); cudaFree(n_total); cudaFree(seg_cnt); cudaFree(trig); cudaFree(sort_ctl);
         cudaFree(res); cudaFree(res_ts); // n_trig and res_n live inside the n_total allocation
         if (ev_ingest) cudaEventDestroy(ev_ingest);
         if (ev_done) cudaEventDestroy(ev_done);
@@ -561,6 +583,9 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     ALLOC(ff.tree, tree_bytes);
     CK(cudaMemset(ff.tree, 0, tree_bytes));
     ALLOC(ff.seg_off, sizeof(uint32_t) * (static_cast<size_t>(max_keys) + 1));
+    CK(cudaMemset(ff.seg_off, 0xff, sizeof(uint32_t) * (static_cast<size_t>(max_keys) + 1)));
+    ALLOC(ff.heavy, sizeof(uint32_t) * max_keys);
+    { const char *e = std::getenv("WFB_LIGHT_MAX"); ff.light_max = e ? static_cast<uint32_t>(std::atoi(e)) : 256u; }
     h->pipelined = (flags & WFB_FFAT_PIPELINED) != 0;
     for (int p = 0; p < (h->pipelined ? 2 : 1); p++) {
         SegScratch &g = h->seg[p];
@@ -568,7 +593,8 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         CK(cudaMemset(g.seg_cnt, 0, sizeof(uint32_t) * max_keys));
         ALLOC(g.n_total, sizeof(uint32_t) * 4);
         CK(cudaMemset(g.n_total, 0, sizeof(uint32_t) * 4));
-        g.n_trig = g.n_total + 1; g.res_n = nullptr;
+        g.n_trig = g.n_total + 1; g.res_n = nullptr; g.n_heavy = g.n_total + 3;
+        ALLOC(g.sort_ctl, sizeof(uint32_t) * RadixSorter::CTL_WORDS);
         CK(cudaEventCreateWithFlags(&g.ev_ingest, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming));
     }
@@ -591,7 +617,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaDeviceSynchronize();
     FfatDev &ff = h->ff;
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
-    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off);
+    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off); cudaFree(ff.heavy);
     for (int p = 0; p < 2; p++) h->seg[p].destroy();
     h->sorter.destroy();
     if (h->s2) cudaStreamDestroy(h->s2);
@@ -655,23 +681,20 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
     const uint64_t before = h->sorter.launches;
     int rc = h->sorter.sort<uint32_t>(g.slotsA, g.slotsB, g.posA, g.posB, g.n_total, 0, g.total, h->sort_passes, s, &sorted_slots,
                                       &sorted_pos, h->move_payload ? g.lifted : nullptr, h->move_payload ? g.lifted_sorted : nullptr,
-                                      h->ops->result_bytes);
+                                      h->ops->result_bytes, g.hist_ready ? g.sort_ctl : nullptr, ff.seg_off, ff.max_keys);
     if (rc) return rc;
     h->launches += h->sorter.launches - before;
-    // first sorted position of every key present in the segment
-    k_seg_starts<<<std::min((g.total + 255u) / 256u, static_cast<uint32_t>(g_num_sms) * 8u), 256, 0, s>>>(sorted_slots, g.n_total,
-                                                                                                         ff.max_keys, ff.seg_off);
-    CK(cudaGetLastError());
-    h->launches++;
+    (void) sorted_slots; // the last pass also recorded the first sorted position of every key in ff.seg_off
     h->mark(2, s);
     // one warp per key: pane fold, FlatFAT update; then one thread per fired window
     uint32_t ugrid = std::max(1u, std::min((ff.max_keys + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u));
     rc = h->ops->ffat_update(ff, h->move_payload ? g.lifted_sorted : g.lifted, sorted_pos, g.batch_off, g.d_batches, g.nbatches,
-                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u, h->pp());
+                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u, h->pp(),
+                             h->ff.light_max ? std::max(1u, std::min((ff.max_keys + 127u) / 128u, static_cast<uint32_t>(g_num_sms) * 16u)) : 0u);
     if (rc) return rc;
     rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp());
     if (rc) return rc;
-    h->launches += 2;
+    h->launches += h->ff.light_max ? 3 : 2;
     return 0;
 }
 
@@ -728,11 +751,15 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     g.nbatches = nbatches; g.total = static_cast<uint32_t>(total);
 
     FfatDev ff = h->ff; // this call's view of the state: per-segment buffers of parity `par`
-    ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap;
+    ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap; ff.n_heavy = g.n_heavy;
 
+    const bool fuse_hist = h->sort_passes <= 4; // the streaming pass also counts the digits of the slot sort that follows
+    if (fuse_hist) { rc = RadixSorter::prepare(g.sort_ctl, h->sort_passes, s); if (rc) return rc; }
     h->mark(0, s);
     // 1. streaming pass: [map -> filter ->] lift, key -> slot, stable compaction over the whole segment
     TileArgs a; std::memset(&a, 0, sizeof(a));
+    if (fuse_hist) { a.sort_ctl = g.sort_ctl; a.sort_passes = h->sort_passes; }
+    g.hist_ready = fuse_hist;
     a.batches = g.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
     a.lifted = g.lifted; a.slots = g.slotsA; a.batch_off = g.batch_off; a.n_total = g.n_total; a.ff = ff;
     h->ts.next_launch(a);
