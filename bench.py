@@ -114,19 +114,18 @@ class ClockSampler:
 # CPU arm: the reference's CPU Map -> Filter -> Ffat_Windows path on the host cores
 # ----------------------------------------------------------------------------------------------------------
 def cpu_pipeline(kind, threads, target_seconds, keys_per_thread=64):
-    """Bounded steady-state sample: `threads` replicas (keyby shards), each owning `keys_per_thread` keys of a
-    uniform-key tuple64 stream; state primed until every key fires windows, then timed. Returns (tuples/s, desc)."""
+    """Bounded steady-state sample: `threads` replicas, each a keyby shard owning `keys_per_thread` keys and fed its own
+    (already routed) tuple64 stream; state primed until every key fires windows, then timed. Returns (tuples/s, desc)."""
     from oracle import oracle as O
-    nkeys = keys_per_thread * threads
-    n_buf = 1 << 21
-    tuples, ts = O.gen_tuple64(0, n_buf, O.KEY_UNIFORM, nkeys)
-    pipes = [O.CpuPipe(kind, 1, 2, 1.0000001, 1, 1, WIN, SLIDE, s, threads) for s in range(threads)]
+    n_buf = 1 << 18
+    bufs = [O.gen_tuple64(s * n_buf, n_buf, O.KEY_UNIFORM, keys_per_thread) for s in range(threads)]
+    pipes = [O.CpuPipe(kind, 1, 2, 1.0000001, 1, 1, WIN, SLIDE, 0, 1) for _ in range(threads)]
 
     def run_all(reps):
-        def work(p):
+        def work(p, buf):
             for _ in range(reps):
-                p.run(tuples, ts, BATCH)
-        th = [threading.Thread(target=work, args=(p,)) for p in pipes]
+                p.run(buf[0], buf[1], BATCH)
+        th = [threading.Thread(target=work, args=(p, b)) for p, b in zip(pipes, bufs)]
         t0 = time.perf_counter()
         for t in th:
             t.start()
@@ -134,7 +133,7 @@ def cpu_pipeline(kind, threads, target_seconds, keys_per_thread=64):
             t.join()
         return time.perf_counter() - t0
 
-    prime_reps = int(np.ceil(WIN * nkeys / SIGMA / n_buf)) + 1   # every key past its first window
+    prime_reps = int(np.ceil(WIN * keys_per_thread / SIGMA / n_buf)) + 1   # every key past its first window
     run_all(prime_reps)
     dt1 = run_all(1)
     reps = max(1, int(target_seconds / max(dt1, 1e-3)))
@@ -143,11 +142,10 @@ def cpu_pipeline(kind, threads, target_seconds, keys_per_thread=64):
     nwin = sum(p.windows for p in pipes) - w0
     for p in pipes:
         p.close()
-    tps = reps * n_buf / dt
-    desc = (f"{reps} x {n_buf} tuple64 (uniform over {nkeys} keys = {keys_per_thread}/thread, win {WIN} slide {SLIDE}, "
-            f"state primed to steady state; {nwin} windows in the timed sample); "
-            f"{'reference wf/flatfat.hpp under the restated FFAT_Replica loop' if kind == 'reference' else 'oracle port of map.hpp/filter.hpp/ffat_replica.hpp/flatfat.hpp'}; "
-            f"{threads} keyby-sharded replica threads")
+    tps = reps * n_buf * threads / dt
+    desc = (f"{threads} replica threads x {reps} x {n_buf} tuple64 (each thread = one keyby shard with {keys_per_thread} uniform keys, "
+            f"already routed; win {WIN} slide {SLIDE}; state primed to steady state; {nwin} windows in the timed sample); "
+            f"{'reference wf/flatfat.hpp under the restated FFAT_Replica loop' if kind == 'reference' else 'oracle port of map.hpp/filter.hpp/ffat_replica.hpp/flatfat.hpp'}")
     return tps, desc
 
 
@@ -174,7 +172,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "tuples/sec, Map->Filter->Ffat_Windows (CB win 4096 slide 64) pipeline", "value": v,
         "unit": "tuples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (1 << 21) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * (1 << 18) * threads / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64+f64", "data": "synthetic",
         "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES, "win": WIN, "slide": SLIDE,
                    "note": "CPU path of the reference on host cores; bounded steady-state sample per step"},
@@ -209,7 +207,7 @@ def run_ours(args):
     nb = args.nb
     B = (nb - 1) * SLIDE + WIN
     f = ops.functors(**MAP, **FILT)
-    pipelined = not args.no_pipeline
+    pipelined = args.pipeline
 
     # ---- input ring, resident in HBM (larger than L2: ring * seg_tuples * 64 B) ---------------------------------
     # N = 1: one fused call per segment. N > 1: rank r owns the K batches [r*K, (r+1)*K) of every
@@ -314,7 +312,7 @@ def run_ours(args):
                        "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0", "selectivity": SIGMA,
                        "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
                        "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
-                       "pipelined": not args.no_pipeline,
+                       "pipelined": args.pipeline,
                        "parallelism": f"keyby{world}" + ("" if world == 1 else " (fused Map->Filter->lift->shard | NCCL all-to-all of 32-B results | Ffat on the key shard)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -418,7 +416,7 @@ def main():
     ap.add_argument("--nb", type=int, default=65, help="withNumWinPerBatch")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--no-pipeline", action="store_true", help="results of a segment returned by the same call (no overlap)")
+    ap.add_argument("--pipeline", action="store_true", help="WFB_FFAT_PIPELINED handle: results one call late, sort+update overlap the next ingest")
     ap.add_argument("--prime-steps", type=int, default=-1, help="override state priming (ncu runs); default: steady state")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
