@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwfb200.so")
+LIB_PATH = os.environ.get("WFB_LIB") or os.path.join(HERE, "libwfb200.so")  # WFB_LIB: another build of the same library (kernel tuning)
 
 u8p, vp = C.c_void_p, C.c_void_p
 u32, u64, i32, i64, f64 = C.c_uint32, C.c_uint64, C.c_int32, C.c_int64, C.c_double

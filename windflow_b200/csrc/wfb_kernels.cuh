@@ -17,6 +17,7 @@
 //   k_ffat_update          one warp per key: ordered pane fold, FlatFAT leaf write + path update, window
 //                          queries (wf/flatfat_gpu.hpp:62-139, wf/ffat_replica_gpu.hpp:830-867)
 #pragma once
+#include <type_traits>
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -100,11 +101,12 @@ struct TileArgs {
     uint64_t tmap_base;        // global address the 2-D tensor map starts at (rows of 64 bytes)
     uint32_t use_tmap;         // 1: `tmap` is valid for this launch
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
+    uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
     // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
     uint32_t nshards, region_cap;
     uint32_t *shard_counts;    // nshards totals (device)
     // MODE_INGEST: digit histograms of the slot sort that follows (RadixSorter ctl), accumulated per CTA in shared memory
-    uint32_t *sort_ctl; uint32_t sort_passes;
+    uint32_t *sort_ctl; uint32_t sort_passes, sort_shift, sort_dbits; // sort_dbits: digit width of a pass (8, or 10 for the wide pass)
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
     unsigned char *lifted;     // result_t per surviving tuple
     uint32_t *slots;           // slot per surviving tuple
@@ -280,6 +282,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, in
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const void *tmap, int32_t c0, int32_t c1, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void *tmap, int32_t c0, int32_t c1, const void *smem_src)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     uint64_t *empty = staged + STAGES;                           // STAGES  epilogue -> producer
     StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);  // STAGES
     uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 [x MAX_SHARDS] (double-buffered by iteration parity)
-    uint32_t *s_hist = reinterpret_cast<uint32_t *>(ctl + 1024);      // MODE_INGEST: [pass][256] digit counts of this CTA
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(ctl + 1024);      // MODE_INGEST: [pass][1 << sort_dbits] digit counts of this CTA (1024 words)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto stage_buf = [&](uint32_t s) { return smem + s * SM::stage_bytes; };
@@ -323,6 +330,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     if (warp == 0) {
         // ================================= PRODUCER =================================
         if (lane == 0) {
+            const uint64_t pol_first = l2_policy_evict_first();
             for (uint32_t it = 0;; it++) {
                 const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], par ^ 1u); // a fresh barrier passes the wait on parity 1
@@ -348,7 +356,10 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 if (tsp != nullptr && bulk_ok(tsp, cnt * 8u)) { flags |= TF_TS_SMEM; tx += cnt * 8u; }
                 m.tile = t; m.batch = bi; m.first = first; m.cnt = cnt; m.flags = flags;
                 if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
-                if (flags & TF_SWZ) tma_load_2d(stage_buf(s), &tmap, 0, static_cast<int32_t>(off >> 6), &full[s]);
+                if (a.l2_hints) { // read-once stream: first in line for eviction
+                    if (flags & TF_SWZ) tma_load_2d_hint(stage_buf(s), &tmap, 0, static_cast<int32_t>(off >> 6), &full[s], pol_first);
+                    else if (!(flags & TF_FALLBACK)) bulk_g2s_hint(stage_buf(s), src, cnt * TB, &full[s], pol_first);
+                } else if (flags & TF_SWZ) tma_load_2d(stage_buf(s), &tmap, 0, static_cast<int32_t>(off >> 6), &full[s]);
                 else if (!(flags & TF_FALLBACK)) bulk_g2s(stage_buf(s), src, cnt * TB, &full[s]);
                 if (flags & TF_TS_SMEM) bulk_g2s(stage_aux(s), tsp, cnt * 8u, &full[s]);
             }
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 if constexpr (MODE == MODE_INGEST) {
                     if (a.sort_ctl != nullptr) { // every consumer is done counting: add this CTA's digit counts to the global ones
                         consumer_bar();
-                        for (uint32_t i = ctid; i < a.sort_passes * 256u; i += TILE) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&a.sort_ctl[i], c); }
+                        for (uint32_t i = ctid; i < (a.sort_passes << a.sort_dbits); i += TILE) { const uint32_t c = s_hist[i]; if (c) atomicAdd(&a.sort_ctl[i], c); }
                     }
                 }
                 break;
@@ -411,7 +422,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     slot = slot_of_key(a.ff, P::key(tup, prm));
                     if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
                     if (a.sort_ctl != nullptr) // digit counts for the radix passes over the slots (invalid slots sort last)
-                        for (uint32_t ps = 0; ps < a.sort_passes; ps++) atomicAdd(&s_hist[ps * 256 + ((slot >> (8 * ps)) & 255u)], 1u);
+                        for (uint32_t ps = 0; ps < a.sort_passes; ps++)
+                            atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
                 }
             }
             if constexpr (MODE == MODE_SHARD) {
@@ -624,7 +636,10 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if (MODE == MODE_MAP && (m.flags & TF_SWZ)) {
                 if (lane == 0) tma_store_2d(&tmap, 0, static_cast<int32_t>((reinterpret_cast<uint64_t>(dst) - a.tmap_base) >> 6), buf);
             } else if (bulk_ok(dst, bytes)) {
-                if (lane == 0 && bytes) bulk_s2g(dst, buf, bytes);
+                if (lane == 0 && bytes) {
+                    if ((MODE == MODE_INGEST) && a.l2_hints) bulk_s2g_hint(dst, buf, bytes, l2_policy_evict_last());
+                    else bulk_s2g(dst, buf, bytes);
+                }
             } else {
                 uint64_t *d8 = reinterpret_cast<uint64_t *>(dst);
                 const uint64_t *s8 = reinterpret_cast<const uint64_t *>(buf);
@@ -829,7 +844,7 @@ template <class K> struct OsCfg { static constexpr int MAX_ITEMS = sizeof(K) == 
 
 template <class K>
 __global__ void __launch_bounds__(256) k_radix_ghist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
-                                                     uint32_t passes, uint32_t *__restrict__ ctl)
+                                                     uint32_t passes, uint32_t *__restrict__ ctl, uint32_t base_shift)
 {
     __shared__ uint32_t h[OS_MAX_PASSES * 256];
     const uint32_t n = n_ptr ? *n_ptr : n_host;
@@ -837,7 +852,7 @@ __global__ void __launch_bounds__(256) k_radix_ghist(const K *__restrict__ keys,
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const K k = keys[i];
-        for (uint32_t p = 0; p < passes; p++) atomicAdd(&h[p * 256 + (static_cast<uint32_t>(k >> (8 * p)) & 255u)], 1u);
+        for (uint32_t p = 0; p < passes; p++) atomicAdd(&h[p * 256 + (static_cast<uint32_t>(k >> (base_shift + 8 * p)) & 255u)], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < passes * 256; i += blockDim.x) if (h[i]) atomicAdd(&ctl[i], h[i]);
@@ -851,7 +866,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
                                                               uint64_t *__restrict__ tile_state, uint32_t epoch,
                                                               const unsigned char *__restrict__ payload_in,
                                                               unsigned char *__restrict__ payload_out, uint32_t payload_bytes,
-                                                              uint32_t *__restrict__ seg_first, uint32_t seg_first_n)
+                                                              uint32_t *__restrict__ seg_first, uint32_t seg_first_n,
+                                                              uint32_t base_shift)
 {
     __shared__ uint32_t cntw[OS_THREADS / 32][256]; // per-warp digit counts -> exclusive offsets over the warps
     __shared__ uint32_t dig_off[256];               // exclusive offset of each digit inside the tile
@@ -865,7 +881,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = n_ptr ? *n_ptr : n_host;
     const uint32_t num_tiles = (n + OS_TILE - 1) / OS_TILE;
-    const uint32_t shift = 8 * pass;
+    const uint32_t shift = base_shift + 8 * pass;
     if (tid == 0) s_tile = atomicAdd(&ctl[passes * 256 + pass], 1u);
 #pragma unroll
     for (int w = 0; w < OS_THREADS / 32; w++) cntw[w][tid] = 0;
@@ -967,6 +983,176 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
             } else {
                 const uint64_t *src = reinterpret_cast<const uint64_t *>(payload_in + static_cast<size_t>(v) * payload_bytes);
                 uint64_t *dstp = reinterpret_cast<uint64_t *>(payload_out + static_cast<size_t>(dst) * payload_bytes);
+                for (uint32_t q = 0; q < payload_bytes / 8; q++) dstp[q] = src[q];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Wide partition: ONE stable pass on a 10-bit digit (1024 bins) without a chained scan -- with 1024 bins a tile holds
+// only a few elements per bin, so the look-back chains of k_onesweep_pass are long and cheap to avoid:
+//   k_wide_tile_hist  per-tile digit counts H[tile][1024] (16-bit) + their sums over chunks of 2^chunk_shift tiles
+//                     C[chunk][1024] (+ the global counts ctl[1024] unless the producer of the keys already made them)
+//   k_wide_scatter    rank inside the tile (warp match_any, warps in index order), base of (tile, digit) =
+//                     exclusive scan of ctl over the digits + C rows of the earlier chunks + H rows of the earlier
+//                     tiles of the own chunk; elements go straight to their final position
+// The window operator uses it to split a segment's (slot, arrival position) pairs into 1024 buckets of consecutive
+// slots (k_ffat_update_buckets finishes the grouping inside each bucket).
+// ------------------------------------------------------------------------------------------------------
+#ifndef WFB_OSW_MINBLOCKS
+#define WFB_OSW_MINBLOCKS 4
+#endif
+constexpr uint32_t OSW_BITS = 10, OSW_DIGITS = 1u << OSW_BITS;
+constexpr uint32_t OSW_THREADS = 256, OSW_ITEMS = 16, OSW_TILE = OSW_THREADS * OSW_ITEMS; // 4096 elements per tile
+
+template <class K>
+__global__ void __launch_bounds__(OSW_THREADS) k_wide_tile_hist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
+                                                                uint32_t shift, uint32_t chunk_shift, uint16_t *__restrict__ H,
+                                                                uint32_t *__restrict__ C, uint32_t *__restrict__ ctl_counts)
+{
+    static_assert(OSW_THREADS * 4 == OSW_DIGITS, "four digits per thread");
+    __shared__ __align__(16) uint32_t h[OSW_DIGITS];
+    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
+    const uint32_t start = tile * OSW_TILE;
+    if (start >= n) return;
+    reinterpret_cast<uint4 *>(h)[tid] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        const uint32_t idx = start + r * OSW_THREADS + tid;
+        if (idx < n) atomicAdd(&h[static_cast<uint32_t>(keys[idx] >> shift) & (OSW_DIGITS - 1u)], 1u);
+    }
+    __syncthreads();
+    const uint4 c = reinterpret_cast<const uint4 *>(h)[tid];
+    reinterpret_cast<ushort4 *>(H + static_cast<size_t>(tile) * OSW_DIGITS)[tid] =
+        make_ushort4(static_cast<uint16_t>(c.x), static_cast<uint16_t>(c.y), static_cast<uint16_t>(c.z), static_cast<uint16_t>(c.w));
+    uint32_t *crow = C + static_cast<size_t>(tile >> chunk_shift) * OSW_DIGITS + tid * 4;
+    if (c.x) atomicAdd(crow + 0, c.x);
+    if (c.y) atomicAdd(crow + 1, c.y);
+    if (c.z) atomicAdd(crow + 2, c.z);
+    if (c.w) atomicAdd(crow + 3, c.w);
+    if (ctl_counts != nullptr) {
+        if (c.x) atomicAdd(ctl_counts + tid * 4 + 0, c.x);
+        if (c.y) atomicAdd(ctl_counts + tid * 4 + 1, c.y);
+        if (c.z) atomicAdd(ctl_counts + tid * 4 + 2, c.z);
+        if (c.w) atomicAdd(ctl_counts + tid * 4 + 3, c.w);
+    }
+}
+
+// RBYTES: bytes of the payload record that travels with each element (payload_out[dst] = payload_in[index]); 0 = none,
+// -1 = run-time size `payload_bytes` (multiple of 8)
+template <class K, int RBYTES>
+__global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter(const K *__restrict__ keys_in, K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                              const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t shift,
+                                                              uint32_t chunk_shift, const uint16_t *__restrict__ H, const uint32_t *__restrict__ C,
+                                                              const uint32_t *__restrict__ ctl_counts,
+                                                              const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
+                                                              uint32_t payload_bytes)
+{
+    constexpr uint32_t NW = OSW_THREADS / 32;
+    __shared__ __align__(16) uint16_t cntw[NW][OSW_DIGITS]; // per-warp digit counts -> exclusive offsets over the warps
+    __shared__ uint32_t bin_base[OSW_DIGITS];               // global position of the tile's first element of each digit
+    __shared__ uint32_t wsum[NW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+    const uint32_t n = n_ptr ? *n_ptr : n_host;
+    const uint32_t start = tile * OSW_TILE;
+    if (start >= n) return;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(&cntw[0][0]);
+        for (uint32_t i = tid; i < NW * OSW_DIGITS / 8; i += OSW_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    // base of (tile, digit) for digits 4*tid .. 4*tid+3: rows of earlier chunks + rows of earlier tiles of this chunk
+    uint32_t acc[4] = {0, 0, 0, 0};
+    {
+        const uint32_t chunk = tile >> chunk_shift;
+        const uint4 *crow = reinterpret_cast<const uint4 *>(C) + tid;
+#pragma unroll 8
+        for (uint32_t c = 0; c < chunk; c++) { const uint4 v = crow[static_cast<size_t>(c) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+        const ushort4 *hrow = reinterpret_cast<const ushort4 *>(H) + tid;
+#pragma unroll 8
+        for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const ushort4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+    }
+    const uint4 g4 = reinterpret_cast<const uint4 *>(ctl_counts)[tid];
+    const uint32_t gsum = g4.x + g4.y + g4.z + g4.w;
+    uint32_t incl = gsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+
+    // ---- stable in-tile ranks: warp w owns [start + w*32*ITEMS, +32*ITEMS), 32 consecutive elements per round --------
+    K k[OSW_ITEMS];
+    uint32_t rk[OSW_ITEMS];
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+        k[r] = idx < n ? keys_in[idx] : K(0);
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u)) : OSW_DIGITS;
+        const uint32_t mask = __match_any_sync(FULL, d);
+        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
+        __syncwarp();
+        if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] = static_cast<uint16_t>(cntw[warp][d] + __popc(mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t gb = incl - gsum;
+#pragma unroll
+        for (uint32_t w = 0; w < NW; w++) if (w < warp) gb += wsum[w];
+        uint32_t run[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (uint32_t w = 0; w < NW; w++) { // exclusive offsets over the warps
+            ushort4 *row = reinterpret_cast<ushort4 *>(&cntw[w][0]);
+            const ushort4 c = row[tid];
+            row[tid] = make_ushort4(static_cast<uint16_t>(run[0]), static_cast<uint16_t>(run[1]), static_cast<uint16_t>(run[2]), static_cast<uint16_t>(run[3]));
+            run[0] += c.x; run[1] += c.y; run[2] += c.z; run[3] += c.w;
+        }
+        const uint32_t gc[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) { bin_base[tid * 4 + q] = gb + acc[q]; gb += gc[q]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u);
+            const uint32_t dst = bin_base[d] + cntw[warp][d] + rk[r];
+            keys_out[dst] = k[r];
+            vals_out[dst] = idx;
+            rk[r] = dst;
+        }
+    }
+    if constexpr (RBYTES > 0) { // records: read in index order (coalesced), written next to the other records of their bin
+        using V = typename std::conditional<RBYTES % 16 == 0, uint4, uint2>::type;
+        constexpr uint32_t NV = RBYTES / sizeof(V);
+#pragma unroll
+        for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+            const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+            if (idx < n) {
+                const V *src = reinterpret_cast<const V *>(payload_in + static_cast<size_t>(idx) * RBYTES);
+                V *dstp = reinterpret_cast<V *>(payload_out + static_cast<size_t>(rk[r]) * RBYTES);
+                V tmp[NV];
+#pragma unroll
+                for (uint32_t q = 0; q < NV; q++) tmp[q] = src[q];
+#pragma unroll
+                for (uint32_t q = 0; q < NV; q++) dstp[q] = tmp[q];
+            }
+        }
+    } else if constexpr (RBYTES < 0) {
+#pragma unroll 1
+        for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+            const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+            if (idx < n) {
+                const uint64_t *src = reinterpret_cast<const uint64_t *>(payload_in + static_cast<size_t>(idx) * payload_bytes);
+                uint64_t *dstp = reinterpret_cast<uint64_t *>(payload_out + static_cast<size_t>(rk[r]) * payload_bytes);
                 for (uint32_t q = 0; q < payload_bytes / 8; q++) dstp[q] = src[q];
             }
         }
@@ -1097,6 +1283,409 @@ __global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, con
             ff.seg_off[slot] = 0xffffffffu; // the next segment's sort records the key's first position with atomicMin
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_ffat_update_buckets: the window update after ONE wide partition pass (k_wide_scatter) on the top 10 bits of the
+// slot. The pass leaves the segment's (slot, arrival position) pairs in 1024 buckets of at most BK_KEYS consecutive
+// slots, arrival order inside a bucket. One CTA per bucket, in chunks of at most BK_CAP items (arrival order is chunk
+// order). Every phase is built to need as few dependent memory round trips as possible -- the kernel is bound by
+// latency, not by bytes:
+//   1. every thread takes BK_IT consecutive items of the chunk; stable split by key through per-thread private key
+//      counts in shared memory (count, exclusive scan over the threads, place) -> per-key runs of record indices,
+//   2. the FlatFAT siblings of the leaf each key completes in this chunk are copied to shared memory with cp.async while
+//   3. ONE THREAD per key folds its run in arrival order straight from the lifted array, eight masked loads per round
+//      trip; completed panes become FlatFAT leaves, their root paths are recomputed from the staged siblings and fired
+//      groups go to the deferred window list,
+//   4. keys with more than BK_LIGHT items in the chunk are folded by a whole warp instead (ordered shuffle-tree fold,
+//      32 records per load).
+// Per-key bookkeeping (count, position in the open pane, next leaf, next trigger, open-pane accumulator) is computed
+// once per CTA by one thread per key and lives in shared memory across the chunks.
+// `moved` = 1: the partition pass also moved the records (bucket b's records are lifted[boff[b] ..)); 0: records are
+// gathered through the arrival positions.
+// ------------------------------------------------------------------------------------------------------
+#ifdef WFB_BK_TRACE
+__device__ unsigned long long g_bk_trace[1024 * 8];
+#define BK_MARK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_bk_trace[blockIdx.x * 8 + (i)] = t_; } } while (0)
+#else
+#define BK_MARK(i) do { } while (0)
+#endif
+constexpr uint32_t BK_KEYS = 64;      // keys per bucket (at most)
+constexpr uint32_t BK_THREADS = 128;
+constexpr uint32_t BK_IT = 18;        // consecutive items per thread and chunk
+constexpr uint32_t BK_CAP = BK_THREADS * BK_IT; // items per chunk
+constexpr uint32_t BK_LIGHT = 96;     // longest run folded by a single thread
+#ifndef WFB_BK_U
+#define WFB_BK_U 8
+#endif
+#ifndef WFB_BK_MINBLOCKS
+#define WFB_BK_MINBLOCKS 4
+#endif
+constexpr uint32_t BK_U = WFB_BK_U;   // record loads in flight per thread
+
+template <class P>
+__global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_buckets(const FfatDev ff, const unsigned char *__restrict__ lifted,
+                                                                       const uint32_t *__restrict__ bk_slots, const uint32_t *__restrict__ bk_pos,
+                                                                       const uint32_t *__restrict__ digit_counts, uint32_t shift, uint32_t moved,
+                                                                       const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                                       uint32_t nbatches, unsigned char *__restrict__ out_res,
+                                                                       uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
+                                                                       const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    constexpr uint32_t NW = BK_THREADS / 32;
+    constexpr uint32_t DPT = OSW_DIGITS / BK_THREADS;                  // digit counts per thread
+    constexpr uint32_t HS = BK_THREADS + 2;                            // row stride of the private counts (bank-conflict padding)
+    constexpr uint32_t CPB = (RB % 16 == 0) ? 16 : 8;                  // cp.async granule of a record
+    constexpr uint32_t BK_SIBL = RB <= 32 ? 8 : (RB <= 64 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged in shared memory
+    static_assert(DPT % 4 == 0 && BK_KEYS == 64 && BK_THREADS == 128 && RB % 8 == 0, "layout");
+    __shared__ uint32_t s_idx[BK_CAP];                 // record index of the items (into `lifted`), key-major
+    __shared__ uint16_t hist[BK_KEYS][HS];             // items of key k among thread t's items -> exclusive over the threads
+    __shared__ uint32_t htot[2][BK_KEYS];              // per key: items held by threads 0..63 / 64..127
+    __shared__ uint32_t kcnt[BK_KEYS], koff[BK_KEYS];  // items / first index of key k in this chunk
+    __shared__ uint32_t kleft[BK_KEYS];                // items of key k still to come in this segment
+    __shared__ uint32_t kcp[BK_KEYS], kleaf[BK_KEYS];  // items in the open pane, leaf the open pane will be written to
+    __shared__ uint64_t kc[BK_KEYS], kg[BK_KEYS], ktt[BK_KEYS]; // count, groups fired, items until the next trigger
+    __shared__ __align__(16) unsigned char kacc[BK_KEYS * RB];   // open-pane accumulator of key k
+    __shared__ __align__(16) unsigned char s_sib[BK_KEYS * BK_SIBL * RB]; // siblings of the leaf key k completes in this chunk
+    __shared__ uint32_t s_heavy[BK_KEYS];              // keys folded by a warp in this chunk
+    __shared__ uint32_t misc[NW], s_boff[2], s_nheavy;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bucket = blockIdx.x;
+    const uint32_t kpc = min(BK_KEYS, 1u << shift);    // keys of this bucket
+    const uint32_t key_lo = bucket << shift;
+    const uint32_t n = ff.n_leaves, logn = ff.log_leaves;
+    const uint32_t P32 = static_cast<uint32_t>(ff.pane);
+    const uint64_t group_items = ff.slide * ff.nb;
+    const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
+
+    BK_MARK(0);
+    // ---- per-key bookkeeping, one thread per key (loads first: they overlap the histogram scan below) ----------------------
+    uint32_t my_total = 0;
+    uint64_t st_c = 0;
+    alignas(16) R st_acc;
+    const bool has_key = tid < kpc && key_lo + tid < ff.max_keys;
+    if (has_key) {
+        const uint32_t slot = key_lo + tid;
+        my_total = ff.seg_cnt[slot];
+        st_c = ff.cnt[slot];
+        ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, st_acc);
+    }
+    // ---- bucket range = exclusive scan of the pass histogram --------------------------------------------------------------
+    {
+        uint32_t cc[DPT];
+#pragma unroll
+        for (uint32_t q = 0; q < DPT / 4; q++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(digit_counts)[tid * (DPT / 4) + q];
+            cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < DPT; q++) sum += cc[q];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+        if (lane == 31) misc[warp] = incl;
+        __syncthreads();
+        if (tid == bucket / DPT) {
+            uint32_t base = incl - sum;
+            for (uint32_t w = 0; w < warp; w++) base += misc[w];
+            uint32_t own = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < DPT; q++) { if (q < bucket % DPT) base += cc[q]; if (q == bucket % DPT) own = cc[q]; }
+            s_boff[0] = base; s_boff[1] = base + own;
+        }
+    }
+    if (tid < BK_KEYS) {
+        const uint32_t m = my_total;
+        const uint64_t c = st_c;
+        uint64_t g = 0, tt = 0; uint32_t cp = 0, leaf = 0;
+        if (m) {
+            cp = static_cast<uint32_t>(c % P32); leaf = static_cast<uint32_t>((c / P32) & (n - 1));
+            if (c < ff.B) { g = 0; tt = ff.B - c; }
+            else { g = 1 + (c - ff.B) / group_items; tt = ff.B + g * group_items - c; }
+            if (cp) st_rec<R>(kacc + tid * RB, st_acc);
+        }
+        kleft[tid] = m; kc[tid] = c; kg[tid] = g; ktt[tid] = tt; kcp[tid] = cp; kleaf[tid] = leaf;
+    }
+    const uint32_t any_items = __syncthreads_or(my_total != 0);
+    BK_MARK(1);
+    if (!any_items) return;
+    uint32_t cursor = s_boff[0];
+    const uint32_t bend = s_boff[1];
+    if (moved)
+        for (size_t o = static_cast<size_t>(tid) * 128; o < static_cast<size_t>(bend - cursor) * RB; o += BK_THREADS * 128) // the bucket's block -> L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lifted + static_cast<size_t>(cursor) * RB + o));
+
+    while (cursor < bend) {
+        const uint32_t nsel = min(BK_CAP, bend - cursor);
+        // ---- 1. stable split of the chunk's items by key: thread t owns items [t*BK_IT, +BK_IT) --------------------------------------
+        uint32_t ek[BK_IT], ep[BK_IT]; // local key (BK_KEYS = none), record index
+#pragma unroll
+        for (uint32_t r = 0; r < BK_IT; r++) {
+            const uint32_t i = tid * BK_IT + r;
+            ek[r] = BK_KEYS; ep[r] = cursor + i;
+            if (i < nsel) {
+                const uint32_t lk = bk_slots[cursor + i] - key_lo; // slots outside the bucket's keys (invalid slots) are dropped
+                if (!moved) ep[r] = bk_pos[cursor + i];             // records still in arrival order: the index is the position
+                if (lk < kpc) ek[r] = lk;
+            }
+        }
+        {
+            uint32_t *z = reinterpret_cast<uint32_t *>(&hist[0][0]);
+            for (uint32_t i = tid; i < BK_KEYS * HS / 2; i += BK_THREADS) z[i] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t r = 0; r < BK_IT; r++) if (ek[r] < BK_KEYS) hist[ek[r]][tid]++; // column tid is private to this thread
+        __syncthreads();
+        { // key (tid & 63), threads [64*(tid >> 6), +64): exclusive scan of the private counts over the threads
+            const uint32_t k = tid & 63u, half = tid >> 6;
+            uint16_t *row = &hist[k][half * 64];
+            uint32_t run = 0;
+#pragma unroll 16
+            for (uint32_t i = 0; i < 64; i++) { const uint32_t c = row[i]; row[i] = static_cast<uint16_t>(run); run += c; }
+            htot[half][k] = run;
+        }
+        __syncthreads();
+        BK_MARK(2);
+        if (warp == 0) { // keys lane and lane+32: chunk totals, exclusive scan over the keys, keys with long runs
+            const uint32_t a0 = htot[0][lane] + htot[1][lane], a1 = htot[0][lane + 32] + htot[1][lane + 32];
+            uint32_t i0 = a0, i1 = a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v0 = __shfl_up_sync(FULL, i0, o), v1 = __shfl_up_sync(FULL, i1, o);
+                if (lane >= static_cast<uint32_t>(o)) { i0 += v0; i1 += v1; }
+            }
+            const uint32_t t0 = __shfl_sync(FULL, i0, 31);
+            kcnt[lane] = a0; kcnt[lane + 32] = a1;
+            koff[lane] = i0 - a0; koff[lane + 32] = t0 + i1 - a1;
+            // long runs and runs that complete a second pane are folded by a warp
+            const bool h0 = a0 > BK_LIGHT || a0 - min(a0, P32 - kcp[lane]) >= P32;
+            const bool h1 = a1 > BK_LIGHT || a1 - min(a1, P32 - kcp[lane + 32]) >= P32;
+            const uint32_t b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
+            if (h0) s_heavy[__popc(b0 & lanemask_lt())] = lane;
+            if (h1) s_heavy[__popc(b0) + __popc(b1 & lanemask_lt())] = lane + 32;
+            if (lane == 0) s_nheavy = __popc(b0) + __popc(b1);
+        }
+        __syncthreads();
+        {
+            const uint32_t hb = tid >> 6;
+#pragma unroll
+            for (uint32_t r = 0; r < BK_IT; r++) {
+                const uint32_t k = ek[r];
+                if (k < BK_KEYS) {
+                    const uint32_t rank = hist[k][tid];
+                    hist[k][tid] = static_cast<uint16_t>(rank + 1);
+                    s_idx[koff[k] + (hb ? htot[0][k] : 0u) + rank] = ep[r];
+                }
+            }
+        }
+        // ---- 2. siblings of the leaf each key completes in this chunk -> shared memory (asynchronous) --------------------------------
+        bool sib_staged = false;
+        if (tid < BK_KEYS) {
+            const uint32_t m = kcnt[tid];
+            const uint32_t sA = min(m, P32 - kcp[tid]);
+            if (m != 0 && m <= BK_LIGHT && m - sA < P32 && kcp[tid] + sA == P32) {
+                const uint32_t leaf = kleaf[tid];
+                const unsigned char *tr = ff.tree + static_cast<size_t>(key_lo + tid) * tree_stride;
+                for (uint32_t l = 0; l < min(logn, BK_SIBL); l++) {
+                    const unsigned char *src = tr + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB;
+                    unsigned char *dst = s_sib + (tid * BK_SIBL + l) * RB;
+#pragma unroll
+                    for (uint32_t q = 0; q < RB / CPB; q++) cp_async<CPB>(dst + q * CPB, src + q * CPB);
+                }
+                sib_staged = true;
+            }
+        }
+        __syncthreads();
+        BK_MARK(3);
+        // ---- 3. two threads per key: thread k folds the items that go into the open pane (and, when that completes the pane,
+        // writes the leaf, the root path and the fired group); thread 64+k folds the items after it into the next open pane.
+        // A run that would complete a second pane is left to a warp (s_heavy), so neither fold has inner bookkeeping.
+        {
+            const uint32_t k = tid & 63u, slot = key_lo + k;
+            const bool second = tid >= BK_KEYS;
+            uint32_t m = kcnt[k];
+            const uint32_t cp0 = kcp[k];
+            const uint32_t segA = min(m, P32 - cp0);
+            if (m > BK_LIGHT || m - segA >= P32) m = 0; // folded by a warp
+            uint32_t seg = m == 0 ? 0u : (second ? m - segA : segA);
+            const bool fresh0 = second || cp0 == 0;
+            const uint32_t *ip = s_idx + koff[k] + (second ? segA : 0u);
+            alignas(16) R acc;
+            if (seg != 0 && !fresh0) ld_rec<R>(kacc + k * RB, acc);
+            const uint32_t mine = seg;
+            bool fresh = fresh0;
+            while (seg != 0) { // plain ordered fold, BK_U masked loads per round trip
+                alignas(16) R it[BK_U];
+                const uint32_t kk = min(seg, BK_U);
+#pragma unroll
+                for (uint32_t q = 0; q < BK_U; q++) if (q < kk) ld_rec<R>(lifted + static_cast<size_t>(ip[q]) * RB, it[q]);
+                if (fresh) acc = it[0]; else P::comb(acc, it[0], acc, prm);
+                fresh = false;
+#pragma unroll
+                for (uint32_t q = 1; q < BK_U; q++) if (q < kk) P::comb(acc, it[q], acc, prm);
+                seg -= kk; ip += kk;
+            }
+            __syncthreads(); // every thread k has read its old open pane: threads 64+k may overwrite it
+            if (second) {
+                if (mine != 0) st_rec<R>(kacc + k * RB, acc); // the new open pane (kcp is set by thread k)
+            } else if (m != 0) {
+                const bool completed = cp0 + segA == P32;
+                uint32_t leafi = kleaf[k];
+                uint64_t g = kg[k];
+                const uint64_t tt = ktt[k];
+                if (completed) { // new leaf, root path, fired group
+                    unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
+                    const uint32_t leaf = leafi;
+                    leafi = (leafi + 1) & (n - 1);
+                    alignas(16) R cur = acc;
+                    st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
+                    if (sib_staged) cp_async_wait_all();
+                    for (uint32_t l0 = 0; l0 < logn; l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
+                        alignas(16) R sb[4];
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; q++) {
+                            const uint32_t l = l0 + q;
+                            if (l < logn) {
+                                if (sib_staged && l < BK_SIBL) ld_rec<R>(s_sib + (k * BK_SIBL + l) * RB, sb[q]);
+                                else ld_rec<R>(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB, sb[q]);
+                            }
+                        }
+#pragma unroll
+                        for (uint32_t q = 0; q < 4; q++) {
+                            const uint32_t l = l0 + q;
+                            if (l < logn) {
+                                alignas(16) R parent = cur;
+                                if ((leaf >> l) & 1u) P::comb(sb[q], cur, parent, prm); else P::comb(cur, sb[q], parent, prm);
+                                cur = parent;
+                                st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                            }
+                        }
+                    }
+                    if (segA == tt) {
+                        const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+                        const uint32_t lp = s_idx[koff[k] + segA - 1];
+                        const uint32_t last_pos = moved ? bk_pos[lp] : lp; // arrival position of the triggering item
+                        const uint32_t obase = atomicAdd(n_out, ff.nb);
+                        bool deferred = (kleft[k] - segA) < P32; // no further pane of this key can complete in this segment
+                        if (deferred) {
+                            const uint32_t ti = atomicAdd(ff.n_trig, 1u);
+                            if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
+                            else deferred = false;
+                        }
+                        if (!deferred) {
+                            const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
+                            for (uint32_t i = 0; i < ff.nb; i++)
+                                ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap, prm);
+                        }
+                        g++;
+                    }
+                } else st_rec<R>(kacc + k * RB, acc); // still the open pane
+                kc[k] += m; kg[k] = g; kleaf[k] = leafi; kleft[k] -= m;
+                ktt[k] = (completed && segA == tt) ? group_items - (m - segA) : tt - m;
+                kcp[k] = completed ? m - segA : cp0 + m;
+            }
+            if (sib_staged) cp_async_wait_all(); // (a staged key always completes its pane: nothing is pending here)
+        }
+        BK_MARK(4);
+        // ---- 3. long runs: one warp per key, ordered shuffle-tree fold of 32 records per load ----------------------------------------
+        if (s_nheavy != 0) { // (block-uniform: written before the last barrier)
+            __syncthreads();
+            for (uint32_t h = warp; h < s_nheavy; h += NW) {
+                const uint32_t k = s_heavy[h];
+                const uint32_t m = kcnt[k], off = koff[k], slot = key_lo + k;
+                uint64_t c = kc[k], g = kg[k], tt = ktt[k];
+                uint32_t cp = kcp[k], leafi = kleaf[k], left = kleft[k];
+                const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+                unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
+                alignas(16) R acc;
+                if (cp) ld_rec<R>(kacc + k * RB, acc);
+                alignas(16) R cur_rec;
+                if (lane < m) ld_rec<R>(lifted + static_cast<size_t>(s_idx[off + lane]) * RB, cur_rec);
+                uint32_t j = 0;
+                while (j < m) {
+                    const uint32_t cnt = min(32u, m - j);
+                    alignas(16) R nxt_rec;
+                    if (j + 32 + lane < m) ld_rec<R>(lifted + static_cast<size_t>(s_idx[off + j + 32 + lane]) * RB, nxt_rec);
+                    uint32_t lo = 0;
+                    while (lo < cnt) { // sub-ranges of the 32 records that fall into one pane
+                        const uint32_t hi = min(cnt, lo + (P32 - cp));
+                        alignas(16) R r = cur_rec;
+#pragma unroll
+                        for (uint32_t o = 1; o < 32; o <<= 1) {
+                            const R other = shfl_down_rec<R>(r, o);
+                            if (lane >= lo && lane + o < hi) P::comb(r, other, r, prm);
+                        }
+                        r = shfl_rec<R>(r, lo);
+                        if (cp == 0) acc = r; else P::comb(acc, r, acc, prm);
+                        const uint32_t take = hi - lo;
+                        cp += take; c += take; left -= take; tt -= take;
+                        if (cp == P32) { // pane complete -> leaf + root path
+                            cp = 0;
+                            const uint32_t leaf = leafi;
+                            leafi = (leafi + 1) & (n - 1);
+                            alignas(16) R sib;
+                            if (lane < logn) ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + ((leaf >> lane) ^ 1u)) * RB, sib);
+                            alignas(16) R cur = acc;
+                            if (lane == 0) st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
+                            for (uint32_t l = 0; l < logn; l++) {
+                                const R sb = shfl_rec<R>(sib, l);
+                                alignas(16) R parent = cur;
+                                if ((leaf >> l) & 1u) P::comb(sb, cur, parent, prm); else P::comb(cur, sb, parent, prm);
+                                cur = parent;
+                                if (lane == 0) st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                            }
+                            __syncwarp();
+                            if (tt == 0) {
+                                const uint32_t last_pos = moved ? bk_pos[s_idx[off + j + hi - 1]] : s_idx[off + j + hi - 1]; // arrival position of the triggering item
+                                uint32_t obase = 0;
+                                if (lane == 0) obase = atomicAdd(n_out, ff.nb);
+                                obase = __shfl_sync(FULL, obase, 0);
+                                bool deferred = left < P32; // no further pane of this key can complete in this segment
+                                if (deferred) {
+                                    uint32_t ti = 0;
+                                    if (lane == 0) ti = atomicAdd(ff.n_trig, 1u);
+                                    ti = __shfl_sync(FULL, ti, 0);
+                                    if (ti < ff.trig_cap) {
+                                        if (lane == 0) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
+                                    } else deferred = false;
+                                }
+                                if (!deferred) {
+                                    const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
+                                    for (uint32_t i = lane; i < ff.nb; i += 32)
+                                        ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap, prm);
+                                }
+                                g++; tt = group_items;
+                                __syncwarp();
+                            }
+                        }
+                        lo = hi;
+                    }
+                    j += cnt;
+                    cur_rec = nxt_rec;
+                }
+                if (lane == 0) {
+                    kc[k] = c; kg[k] = g; ktt[k] = tt; kcp[k] = cp; kleaf[k] = leafi; kleft[k] = left;
+                    if (cp) st_rec<R>(kacc + k * RB, acc);
+                }
+            }
+        }
+        cursor += nsel;
+        __syncthreads(); // the next chunk overwrites the shared buffers
+    }
+    BK_MARK(5);
+    // ---- keys' state back as contiguous blocks -----------------------------------------------------------------------------------
+    if (tid < kpc && my_total) {
+        const uint32_t slot = key_lo + tid;
+        ff.cnt[slot] = kc[tid];
+        if (kcp[tid]) { alignas(16) R a; ld_rec<R>(kacc + tid * RB, a); st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, a); }
+        ff.seg_cnt[slot] = 0;
+    }
+    BK_MARK(6);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -65,6 +65,10 @@ struct ProgramOps {
     int (*ffat_update)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *sorted_pos, const uint32_t *batch_off,
                        const DevBatch *batches, uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts,
                        uint32_t out_cap, uint32_t *n_out, uint32_t grid, cudaStream_t s, uint32_t gather, const void *params, uint32_t lanes_grid);
+    int (*ffat_buckets)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *bk_slots, const uint32_t *bk_pos,
+                        const uint32_t *digit_counts, uint32_t shift, uint32_t moved, const uint32_t *batch_off, const DevBatch *batches,
+                        uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s,
+                        const void *params);
     int (*ffat_windows)(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
                         unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params);
     int (*extract_keys)(const unsigned char *tuples, uint32_t n, uint64_t *keys, uint32_t *dest, uint32_t num_shards, cudaStream_t s,
@@ -144,6 +148,18 @@ int ffat_update_dispatch(const FfatDev &ff, const unsigned char *lifted, const u
 }
 
 template <class P>
+int ffat_buckets_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *bk_slots, const uint32_t *bk_pos,
+                          const uint32_t *digit_counts, uint32_t shift, uint32_t moved, const uint32_t *batch_off, const DevBatch *batches,
+                          uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s,
+                          const void *params)
+{
+    k_ffat_update_buckets<P><<<OSW_DIGITS, BK_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, moved, batch_off, batches,
+                                                               nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
+template <class P>
 int ffat_windows_dispatch(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
                           unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params)
 {
@@ -197,6 +213,7 @@ ProgramOps make_ops()
     o.params_bytes = sizeof(typename P::params_t); o.reserved = 0;
     o.tile_pass = &tile_pass_dispatch<P>;
     o.ffat_update = &ffat_update_dispatch<P>;
+    o.ffat_buckets = &ffat_buckets_dispatch<P>;
     o.ffat_windows = &ffat_windows_dispatch<P>;
     o.extract_keys = &extract_keys_dispatch<P>;
     o.reduce_segments = &reduce_segments_dispatch<P>;

@@ -102,38 +102,38 @@ inline uint32_t tiles_of(uint32_t n) { return (n + TILE - 1) / TILE; }
 // scratch + launcher of the onesweep radix sort (one per engine / window handle)
 struct RadixSorter {
     uint32_t *ctl = nullptr;        // [passes][256] histograms + [passes] tickets
-    uint64_t *state = nullptr;      // [tiles][256] look-back words
-    uint32_t state_tiles = 0;
+    uint64_t *state = nullptr;      // [tiles][digits] look-back words
+    uint64_t state_words = 0;
     uint32_t epoch = 0;
     uint64_t launches = 0;
 
-    int ensure(uint32_t cap_elems, uint32_t min_tile, cudaStream_t s)
+    int ensure(uint32_t cap_elems, uint32_t min_tile, cudaStream_t s, uint32_t digits = 256)
     {
-        if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * (OS_MAX_PASSES * 256 + OS_MAX_PASSES)));
+        if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
         const uint32_t tiles = (cap_elems + min_tile - 1) / min_tile;
-        if (tiles > state_tiles) {
+        if (static_cast<uint64_t>(tiles) * digits > state_words) {
             CK(cudaStreamSynchronize(s));
             cudaFree(state);
-            state_tiles = tiles;
-            CK(cudaMalloc(&state, sizeof(uint64_t) * 256 * state_tiles));
-            CK(cudaMemset(state, 0, sizeof(uint64_t) * 256 * state_tiles));
+            state_words = static_cast<uint64_t>(tiles) * digits;
+            CK(cudaMalloc(&state, sizeof(uint64_t) * state_words));
+            CK(cudaMemset(state, 0, sizeof(uint64_t) * state_words));
         }
         return 0;
     }
-    void destroy() { cudaFree(ctl); cudaFree(state); }
+    void destroy() { cudaFree(ctl); cudaFree(state); cudaFree(wideH); cudaFree(wideC); }
 
     // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
     template <class K, int ITEMS>
     void launch_pass(uint32_t tiles, const K *kin, const uint32_t *vin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host,
                      uint32_t p, uint32_t passes, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
-                     uint32_t *seg_first, uint32_t seg_first_n)
+                     uint32_t *seg_first, uint32_t seg_first_n, uint32_t base_shift)
     {
         k_onesweep_pass<K, ITEMS><<<tiles, OS_THREADS, 0, s>>>(kin, vin, kout, vout, n_ptr, n_host, p, passes, ctl, state, epoch,
-                                                               pin, pout, pbytes, seg_first, seg_first_n);
+                                                               pin, pout, pbytes, seg_first, seg_first_n, base_shift);
     }
 
     // clears the histograms / tickets of the next sort; call it BEFORE a producer that fills the histograms itself
-    static constexpr size_t CTL_WORDS = OS_MAX_PASSES * 256 + OS_MAX_PASSES;
+    static constexpr size_t CTL_WORDS = OS_MAX_PASSES * 256 + OS_MAX_PASSES > OSW_DIGITS + 1 ? OS_MAX_PASSES * 256 + OS_MAX_PASSES : OSW_DIGITS + 1;
     static int prepare(uint32_t *ctl_buf, uint32_t passes, cudaStream_t s)
     {
         passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
@@ -141,11 +141,62 @@ struct RadixSorter {
         return 0;
     }
 
+    // wide pass (10-bit digit): ctl = [1024 counts][ticket]
+    static int prepare_wide(uint32_t *ctl_buf, cudaStream_t s)
+    {
+        WFB_CK(cudaMemsetAsync(ctl_buf, 0, sizeof(uint32_t) * (OSW_DIGITS + 1), s));
+        return 0;
+    }
+    // ONE stable partition pass of (kin[i], i) on the digit (key >> shift) & 1023 into (kout, vout): per-tile counts, then
+    // the scatter (no chained scan). *counts = the 1024 digit counts (ready_ctl if the producer of the keys made them).
+    uint16_t *wideH = nullptr; uint32_t *wideC = nullptr; uint32_t wide_tiles = 0, wide_chunks = 0;
+    template <class K, int RBYTES>
+    void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
+                             uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes)
+    {
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes);
+    }
+    // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
+    template <class K>
+    int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
+                  cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
+                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0)
+    {
+        if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
+        if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
+        const uint32_t tiles = std::max(1u, (cap + OSW_TILE - 1) / OSW_TILE);
+        uint32_t chunk_shift = 4; // chunks of >= 16 tiles, about sqrt(tiles) of them
+        while ((1u << (2 * chunk_shift)) < tiles) chunk_shift++;
+        const uint32_t chunks = (tiles + (1u << chunk_shift) - 1) >> chunk_shift;
+        if (tiles > wide_tiles || chunks > wide_chunks) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(wideH); cudaFree(wideC);
+            wide_tiles = std::max(tiles, wide_tiles); wide_chunks = std::max(chunks, wide_chunks);
+            CK(cudaMalloc(&wideH, sizeof(uint16_t) * OSW_DIGITS * wide_tiles));
+            CK(cudaMalloc(&wideC, sizeof(uint32_t) * OSW_DIGITS * wide_chunks));
+        }
+        uint32_t *c = ready_ctl ? ready_ctl : ctl;
+        if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
+        CK(cudaMemsetAsync(wideC, 0, sizeof(uint32_t) * OSW_DIGITS * chunks, s));
+        k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c);
+#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes)
+        if (!payload_in) WFB_WS(0);
+        else switch (payload_bytes) {
+            case 8: WFB_WS(8); break;   case 16: WFB_WS(16); break; case 24: WFB_WS(24); break; case 32: WFB_WS(32); break;
+            case 48: WFB_WS(48); break; case 64: WFB_WS(64); break; default: WFB_WS(-1); break;
+        }
+#undef WFB_WS
+        CK(cudaGetLastError());
+        launches += 2;
+        *counts = c;
+        return 0;
+    }
+
     template <class K>
     int sort(K *kA, K *kB, uint32_t *vA, uint32_t *vB, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t passes,
              cudaStream_t s, const K **skeys, const uint32_t **svals,
              const unsigned char *payload_in = nullptr, unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0,
-             uint32_t *ready_ctl = nullptr, uint32_t *seg_first = nullptr, uint32_t seg_first_n = 0)
+             uint32_t *ready_ctl = nullptr, uint32_t *seg_first = nullptr, uint32_t seg_first_n = 0, uint32_t base_shift = 0)
     {
         // ready_ctl != nullptr: histograms already accumulated there by the producer of the keys (after prepare())
         uint32_t *const own_ctl = ctl;
@@ -160,12 +211,12 @@ struct RadixSorter {
             if (items > OsCfg<K>::MAX_ITEMS) items = OsCfg<K>::MAX_ITEMS;
         }
         const uint32_t TE = OS_THREADS * static_cast<uint32_t>(items);
-        int rc = ensure(cap, OS_THREADS * 4, s); if (rc) return rc;
+        int rc = ensure(cap, OS_THREADS * 4, s, 256); if (rc) return rc;
         passes = std::min<uint32_t>(std::max(1u, passes), OS_MAX_PASSES);
         const uint32_t tiles = std::max(1u, (cap + TE - 1) / TE);
         if (!hist_ready) {
             CK(cudaMemsetAsync(ctl, 0, sizeof(uint32_t) * (passes * 256 + passes), s));
-            k_radix_ghist<K><<<std::min(tiles, static_cast<uint32_t>(g_num_sms) * 4u), 256, 0, s>>>(kA, n_ptr, n_host, passes, ctl);
+            k_radix_ghist<K><<<std::min(tiles, static_cast<uint32_t>(g_num_sms) * 4u), 256, 0, s>>>(kA, n_ptr, n_host, passes, ctl, base_shift);
             launches++;
         }
         const K *kin = kA; const uint32_t *vin = nullptr;
@@ -176,9 +227,9 @@ struct RadixSorter {
             const unsigned char *pin = last ? payload_in : nullptr;
             unsigned char *pout = last ? payload_out : nullptr;
             uint32_t *sf = last ? seg_first : nullptr;
-            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
-            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
-            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n);
+            if (items == 4) launch_pass<K, 4>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n, base_shift);
+            else if (items == 8 || OsCfg<K>::MAX_ITEMS < 16) launch_pass<K, 8>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n, base_shift);
+            else launch_pass<K, (OsCfg<K>::MAX_ITEMS >= 16 ? 16 : 8)>(tiles, kin, vin, kout, vout, n_ptr, n_host, p, passes, s, pin, pout, payload_bytes, sf, seg_first_n, base_shift);
             kin = kout; vin = vout;
             if (kout == kB) { kout = kA; vout = vA; } else { kout = kB; vout = vB; }
         }
@@ -283,6 +334,11 @@ struct wfb_ffat {
     uint64_t launches = 0;
     size_t state_bytes = 0;
     int win_type = 0;
+    bool buckets = true;          // one wide radix pass + per-bucket CTAs (<= 65536 keys); WFB_UPDATE=lanes selects the
+                                  // full sort + thread-per-key update instead
+    uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
+    bool bucket_move = false;     // WFB_BUCKET_MOVE=1: the wide pass also moves the lifted records into their buckets
+    bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
     uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
     bool move_payload = false;    // tuning knob WFB_SORT_PAYLOAD=1: the last sort pass also moves the lifted records
     // optional per-phase timing (wfb_ffat_timing)
@@ -606,6 +662,24 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
 #undef ALLOC
     uint32_t bits = 0; while ((1ull << bits) < max_keys) bits++;
     h->sort_passes = std::max(1u, (bits + 7) / 8);
+    h->bucket_shift = bits > OSW_BITS ? bits - OSW_BITS : 0;
+    { const char *e = std::getenv("WFB_BUCKET_MOVE"); h->bucket_move = e && std::atoi(e) != 0; }
+    { const char *e = std::getenv("WFB_L2_HINTS"); h->l2_hints = !(e && std::atoi(e) == 0); }
+    { // WFB_L2_PERSIST=<MB>: L2 set-aside for evict-last lines (the lifted records between the ingest pass and the update)
+        const char *e = std::getenv("WFB_L2_PERSIST");
+        if (e && std::atoi(e) > 0) {
+            int dev = 0, maxp = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            const size_t want = std::min<size_t>(static_cast<size_t>(std::atoi(e)) << 20, static_cast<size_t>(maxp));
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            if (std::getenv("WFB_VERBOSE")) std::fprintf(stderr, "[wfb] persisting L2: max %d MB, set %zu MB\n", maxp >> 20, want >> 20);
+        }
+    }
+    { // bucket path: every bucket holds at most BK_KEYS keys and the pane length fits 32 bits
+        const char *e = std::getenv("WFB_UPDATE");
+        h->buckets = !(e && std::strcmp(e, "lanes") == 0) && (1u << h->bucket_shift) <= BK_KEYS && ff.pane < (1ull << 32);
+    }
     h->state_bytes = total;
     *hh = h;
     return 0;
@@ -648,7 +722,7 @@ static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint3
         g.cap = std::max(total, 2 * g.cap);
         const size_t RB = h->ops->result_bytes;
         CK(cudaMalloc(&g.lifted, static_cast<size_t>(g.cap) * RB));
-        if (h->move_payload) CK(cudaMalloc(&g.lifted_sorted, static_cast<size_t>(g.cap) * RB));
+        if (h->move_payload || h->buckets) CK(cudaMalloc(&g.lifted_sorted, static_cast<size_t>(g.cap) * RB));
         CK(cudaMalloc(&g.slotsA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.slotsB, sizeof(uint32_t) * g.cap));
         CK(cudaMalloc(&g.posA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.posB, sizeof(uint32_t) * g.cap));
         const uint64_t per_group = std::max<uint64_t>(1, h->ff.slide * h->ff.nb);
@@ -676,25 +750,43 @@ static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint3
 static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsigned char *out, uint64_t *out_ts, uint32_t out_cap,
                              uint32_t *n_out, cudaStream_t s)
 {
-    // stable sort of (slot, arrival position) by slot: onesweep radix, 8 bits per pass
     const uint32_t *sorted_slots, *sorted_pos;
     const uint64_t before = h->sorter.launches;
-    int rc = h->sorter.sort<uint32_t>(g.slotsA, g.slotsB, g.posA, g.posB, g.n_total, 0, g.total, h->sort_passes, s, &sorted_slots,
+    int rc;
+    if (h->buckets) {
+        // ONE wide radix pass on the top 10 slot bits: 1024 buckets of consecutive keys, arrival order inside a bucket ...
+        const uint32_t *counts = nullptr;
+        rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.n_total, 0, g.total, h->bucket_shift, s,
+                                           g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes));
+        if (rc) return rc;
+        h->launches += h->sorter.launches - before;
+        h->mark(2, s);
+        // ... then one CTA per bucket finishes the job (local split by key, per-key ordered fold, FlatFAT update)
+        rc = h->ops->ffat_buckets(ff, h->bucket_move ? g.lifted_sorted : g.lifted, g.slotsB, g.posB, counts, h->bucket_shift, h->bucket_move ? 1u : 0u, g.batch_off, g.d_batches, g.nbatches, out, out_ts,
+                                  out_cap, n_out, s, h->pp());
+        if (rc) return rc;
+        h->launches += 1;
+    } else {
+        // stable sort of (slot, arrival position) by slot: onesweep radix, 8 bits per pass
+        rc = h->sorter.sort<uint32_t>(g.slotsA, g.slotsB, g.posA, g.posB, g.n_total, 0, g.total, h->sort_passes, s, &sorted_slots,
                                       &sorted_pos, h->move_payload ? g.lifted : nullptr, h->move_payload ? g.lifted_sorted : nullptr,
                                       h->ops->result_bytes, g.hist_ready ? g.sort_ctl : nullptr, ff.seg_off, ff.max_keys);
-    if (rc) return rc;
-    h->launches += h->sorter.launches - before;
-    (void) sorted_slots; // the last pass also recorded the first sorted position of every key in ff.seg_off
-    h->mark(2, s);
-    // one warp per key: pane fold, FlatFAT update; then one thread per fired window
-    uint32_t ugrid = std::max(1u, std::min((ff.max_keys + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u));
-    rc = h->ops->ffat_update(ff, h->move_payload ? g.lifted_sorted : g.lifted, sorted_pos, g.batch_off, g.d_batches, g.nbatches,
-                             out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u, h->pp(),
-                             h->ff.light_max ? std::max(1u, std::min((ff.max_keys + 127u) / 128u, static_cast<uint32_t>(g_num_sms) * 16u)) : 0u);
-    if (rc) return rc;
+        if (rc) return rc;
+        h->launches += h->sorter.launches - before;
+        h->mark(2, s);
+        // one thread per key (one warp per heavy key): pane fold, FlatFAT update
+        uint32_t ugrid = std::max(1u, std::min((ff.max_keys + 7) / 8, static_cast<uint32_t>(g_num_sms) * 8u));
+        rc = h->ops->ffat_update(ff, h->move_payload ? g.lifted_sorted : g.lifted, sorted_pos, g.batch_off, g.d_batches, g.nbatches,
+                                 out, out_ts, out_cap, n_out, ugrid, s, h->move_payload ? 0u : 1u, h->pp(),
+                                 h->ff.light_max ? std::max(1u, std::min((ff.max_keys + 127u) / 128u, static_cast<uint32_t>(g_num_sms) * 16u)) : 0u);
+        if (rc) return rc;
+        h->launches += h->ff.light_max ? 2 : 1;
+    }
+    // deferred window groups: one thread per window
     rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp());
     if (rc) return rc;
-    h->launches += h->ff.light_max ? 3 : 2;
+    h->launches += 1;
     return 0;
 }
 
@@ -753,17 +845,20 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     FfatDev ff = h->ff; // this call's view of the state: per-segment buffers of parity `par`
     ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap; ff.n_heavy = g.n_heavy;
 
-    const bool fuse_hist = h->sort_passes <= 4; // the streaming pass also counts the digits of the slot sort that follows
-    if (fuse_hist) { rc = RadixSorter::prepare(g.sort_ctl, h->sort_passes, s); if (rc) return rc; }
+    const uint32_t npasses = h->buckets ? 1u : h->sort_passes;
+    const uint32_t pshift = h->buckets ? h->bucket_shift : 0u;
+    const bool fuse_hist = npasses <= 4; // the streaming pass also counts the digits of the slot sort that follows
+    if (fuse_hist) { rc = h->buckets ? RadixSorter::prepare_wide(g.sort_ctl, s) : RadixSorter::prepare(g.sort_ctl, npasses, s); if (rc) return rc; }
     h->mark(0, s);
     // 1. streaming pass: [map -> filter ->] lift, key -> slot, stable compaction over the whole segment
     TileArgs a; std::memset(&a, 0, sizeof(a));
-    if (fuse_hist) { a.sort_ctl = g.sort_ctl; a.sort_passes = h->sort_passes; }
+    if (fuse_hist) { a.sort_ctl = g.sort_ctl; a.sort_passes = npasses; a.sort_shift = pshift; a.sort_dbits = h->buckets ? OSW_BITS : 8u; }
     g.hist_ready = fuse_hist;
     a.batches = g.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
     a.lifted = g.lifted; a.slots = g.slotsA; a.batch_off = g.batch_off; a.n_total = g.n_total; a.ff = ff;
     h->ts.next_launch(a);
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
+    a.l2_hints = h->l2_hints ? 1u : 0u;
     uint32_t grid = 0;
     rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
@@ -855,3 +950,8 @@ int wfb_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uin
 }
 
 } // extern "C"
+
+#ifdef WFB_BK_TRACE
+// debug build only: phase timestamps (globaltimer ns) of the last k_ffat_update_buckets launch, 8 per CTA
+extern "C" int wfb_debug_bk_trace(unsigned long long *out) { return cudaMemcpyFromSymbol(out, wfb::g_bk_trace, sizeof(unsigned long long) * 1024 * 8) == cudaSuccess ? 0 : -1; }
+#endif
