@@ -26,7 +26,10 @@
 namespace wfb {
 
 constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pass
-constexpr int STAGES = 4;    // TMA ring depth per CTA
+#ifndef WFB_STAGES
+#define WFB_STAGES 4
+#endif
+constexpr int STAGES = WFB_STAGES;    // TMA ring depth per CTA
 constexpr uint32_t FULL = 0xffffffffu;
 
 enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2, MODE_SHARD = 3 };
@@ -101,6 +104,8 @@ struct TileArgs {
     uint64_t tmap_base;        // global address the 2-D tensor map starts at (rows of 64 bytes)
     uint32_t use_tmap;         // 1: `tmap` is valid for this launch
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
+    uint32_t sparse;           // MODE_INGEST, 1: no global compaction -- tile t owns lifted / slots [t*TILE, +TILE) (survivors first,
+                               // INVALID_SLOT padding), so tiles are independent: no look-back chain, positions are tuple indices
     uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
     // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
     uint32_t nshards, region_cap;
@@ -249,7 +254,8 @@ __device__ __forceinline__ uint32_t slot_of_key(const FfatDev &ff, uint64_t key)
 //                         the compacted records, coalesced stores of the staged slots / timestamps | wait for the
 //                         store to have read shared memory | arrive empty[s].
 // Tickets: every CTA claims one ticket per processed tile plus the failing one, so a launch consumes exactly
-// num_tiles + gridDim.x tickets (the host advances ticket_base by that amount).
+// num_tiles + gridDim.x tickets (the host advances ticket_base by that amount). (Claiming several tiles per atomic was
+// measured: it delays the aggregates the look-backs of the following tiles wait for, 0.10 -> 0.14 ms.)
 // ------------------------------------------------------------------------------------------------------
 constexpr uint32_t TP_THREADS = TILE + 64;         // producer warp + 8 consumer warps + epilogue warp
 constexpr uint32_t TILE_SENTINEL = 0x7fffffffu;
@@ -331,18 +337,21 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
         // ================================= PRODUCER =================================
         if (lane == 0) {
             const uint64_t pol_first = l2_policy_evict_first();
+            DevBatch b = a.one; uint32_t bi = 0, b_end = 0; // batch of the previous tile, first tile after it
+            bool have_batch = false;
             for (uint32_t it = 0;; it++) {
                 const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], par ^ 1u); // a fresh barrier passes the wait on parity 1
+                // claim only now: a claimed tile is loaded at once, so the look-backs of its successors never wait on a stalled ring
                 const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
                 StageMeta &m = meta[s];
                 if (t >= a.num_tiles) { m.tile = TILE_SENTINEL; mbar_arrive(&full[s]); break; }
-                DevBatch b; uint32_t bi = 0;
-                if (a.batches == nullptr) b = a.one;
-                else {
+                if (a.batches != nullptr && !(have_batch && t >= b.tile_begin && t < b_end)) {
                     uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= t
                     while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (a.batches[mid].tile_begin <= t) lo = mid; else hi = mid - 1; }
                     bi = lo; b = a.batches[lo];
+                    b_end = (lo + 1 < a.nbatches) ? a.batches[lo + 1].tile_begin : a.num_tiles;
+                    have_batch = true;
                 }
                 const uint32_t first = (t - b.tile_begin) * TILE;
                 const uint32_t cnt = min(static_cast<uint32_t>(TILE), b.n - first);
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     P::lift(tup, res, prm);
                     slot = slot_of_key(a.ff, P::key(tup, prm));
                     if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
-                    if (a.sort_ctl != nullptr) // digit counts for the radix passes over the slots (invalid slots sort last)
+                    if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
                             atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
                 }
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 if (ctid == 0) { // publish the aggregate right away so that other CTAs' look-backs never wait for us
                     meta[s].count = total;
                     const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
-                    if (m.tile != chain_begin) st_relaxed_u64(&a.tile_state[m.tile], pack_state(a.epoch, ST_AGG, total));
+                    if (m.tile != chain_begin && !(MODE == MODE_INGEST && a.sparse)) st_relaxed_u64(&a.tile_state[m.tile], pack_state(a.epoch, ST_AGG, total));
                 }
                 if (keep) {
                     if constexpr (MODE == MODE_FILTER) {
@@ -589,7 +598,10 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); mbar_arrive(&empty[s]); }
                 continue;
             }
-            if constexpr (MODE != MODE_MAP) {
+            if (MODE == MODE_INGEST && a.sparse) {
+                excl = t * TILE; // the tile's own region
+                if (lane == 0 && t == 0) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists filled by the update kernels
+            } else if constexpr (MODE != MODE_MAP) {
                 const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
                 if (t != chain_begin) {
                     int64_t idx = static_cast<int64_t>(t) - 1;
@@ -653,7 +665,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             }
             if constexpr (MODE == MODE_INGEST) {
                 const uint32_t *ssl = reinterpret_cast<const uint32_t *>(stage_aux(s));
-                for (uint32_t i = lane; i < tile_count; i += 32) a.slots[excl + i] = ssl[i];
+                if (a.sparse) for (uint32_t i = lane; i < TILE; i += 32) a.slots[excl + i] = i < tile_count ? ssl[i] : INVALID_SLOT;
+                else for (uint32_t i = lane; i < tile_count; i += 32) a.slots[excl + i] = ssl[i];
             }
             __syncwarp();
             if (lane == 0) {
@@ -1009,7 +1022,7 @@ constexpr uint32_t OSW_THREADS = 256, OSW_ITEMS = 16, OSW_TILE = OSW_THREADS * O
 template <class K>
 __global__ void __launch_bounds__(OSW_THREADS) k_wide_tile_hist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
                                                                 uint32_t shift, uint32_t chunk_shift, uint16_t *__restrict__ H,
-                                                                uint32_t *__restrict__ C, uint32_t *__restrict__ ctl_counts)
+                                                                uint32_t *__restrict__ C, uint32_t *__restrict__ ctl_counts, uint32_t skip_invalid)
 {
     static_assert(OSW_THREADS * 4 == OSW_DIGITS, "four digits per thread");
     __shared__ __align__(16) uint32_t h[OSW_DIGITS];
@@ -1022,7 +1035,7 @@ __global__ void __launch_bounds__(OSW_THREADS) k_wide_tile_hist(const K *__restr
 #pragma unroll
     for (uint32_t r = 0; r < OSW_ITEMS; r++) {
         const uint32_t idx = start + r * OSW_THREADS + tid;
-        if (idx < n) atomicAdd(&h[static_cast<uint32_t>(keys[idx] >> shift) & (OSW_DIGITS - 1u)], 1u);
+        if (idx < n) { const K kk = keys[idx]; if (!(skip_invalid && kk == static_cast<K>(~K(0)))) atomicAdd(&h[static_cast<uint32_t>(kk >> shift) & (OSW_DIGITS - 1u)], 1u); }
     }
     __syncthreads();
     const uint4 c = reinterpret_cast<const uint4 *>(h)[tid];
@@ -1049,7 +1062,7 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
                                                               uint32_t chunk_shift, const uint16_t *__restrict__ H, const uint32_t *__restrict__ C,
                                                               const uint32_t *__restrict__ ctl_counts,
                                                               const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
-                                                              uint32_t payload_bytes)
+                                                              uint32_t payload_bytes, uint32_t skip_invalid)
 {
     constexpr uint32_t NW = OSW_THREADS / 32;
     __shared__ __align__(16) uint16_t cntw[NW][OSW_DIGITS]; // per-warp digit counts -> exclusive offsets over the warps
@@ -1093,10 +1106,10 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
 #pragma unroll
     for (uint32_t r = 0; r < OSW_ITEMS; r++) {
         const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
-        const bool valid = idx < n;
+        const bool valid = idx < n && !(skip_invalid && k[r] == static_cast<K>(~K(0)));
         const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u)) : OSW_DIGITS;
         const uint32_t mask = __match_any_sync(FULL, d);
-        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
+        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0xffffffffu; // 0xffffffff: not an element
         __syncwarp();
         if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] = static_cast<uint16_t>(cntw[warp][d] + __popc(mask));
         __syncwarp();
@@ -1122,7 +1135,7 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
 #pragma unroll
     for (uint32_t r = 0; r < OSW_ITEMS; r++) {
         const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
-        if (idx < n) {
+        if (rk[r] != 0xffffffffu) {
             const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u);
             const uint32_t dst = bin_base[d] + cntw[warp][d] + rk[r];
             keys_out[dst] = k[r];
@@ -1136,7 +1149,7 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
 #pragma unroll
         for (uint32_t r = 0; r < OSW_ITEMS; r++) {
             const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
-            if (idx < n) {
+            if (rk[r] != 0xffffffffu) {
                 const V *src = reinterpret_cast<const V *>(payload_in + static_cast<size_t>(idx) * RBYTES);
                 V *dstp = reinterpret_cast<V *>(payload_out + static_cast<size_t>(rk[r]) * RBYTES);
                 V tmp[NV];
@@ -1150,7 +1163,7 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
 #pragma unroll 1
         for (uint32_t r = 0; r < OSW_ITEMS; r++) {
             const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
-            if (idx < n) {
+            if (rk[r] != 0xffffffffu) {
                 const uint64_t *src = reinterpret_cast<const uint64_t *>(payload_in + static_cast<size_t>(idx) * payload_bytes);
                 uint64_t *dstp = reinterpret_cast<uint64_t *>(payload_out + static_cast<size_t>(rk[r]) * payload_bytes);
                 for (uint32_t q = 0; q < payload_bytes / 8; q++) dstp[q] = src[q];

@@ -152,15 +152,16 @@ struct RadixSorter {
     uint16_t *wideH = nullptr; uint32_t *wideC = nullptr; uint32_t wide_tiles = 0, wide_chunks = 0;
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
-                             uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes)
+                             uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
+                             uint32_t skip_invalid)
     {
-        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes);
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid);
     }
     // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
     template <class K>
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
-                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0)
+                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false)
     {
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
@@ -178,8 +179,8 @@ struct RadixSorter {
         uint32_t *c = ready_ctl ? ready_ctl : ctl;
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
         CK(cudaMemsetAsync(wideC, 0, sizeof(uint32_t) * OSW_DIGITS * chunks, s));
-        k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c);
-#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes)
+        k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c, skip_invalid ? 1u : 0u);
+#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u)
         if (!payload_in) WFB_WS(0);
         else switch (payload_bytes) {
             case 8: WFB_WS(8); break;   case 16: WFB_WS(16); break; case 24: WFB_WS(24); break; case 32: WFB_WS(32); break;
@@ -298,6 +299,7 @@ struct SegScratch {
     uint32_t *batch_off = nullptr; uint32_t batch_off_cap = 0;
     DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
     uint32_t *n_total = nullptr;
+    bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
     uint32_t *n_heavy = nullptr;
@@ -339,6 +341,7 @@ struct wfb_ffat {
     uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
     bool bucket_move = false;     // WFB_BUCKET_MOVE=1: the wide pass also moves the lifted records into their buckets
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
+    bool sparse_ingest = true;    // WFB_SPARSE=0: the bucket path also compacts the survivors over the whole segment
     uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
     bool move_payload = false;    // tuning knob WFB_SORT_PAYLOAD=1: the last sort pass also moves the lifted records
     // optional per-phase timing (wfb_ffat_timing)
@@ -665,6 +668,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     h->bucket_shift = bits > OSW_BITS ? bits - OSW_BITS : 0;
     { const char *e = std::getenv("WFB_BUCKET_MOVE"); h->bucket_move = e && std::atoi(e) != 0; }
     { const char *e = std::getenv("WFB_L2_HINTS"); h->l2_hints = !(e && std::atoi(e) == 0); }
+    { const char *e = std::getenv("WFB_SPARSE"); h->sparse_ingest = !(e && std::atoi(e) == 0); }
     { // WFB_L2_PERSIST=<MB>: L2 set-aside for evict-last lines (the lifted records between the ingest pass and the update)
         const char *e = std::getenv("WFB_L2_PERSIST");
         if (e && std::atoi(e) > 0) {
@@ -756,9 +760,9 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
     if (h->buckets) {
         // ONE wide radix pass on the top 10 slot bits: 1024 buckets of consecutive keys, arrival order inside a bucket ...
         const uint32_t *counts = nullptr;
-        rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.n_total, 0, g.total, h->bucket_shift, s,
+        rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.sparse ? nullptr : g.n_total, g.total, g.total, h->bucket_shift, s,
                                            g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
-                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes));
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
@@ -837,10 +841,20 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         return 0;
     }
     nbatches = static_cast<uint32_t>(hb.size());
-    rc = ffat_ensure_segment(h, g, static_cast<uint32_t>(total), nbatches, s); if (rc) return rc;
+    // bucket path: no global compaction in the streaming pass -- tile t owns positions [t*TILE, +TILE) of the segment
+    const bool sparse = h->buckets && h->sparse_ingest;
+    const uint64_t seg_cap = sparse ? static_cast<uint64_t>(tiles) * TILE : total;
+    if (seg_cap > 0x7fffffffull) return WFB_E_BADARG;
+    rc = ffat_ensure_segment(h, g, static_cast<uint32_t>(seg_cap), nbatches, s); if (rc) return rc;
     rc = h->ts.ensure_tiles(tiles); if (rc) return rc;
     CK(cudaMemcpyAsync(g.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
-    g.nbatches = nbatches; g.total = static_cast<uint32_t>(total);
+    g.nbatches = nbatches; g.total = static_cast<uint32_t>(seg_cap); g.sparse = sparse;
+    if (sparse) { // first position of every batch (the compacting pass writes the compact offsets itself)
+        std::vector<uint32_t> boff(nbatches + 1);
+        for (uint32_t i = 0; i < nbatches; i++) boff[i] = hb[i].tile_begin * TILE;
+        boff[nbatches] = tiles * TILE;
+        CK(cudaMemcpyAsync(g.batch_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+    }
 
     FfatDev ff = h->ff; // this call's view of the state: per-segment buffers of parity `par`
     ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap; ff.n_heavy = g.n_heavy;
@@ -859,6 +873,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     h->ts.next_launch(a);
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     a.l2_hints = h->l2_hints ? 1u : 0u;
+    a.sparse = sparse ? 1u : 0u;
     uint32_t grid = 0;
     rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
