@@ -219,15 +219,15 @@ def run_ours(args):
         b = ops.gen_tuple64(start, seg_tuples, ops.KEY_UNIFORM, NKEYS)
         b.watermark = start
         segs_whole.append(b)
-        segs.append([ops.DeviceBatch(b.tuples[i * BATCH * 64:(i + 1) * BATCH * 64], b.ts[i * BATCH:(i + 1) * BATCH], BATCH,
-                                     watermark=start + i * BATCH) for i in range(bps)])
+        segs.append(ops.Segment([ops.DeviceBatch(b.tuples[i * BATCH * 64:(i + 1) * BATCH * 64], b.ts[i * BATCH:(i + 1) * BATCH], BATCH,
+                                                 watermark=start + i * BATCH) for i in range(bps)]))
     torch.cuda.synchronize()
 
     if world == 1:
         ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=NKEYS, dense_keys=True, pipelined=pipelined)
         pipe = None
     else:
-        pipe = multigpu.KeyShardedPipeline(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=pipelined)
+        pipe = multigpu.KeyShardedPipeline(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=not args.sync_exchange)
         ff = pipe.ff
     cap = ff.max_results(seg_tuples * (2 if world > 1 else 1))
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
@@ -293,6 +293,9 @@ def run_ours(args):
     # ---- e2e: the same call with HOST (pinned) buffers, copies inside the timed region ------------------------------
     e2e = run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev, args, world, out, n_out)
 
+    if pipe is not None:
+        pipe.flush(out, out_ts, n_out)
+        torch.cuda.synchronize()
     if rank == 0:
         peak, peak_src = measured_peaks()
         ingest_ms_avg = ing_ms / max(1, calls)
@@ -312,8 +315,8 @@ def run_ours(args):
                        "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0", "selectivity": SIGMA,
                        "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
                        "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
-                       "pipelined": args.pipeline,
-                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (fused Map->Filter->lift->shard | NCCL all-to-all of 32-B results | Ffat on the key shard)")},
+                       "pipelined": args.pipeline if world == 1 else (not args.sync_exchange),
+                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (Map->Filter->lift + partition by key % N | NCCL all-to-all of 32-B results | Ffat on the key shard, records read in place)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
@@ -417,6 +420,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline", action="store_true", help="WFB_FFAT_PIPELINED handle: results one call late, sort+update overlap the next ingest")
+    ap.add_argument("--sync-exchange", action="store_true", help="N > 1: exchange and window update of a step right after its source pass (no overlap with the next step)")
     ap.add_argument("--prime-steps", type=int, default=-1, help="override state priming (ncu runs); default: steady state")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

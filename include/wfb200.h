@@ -169,6 +169,10 @@ uint64_t wfb_ffat_launches(const wfb_ffat_t *h);
 /* params_t of a registered program used by the key extractor, lift and combine (see wfb_engine_set_params). */
 int wfb_ffat_set_params(wfb_ffat_t *h, const void *params, size_t bytes);
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h);
+/* Dense-key handle that owns one shard of a keyby (keys with key % num_shards == shard, the routing rule of
+ * wf/keyby_emitter.hpp:215-217 for integer keys): key -> slot key / num_shards, so max_keys counts the shard's keys only.
+ * A key of another shard sets the capacity error flag. Call before the first batch. */
+int wfb_ffat_set_key_shard(wfb_ffat_t *h, uint32_t num_shards, uint32_t shard);
 
 /* Count-based windows over `nbatches` consecutive input batches (one stream segment). Per key, items are
  * appended in arrival order; whenever the key's count reaches the trigger (first (Nb-1)*slide+win, then every

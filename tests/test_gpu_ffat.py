@@ -286,3 +286,47 @@ def test_ffat_full_size_property(wfb, oracle):
     assert np.array_equal(srt["key"], np.repeat(np.arange(nkeys), 4))
     assert np.array_equal(srt["id"], np.tile(np.arange(4), nkeys))
     assert ff.stats()[1] == 0
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_ffat_key_shard_replicas(wfb, oracle, shards):
+    """`shards` replicas, each owning the keys with key % shards == r on compact slots (wfb_ffat_set_key_shard) and fed
+    its keys' tuples in arrival order, together produce the windows of one operator over the whole stream; the in-place
+    path of the lifted-record program is used when the chunks sit at their tile positions."""
+    import torch
+    O, ops = oracle, wfb
+    win, slide, nb, nkeys, n, batch = 64, 16, 3, 50, 80000, 5000
+    t, ts = O.gen_tuple64(0, n, O.KEY_UNIFORM, nkeys)
+    go = O.FfatGpuOracle(win, slide, nb)
+    reps = []
+    for r in range(shards):
+        ff = ops.FfatWindowsGPU(ops.PROG_LIFTED32, win, slide, nb, max_keys=(nkeys + shards - 1) // shards, dense_keys=True)
+        ff.set_key_shard(shards, r)
+        reps.append(ff)
+    got, gts, exp, ets = [], [], [], []
+    for b in range(0, n, batch):
+        tb, tsb = t[b:b + batch], ts[b:b + batch]
+        r_, rt_ = go.process_batch(O.lift_tuple64(tb), int(ts[b]))
+        exp.append(r_); ets.append(rt_)
+        lifted = O.lift_tuple64(tb)
+        for r, ff in enumerate(reps):
+            mine = lifted[lifted["key"] % shards == r]
+            # two chunks laid out at their tile positions in one buffer (what the multi-GPU receive side does)
+            h = len(mine) // 2
+            off2 = ((h + 255) // 256) * 256
+            buf = torch.zeros((off2 + len(mine) - h) * 32, dtype=torch.uint8, device="cuda")
+            buf[:h * 32] = torch.from_numpy(mine[:h].view(np.uint8).copy()).cuda()
+            buf[off2 * 32:(off2 + len(mine) - h) * 32] = torch.from_numpy(mine[h:].view(np.uint8).copy()).cuda()
+            chunks = [ops.DeviceBatch(buf[:h * 32], None, h, int(ts[b])), ops.DeviceBatch(buf[off2 * 32:], None, len(mine) - h, int(ts[b]))]
+            out, out_ts, n_out = ff.process(chunks)
+            torch.cuda.synchronize()
+            g_, gt_ = ff.results_to_host(out, out_ts, n_out)
+            got.append(g_); gts.append(gt_)
+    _check(O, np.concatenate(got), np.concatenate(gts), np.concatenate(exp), np.concatenate(ets))
+    for ff in reps:
+        assert ff.stats()[1] == 0
+    # a key of another shard is a capacity error, not a silent drop
+    bad = O.lift_tuple64(t[:10]); bad["key"] = 1
+    reps[0].process([ops.DeviceBatch.from_host(bad, None, 0)])
+    torch.cuda.synchronize()
+    assert reps[0].stats()[1] & 1

@@ -72,3 +72,11 @@ def test_keyby_sharded_exchange_gloo_world2(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "MULTI_OK" in out.stdout
+
+
+def test_tile_layout():
+    """Receive-buffer layout of the in-place window update: chunk s starts at 256 * (tiles of the chunks before it)."""
+    from windflow_b200 import multigpu as M
+    offs, total = M.tile_layout([0, 1, 256, 257, 0, 1000])
+    assert offs == [0, 0, 256, 512, 1024, 1024] and total == 1024 + 1024
+    assert M.tile_layout([]) == ([], 0)

@@ -43,6 +43,7 @@ SYMBOLS = {
     "wfb_engine_launches": (u64, [vp]),
     "wfb_engine_set_params": (C.c_int, [vp, vp, C.c_size_t]),
     "wfb_ffat_set_params": (C.c_int, [vp, vp, C.c_size_t]),
+    "wfb_ffat_set_key_shard": (C.c_int, [vp, u32, u32]),
     "wfb_engine_set_key_bits": (C.c_int, [vp, u32]),
     "wfb_map": (C.c_int, [vp, C.POINTER(Functors), vp, u32, vp]),
     "wfb_map_filter": (C.c_int, [vp, C.POINTER(Functors), vp, vp, u32, vp, vp, vp, vp]),

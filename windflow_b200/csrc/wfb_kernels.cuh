@@ -67,7 +67,8 @@ struct FfatDev {
     uint32_t max_keys;
     uint32_t *n_slots;         // number of keys inserted so far
     uint32_t *err_flags;       // bit0: key table full, bit1: output capacity exceeded
-    uint32_t dense;            // 1: slot = key (keys < max_keys)
+    uint32_t dense;            // 1: slot = key (keys < max_keys), or key / key_div for one shard of a keyby
+    uint32_t key_div, key_rem; // dense: the handle owns the keys with key % key_div == key_rem (key_div <= 1: all keys)
     // per-slot state
     uint64_t *slot_key;        // key of each slot
     uint64_t *cnt;             // lifted results appended so far (Key_Descriptor::count)
@@ -106,6 +107,8 @@ struct TileArgs {
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
     uint32_t sparse;           // MODE_INGEST, 1: no global compaction -- tile t owns lifted / slots [t*TILE, +TILE) (survivors first,
                                // INVALID_SLOT padding), so tiles are independent: no look-back chain, positions are tuple indices
+    uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
+                               // batches lie at their tile positions in one buffer: nothing is copied, only the slots are written
     uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
     // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
     uint32_t nshards, region_cap;
@@ -207,9 +210,18 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     return x;
 }
 
+__device__ __forceinline__ uint64_t key_of_slot(const FfatDev &ff, uint32_t slot)
+{
+    return ff.dense ? (ff.key_div > 1 ? static_cast<uint64_t>(slot) * ff.key_div + ff.key_rem : static_cast<uint64_t>(slot)) : ff.slot_key[slot];
+}
+
 __device__ __forceinline__ uint32_t slot_of_key(const FfatDev &ff, uint64_t key)
 {
     if (ff.dense) {
+        if (ff.key_div > 1) { // one shard of a keyby: keys with key % key_div == key_rem, compact slots
+            if (key % ff.key_div != ff.key_rem) { atomicOr(ff.err_flags, 1u); return INVALID_SLOT; }
+            key /= ff.key_div;
+        }
         if (key >= ff.max_keys) { atomicOr(ff.err_flags, 1u); return INVALID_SLOT; }
         return static_cast<uint32_t>(key);
     }
@@ -428,8 +440,11 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if constexpr (MODE == MODE_INGEST) {
                 if (keep) {
                     P::lift(tup, res, prm);
-                    slot = slot_of_key(a.ff, P::key(tup, prm));
-                    if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                    if (a.nshards) slot = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); // keyby across GPUs: the "slot" is the destination
+                    else {
+                        slot = slot_of_key(a.ff, P::key(tup, prm));
+                        if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                    }
                     if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
                             atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
@@ -499,11 +514,13 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     if constexpr (MODE == MODE_FILTER) {
                         TileIO<T>::store(buf, local, tup);
                         if (b.ts_out != nullptr) reinterpret_cast<uint64_t *>(stage_aux(s) + TILE * 8)[local] = ts;
+                    } else if (MODE == MODE_INGEST && a.inplace) {
+                        reinterpret_cast<uint32_t *>(stage_aux(s))[ctid] = slot; // the record stays where it is: position = tuple index
                     } else {
                         TileIO<R>::store(buf, local, res);
                         reinterpret_cast<uint32_t *>(stage_aux(s))[local] = slot;
                     }
-                }
+                } else if (MODE == MODE_INGEST && a.inplace) reinterpret_cast<uint32_t *>(stage_aux(s))[ctid] = INVALID_SLOT;
             }
             fence_async_smem();
             __syncwarp();
@@ -600,7 +617,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             }
             if (MODE == MODE_INGEST && a.sparse) {
                 excl = t * TILE; // the tile's own region
-                if (lane == 0 && t == 0) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists filled by the update kernels
+                if (lane == 0 && t == 0 && a.ff.n_trig != nullptr) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists filled by the update kernels
             } else if constexpr (MODE != MODE_MAP) {
                 const uint32_t chain_begin = (MODE == MODE_FILTER) ? b.tile_begin : 0u;
                 if (t != chain_begin) {
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             uint32_t bytes;
             if constexpr (MODE == MODE_MAP) { dst = b.out + static_cast<size_t>(m.first) * TB; bytes = m.cnt * TB; }
             else if constexpr (MODE == MODE_FILTER) { dst = b.out + static_cast<size_t>(excl) * TB; bytes = tile_count * TB; }
-            else { dst = a.lifted + static_cast<size_t>(excl) * RB; bytes = tile_count * RB; }
+            else { dst = a.lifted + static_cast<size_t>(excl) * RB; bytes = a.inplace ? 0u : tile_count * RB; }
             if (MODE == MODE_MAP && (m.flags & TF_SWZ)) {
                 if (lane == 0) tma_store_2d(&tmap, 0, static_cast<int32_t>((reinterpret_cast<uint64_t>(dst) - a.tmap_base) >> 6), buf);
             } else if (bulk_ok(dst, bytes)) {
@@ -665,7 +682,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             }
             if constexpr (MODE == MODE_INGEST) {
                 const uint32_t *ssl = reinterpret_cast<const uint32_t *>(stage_aux(s));
-                if (a.sparse) for (uint32_t i = lane; i < TILE; i += 32) a.slots[excl + i] = i < tile_count ? ssl[i] : INVALID_SLOT;
+                if (a.sparse) for (uint32_t i = lane; i < TILE; i += 32) a.slots[excl + i] = i < (a.inplace ? m.cnt : tile_count) ? ssl[i] : INVALID_SLOT;
                 else for (uint32_t i = lane; i < tile_count; i += 32) a.slots[excl + i] = ssl[i];
             }
             __syncwarp();
@@ -1062,8 +1079,9 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
                                                               uint32_t chunk_shift, const uint16_t *__restrict__ H, const uint32_t *__restrict__ C,
                                                               const uint32_t *__restrict__ ctl_counts,
                                                               const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
-                                                              uint32_t payload_bytes, uint32_t skip_invalid)
+                                                              uint32_t payload_bytes, uint32_t skip_invalid, uint32_t region_stride)
 {
+    // region_stride != 0: bin d starts at d * region_stride (fixed-capacity regions; elements beyond the capacity are dropped)
     constexpr uint32_t NW = OSW_THREADS / 32;
     __shared__ __align__(16) uint16_t cntw[NW][OSW_DIGITS]; // per-warp digit counts -> exclusive offsets over the warps
     __shared__ uint32_t bin_base[OSW_DIGITS];               // global position of the tile's first element of each digit
@@ -1129,7 +1147,7 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
         }
         const uint32_t gc[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-        for (int q = 0; q < 4; q++) { bin_base[tid * 4 + q] = gb + acc[q]; gb += gc[q]; }
+        for (int q = 0; q < 4; q++) { bin_base[tid * 4 + q] = (region_stride ? (tid * 4 + q) * region_stride : gb) + acc[q]; gb += gc[q]; }
     }
     __syncthreads();
 #pragma unroll
@@ -1138,8 +1156,9 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
         if (rk[r] != 0xffffffffu) {
             const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u);
             const uint32_t dst = bin_base[d] + cntw[warp][d] + rk[r];
-            keys_out[dst] = k[r];
-            vals_out[dst] = idx;
+            if (region_stride && dst - d * region_stride >= region_stride) { rk[r] = 0xffffffffu; continue; } // region overflow (the caller sees the count)
+            if (keys_out != nullptr) keys_out[dst] = k[r];
+            if (vals_out != nullptr) vals_out[dst] = idx;
             rk[r] = dst;
         }
     }
@@ -1170,6 +1189,92 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_shard_scatter: the partition pass of wfb_shard_lift when there are only a few bins (destination GPUs): stable
+// partition of the lifted records by dest[i] (INVALID_SLOT = dropped) into fixed-capacity regions. Same tiles and the
+// same per-tile counts (H rows, chunk sums C) as k_wide_scatter, but the ranks come from one ballot per bin and round
+// and the records of a bin leave a warp in runs (coalesced). nbins <= 32.
+// ------------------------------------------------------------------------------------------------------
+template <int RBYTES>
+__global__ void __launch_bounds__(OSW_THREADS) k_shard_scatter(const uint32_t *__restrict__ dest, uint32_t n, uint32_t nbins, uint32_t chunk_shift,
+                                                               const uint16_t *__restrict__ H, const uint32_t *__restrict__ C,
+                                                               const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
+                                                               uint32_t region_stride)
+{
+    constexpr uint32_t NW = OSW_THREADS / 32;
+    __shared__ uint32_t base[32];        // first output position of bin b for this tile
+    __shared__ uint32_t wtot[NW][32];    // items of bin b held by warp w -> exclusive over the warps
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+    const uint32_t start = tile * OSW_TILE;
+    if (start >= n) return;
+    if (tid < 32) {
+        uint32_t acc = 0;
+        if (tid < nbins) {
+            const uint32_t chunk = tile >> chunk_shift;
+            for (uint32_t c = 0; c < chunk; c++) acc += C[static_cast<size_t>(c) * OSW_DIGITS + tid];
+            for (uint32_t t = chunk << chunk_shift; t < tile; t++) acc += H[static_cast<size_t>(t) * OSW_DIGITS + tid];
+        }
+        base[tid] = tid * region_stride + acc;
+    }
+    // warp w owns [start + w*32*ITEMS, +32*ITEMS), 32 consecutive positions per round; lane b keeps bin b's running count
+    uint32_t running = 0;
+    uint16_t code[OSW_ITEMS]; // bin (5 bits) | rank inside the warp << 5; 0xffff: dropped
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+        const uint32_t d = idx < n ? dest[idx] : INVALID_SLOT;
+        const uint32_t any = __ballot_sync(FULL, d < nbins);
+        code[r] = 0xffffu;
+        if (any == 0) continue; // (survivors are at the front of every 256-position tile: the tail rounds are empty)
+        uint32_t mine = 0, add = 0;
+        for (uint32_t b = 0; b < nbins; b++) {
+            const uint32_t bal = __ballot_sync(FULL, d == b);
+            if (d == b) mine = __popc(bal & lanemask_lt());
+            if (lane == b) add = __popc(bal);
+        }
+        const uint32_t before = __shfl_sync(FULL, running, d < nbins ? d : 0u);
+        if (d < nbins) code[r] = static_cast<uint16_t>(d | ((before + mine) << 5));
+        running += add;
+    }
+    wtot[warp][lane] = running;
+    __syncthreads();
+    if (tid < 32) { // exclusive offsets over the warps
+        uint32_t run = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < NW; w++) { const uint32_t c = wtot[w][tid]; wtot[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+    using V = typename std::conditional<RBYTES % 16 == 0, uint4, uint2>::type;
+    constexpr uint32_t NV = RBYTES / sizeof(V);
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        if (code[r] != 0xffffu) {
+            const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
+            const uint32_t b = code[r] & 31u, rank = code[r] >> 5;
+            const uint32_t local = base[b] - b * region_stride + wtot[warp][b] + rank; // position inside the region
+            if (local < region_stride) {
+                const V *src = reinterpret_cast<const V *>(payload_in + static_cast<size_t>(idx) * RBYTES);
+                V *dstp = reinterpret_cast<V *>(payload_out + (static_cast<size_t>(b) * region_stride + local) * RBYTES);
+                V tmp[NV];
+#pragma unroll
+                for (uint32_t q = 0; q < NV; q++) tmp[q] = src[q];
+#pragma unroll
+                for (uint32_t q = 0; q < NV; q++) dstp[q] = tmp[q];
+            }
+        }
+    }
+}
+
+// counts of the destination partition (wfb_shard_lift): counts_out[0 .. nshards) + overflow flag at [MAX_SHARDS]
+static __global__ void k_shard_counts(const uint32_t *__restrict__ digit_counts, uint32_t nshards, uint32_t region_cap, uint32_t *__restrict__ counts_out)
+{
+    const uint32_t d = threadIdx.x;
+    const uint32_t c = d < nshards ? digit_counts[d] : 0u;
+    if (d < MAX_SHARDS) counts_out[d] = c;
+    const uint32_t over = __ballot_sync(FULL, c > region_cap);
+    if (d == 0) counts_out[MAX_SHARDS] = over ? 1u : 0u;
 }
 
 // seg_off[slot] = first sorted position of each key present in the segment (its length is seg_cnt[slot])
@@ -1230,7 +1335,7 @@ __global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, con
         unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
         if (act) {
             off = ff.seg_off[slot]; c = ff.cnt[slot];
-            key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+            key = key_of_slot(ff, slot);
             if (c % P_ != 0) ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc);
             g = (c < ff.B) ? 0 : 1 + (c - ff.B) / group_items;
             trig = ff.B + g * group_items;
@@ -1580,7 +1685,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                         }
                     }
                     if (segA == tt) {
-                        const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+                        const uint64_t key = key_of_slot(ff, slot);
                         const uint32_t lp = s_idx[koff[k] + segA - 1];
                         const uint32_t last_pos = moved ? bk_pos[lp] : lp; // arrival position of the triggering item
                         const uint32_t obase = atomicAdd(n_out, ff.nb);
@@ -1613,7 +1718,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                 const uint32_t m = kcnt[k], off = koff[k], slot = key_lo + k;
                 uint64_t c = kc[k], g = kg[k], tt = ktt[k];
                 uint32_t cp = kcp[k], leafi = kleaf[k], left = kleft[k];
-                const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+                const uint64_t key = key_of_slot(ff, slot);
                 unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
                 alignas(16) R acc;
                 if (cp) ld_rec<R>(kacc + k * RB, acc);
@@ -1800,7 +1905,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
         if (m == 0) continue;
         const uint32_t off = ff.seg_off[slot];
         uint64_t c = ff.cnt[slot];
-        const uint64_t key = ff.dense ? static_cast<uint64_t>(slot) : ff.slot_key[slot];
+        const uint64_t key = key_of_slot(ff, slot);
         unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
         alignas(16) R acc;
         if (c % P_ != 0) ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, acc); // every lane keeps a copy

@@ -3,6 +3,7 @@
 // programs; an application instantiates it for its own functors with wfb::register_program<MyProgram>() (see
 // INTEGRATION.md section 3) and then uses the same C ABI with the returned program id.
 #pragma once
+#include <type_traits>
 #include <algorithm>
 #include <cstring>
 #include <cuda.h>
@@ -80,6 +81,10 @@ struct ProgramOps {
     int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
                   uint64_t *out_ts, cudaStream_t s);
 };
+
+// P::passthrough (optional): map is a no-op and lift the identity (tuple_t == result_t)
+template <class P, class = void> struct program_passthrough : std::false_type {};
+template <class P> struct program_passthrough<P, std::void_t<decltype(P::passthrough)>> : std::integral_constant<bool, P::passthrough && std::is_same<typename P::tuple_t, typename P::result_t>::value> {};
 
 template <class P>
 inline typename P::params_t load_params(const void *params)
@@ -210,7 +215,7 @@ ProgramOps make_ops()
     ProgramOps o;
     o.tuple_bytes = sizeof(typename P::tuple_t);
     o.result_bytes = sizeof(typename P::result_t);
-    o.params_bytes = sizeof(typename P::params_t); o.reserved = 0;
+    o.params_bytes = sizeof(typename P::params_t); o.reserved = program_passthrough<P>::value ? 1u : 0u; // bit 0: records pass through unchanged
     o.tile_pass = &tile_pass_dispatch<P>;
     o.ffat_update = &ffat_update_dispatch<P>;
     o.ffat_buckets = &ffat_buckets_dispatch<P>;

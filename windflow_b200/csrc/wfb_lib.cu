@@ -153,15 +153,15 @@ struct RadixSorter {
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
                              uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
-                             uint32_t skip_invalid)
+                             uint32_t skip_invalid, uint32_t region_stride)
     {
-        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid);
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride);
     }
     // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
     template <class K>
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
-                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false)
+                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0)
     {
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
@@ -180,7 +180,24 @@ struct RadixSorter {
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
         CK(cudaMemsetAsync(wideC, 0, sizeof(uint32_t) * OSW_DIGITS * chunks, s));
         k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c, skip_invalid ? 1u : 0u);
-#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u)
+        if (region_stride && few_bins && payload_in && few_bins <= 32 && (payload_bytes == 16 || payload_bytes == 24 || payload_bytes == 32 || payload_bytes == 64)) {
+            // a few fixed-capacity regions (destination GPUs): ranks from ballots, records leave in runs
+            const uint32_t *d32 = reinterpret_cast<const uint32_t *>(kin);
+            static_assert(sizeof(K) == 4 || sizeof(K) == 8, "key width");
+            if (sizeof(K) == 4) {
+                switch (payload_bytes) {
+                    case 16: k_shard_scatter<16><<<tiles, OSW_THREADS, 0, s>>>(d32, n_host, few_bins, chunk_shift, wideH, wideC, payload_in, payload_out, region_stride); break;
+                    case 24: k_shard_scatter<24><<<tiles, OSW_THREADS, 0, s>>>(d32, n_host, few_bins, chunk_shift, wideH, wideC, payload_in, payload_out, region_stride); break;
+                    case 32: k_shard_scatter<32><<<tiles, OSW_THREADS, 0, s>>>(d32, n_host, few_bins, chunk_shift, wideH, wideC, payload_in, payload_out, region_stride); break;
+                    default: k_shard_scatter<64><<<tiles, OSW_THREADS, 0, s>>>(d32, n_host, few_bins, chunk_shift, wideH, wideC, payload_in, payload_out, region_stride); break;
+                }
+                CK(cudaGetLastError());
+                launches += 2;
+                *counts = c;
+                return 0;
+            }
+        }
+#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride)
         if (!payload_in) WFB_WS(0);
         else switch (payload_bytes) {
             case 8: WFB_WS(8); break;   case 16: WFB_WS(16); break; case 24: WFB_WS(24); break; case 32: WFB_WS(32); break;
@@ -256,6 +273,8 @@ struct wfb_engine {
     uint64_t *keysA = nullptr, *keysB = nullptr;
     uint32_t *idxA = nullptr, *idxB = nullptr, *destA = nullptr, *destB = nullptr;
     uint32_t *head = nullptr, *seg_begin = nullptr, *H = nullptr;
+    // wfb_shard_lift: lifted records / destinations of one segment, tile t owns positions [t*TILE, +TILE)
+    unsigned char *sh_lifted = nullptr; uint32_t *sh_dest = nullptr, *sh_ctl = nullptr; uint64_t sh_cap = 0;
     uint32_t h_tiles = 0;
     RadixSorter sorter;
 
@@ -286,6 +305,7 @@ struct wfb_engine {
     {
         cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
         cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+        cudaFree(sh_lifted); cudaFree(sh_dest); cudaFree(sh_ctl);
         sorter.destroy();
     }
 };
@@ -300,6 +320,7 @@ struct SegScratch {
     DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
     uint32_t *n_total = nullptr;
     bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
+    const unsigned char *lifted_src = nullptr; // records of this segment: `lifted`, or the caller's buffer (in-place ingest)
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
     uint32_t *n_heavy = nullptr;
@@ -341,6 +362,7 @@ struct wfb_ffat {
     uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
     bool bucket_move = false;     // WFB_BUCKET_MOVE=1: the wide pass also moves the lifted records into their buckets
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
+    bool inplace_ok = true;       // WFB_INPLACE=0: always copy the records of a pass-through program
     bool sparse_ingest = true;    // WFB_SPARSE=0: the bucket path also compacts the survivors over the whole segment
     uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
     bool move_payload = false;    // tuning knob WFB_SORT_PAYLOAD=1: the last sort pass also moves the lifted records
@@ -558,6 +580,8 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
 int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
                    void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream)
 {
+    // Map -> Filter -> lift in one streaming pass (no compaction chain: tile t owns positions [t*TILE, +TILE)), then one
+    // stable partition pass on the destination (key % num_shards) that moves the lifted records into the shard regions.
     if (!e || !counts_dev || !out_regions || num_shards == 0 || num_shards > MAX_SHARDS || (nbatches && !batches_h)) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = e->ts.enter(s); if (rc) return rc;
@@ -576,19 +600,40 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
         hb.push_back(b);
     }
     if (total == 0) return 0;
-    if (total > 0x7fffffffull) return WFB_E_BADARG;
+    const uint64_t positions = static_cast<uint64_t>(tiles) * TILE;
+    if (positions > 0x7fffffffull) return WFB_E_BADARG;
     nbatches = static_cast<uint32_t>(hb.size());
-    rc = e->ts.ensure_tiles(tiles * SHARD_STATE_WORDS); if (rc) return rc;
+    const size_t RB = e->ops->result_bytes;
+    if (positions > e->sh_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(e->sh_lifted); cudaFree(e->sh_dest);
+        e->sh_cap = std::max<uint64_t>(positions, 2 * e->sh_cap);
+        CK(cudaMalloc(&e->sh_lifted, e->sh_cap * RB));
+        CK(cudaMalloc(&e->sh_dest, e->sh_cap * sizeof(uint32_t)));
+    }
+    if (!e->sh_ctl) CK(cudaMalloc(&e->sh_ctl, sizeof(uint32_t) * RadixSorter::CTL_WORDS));
+    rc = e->ts.ensure_tiles(tiles); if (rc) return rc;
     rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
     CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    rc = RadixSorter::prepare_wide(e->sh_ctl, s); if (rc) return rc;
     TileArgs a; std::memset(&a, 0, sizeof(a));
     a.batches = e->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
-    a.lifted = static_cast<unsigned char *>(out_regions); a.nshards = num_shards; a.region_cap = region_capacity; a.shard_counts = counts_dev;
+    a.lifted = e->sh_lifted; a.slots = e->sh_dest; a.nshards = num_shards; a.sparse = 1; a.l2_hints = 1;
+    a.sort_ctl = e->sh_ctl; a.sort_passes = 1; a.sort_shift = 0; a.sort_dbits = OSW_BITS;
     e->ts.next_launch(a);
     uint32_t grid = 0;
-    rc = e->ops->tile_pass(MODE_SHARD, a, pre ? static_cast<const void *>(pre) : e->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+    rc = e->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : e->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     e->ts.launched(tiles, grid);
     e->launches++;
+    const uint32_t *counts = nullptr;
+    const uint64_t before = e->sorter.launches;
+    rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, nullptr, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), 0, s,
+                                       e->sh_ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
+                                       region_capacity, num_shards);
+    if (rc) return rc;
+    k_shard_counts<<<1, 32, 0, s>>>(counts, num_shards, region_capacity, counts_dev);
+    CK(cudaGetLastError());
+    e->launches += e->sorter.launches - before + 1;
     return 0;
 }
 
@@ -669,6 +714,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     { const char *e = std::getenv("WFB_BUCKET_MOVE"); h->bucket_move = e && std::atoi(e) != 0; }
     { const char *e = std::getenv("WFB_L2_HINTS"); h->l2_hints = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_SPARSE"); h->sparse_ingest = !(e && std::atoi(e) == 0); }
+    { const char *e = std::getenv("WFB_INPLACE"); h->inplace_ok = !(e && std::atoi(e) == 0); }
     { // WFB_L2_PERSIST=<MB>: L2 set-aside for evict-last lines (the lifted records between the ingest pass and the update)
         const char *e = std::getenv("WFB_L2_PERSIST");
         if (e && std::atoi(e) > 0) {
@@ -715,6 +761,12 @@ int wfb_ffat_set_params(wfb_ffat_t *h, const void *params, size_t bytes)
     return 0;
 }
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes : 0; }
+int wfb_ffat_set_key_shard(wfb_ffat_t *h, uint32_t num_shards, uint32_t shard)
+{
+    if (!h || num_shards == 0 || shard >= num_shards || !h->ff.dense || h->call_no != 0) return WFB_E_BADARG;
+    h->ff.key_div = num_shards; h->ff.key_rem = shard;
+    return 0;
+}
 
 static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint32_t nbatches, cudaStream_t s)
 {
@@ -726,7 +778,7 @@ static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint3
         g.cap = std::max(total, 2 * g.cap);
         const size_t RB = h->ops->result_bytes;
         CK(cudaMalloc(&g.lifted, static_cast<size_t>(g.cap) * RB));
-        if (h->move_payload || h->buckets) CK(cudaMalloc(&g.lifted_sorted, static_cast<size_t>(g.cap) * RB));
+        if (h->move_payload || h->bucket_move) CK(cudaMalloc(&g.lifted_sorted, static_cast<size_t>(g.cap) * RB));
         CK(cudaMalloc(&g.slotsA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.slotsB, sizeof(uint32_t) * g.cap));
         CK(cudaMalloc(&g.posA, sizeof(uint32_t) * g.cap)); CK(cudaMalloc(&g.posB, sizeof(uint32_t) * g.cap));
         const uint64_t per_group = std::max<uint64_t>(1, h->ff.slide * h->ff.nb);
@@ -767,7 +819,7 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
         // ... then one CTA per bucket finishes the job (local split by key, per-key ordered fold, FlatFAT update)
-        rc = h->ops->ffat_buckets(ff, h->bucket_move ? g.lifted_sorted : g.lifted, g.slotsB, g.posB, counts, h->bucket_shift, h->bucket_move ? 1u : 0u, g.batch_off, g.d_batches, g.nbatches, out, out_ts,
+        rc = h->ops->ffat_buckets(ff, h->bucket_move ? g.lifted_sorted : g.lifted_src, g.slotsB, g.posB, counts, h->bucket_shift, h->bucket_move ? 1u : 0u, g.batch_off, g.d_batches, g.nbatches, out, out_ts,
                                   out_cap, n_out, s, h->pp());
         if (rc) return rc;
         h->launches += 1;
@@ -870,6 +922,14 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
     g.hist_ready = fuse_hist;
     a.batches = g.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
     a.lifted = g.lifted; a.slots = g.slotsA; a.batch_off = g.batch_off; a.n_total = g.n_total; a.ff = ff;
+    g.lifted_src = g.lifted;
+    if (sparse && !h->pipelined && !h->bucket_move && (h->ops->reserved & 1u) && h->inplace_ok) {
+        // pass-through program and every batch at its tile position inside one buffer: read the records where they are
+        const unsigned char *base = hb[0].tuples;
+        bool ok = (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
+        for (uint32_t i = 0; ok && i < nbatches; i++) ok = hb[i].tuples == base + static_cast<size_t>(hb[i].tile_begin) * TILE * h->ops->tuple_bytes;
+        if (ok) { a.inplace = 1; g.lifted_src = base; }
+    }
     h->ts.next_launch(a);
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     a.l2_hints = h->l2_hints ? 1u : 0u;

@@ -121,6 +121,7 @@ struct ProgLifted32 {
     using key_t = uint64_t;
     using params_t = wfb_functors_t;
     static constexpr int id = WFB_PROG_LIFTED32;
+    static constexpr bool passthrough = true; // map is a no-op and lift the identity: the window operator may read the records in place
 
     __host__ __device__ static void map(tuple_t &, const params_t &) {}
     __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }

@@ -64,41 +64,142 @@ def exchange_regions(regions, region_cap, send_counts_h, recv_counts_h, item_byt
     return recv_buf, offs
 
 
+TILE = 256  # positions per tile of the window operator's streaming pass (csrc/wfb_kernels.cuh)
+
+
+def tile_layout(counts):
+    """Record offsets that put chunk s of a segment at its tile position (the layout the window operator reads in place):
+    chunk s starts at 256 * (tiles of the chunks before it). Returns (offsets, total records incl. padding)."""
+    offs, tiles = [], 0
+    for c in counts:
+        offs.append(tiles * TILE)
+        tiles += (int(c) + TILE - 1) // TILE
+    return offs, tiles * TILE
+
+
+class _Slot:
+    """Buffers of one step in flight (two of them: the exchange of step i-1 overlaps the source pass of step i)."""
+
+    def __init__(self, world, dev):
+        self.regions = None
+        self.region_cap = 0
+        self.counts = torch.zeros(9, dtype=torch.int32, device=dev)
+        self.send_meta = torch.zeros(world, 2, dtype=torch.int64, device=dev)
+        self.recv_meta = torch.zeros(world, 2, dtype=torch.int64, device=dev)
+        self.h_counts = torch.zeros(9, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(9, dtype=torch.int32)
+        self.h_recv = torch.zeros(world, 2, dtype=torch.int64).pin_memory() if dev.type == "cuda" else torch.zeros(world, 2, dtype=torch.int64)
+        self.recv = None
+        self.ev_src = torch.cuda.Event()
+        self.ev_meta = torch.cuda.Event()
+        self.ev_a2a = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.used = False
+
+
 class KeyShardedPipeline:
     """Map_GPU -> Filter_GPU -> (keyby across GPUs) -> Ffat_Windows_GPU on this rank's key shard.
 
-    Source side: ONE fused pass (wfb_shard_lift): map, filter, lift and the stable partition of the 32-byte lifted
-    results by key % world. Exchange: sizes + watermarks in one small all-to-all, then the records (NCCL, NVLink).
-    Destination side: the window operator instantiated for already-lifted records (WFB_PROG_LIFTED32)."""
+    Source side (wfb_shard_lift): one streaming pass (map, filter, lift; no compaction chain) and one stable partition
+    pass that moves the 32-byte lifted results into `world` destination regions. Exchange: sizes + watermarks in one
+    small all-to-all, then the records (NCCL, NVLink), each source's chunk landing at its tile position of the receive
+    buffer. Destination side: the window operator instantiated for already-lifted records (WFB_PROG_LIFTED32) reads the
+    received records in place.
+
+    pipelined=True: the exchange and the window update of step i-1 are issued behind the source pass of step i (the
+    host never waits for the GPU: the sizes it needs were produced a step ago), so results arrive one step() late and
+    flush() delivers the last ones."""
 
     def __init__(self, ops, functors, win, slide, nb, max_keys, rank, world, device, pipelined=True):
         self.ops, self.f, self.rank, self.world, self.dev = ops, functors, rank, world, device
         self.eng = ops.Engine(ops.PROG_TUPLE64)
-        self.ff = ops.FfatWindowsGPU(ops.PROG_LIFTED32, win, slide, nb, max_keys=max_keys, dense_keys=True, pipelined=pipelined)
+        # the rank's replica owns the keys with key % world == rank: compact slots key // world
+        self.ff = ops.FfatWindowsGPU(ops.PROG_LIFTED32, win, slide, nb, max_keys=(max_keys + world - 1) // world, dense_keys=True,
+                                     pipelined=False)
+        if world > 1:
+            self.ff.set_key_shard(world, rank)
         self.rb = self.eng.result_bytes
-        self.regions = self.recv = None
-        self.region_cap = 0
-        self.counts = torch.zeros(9, dtype=torch.int32, device=device)
+        self.overlap = bool(pipelined)
+        self.slots = [_Slot(world, device), _Slot(world, device)]
+        self.comm = torch.cuda.Stream(device)
+        self.step_no = 0
+        self.pending = None
 
-    def _ensure(self, n):
-        if self.region_cap < n:
-            self.region_cap = n  # worst case: every item of the segment survives and goes to one shard
-            self.regions = torch.empty(self.world * n * self.rb, dtype=torch.uint8, device=self.dev)
+    # ---- source side of a step: fused pass + partition by destination, then the sizes travel ------------------------
+    def _source(self, sl, batches, watermark):
+        n = getattr(batches, "total", None) or sum(b.n for b in batches)
+        if sl.region_cap < n:
+            if sl.used:
+                torch.cuda.synchronize(self.dev)
+            sl.region_cap = n  # worst case: every item of the segment survives and goes to one shard
+            sl.regions = torch.empty(self.world * n * self.rb, dtype=torch.uint8, device=self.dev)
+        main = torch.cuda.current_stream(self.dev)
+        self.eng.shard_lift(batches, self.f, self.world, sl.regions, sl.region_cap, sl.counts)
+        sl.send_meta[:, 0].copy_(sl.counts[:self.world])
+        sl.send_meta[:, 1].fill_(int(watermark))
+        sl.ev_src.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(sl.ev_src)
+            dist.all_to_all_single(sl.recv_meta, sl.send_meta)
+            sl.h_counts.copy_(sl.counts, non_blocking=True)
+            sl.h_recv.copy_(sl.recv_meta, non_blocking=True)
+            sl.ev_meta.record(self.comm)
+        sl.used = True
 
-    def step(self, batches, watermark, out, out_ts, n_out):
-        """batches: this rank's K batches of the global step. Results of the window operator go to out."""
-        ops = self.ops
-        self._ensure(sum(b.n for b in batches))
-        self.eng.shard_lift(batches, self.f, self.world, self.regions, self.region_cap, self.counts)
-        cnt_h = self.counts.cpu().tolist()                         # the only host sync of the source side
-        if cnt_h[8]:
+    # ---- exchange of the records (communication stream) -----------------------------------------------------------------
+    def _exchange(self, sl):
+        sl.ev_meta.synchronize()  # sizes of this step on the host (a step old when pipelined: no GPU stall)
+        cnt = sl.h_counts.tolist()
+        if cnt[8]:
             raise RuntimeError("wfb_shard_lift: shard region overflow")
-        send_counts_h = cnt_h[:self.world]
-        send_counts = torch.tensor(send_counts_h, dtype=torch.int64, device=self.dev)
-        rc, rw = exchange_counts(send_counts, watermark)
-        recv_counts_h, wms = rc.cpu().tolist(), rw.cpu().tolist()
-        self.recv, offs = exchange_regions(self.regions, self.region_cap, send_counts_h, recv_counts_h, self.rb, self.recv)
-        chunks = [ops.DeviceBatch(self.recv[offs[s] * self.rb:offs[s + 1] * self.rb], None, offs[s + 1] - offs[s], wms[s])
+        send = cnt[:self.world]
+        rm = sl.h_recv.tolist()
+        recv_counts, wms = [int(r[0]) for r in rm], [int(r[1]) for r in rm]
+        offs, total = tile_layout(recv_counts)
+        if sl.recv is None or sl.recv.numel() < max(1, total) * self.rb:
+            torch.cuda.synchronize(self.dev)
+            sl.recv = torch.empty(max(1, total) * self.rb * 5 // 4, dtype=torch.uint8, device=self.dev)
+        rb, cap = self.rb, sl.region_cap
+        ins = [sl.regions[d * cap * rb:(d * cap + send[d]) * rb] for d in range(self.world)]
+        outs = [sl.recv[offs[s] * rb:(offs[s] + recv_counts[s]) * rb] for s in range(self.world)]
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(sl.ev_done)  # the window update that read this receive buffer two steps ago
+            dist.all_to_all(outs, ins)
+            sl.ev_a2a.record(self.comm)
+        return recv_counts, wms, offs
+
+    # ---- destination side: window update on the received chunks (source-rank order = global stream order) ---------
+    def _update(self, sl, recv_counts, wms, offs, out, out_ts, n_out):
+        ops, rb = self.ops, self.rb
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_event(sl.ev_a2a)
+        chunks = [ops.DeviceBatch(sl.recv[offs[s] * rb:(offs[s] + recv_counts[s]) * rb], None, recv_counts[s], wms[s])
                   for s in range(self.world)]
         self.ff.process(chunks, pre=None, out=out, out_ts=out_ts, n_out=n_out)
-        return sum(recv_counts_h)
+        sl.ev_done.record(main)
+        return sum(recv_counts)
+
+    def step(self, batches, watermark, out, out_ts, n_out):
+        """batches: this rank's K batches of the global step. Window results go to out (of the previous step when
+        pipelined). Returns the number of records the window operator consumed in this call."""
+        cur = self.slots[self.step_no & 1]
+        self.step_no += 1
+        if not self.overlap:
+            self._source(cur, batches, watermark)
+            return self._update(cur, *self._exchange(cur), out, out_ts, n_out)
+        prev, ex = self.pending, None
+        if prev is not None:
+            ex = self._exchange(prev)       # records of step i-1 travel while ...
+        self._source(cur, batches, watermark)  # ... the source pass of step i runs
+        self.pending = cur
+        if prev is None:
+            n_out.zero_()
+            return 0
+        return self._update(prev, *ex, out, out_ts, n_out)
+
+    def flush(self, out, out_ts, n_out):
+        """Delivers the results of the step still in flight (pipelined mode)."""
+        prev, self.pending = self.pending, None
+        if prev is None:
+            n_out.zero_()
+            return 0
+        return self._update(prev, *self._exchange(prev), out, out_ts, n_out)

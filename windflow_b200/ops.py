@@ -171,7 +171,19 @@ class Engine:
         return out, seg
 
 
-def _cbatches(batches):
+class Segment(list):
+    """A list of DeviceBatch whose C descriptor array is built once: a replica that re-submits the same device buffers
+    (a ring of input segments) does not pay the per-batch Python / ctypes cost on every call. Immutable by convention."""
+
+    def __init__(self, batches):
+        super().__init__(batches)
+        self.carr = _cbatches(self, cache=False)
+        self.total = sum(b.n for b in self)
+
+
+def _cbatches(batches, cache=True):
+    if cache and isinstance(batches, Segment):
+        return batches.carr
     arr = (CBatch * len(batches))()
     for i, b in enumerate(batches):
         arr[i].tuples = b.tuples.data_ptr()
@@ -216,6 +228,10 @@ class FfatWindowsGPU:
     def state_bytes(self):
         return int(self.L.wfb_ffat_state_bytes(self.h))
 
+    def set_key_shard(self, num_shards, shard):
+        """Dense-key handle of one keyby shard: keys with key % num_shards == shard, slot = key // num_shards."""
+        check(self.L.wfb_ffat_set_key_shard(self.h, num_shards, shard), "wfb_ffat_set_key_shard")
+
     def max_results(self, n_items):
         """Upper bound on the results one call over n_items input items can produce."""
         return (n_items // max(1, self.slide * self.nb) + 65536) * self.nb
@@ -223,7 +239,7 @@ class FfatWindowsGPU:
     def process(self, batches, pre=None, out=None, out_ts=None, n_out=None, stream=None):
         """One stream segment (list of DeviceBatch). Returns (out uint8 tensor, out_ts int64 tensor, n_out tensor)."""
         dev = batches[0].tuples.device
-        total = sum(b.n for b in batches)
+        total = batches.total if isinstance(batches, Segment) else sum(b.n for b in batches)
         if out is None:
             cap = self.max_results(total)
             out = torch.empty(cap * self.res_dtype.itemsize, dtype=torch.uint8, device=dev)
@@ -231,12 +247,7 @@ class FfatWindowsGPU:
         cap = out.numel() // self.res_dtype.itemsize
         if n_out is None:
             n_out = torch.zeros(1, dtype=torch.int32, device=dev)
-        arr = (CBatch * len(batches))()
-        for i, b in enumerate(batches):
-            arr[i].tuples = b.tuples.data_ptr()
-            arr[i].ts = b.ts.data_ptr() if b.ts is not None else None
-            arr[i].watermark = b.watermark
-            arr[i].n = b.n
+        arr = _cbatches(batches)
         check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                          _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
               "wfb_ffat_process_cb")
