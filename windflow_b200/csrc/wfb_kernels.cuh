@@ -8,7 +8,6 @@
 //                          shared memory and written with a TMA bulk store.
 //                            MODE_MAP     in-place Map_GPU                 (wf/map_gpu.hpp:61-76)
 //                            MODE_FILTER  [Map_GPU ->] Filter_GPU          (wf/filter_gpu.hpp:72-88, :555-570)
-//                            MODE_SHARD   [Map -> Filter ->] lift + stable partition by key % n (multi-GPU keyby)
 //                            MODE_INGEST  [Map -> Filter ->] lift + key->slot for Ffat_Windows_GPU
 //                                         (wf/ffat_replica_gpu.hpp:94-121)
 //   k_radix_hist / k_radix_scan / k_radix_scatter   stable LSD radix passes over (slot, position) pairs: the
@@ -32,9 +31,8 @@ constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pas
 constexpr int STAGES = WFB_STAGES;    // TMA ring depth per CTA
 constexpr uint32_t FULL = 0xffffffffu;
 
-enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2, MODE_SHARD = 3 };
+enum { MODE_MAP = 0, MODE_FILTER = 1, MODE_INGEST = 2 };
 constexpr uint32_t MAX_SHARDS = 8;
-constexpr uint32_t SHARD_STATE_WORDS = 2 + MAX_SHARDS; // per tile: 2 packed aggregate words + one prefix word per shard
 
 // decoupled look-back tile state: [63:34] epoch, [33:32] status, [31:0] value
 constexpr uint64_t ST_AGG = 1, ST_PREFIX = 2;
@@ -110,9 +108,8 @@ struct TileArgs {
     uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
                                // batches lie at their tile positions in one buffer: nothing is copied, only the slots are written
     uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
-    // MODE_SHARD: lifted records go to `nshards` regions of `region_cap` records each, starting at `lifted`
+    // MODE_INGEST with nshards != 0 (wfb_shard_lift): the "slot" of a tuple is its destination key % nshards
     uint32_t nshards, region_cap;
-    uint32_t *shard_counts;    // nshards totals (device)
     // MODE_INGEST: digit histograms of the slot sort that follows (RadixSorter ctl), accumulated per CTA in shared memory
     uint32_t *sort_ctl; uint32_t sort_passes, sort_shift, sort_dbits; // sort_dbits: digit width of a pass (8, or 10 for the wide pass)
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
@@ -276,14 +273,13 @@ enum { TF_SWZ = 1u, TF_FALLBACK = 2u, TF_TS_SMEM = 4u };
 struct StageMeta {
     uint32_t tile, batch, first, cnt, flags, count; // count: survivors (written by the consumers)
     uint32_t pad[2];
-    uint32_t bcount[MAX_SHARDS];                    // MODE_SHARD: survivors per destination shard
 };
 
 template <class P, int MODE>
 struct TilePassSmem {
     using T = typename P::tuple_t;
     using R = typename P::result_t;
-    static constexpr uint32_t rec_bytes = ((MODE == MODE_INGEST || MODE == MODE_SHARD) && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
+    static constexpr uint32_t rec_bytes = (MODE == MODE_INGEST && sizeof(R) > sizeof(T)) ? sizeof(R) : sizeof(T);
     static constexpr uint32_t tile_bytes = (TILE * rec_bytes + 1023u) & ~1023u; // swizzled stages need 512-B alignment
     static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : (MODE == MODE_FILTER ? TILE * 16u : 0u); // slots | ts in + ts out
     static constexpr uint32_t stage_bytes = tile_bytes + aux_bytes;
@@ -450,38 +446,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                             atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
                 }
             }
-            if constexpr (MODE == MODE_SHARD) {
-                // ---- stable partition by destination shard: one ballot per shard, ONE named barrier --------------------
-                uint32_t dest = 0, myrank = 0;
-                if (keep) { P::lift(tup, res, prm); dest = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); }
-                uint32_t *wt = warp_tot + (it & 1u) * ((TILE / 32) * MAX_SHARDS);
-                for (uint32_t sh = 0; sh < a.nshards; sh++) {
-                    const uint32_t bal = __ballot_sync(FULL, keep && dest == sh);
-                    if (lane == 0) wt[cwarp * MAX_SHARDS + sh] = __popc(bal);
-                    if (keep && dest == sh) myrank = __popc(bal & lanemask_lt());
-                }
-                consumer_bar();
-                uint32_t local = myrank, all = 0;
-                uint64_t pk0 = 0, pk1 = 0; // tile counts of shards 0-3 / 4-7, 10 bits each (a tile holds <= 256 items)
-                for (uint32_t sh = 0; sh < a.nshards; sh++) {
-                    uint32_t tot = 0, before = 0;
-#pragma unroll
-                    for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = wt[w * MAX_SHARDS + sh]; if (w < cwarp) before += c; tot += c; }
-                    if (sh < dest) local += tot;            // shards are laid out one after the other inside the tile
-                    else if (sh == dest) local += before;
-                    all += tot;
-                    if (sh < 4) pk0 |= static_cast<uint64_t>(tot) << (10 * sh); else pk1 |= static_cast<uint64_t>(tot) << (10 * (sh - 4));
-                    if (ctid == sh) meta[s].bcount[sh] = tot;
-                }
-                if (ctid == 0 && m.tile != 0) { // publish the aggregates at once: [epoch 22 | status 2 | 4 x 10-bit counts]
-                    uint64_t *st = a.tile_state + static_cast<size_t>(m.tile) * SHARD_STATE_WORDS;
-                    const uint64_t tag = (static_cast<uint64_t>(a.epoch & 0x3fffffu) << 42) | (ST_AGG << 40);
-                    st_relaxed_u64(st + 0, tag | pk0);
-                    st_relaxed_u64(st + 1, tag | pk1);
-                }
-                if (ctid == 0) meta[s].count = all;
-                if (keep) TileIO<R>::store(buf, local, res);
-            } else if constexpr (MODE == MODE_MAP) {
+            if constexpr (MODE == MODE_MAP) {
                 consumer_bar(); // every consumer has read its tuple: overwrite the stage with the results
                 if (active) {
                     if constexpr (CAN_SWZ) {
@@ -538,83 +503,6 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if (a.batches == nullptr) b = a.one; else b = a.batches[m.batch];
             const uint32_t t = m.tile, tile_count = m.count;
             uint32_t excl = 0;
-            if constexpr (MODE == MODE_SHARD) {
-                // One warp-wide decoupled look-back resolves ALL shards: lane l inspects tile t-1-l (then t-33-l ...), whose
-                // state is 2 packed AGGREGATE words (all shards' tile counts) + one PREFIX word per shard.
-                const uint32_t mycnt = (lane < a.nshards) ? m.bcount[lane] : 0u;
-                uint32_t mybase = mycnt; // exclusive prefix of the shard counts = offset of the shard's run in the stage
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, mybase, o); if (lane >= static_cast<uint32_t>(o)) mybase += v; }
-                mybase -= mycnt;
-                uint32_t sums[MAX_SHARDS];
-#pragma unroll
-                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) sums[sh] = 0;
-                if (t != 0) {
-                    const uint64_t etag = static_cast<uint64_t>(a.epoch & 0x3fffffu);
-                    uint32_t done = 0;
-                    const uint32_t full_mask = (1u << a.nshards) - 1u;
-                    int64_t idx = static_cast<int64_t>(t) - 1;
-                    while (done != full_mask) {
-                        const int64_t my = idx - lane;
-                        uint64_t a0 = 0, a1 = 0, pre[MAX_SHARDS];
-                        if (my >= 0) {
-                            const uint64_t *st = a.tile_state + static_cast<size_t>(my) * SHARD_STATE_WORDS;
-#pragma unroll
-                            for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) pre[sh] = (sh < a.nshards) ? ld_relaxed_u64(st + 2 + sh) : 0;
-                            if (my != 0) { // tile 0 never publishes aggregates (its prefixes are its counts)
-                                do { a0 = ld_relaxed_u64(st + 0); } while ((a0 >> 42) != etag || ((a0 >> 40) & 3u) != ST_AGG);
-                                do { a1 = ld_relaxed_u64(st + 1); } while ((a1 >> 42) != etag || ((a1 >> 40) & 3u) != ST_AGG);
-                            } else {
-#pragma unroll
-                                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++)
-                                    if (sh < a.nshards) while ((pre[sh] >> 34) != (a.epoch & 0x3fffffffu) || ((pre[sh] >> 32) & 3u) != ST_PREFIX) pre[sh] = ld_relaxed_u64(st + 2 + sh);
-                            }
-                        }
-#pragma unroll
-                        for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) {
-                            if (sh >= a.nshards || (done >> sh) & 1u) continue;
-                            bool isP; uint32_t val;
-                            if (my < 0) { isP = true; val = 0; }
-                            else {
-                                isP = ((pre[sh] >> 34) == (a.epoch & 0x3fffffffu)) && (((pre[sh] >> 32) & 3u) == ST_PREFIX);
-                                val = isP ? static_cast<uint32_t>(pre[sh]) : static_cast<uint32_t>(((sh < 4 ? a0 : a1) >> (10 * (sh & 3))) & 1023u);
-                            }
-                            const uint32_t pmask = __ballot_sync(FULL, isP);
-                            const uint32_t firstp = pmask ? (__ffs(pmask) - 1) : 32;
-                            uint32_t v = (lane <= firstp) ? val : 0u;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                            sums[sh] += v;
-                            if (pmask) done |= 1u << sh;
-                        }
-                        idx -= 32;
-                    }
-                }
-#pragma unroll
-                for (uint32_t sh = 0; sh < MAX_SHARDS; sh++) if (lane == sh) excl = sums[sh];
-                if (lane < a.nshards) {
-                    st_relaxed_u64(a.tile_state + static_cast<size_t>(t) * SHARD_STATE_WORDS + 2 + lane, pack_state(a.epoch, ST_PREFIX, excl + mycnt));
-                    if (t == a.num_tiles - 1) a.shard_counts[lane] = excl + mycnt;
-                    if (excl + mycnt > a.region_cap) atomicOr(a.shard_counts + MAX_SHARDS, 2u);
-                }
-                __syncwarp();
-                for (uint32_t sh = 0; sh < a.nshards; sh++) {
-                    const uint32_t c = __shfl_sync(FULL, mycnt, sh), bs = __shfl_sync(FULL, mybase, sh), ex = __shfl_sync(FULL, excl, sh);
-                    if (c == 0 || ex + c > a.region_cap) continue;
-                    unsigned char *dsts = a.lifted + (static_cast<size_t>(sh) * a.region_cap + ex) * RB;
-                    const unsigned char *srcs = buf + static_cast<size_t>(bs) * RB;
-                    const uint32_t nbytes = c * RB;
-                    if (bulk_ok(dsts, nbytes) && (reinterpret_cast<uintptr_t>(srcs) & 15u) == 0) { if (lane == 0) bulk_s2g(dsts, srcs, nbytes); }
-                    else {
-                        uint64_t *d8 = reinterpret_cast<uint64_t *>(dsts);
-                        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(srcs);
-                        for (uint32_t w = lane; w < nbytes / 8; w += 32) d8[w] = s8[w];
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) { bulk_commit(); bulk_wait_read<0>(); mbar_arrive(&empty[s]); }
-                continue;
-            }
             if (MODE == MODE_INGEST && a.sparse) {
                 excl = t * TILE; // the tile's own region
                 if (lane == 0 && t == 0 && a.ff.n_trig != nullptr) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists filled by the update kernels

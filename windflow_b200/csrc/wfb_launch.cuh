@@ -128,7 +128,6 @@ int tile_pass_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_
     case MODE_MAP: return launch_tile_pass<P, MODE_MAP>(a, params, want_grid, s, grid_used, span_begin, span_end);
     case MODE_FILTER: return launch_tile_pass<P, MODE_FILTER>(a, params, want_grid, s, grid_used, span_begin, span_end);
     case MODE_INGEST: return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
-    case MODE_SHARD: return launch_tile_pass<P, MODE_SHARD>(a, params, want_grid, s, grid_used, span_begin, span_end);
     }
     return WFB_E_BADARG;
 }
