@@ -1299,12 +1299,14 @@ __global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, con
 // latency, not by bytes:
 //   1. every thread takes BK_IT consecutive items of the chunk; stable split by key through per-thread private key
 //      counts in shared memory (count, exclusive scan over the threads, place) -> per-key runs of record indices,
-//   2. the FlatFAT siblings of the leaf each key completes in this chunk are copied to shared memory with cp.async while
-//   3. ONE THREAD per key folds its run in arrival order straight from the lifted array, eight masked loads per round
-//      trip; completed panes become FlatFAT leaves, their root paths are recomputed from the staged siblings and fired
-//      groups go to the deferred window list,
-//   4. keys with more than BK_LIGHT items in the chunk are folded by a whole warp instead (ordered shuffle-tree fold,
-//      32 records per load).
+//   2. the FlatFAT siblings of the leaf each key completes first in this chunk are copied to shared memory with cp.async
+//      while
+//   3. ONE THREAD per segment (the items of a run that fall into one pane) folds its items in arrival order straight
+//      from the lifted array, eight masked loads per round trip; then one thread per key walks its segments in order:
+//      completed panes become FlatFAT leaves, their root paths are recomputed (staged siblings for the first) and fired
+//      groups go to the deferred window list; the last partial segment is the new open pane,
+//   4. a chunk with more segments than threads (tiny panes) is folded one warp per key instead (ordered shuffle-tree
+//      fold, 32 records per load).
 // Per-key bookkeeping (count, position in the open pane, next leaf, next trigger, open-pane accumulator) is computed
 // once per CTA by one thread per key and lives in shared memory across the chunks.
 // `moved` = 1: the partition pass also moved the records (bucket b's records are lifted[boff[b] ..)); 0: records are
@@ -1320,7 +1322,6 @@ constexpr uint32_t BK_KEYS = 64;      // keys per bucket (at most)
 constexpr uint32_t BK_THREADS = 128;
 constexpr uint32_t BK_IT = 18;        // consecutive items per thread and chunk
 constexpr uint32_t BK_CAP = BK_THREADS * BK_IT; // items per chunk
-constexpr uint32_t BK_LIGHT = 96;     // longest run folded by a single thread
 #ifndef WFB_BK_U
 #define WFB_BK_U 8
 #endif
@@ -1347,7 +1348,8 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
     constexpr uint32_t BK_SIBL = RB <= 32 ? 8 : (RB <= 64 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged in shared memory
     static_assert(DPT % 4 == 0 && BK_KEYS == 64 && BK_THREADS == 128 && RB % 8 == 0, "layout");
     __shared__ uint32_t s_idx[BK_CAP];                 // record index of the items (into `lifted`), key-major
-    __shared__ uint16_t hist[BK_KEYS][HS];             // items of key k among thread t's items -> exclusive over the threads
+    __shared__ __align__(16) uint16_t hist[BK_KEYS][HS]; // items of key k among thread t's items -> exclusive over the threads;
+                                                       // after the split: segment descriptors and segment results (fold phase)
     __shared__ uint32_t htot[2][BK_KEYS];              // per key: items held by threads 0..63 / 64..127
     __shared__ uint32_t kcnt[BK_KEYS], koff[BK_KEYS];  // items / first index of key k in this chunk
     __shared__ uint32_t kleft[BK_KEYS];                // items of key k still to come in this segment
@@ -1356,7 +1358,11 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
     __shared__ __align__(16) unsigned char kacc[BK_KEYS * RB];   // open-pane accumulator of key k
     __shared__ __align__(16) unsigned char s_sib[BK_KEYS * BK_SIBL * RB]; // siblings of the leaf key k completes in this chunk
     __shared__ uint32_t s_heavy[BK_KEYS];              // keys folded by a warp in this chunk
-    __shared__ uint32_t misc[NW], s_boff[2], s_nheavy;
+    __shared__ uint32_t ksegb[BK_KEYS];                // first segment of key k (a segment = the items of a run that fall into one pane)
+    __shared__ uint32_t misc[NW], s_boff[2], s_nheavy, s_nseg;
+    constexpr bool SEG_OK = BK_THREADS * (RB + 4) <= sizeof(uint16_t) * BK_KEYS * HS; // segment results + descriptors alias the private counts
+    unsigned char *seg_res = reinterpret_cast<unsigned char *>(&hist[0][0]);                       // BK_THREADS x result_t
+    uint32_t *seg_desc = reinterpret_cast<uint32_t *>(seg_res + BK_THREADS * RB);                  // key | index of the segment in its run << 8
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bucket = blockIdx.x;
@@ -1468,13 +1474,25 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
             const uint32_t t0 = __shfl_sync(FULL, i0, 31);
             kcnt[lane] = a0; kcnt[lane + 32] = a1;
             koff[lane] = i0 - a0; koff[lane + 32] = t0 + i1 - a1;
-            // long runs and runs that complete a second pane are folded by a warp
-            const bool h0 = a0 > BK_LIGHT || a0 - min(a0, P32 - kcp[lane]) >= P32;
-            const bool h1 = a1 > BK_LIGHT || a1 - min(a1, P32 - kcp[lane + 32]) >= P32;
+            // segments of the runs: the items that complete the open pane, then one segment per further pane
+            const uint32_t c0 = kcp[lane], c1 = kcp[lane + 32];
+            const uint32_t f0 = min(a0, P32 - c0), f1 = min(a1, P32 - c1);
+            const uint32_t n0 = a0 ? 1u + (a0 - f0 + P32 - 1) / P32 : 0u, n1 = a1 ? 1u + (a1 - f1 + P32 - 1) / P32 : 0u;
+            uint32_t s0 = n0, s1 = n1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v0 = __shfl_up_sync(FULL, s0, o), v1 = __shfl_up_sync(FULL, s1, o);
+                if (lane >= static_cast<uint32_t>(o)) { s0 += v0; s1 += v1; }
+            }
+            const uint32_t st0 = __shfl_sync(FULL, s0, 31), nseg = st0 + __shfl_sync(FULL, s1, 31);
+            ksegb[lane] = s0 - n0; ksegb[lane + 32] = st0 + s1 - n1;
+            // more segments than threads (tiny panes): every run of the chunk is folded by a warp instead
+            const bool fallback = !SEG_OK || nseg > BK_THREADS;
+            const bool h0 = fallback && a0 != 0, h1 = fallback && a1 != 0;
             const uint32_t b0 = __ballot_sync(FULL, h0), b1 = __ballot_sync(FULL, h1);
             if (h0) s_heavy[__popc(b0 & lanemask_lt())] = lane;
             if (h1) s_heavy[__popc(b0) + __popc(b1 & lanemask_lt())] = lane + 32;
-            if (lane == 0) s_nheavy = __popc(b0) + __popc(b1);
+            if (lane == 0) { s_nheavy = __popc(b0) + __popc(b1); s_nseg = fallback ? 0u : nseg; }
         }
         __syncthreads();
         {
@@ -1489,43 +1507,41 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                 }
             }
         }
-        // ---- 2. siblings of the leaf each key completes in this chunk -> shared memory (asynchronous) --------------------------------
+        __syncthreads(); // the private counts are dead: their memory now holds the segment descriptors / results
+        // ---- 2. segment descriptors; siblings of the first leaf each key completes -> shared memory (asynchronous) -----------------
+        const uint32_t nseg = s_nseg;
         bool sib_staged = false;
-        if (tid < BK_KEYS) {
+        if (tid < BK_KEYS && nseg != 0) {
             const uint32_t m = kcnt[tid];
-            const uint32_t sA = min(m, P32 - kcp[tid]);
-            if (m != 0 && m <= BK_LIGHT && m - sA < P32 && kcp[tid] + sA == P32) {
-                const uint32_t leaf = kleaf[tid];
-                const unsigned char *tr = ff.tree + static_cast<size_t>(key_lo + tid) * tree_stride;
-                for (uint32_t l = 0; l < min(logn, BK_SIBL); l++) {
-                    const unsigned char *src = tr + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB;
-                    unsigned char *dst = s_sib + (tid * BK_SIBL + l) * RB;
+            if (m != 0) {
+                const uint32_t cp0 = kcp[tid], first = min(m, P32 - cp0), ns = 1u + (m - first + P32 - 1) / P32, sb = ksegb[tid];
+                for (uint32_t j = 0; j < ns; j++) seg_desc[sb + j] = tid | (j << 8);
+                if (cp0 + first == P32) {
+                    const uint32_t leaf = kleaf[tid];
+                    const unsigned char *tr = ff.tree + static_cast<size_t>(key_lo + tid) * tree_stride;
+                    for (uint32_t l = 0; l < min(logn, BK_SIBL); l++) {
+                        const unsigned char *src = tr + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB;
+                        unsigned char *dst = s_sib + (tid * BK_SIBL + l) * RB;
 #pragma unroll
-                    for (uint32_t q = 0; q < RB / CPB; q++) cp_async<CPB>(dst + q * CPB, src + q * CPB);
+                        for (uint32_t q = 0; q < RB / CPB; q++) cp_async<CPB>(dst + q * CPB, src + q * CPB);
+                    }
+                    sib_staged = true;
                 }
-                sib_staged = true;
             }
         }
         __syncthreads();
         BK_MARK(3);
-        // ---- 3. two threads per key: thread k folds the items that go into the open pane (and, when that completes the pane,
-        // writes the leaf, the root path and the fired group); thread 64+k folds the items after it into the next open pane.
-        // A run that would complete a second pane is left to a warp (s_heavy), so neither fold has inner bookkeeping.
-        {
-            const uint32_t k = tid & 63u, slot = key_lo + k;
-            const bool second = tid >= BK_KEYS;
-            uint32_t m = kcnt[k];
-            const uint32_t cp0 = kcp[k];
-            const uint32_t segA = min(m, P32 - cp0);
-            if (m > BK_LIGHT || m - segA >= P32) m = 0; // folded by a warp
-            uint32_t seg = m == 0 ? 0u : (second ? m - segA : segA);
-            const bool fresh0 = second || cp0 == 0;
-            const uint32_t *ip = s_idx + koff[k] + (second ? segA : 0u);
+        // ---- 3a. one thread per segment: plain ordered fold of at most one pane of items, BK_U masked loads per round trip ---------
+        if (tid < nseg) {
+            const uint32_t d = seg_desc[tid], k = d & 255u, j = d >> 8;
+            const uint32_t m = kcnt[k], cp0 = kcp[k], first = min(m, P32 - cp0);
+            const uint32_t start = j == 0 ? 0u : first + (j - 1) * P32;
+            uint32_t seg = j == 0 ? first : min(P32, m - start);
+            bool fresh = j != 0 || cp0 == 0;
+            const uint32_t *ip = s_idx + koff[k] + start;
             alignas(16) R acc;
-            if (seg != 0 && !fresh0) ld_rec<R>(kacc + k * RB, acc);
-            const uint32_t mine = seg;
-            bool fresh = fresh0;
-            while (seg != 0) { // plain ordered fold, BK_U masked loads per round trip
+            if (!fresh) ld_rec<R>(kacc + k * RB, acc);
+            while (seg != 0) {
                 alignas(16) R it[BK_U];
                 const uint32_t kk = min(seg, BK_U);
 #pragma unroll
@@ -1536,66 +1552,90 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                 for (uint32_t q = 1; q < BK_U; q++) if (q < kk) P::comb(acc, it[q], acc, prm);
                 seg -= kk; ip += kk;
             }
-            __syncthreads(); // every thread k has read its old open pane: threads 64+k may overwrite it
-            if (second) {
-                if (mine != 0) st_rec<R>(kacc + k * RB, acc); // the new open pane (kcp is set by thread k)
-            } else if (m != 0) {
-                const bool completed = cp0 + segA == P32;
-                uint32_t leafi = kleaf[k];
-                uint64_t g = kg[k];
-                const uint64_t tt = ktt[k];
-                if (completed) { // new leaf, root path, fired group
-                    unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
-                    const uint32_t leaf = leafi;
-                    leafi = (leafi + 1) & (n - 1);
-                    alignas(16) R cur = acc;
-                    st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
-                    if (sib_staged) cp_async_wait_all();
-                    for (uint32_t l0 = 0; l0 < logn; l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
-                        alignas(16) R sb[4];
+            st_rec<R>(seg_res + tid * RB, acc);
+        }
+        __syncthreads();
+        // ---- 3b. one thread per key, its segments in order: completed panes -> leaf + root path + fired group; the rest is the open
+        // pane. The loop over the segments is warp-uniform: a group that cannot be deferred (another pane of the key completes
+        // in this stream segment and would overwrite ring leaves the windows still need) is evaluated by the whole warp at once.
+        if (tid < BK_KEYS && nseg != 0) { // warps 0 and 1, whole
+            const uint32_t k = tid, slot = key_lo + k, m = kcnt[k];
+            const uint32_t cp0 = kcp[k], first = min(m, P32 - cp0), ns = m ? 1u + (m - first + P32 - 1) / P32 : 0u, sb = ksegb[k];
+            uint32_t leafi = kleaf[k], new_cp = cp0, consumed = 0;
+            uint64_t g = kg[k], tt = ktt[k]; // tt: index (1-based) of the run's item that fires the next group
+            const uint32_t left0 = kleft[k];
+            unsigned char *tree = ff.tree + static_cast<size_t>(slot) * tree_stride;
+            const uint64_t key = key_of_slot(ff, slot < ff.max_keys ? slot : 0u);
+            for (uint32_t j = 0; __any_sync(FULL, j < ns); j++) {
+                bool eval_now = false;
+                uint32_t ev_obase = 0, ev_pos = 0;
+                uint64_t ev_g = 0;
+                if (j < ns) {
+                    const uint32_t len = j == 0 ? first : min(P32, m - consumed);
+                    consumed += len;
+                    alignas(16) R cur;
+                    ld_rec<R>(seg_res + (sb + j) * RB, cur);
+                    const bool completes = (j == 0 ? cp0 + len : len) == P32;
+                    if (!completes) { st_rec<R>(kacc + k * RB, cur); new_cp = (j == 0 ? cp0 : 0u) + len; } // (only the last segment)
+                    else {
+                        new_cp = 0;
+                        const uint32_t leaf = leafi;
+                        leafi = (leafi + 1) & (n - 1);
+                        st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
+                        if (sib_staged) cp_async_wait_all();
+                        for (uint32_t l0 = 0; l0 < logn; l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
+                            alignas(16) R sbl[4];
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) {
-                            const uint32_t l = l0 + q;
-                            if (l < logn) {
-                                if (sib_staged && l < BK_SIBL) ld_rec<R>(s_sib + (k * BK_SIBL + l) * RB, sb[q]);
-                                else ld_rec<R>(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB, sb[q]);
+                            for (uint32_t q = 0; q < 4; q++) {
+                                const uint32_t l = l0 + q;
+                                if (l < logn) {
+                                    if (sib_staged && l < BK_SIBL) ld_rec<R>(s_sib + (k * BK_SIBL + l) * RB, sbl[q]);
+                                    else ld_rec<R>(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB, sbl[q]);
+                                }
+                            }
+#pragma unroll
+                            for (uint32_t q = 0; q < 4; q++) {
+                                const uint32_t l = l0 + q;
+                                if (l < logn) {
+                                    alignas(16) R parent = cur;
+                                    if ((leaf >> l) & 1u) P::comb(sbl[q], cur, parent, prm); else P::comb(cur, sbl[q], parent, prm);
+                                    cur = parent;
+                                    st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                                }
                             }
                         }
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; q++) {
-                            const uint32_t l = l0 + q;
-                            if (l < logn) {
-                                alignas(16) R parent = cur;
-                                if ((leaf >> l) & 1u) P::comb(sb[q], cur, parent, prm); else P::comb(cur, sb[q], parent, prm);
-                                cur = parent;
-                                st_rec<R>(tree + static_cast<size_t>(level_off(n, l + 1) + (leaf >> (l + 1))) * RB, cur);
+                        sib_staged = false; // the next pane of the same run reads the tree it has just written
+                        if (consumed == tt) {
+                            const uint32_t lp = s_idx[koff[k] + consumed - 1];
+                            const uint32_t last_pos = moved ? bk_pos[lp] : lp; // arrival position of the triggering item
+                            const uint32_t obase = atomicAdd(n_out, ff.nb);
+                            bool deferred = (left0 - consumed) < P32; // no further pane of this key can complete in this segment
+                            if (deferred) {
+                                const uint32_t ti = atomicAdd(ff.n_trig, 1u);
+                                if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
+                                else deferred = false;
                             }
+                            if (!deferred) { eval_now = true; ev_obase = obase; ev_pos = last_pos; ev_g = g; }
+                            g++; tt += group_items;
                         }
                     }
-                    if (segA == tt) {
-                        const uint64_t key = key_of_slot(ff, slot);
-                        const uint32_t lp = s_idx[koff[k] + segA - 1];
-                        const uint32_t last_pos = moved ? bk_pos[lp] : lp; // arrival position of the triggering item
-                        const uint32_t obase = atomicAdd(n_out, ff.nb);
-                        bool deferred = (kleft[k] - segA) < P32; // no further pane of this key can complete in this segment
-                        if (deferred) {
-                            const uint32_t ti = atomicAdd(ff.n_trig, 1u);
-                            if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
-                            else deferred = false;
-                        }
-                        if (!deferred) {
-                            const uint64_t wm = batch_watermark(batch_off, batches, nbatches, last_pos);
-                            for (uint32_t i = 0; i < ff.nb; i++)
-                                ffat_eval_window<P>(ff, tree, key, g * ff.nb + i, wm, obase + i, out_res, out_ts, out_cap, prm);
-                        }
-                        g++;
-                    }
-                } else st_rec<R>(kacc + k * RB, acc); // still the open pane
-                kc[k] += m; kg[k] = g; kleaf[k] = leafi; kleft[k] -= m;
-                ktt[k] = (completed && segA == tt) ? group_items - (m - segA) : tt - m;
-                kcp[k] = completed ? m - segA : cp0 + m;
+                }
+                // groups to evaluate before their key's next pane: one after the other, the warp's lanes share the windows
+                uint32_t pend = __ballot_sync(FULL, eval_now);
+                while (pend) {
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint32_t e_slot = __shfl_sync(FULL, slot, src), e_obase = __shfl_sync(FULL, ev_obase, src), e_pos = __shfl_sync(FULL, ev_pos, src);
+                    const uint64_t e_key = __shfl_sync(FULL, key, src), e_g = __shfl_sync(FULL, ev_g, src);
+                    const unsigned char *e_tree = ff.tree + static_cast<size_t>(e_slot) * tree_stride;
+                    const uint64_t wm = batch_watermark(batch_off, batches, nbatches, e_pos);
+                    for (uint32_t i = lane; i < ff.nb; i += 32)
+                        ffat_eval_window<P>(ff, e_tree, e_key, e_g * ff.nb + i, wm, e_obase + i, out_res, out_ts, out_cap, prm);
+                }
+                __syncwarp(); // the evaluated windows read tree nodes another lane has just written, and it may overwrite them next
             }
-            if (sib_staged) cp_async_wait_all(); // (a staged key always completes its pane: nothing is pending here)
+            if (sib_staged) cp_async_wait_all(); // (a staged key always completes its first segment: nothing is pending here)
+            if (m != 0) { kc[k] += m; kg[k] = g; ktt[k] = tt - m; kcp[k] = new_cp; kleaf[k] = leafi; kleft[k] = left0 - m; }
         }
         BK_MARK(4);
         // ---- 3. long runs: one warp per key, ordered shuffle-tree fold of 32 records per load ----------------------------------------
