@@ -38,6 +38,7 @@ FILT = dict(filt_kind=1, mod=1)
 SIGMA = 0.5  # selectivity of (ivalue & 1) == 0 on the synthetic stream
 
 # algorithmic bytes. SURVEY 8d pipeline figure and the dominant kernel's own compulsory traffic.
+METRIC = "tuples/sec, Map_GPU->Filter_GPU->Ffat_Windows_GPU (CB win 4096 slide 64) pipeline"
 PIPELINE_BYTES_PER_TUPLE = 123.3        # read I + sigma*(3R + (O+12R)/S), I=72 R=32 O=40 S=64
 INGEST_BYTES_PER_TUPLE = 64 + SIGMA * (32 + 4)   # k_tile_pass<INGEST>: read tuple, write sigma*(lifted result + slot)
 
@@ -170,12 +171,15 @@ def run_reference(args):
             vals.append(tps)
     v = float(np.mean(vals))
     line = {
-        "impl": "reference", "metric": "tuples/sec, Map->Filter->Ffat_Windows (CB win 4096 slide 64) pipeline", "value": v,
+        "impl": "reference", "metric": METRIC, "value": v,
         "unit": "tuples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (1 << 18) * threads / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64+f64", "data": "synthetic",
-        "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES, "win": WIN, "slide": SLIDE,
-                   "note": "CPU path of the reference on host cores; bounded steady-state sample per step"},
+        "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES, "keys": NKEYS, "key_dist": "uniform",
+                   "win": WIN, "slide": SLIDE, "wins_per_batch": args.nb, "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0",
+                   "selectivity": SIGMA,
+                   "note": "the reference's CPU Map->Filter->Ffat_Windows path on this box's host cores (all of them); every step is a "
+                           "bounded steady-state sample of the same stream"},
         "cpu_baseline": {"value": v, "unit": "tuples/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -305,7 +309,7 @@ def run_ours(args):
         cpu_threads = min(os.cpu_count() or 1, 32)
         cpu_tps, cpu_desc = cpu_pipeline(cpu_kind, cpu_threads, args.cpu_seconds)
         line = {
-            "metric": "tuples/sec, Map_GPU->Filter_GPU->Ffat_Windows_GPU (CB win 4096 slide 64) pipeline",
+            "metric": METRIC,
             "value": value, "unit": "tuples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i64+f64", "data": "synthetic",

@@ -118,6 +118,13 @@ int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f,
                    const void *tuples_in, const uint64_t *ts_in, uint32_t n,
                    void *tuples_out, uint64_t *ts_out, uint32_t *n_out_dev, void *stream);
 
+/* The same operator over K queued batches in ONE launch (a replica that finds several batches on its input channel):
+ * batch i is compacted into (out[i].tuples, out[i].ts) and its survivor count written to n_out_dev[i]; results are
+ * identical to K wfb_map_filter calls. in[i].ts may be NULL (then out[i].ts is not written). out[i].tuples may be
+ * in[i].tuples (in-place compaction of every batch). */
+int wfb_map_filter_batches(wfb_engine_t *e, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h,
+                           uint32_t nbatches, uint32_t *n_out_dev, void *stream);
+
 /* ---- Reduce_GPU, per batch -------------------------------------------------------------------------
  * keyed: one output item per distinct key, ascending key order, tuple = fold of the program's reduce functor
  * over the key's items, ts = max ts. replaces Extract_Keys_Kernel + sort_by_key + reduce_by_key + D2D,

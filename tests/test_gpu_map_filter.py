@@ -141,3 +141,32 @@ def test_device_generator_matches_host(wfb, oracle):
     torch.cuda.synchronize()
     t, ts = O.gen_tuple64(0, 20000, O.KEY_ZIPF, 5000, cdf=cdf)
     assert ops.to_host(b.tuples, ops.TUPLE64).tobytes() == t.tobytes()
+
+
+@pytest.mark.parametrize("inplace", [False, True])
+def test_map_filter_batches(wfb, oracle, inplace):
+    """K queued batches (ragged sizes, one empty) in one launch == K single-batch calls == the oracle, byte for byte."""
+    import torch
+    O, ops = oracle, wfb
+    sizes = [65536, 1, 0, 257, 4097, 30000, 255, 65536]
+    f = ops.functors(map_kind=1, iadd=2, fscale=1.0000001, filt_kind=2, mod=3)
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    ins, outs, hosts, start = [], [], [], 0
+    for n in sizes:
+        t, ts = O.gen_tuple64(start, n, O.KEY_UNIFORM, 1000)
+        t["pad"] = np.arange(n * 4, dtype=np.uint64).reshape(n, 4) + start
+        hosts.append((t, ts)); start += n
+        b = ops.DeviceBatch.from_host(t, ts) if n else ops.DeviceBatch(torch.empty(0, dtype=torch.uint8, device="cuda"), torch.empty(0, dtype=torch.int64, device="cuda"), 0, 0)
+        ins.append(b)
+        outs.append(b if inplace else ops.DeviceBatch(torch.empty_like(b.tuples), torch.empty_like(b.ts), n, 0))
+    n_out = torch.full((len(sizes),), 12345, dtype=torch.int32, device="cuda")
+    eng.map_filter_batches(ins, f, outs, n_out)
+    torch.cuda.synchronize()
+    no = n_out.cpu().numpy()
+    for i, (t, ts) in enumerate(hosts):
+        exp, exp_ts, _ = O.map_filter_tuple64(t, ts, 1, 2, 1.0000001, 2, 3)
+        assert no[i] == len(exp)
+        got = ops.to_host(outs[i].tuples, ops.TUPLE64, len(exp)) if len(exp) else exp
+        assert got.tobytes() == exp.tobytes()
+        if len(exp):
+            assert np.array_equal(ops.ts_to_host(outs[i].ts, len(exp)), exp_ts)

@@ -46,6 +46,13 @@ def main():
     tps = BATCH / (ms * 1e-3); bpt = 72 * (1 + sigma)
     print(json.dumps({"config": "cfg2 Map_GPU->Filter_GPU fused, one call per batch of 65536 x 64 B", "tuples_per_s": tps, "ms_per_batch": ms,
                       "selectivity": sigma, "bytes_per_tuple": bpt, "achieved_gbs": tps * bpt / 1e9, "frac_of_measured_peak": tps * bpt / 1e9 / peak}))
+    ob = [ops.DeviceBatch(torch.empty_like(b.tuples), torch.empty_like(b.ts), BATCH, 0) for b in batches]
+    nos = torch.zeros(ring, dtype=torch.int32, device=dev)
+    seg_in, seg_out = ops.Segment(batches), ops.Segment(ob)
+    ms = timed(lambda i: eng.map_filter_batches(seg_in, f, seg_out, nos), max(10, a.iters // 4))
+    tps = ring * BATCH / (ms * 1e-3)
+    print(json.dumps({"config": f"cfg2 Map_GPU->Filter_GPU fused, {ring} queued batches of 65536 x 64 B per call (wfb_map_filter_batches)", "tuples_per_s": tps,
+                      "ms_per_call": ms, "selectivity": sigma, "bytes_per_tuple": bpt, "achieved_gbs": tps * bpt / 1e9, "frac_of_measured_peak": tps * bpt / 1e9 / peak}))
     # ---- cfg 3 --------------------------------------------------------------------------------------------------
     cdf = torch.from_numpy(zipf_cdf(1000000)).to(dev)
     zb = [ops.gen_tuple64(i * BATCH, BATCH, ops.KEY_ZIPF, 1000000, zipf_cdf=cdf) for i in range(ring)]

@@ -493,6 +493,43 @@ int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f, const void *tuples_
     return run_single(e, MODE_FILTER, f, b, s);
 }
 
+int wfb_map_filter_batches(wfb_engine_t *e, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches,
+                           uint32_t *n_out_dev, void *stream)
+{
+    if (!e || !f || !n_out_dev || (nbatches && (!in_h || !out_h))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nbatches == 0) return 0;
+    int rc = e->ts.enter(s); if (rc) return rc;
+    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t) * nbatches, s)); // empty batches keep 0
+    std::vector<DevBatch> hb; hb.reserve(nbatches);
+    uint32_t tiles = 0; uint64_t span_begin = ~0ull, span_end = 0;
+    for (uint32_t i = 0; i < nbatches; i++) {
+        if (in_h[i].n == 0) continue;
+        if (!in_h[i].tuples || !out_h[i].tuples) return WFB_E_BADARG;
+        DevBatch b; std::memset(&b, 0, sizeof(b));
+        b.tuples = static_cast<const unsigned char *>(in_h[i].tuples); b.ts = in_h[i].ts;
+        b.out = static_cast<unsigned char *>(const_cast<void *>(out_h[i].tuples));
+        b.ts_out = in_h[i].ts ? const_cast<uint64_t *>(out_h[i].ts) : nullptr;
+        b.n_out = n_out_dev + i; b.n = in_h[i].n; b.tile_begin = tiles;
+        tiles += tiles_of(b.n);
+        const uint64_t p0 = reinterpret_cast<uint64_t>(b.tuples);
+        span_begin = std::min(span_begin, p0); span_end = std::max(span_end, p0 + static_cast<uint64_t>(b.n) * e->ops->tuple_bytes);
+        hb.push_back(b);
+    }
+    if (hb.empty()) return 0;
+    rc = e->ts.ensure_tiles(tiles); if (rc) return rc;
+    rc = e->ts.ensure_batches(static_cast<uint32_t>(hb.size())); if (rc) return rc;
+    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * hb.size(), cudaMemcpyHostToDevice, s));
+    TileArgs a; std::memset(&a, 0, sizeof(a));
+    a.batches = e->ts.d_batches; a.nbatches = static_cast<uint32_t>(hb.size()); a.num_tiles = tiles; a.l2_hints = 1;
+    e->ts.next_launch(a);
+    uint32_t grid = 0;
+    rc = e->ops->tile_pass(MODE_FILTER, a, f, tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+    e->ts.launched(tiles, grid);
+    e->launches++;
+    return 0;
+}
+
 int wfb_engine_set_key_bits(wfb_engine_t *e, uint32_t bits)
 {
     if (!e || bits == 0 || bits > 64) return WFB_E_BADARG;

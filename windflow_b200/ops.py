@@ -126,6 +126,12 @@ class Engine:
                                     _ptr(out.tuples), _ptr(out.ts), _ptr(n_out), _stream_ptr(stream)), "wfb_map_filter")
         return out, n_out
 
+    def map_filter_batches(self, batches, f, outs, n_out, stream=None):
+        """[Map_GPU ->] Filter_GPU over K queued batches in one launch: batch i compacted into outs[i], n_out[i] survivors."""
+        check(self.L.wfb_map_filter_batches(self.h, C.byref(f), _cbatches(batches), _cbatches(outs), len(batches), _ptr(n_out),
+                                            _stream_ptr(stream)), "wfb_map_filter_batches")
+        return outs, n_out
+
     def reduce_by_key(self, batch, out=None, n_out=None, stream=None):
         if out is None:
             out = DeviceBatch(torch.empty_like(batch.tuples), torch.empty_like(batch.ts), batch.n, batch.watermark)
