@@ -131,6 +131,11 @@ int wfb_map_filter_batches(wfb_engine_t *e, const wfb_functors_t *f, const wfb_b
  * wf/reduce_gpu.hpp:75-105, :226-262. */
 int wfb_reduce_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n,
                       void *out_tuples, uint64_t *out_ts, uint32_t *n_out_dev, void *stream);
+/* The same operator over K queued batches in ONE launch sequence: batch i reduced into (out[i].tuples, out[i].ts) with
+ * n_out_dev[i] items (ascending key); results are identical to K wfb_reduce_by_key calls. Keys must fit the engine's
+ * key_bits (wfb_engine_set_key_bits) and key_bits + ceil(log2 K) <= 64. */
+int wfb_reduce_by_key_batches(wfb_engine_t *e, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches,
+                              uint32_t *n_out_dev, void *stream);
 /* un-keyed: whole batch -> one item. replaces thrust::reduce, wf/reduce_gpu.hpp:264-286. */
 int wfb_reduce_all(wfb_engine_t *e, const void *tuples, const uint64_t *ts, uint32_t n,
                    void *out_tuple, uint64_t *out_ts, void *stream);

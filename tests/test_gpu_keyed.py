@@ -75,6 +75,41 @@ def test_reduce_by_key(wfb, oracle, n, dist):
     assert np.array_equal(ops.ts_to_host(out.ts)[:k], ets)
 
 
+@pytest.mark.parametrize("sizes", [[65536], [3000, 0, 1, 65536, 257, 40000, 5], [1000] * 9])
+def test_reduce_by_key_batches(wfb, oracle, sizes):
+    """Reduce_GPU over K queued batches in one launch sequence == the oracle per batch (ascending keys, ts = max)."""
+    import torch
+    O, ops = oracle, wfb
+    eng = ops.Engine(ops.PROG_TUPLE64)
+    eng.set_key_bits(20)
+    ins, outs, hosts = [], [], []
+    for i, n in enumerate(sizes):
+        t, ts = O.gen_tuple64(1000 * i, n, O.KEY_ZIPF if i % 2 == 0 else O.KEY_UNIFORM, 1000000 if i % 2 == 0 else 37)
+        ts = (ts * 7919) % 100003
+        hosts.append((t, ts))
+        if n:
+            b = ops.DeviceBatch.from_host(t, ts)
+        else:
+            b = ops.DeviceBatch(torch.empty(0, dtype=torch.uint8, device="cuda"), torch.empty(0, dtype=torch.int64, device="cuda"), 0, 0)
+        ins.append(b)
+        outs.append(ops.DeviceBatch(torch.empty_like(b.tuples), torch.empty_like(b.ts), n, 0))
+    n_out = torch.full((len(sizes),), 777, dtype=torch.int32, device="cuda")
+    eng.reduce_by_key_batches(ins, outs, n_out)
+    torch.cuda.synchronize()
+    no = n_out.cpu().numpy()
+    for i, (t, ts) in enumerate(hosts):
+        if len(t) == 0:
+            assert no[i] == 0
+            continue
+        exp, ets = O.reduce_tuple64(t, ts)
+        assert no[i] == len(exp), (i, no[i], len(exp))
+        got = ops.to_host(outs[i].tuples, ops.TUPLE64)[:len(exp)]
+        assert np.array_equal(got["key"], exp["key"]) and np.array_equal(got["ivalue"], exp["ivalue"])
+        assert np.allclose(got["fvalue"], exp["fvalue"], rtol=1e-6, atol=0)
+        assert np.array_equal(got["id"], exp["id"]) and np.array_equal(got["pad"], exp["pad"])
+        assert np.array_equal(ops.ts_to_host(outs[i].ts)[:len(exp)], ets)
+
+
 @pytest.mark.parametrize("n", [1, 100, 1024, 65536, 77777])
 def test_reduce_all(wfb, oracle, n):
     import torch

@@ -62,6 +62,13 @@ def main():
     tps = BATCH / (ms * 1e-3); bpt = 72 * (1 + d)
     print(json.dumps({"config": "cfg3 Reduce_GPU keyed, 1M keys Zipf-0.8, one call per batch of 65536", "tuples_per_s": tps, "ms_per_batch": ms,
                       "distinct_fraction": d, "bytes_per_tuple": bpt, "achieved_gbs": tps * bpt / 1e9, "frac_of_measured_peak": tps * bpt / 1e9 / peak}))
+    zo = [ops.DeviceBatch(torch.empty_like(b.tuples), torch.empty_like(b.ts), BATCH, 0) for b in zb]
+    zin, zout = ops.Segment(zb), ops.Segment(zo)
+    ms = timed(lambda i: eng3.reduce_by_key_batches(zin, zout, nos), max(10, a.iters // 8))
+    tps = ring * BATCH / (ms * 1e-3)
+    print(json.dumps({"config": f"cfg3 Reduce_GPU keyed, 1M keys Zipf-0.8, {ring} queued batches per call (wfb_reduce_by_key_batches)", "tuples_per_s": tps,
+                      "ms_per_call": ms, "distinct_fraction": float(nos.sum().item()) / (ring * BATCH), "bytes_per_tuple": bpt,
+                      "achieved_gbs": tps * bpt / 1e9, "frac_of_measured_peak": tps * bpt / 1e9 / peak}))
     # ---- cfg 4 --------------------------------------------------------------------------------------------------
     for nb in (65, 1):
         for bps in (1, 64):

@@ -2008,6 +2008,188 @@ __global__ void __launch_bounds__(256) k_reduce_segments(const unsigned char *__
     }
 }
 
+// ---- Reduce_GPU over K queued batches in one launch sequence: composite sort key (batch index << key_bits) | key ----------
+// batch of global element index gi (boff has nb+1 ascending entries)
+__device__ __forceinline__ uint32_t batch_of(const uint32_t *__restrict__ boff, uint32_t nb, uint32_t gi)
+{
+    uint32_t lo = 0, hi = nb - 1;
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (boff[mid] <= gi) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+template <class P>
+__global__ void k_extract_keys_batches(const DevBatch *__restrict__ batches, const uint32_t *__restrict__ boff, uint32_t nb, uint32_t total,
+                                       uint32_t key_bits, uint64_t *__restrict__ keys, const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    const uint64_t mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += gridDim.x * blockDim.x) {
+        const uint32_t b = batch_of(boff, nb, gi);
+        const T *t = reinterpret_cast<const T *>(batches[b].tuples + static_cast<size_t>(gi - boff[b]) * sizeof(T));
+        keys[gi] = (key_bits >= 64 ? 0ull : (static_cast<uint64_t>(b) << key_bits)) | (P::key(*t, prm) & mask);
+    }
+}
+
+constexpr uint32_t SEGT = 2048; // sorted positions per tile of the head count / finish kernels (256 threads x 8)
+
+// counts[tile] = segment heads (sorted position whose key differs from its predecessor) in the tile
+static __global__ void __launch_bounds__(256) k_head_tile_counts(const uint64_t *__restrict__ skeys, uint32_t n, uint32_t *__restrict__ counts)
+{
+    __shared__ uint32_t wsum[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, base = blockIdx.x * SEGT;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) {
+        const uint32_t i = base + r * 256 + tid;
+        if (i < n && (i == 0 || skeys[i] != skeys[i - 1])) c++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; counts[blockIdx.x] = t; }
+}
+
+// tile_base = exclusive scan of the tile counts. seg_begin[k] = first sorted position of the k-th segment (global numbering),
+// first_seg[b] = number of the first segment of batch b (0xffffffff when the batch has none), *n_segs = total, seg_begin[total] = n
+static __global__ void __launch_bounds__(256) k_seg_finish_batches(const uint64_t *__restrict__ skeys, uint32_t n, uint32_t key_bits,
+                                                            const uint32_t *__restrict__ tile_base, uint32_t *__restrict__ seg_begin,
+                                                            uint32_t *__restrict__ first_seg, uint32_t *__restrict__ n_segs)
+{
+    __shared__ uint32_t wsum[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t first = blockIdx.x * SEGT + tid * (SEGT / 256); // thread t owns 8 consecutive positions
+    bool head[SEGT / 256];
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) {
+        const uint32_t i = first + r;
+        head[r] = i < n && (i == 0 || skeys[i] != skeys[i - 1]);
+        mine += head[r] ? 1u : 0u;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t k = tile_base[blockIdx.x] + incl - mine;
+    for (uint32_t w = 0; w < warp; w++) k += wsum[w];
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) {
+        const uint32_t i = first + r;
+        if (head[r]) {
+            seg_begin[k] = i;
+            const uint64_t b = key_bits >= 64 ? 0ull : (skeys[i] >> key_bits);
+            if (i == 0 || (key_bits < 64 && (skeys[i - 1] >> key_bits) != b)) first_seg[b] = k;
+            k++;
+        }
+        if (i == n - 1) { *n_segs = k; seg_begin[k] = n; }
+    }
+}
+
+// n_out[b] = segments of batch b (first_seg[] is ascending over the batches that have segments)
+static __global__ void k_batch_seg_counts(const uint32_t *__restrict__ first_seg, uint32_t nb, const uint32_t *__restrict__ n_segs,
+                                          const DevBatch *__restrict__ batches)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t next = *n_segs;
+        for (uint32_t b = nb; b-- > 0;) {
+            uint32_t c = 0;
+            if (first_seg[b] != 0xffffffffu) { c = next - first_seg[b]; next = first_seg[b]; }
+            if (batches[b].n_out != nullptr) *batches[b].n_out = c;
+        }
+    }
+}
+
+constexpr uint32_t RB_LONG = 48; // segments longer than this are folded by a warp (k_reduce_segments_batches), the others by one thread
+
+// one THREAD per segment (most keys of a batch occur once or twice): sequential fold, 4 tuples in flight; long segments
+// are put on a list for the warp kernel
+template <class P>
+__global__ void __launch_bounds__(128) k_reduce_segments_batches_short(const DevBatch *__restrict__ batches, const uint32_t *__restrict__ boff,
+                                                                       const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx,
+                                                                       const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ first_seg,
+                                                                       const uint32_t *__restrict__ n_segs, uint32_t key_bits,
+                                                                       uint32_t *__restrict__ long_list, uint32_t *__restrict__ n_long,
+                                                                       const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    const uint32_t nk = *n_segs;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
+        const uint32_t sb = seg_begin[k], se = seg_begin[k + 1];
+        if (se - sb > RB_LONG) { long_list[atomicAdd(n_long, 1u)] = k; continue; }
+        const uint32_t b = key_bits >= 64 ? 0u : static_cast<uint32_t>(skeys[sb] >> key_bits);
+        const unsigned char *tuples = batches[b].tuples;
+        const uint64_t *ts = batches[b].ts;
+        const uint32_t base = boff[b];
+        alignas(16) T acc; uint64_t mts = 0;
+        {
+            const uint32_t i = sidx[sb] - base;
+            ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), acc);
+            mts = ts ? ts[i] : 0;
+        }
+        for (uint32_t j = sb + 1; j < se; j += 2) { // two tuples in flight
+            const uint32_t i0 = sidx[j] - base, i1 = (j + 1 < se) ? sidx[j + 1] - base : i0;
+            alignas(16) T t0, t1;
+            ld_rec<T>(tuples + static_cast<size_t>(i0) * sizeof(T), t0);
+            if (j + 1 < se) ld_rec<T>(tuples + static_cast<size_t>(i1) * sizeof(T), t1);
+            const uint64_t s0 = ts ? ts[i0] : 0, s1 = (ts && j + 1 < se) ? ts[i1] : 0;
+            acc = P::reduce(acc, t0, prm); mts = mts < s0 ? s0 : mts;
+            if (j + 1 < se) { acc = P::reduce(acc, t1, prm); mts = mts < s1 ? s1 : mts; }
+        }
+        const uint32_t o = k - first_seg[b];
+        st_rec<T>(batches[b].out + static_cast<size_t>(o) * sizeof(T), acc);
+        if (batches[b].ts_out) batches[b].ts_out[o] = mts;
+    }
+}
+
+// one warp per long segment (list filled by the kernel above; long_list == nullptr: every segment): ordered fold with
+// P::reduce, ts = max; output = the batch's out buffers
+template <class P>
+__global__ void __launch_bounds__(256) k_reduce_segments_batches(const DevBatch *__restrict__ batches, const uint32_t *__restrict__ boff,
+                                                                 const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx,
+                                                                 const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ first_seg,
+                                                                 const uint32_t *__restrict__ n_segs, uint32_t key_bits,
+                                                                 const uint32_t *__restrict__ long_list, const uint32_t *__restrict__ n_long,
+                                                                 const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nk = long_list ? *n_long : *n_segs;
+    for (uint32_t kk = gwarp; kk < nk; kk += nwarps) {
+        const uint32_t k = long_list ? long_list[kk] : kk;
+        const uint32_t sb = seg_begin[k], se = seg_begin[k + 1];
+        const uint32_t b = key_bits >= 64 ? 0u : static_cast<uint32_t>(skeys[sb] >> key_bits);
+        const DevBatch bt = batches[b];
+        const uint32_t base = boff[b];
+        alignas(16) T acc; uint64_t mts = 0; bool have = false;
+        for (uint32_t j = sb; j < se; j += 32) {
+            const uint32_t take = min(32u, se - j);
+            alignas(16) T t; uint64_t tt = 0;
+            if (lane < take) {
+                const uint32_t i = sidx[j + lane] - base;
+                ld_rec<T>(bt.tuples + static_cast<size_t>(i) * sizeof(T), t);
+                tt = bt.ts ? bt.ts[i] : 0;
+            }
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+                const T other = shfl_down_rec<T>(t, o);
+                const uint64_t ots = __shfl_down_sync(FULL, tt, o);
+                if (lane + o < take) { t = P::reduce(t, other, prm); tt = tt < ots ? ots : tt; }
+            }
+            t = shfl_rec<T>(t, 0); tt = __shfl_sync(FULL, tt, 0);
+            if (!have) { acc = t; mts = tt; have = true; }
+            else { acc = P::reduce(acc, t, prm); mts = mts < tt ? tt : mts; }
+        }
+        if (lane == 0) {
+            const uint32_t o = k - first_seg[b];
+            st_rec<T>(bt.out + static_cast<size_t>(o) * sizeof(T), acc);
+            if (bt.ts_out) bt.ts_out[o] = mts;
+        }
+    }
+}
+
 // Reduce_GPU un-keyed: the whole batch folded into one item, starting from a default-constructed item
 // (thrust::reduce with init = batch_item_gpu_t<tuple_t>(), wf/reduce_gpu.hpp:264-273). One CTA of 1024 threads.
 template <class P>

@@ -80,6 +80,12 @@ struct ProgramOps {
                       const void *params);
     int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
                   uint64_t *out_ts, cudaStream_t s);
+    // Reduce_GPU over K queued batches
+    int (*extract_keys_batches)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, uint32_t key_bits, uint64_t *keys,
+                                cudaStream_t s, const void *params);
+    int (*reduce_segments_batches)(const DevBatch *batches, const uint32_t *boff, const uint64_t *skeys, const uint32_t *sidx,
+                                   const uint32_t *seg_begin, const uint32_t *first_seg, const uint32_t *n_segs, uint32_t key_bits,
+                                   uint32_t total, uint32_t *long_list, uint32_t *n_long, cudaStream_t s, const void *params);
 };
 
 // P::passthrough (optional): map is a no-op and lift the identity (tuple_t == result_t)
@@ -192,6 +198,27 @@ int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, co
     return 0;
 }
 template <class P>
+int extract_keys_batches_dispatch(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, uint32_t key_bits, uint64_t *keys,
+                                  cudaStream_t s, const void *params)
+{
+    k_extract_keys_batches<P><<<grid_for(total, 256), 256, 0, s>>>(batches, boff, nb, total, key_bits, keys, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int reduce_segments_batches_dispatch(const DevBatch *batches, const uint32_t *boff, const uint64_t *skeys, const uint32_t *sidx,
+                                     const uint32_t *seg_begin, const uint32_t *first_seg, const uint32_t *n_segs, uint32_t key_bits,
+                                     uint32_t total, uint32_t *long_list, uint32_t *n_long, cudaStream_t s, const void *params)
+{
+    // short segments: one thread each; long ones (listed by the first kernel): one warp each
+    k_reduce_segments_batches_short<P><<<grid_for(total, 128), 128, 0, s>>>(batches, boff, skeys, sidx, seg_begin, first_seg, n_segs, key_bits,
+                                                                            long_list, n_long, load_params<P>(params));
+    k_reduce_segments_batches<P><<<std::max(1u, std::min(grid_for(total / RB_LONG + 1, 8), static_cast<uint32_t>(wfb::num_sms()) * 8u)), 256, 0, s>>>(
+        batches, boff, skeys, sidx, seg_begin, first_seg, n_segs, key_bits, long_list, n_long, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
 int reduce_all_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, unsigned char *out_tuple, uint64_t *out_ts, cudaStream_t s,
                         const void *params)
 {
@@ -223,6 +250,8 @@ ProgramOps make_ops()
     o.reduce_segments = &reduce_segments_dispatch<P>;
     o.reduce_all = &reduce_all_dispatch<P>;
     o.gather = &gather_dispatch<P>;
+    o.extract_keys_batches = &extract_keys_batches_dispatch<P>;
+    o.reduce_segments_batches = &reduce_segments_batches_dispatch<P>;
     return o;
 }
 

@@ -275,6 +275,9 @@ struct wfb_engine {
     uint32_t *head = nullptr, *seg_begin = nullptr, *H = nullptr;
     // wfb_shard_lift: lifted records / destinations of one segment, tile t owns positions [t*TILE, +TILE)
     unsigned char *sh_lifted = nullptr; uint32_t *sh_dest = nullptr, *sh_ctl = nullptr; uint64_t sh_cap = 0;
+    // wfb_reduce_by_key_batches: element offset of every batch, first segment of every batch, segment total
+    uint32_t *rb_off = nullptr, *rb_first = nullptr, *rb_total = nullptr; uint32_t rb_cap = 0;
+    uint32_t *rb_long = nullptr; uint32_t rb_long_cap = 0; // segments folded by a warp; rb_total[1] = their number
     uint32_t h_tiles = 0;
     RadixSorter sorter;
 
@@ -306,6 +309,7 @@ struct wfb_engine {
         cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
         cudaFree(head); cudaFree(seg_begin); cudaFree(H);
         cudaFree(sh_lifted); cudaFree(sh_dest); cudaFree(sh_ctl);
+        cudaFree(rb_off); cudaFree(rb_first); cudaFree(rb_total); cudaFree(rb_long);
         sorter.destroy();
     }
 };
@@ -569,6 +573,71 @@ int wfb_reduce_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, u
                                  static_cast<unsigned char *>(out_tuples), ts ? out_ts : nullptr, n, s, e->pp());
     if (rc) return rc;
     e->launches++;
+    return 0;
+}
+
+int wfb_reduce_by_key_batches(wfb_engine_t *e, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches, uint32_t *n_out_dev,
+                              void *stream)
+{
+    if (!e || !n_out_dev || (nbatches && (!in_h || !out_h))) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nbatches == 0) return 0;
+    uint32_t bbits = 0; while ((1ull << bbits) < nbatches) bbits++;
+    if (e->key_bits + bbits > 64) return WFB_E_BADARG;
+    int rc = e->ts.enter(s); if (rc) return rc;
+    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t) * nbatches, s));
+    std::vector<DevBatch> hb(nbatches);
+    std::vector<uint32_t> boff(nbatches + 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nbatches; i++) { // (empty batches keep their index: the composite key carries it)
+        if (in_h[i].n && (!in_h[i].tuples || !out_h[i].tuples)) return WFB_E_BADARG;
+        DevBatch b; std::memset(&b, 0, sizeof(b));
+        b.tuples = static_cast<const unsigned char *>(in_h[i].tuples); b.ts = in_h[i].ts;
+        b.out = static_cast<unsigned char *>(const_cast<void *>(out_h[i].tuples));
+        b.ts_out = in_h[i].ts ? const_cast<uint64_t *>(out_h[i].ts) : nullptr;
+        b.n_out = n_out_dev + i; b.n = in_h[i].n;
+        hb[i] = b; boff[i] = static_cast<uint32_t>(total); total += b.n;
+    }
+    boff[nbatches] = static_cast<uint32_t>(total);
+    if (total == 0) return 0;
+    if (total > 0x7fffffffull) return WFB_E_BADARG;
+    const uint32_t n = static_cast<uint32_t>(total);
+    rc = e->ensure_sort(n, s); if (rc) return rc;
+    rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
+    if (nbatches > e->rb_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(e->rb_off); cudaFree(e->rb_first);
+        e->rb_cap = std::max(nbatches, 2 * e->rb_cap);
+        CK(cudaMalloc(&e->rb_off, sizeof(uint32_t) * (static_cast<size_t>(e->rb_cap) + 1)));
+        CK(cudaMalloc(&e->rb_first, sizeof(uint32_t) * e->rb_cap));
+        if (!e->rb_total) CK(cudaMalloc(&e->rb_total, sizeof(uint32_t) * 2));
+    }
+    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->rb_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(e->rb_first, 0xff, sizeof(uint32_t) * nbatches, s));
+    CK(cudaMemsetAsync(e->rb_total, 0, sizeof(uint32_t) * 2, s));
+    if (n / RB_LONG + 1 > e->rb_long_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(e->rb_long);
+        e->rb_long_cap = std::max(n / RB_LONG + 1, 2 * e->rb_long_cap);
+        CK(cudaMalloc(&e->rb_long, sizeof(uint32_t) * e->rb_long_cap));
+    }
+    const uint32_t kb = nbatches == 1 ? 64u : e->key_bits; // a single batch needs no composite key
+    rc = e->ops->extract_keys_batches(e->ts.d_batches, e->rb_off, nbatches, n, kb, e->keysA, s, e->pp()); if (rc) return rc;
+    const uint64_t *skeys; const uint32_t *sidx;
+    const uint64_t before = e->sorter.launches;
+    const uint32_t sort_bits = nbatches == 1 ? e->key_bits : e->key_bits + bbits;
+    rc = e->sorter.sort<uint64_t>(e->keysA, e->keysB, e->idxA, e->idxB, nullptr, n, n, (sort_bits + 7) / 8, s, &skeys, &sidx); if (rc) return rc;
+    const uint32_t tiles = (n + SEGT - 1) / SEGT;
+    k_head_tile_counts<<<tiles, 256, 0, s>>>(skeys, n, e->head);
+    k_scan_u32<<<1, 1024, 0, s>>>(e->head, e->head, tiles, nullptr);
+    k_seg_finish_batches<<<tiles, 256, 0, s>>>(skeys, n, kb, e->head, e->seg_begin, e->rb_first, e->rb_total);
+    k_batch_seg_counts<<<1, 32, 0, s>>>(e->rb_first, nbatches, e->rb_total, e->ts.d_batches);
+    CK(cudaGetLastError());
+    rc = e->ops->reduce_segments_batches(e->ts.d_batches, e->rb_off, skeys, sidx, e->seg_begin, e->rb_first, e->rb_total, kb, n, e->rb_long,
+                                         e->rb_total + 1, s, e->pp());
+    if (rc) return rc;
+    e->launches += 7 + (e->sorter.launches - before);
     return 0;
 }
 

@@ -141,6 +141,12 @@ class Engine:
                                        _ptr(n_out), _stream_ptr(stream)), "wfb_reduce_by_key")
         return out, n_out
 
+    def reduce_by_key_batches(self, batches, outs, n_out, stream=None):
+        """Reduce_GPU over K queued batches in one launch sequence: batch i reduced into outs[i], n_out[i] distinct keys."""
+        check(self.L.wfb_reduce_by_key_batches(self.h, _cbatches(batches), _cbatches(outs), len(batches), _ptr(n_out), _stream_ptr(stream)),
+              "wfb_reduce_by_key_batches")
+        return outs, n_out
+
     def reduce_all(self, batch, stream=None):
         out_t = torch.empty(self.tuple_bytes, dtype=torch.uint8, device=batch.tuples.device)
         out_ts = torch.zeros(1, dtype=torch.int64, device=batch.tuples.device)
