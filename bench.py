@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batches-per-step", type=int, default=64)
+    ap.add_argument("--batches-per-step", type=int, default=128, help="queued batches the replica hands to the operator per call (one stream segment)")
     ap.add_argument("--ring", type=int, default=4)
     ap.add_argument("--nb", type=int, default=65, help="withNumWinPerBatch")
     ap.add_argument("--e2e-steps", type=int, default=12)

@@ -1,20 +1,24 @@
 // wfb_kernels.cuh -- hand-written sm_100a kernels of the WindFlow GPU operator hot path, templated on a
 // "program" (record schema + functors, see wfb_programs.cuh).
 //
-// Kernel inventory (DESIGN.md section 4 has the roofline of each):
-//   k_tile_pass<P, MODE>   streaming tile pass: TMA bulk load of a tile of tuples into shared memory
-//                          (cp.async.bulk + mbarrier, STAGES-deep), per-tuple map / filter in registers,
-//                          block scan + decoupled look-back for the stable output offset, survivors staged in
-//                          shared memory and written with a TMA bulk store.
-//                            MODE_MAP     in-place Map_GPU                 (wf/map_gpu.hpp:61-76)
-//                            MODE_FILTER  [Map_GPU ->] Filter_GPU          (wf/filter_gpu.hpp:72-88, :555-570)
-//                            MODE_INGEST  [Map -> Filter ->] lift + key->slot for Ffat_Windows_GPU
-//                                         (wf/ffat_replica_gpu.hpp:94-121)
-//   k_radix_hist / k_radix_scan / k_radix_scatter   stable LSD radix passes over (slot, position) pairs: the
-//                          replacement of thrust::sort_by_key (wf/ffat_replica_gpu.hpp:751, keyby_emitter_gpu.hpp:547)
-//   k_slot_offsets         exclusive scan of the per-key counts of a stream segment
-//   k_ffat_update          one warp per key: ordered pane fold, FlatFAT leaf write + path update, window
-//                          queries (wf/flatfat_gpu.hpp:62-139, wf/ffat_replica_gpu.hpp:830-867)
+// Kernel inventory (DESIGN.md sections 3-4 have the algorithms and the measured roofline of each):
+//   k_tile_pass<P, MODE>     streaming tile pass, persistent warp-specialised CTAs: TMA load of a tile of tuples
+//                            (cp.async.bulk.tensor / cp.async.bulk + mbarrier rings), per-tuple map / filter / lift / key->slot
+//                            in registers, survivors staged in shared memory, TMA bulk store.
+//                              MODE_MAP     in-place Map_GPU                 (wf/map_gpu.hpp:61-76)
+//                              MODE_FILTER  [Map_GPU ->] Filter_GPU, compacted per batch with a decoupled look-back
+//                                           (wf/filter_gpu.hpp:72-88, :555-570)
+//                              MODE_INGEST  [Map -> Filter ->] lift + key->slot for Ffat_Windows_GPU, or -> destination for
+//                                           wfb_shard_lift (wf/ffat_replica_gpu.hpp:94-121); chain-free ("sparse") on the bucket path
+//   k_wide_tile_hist / k_wide_scatter / k_shard_scatter   one stable partition pass on a 10-bit digit (window path: 1024
+//                            buckets of slots; multi-GPU: destinations, with the records)
+//   k_ffat_update_buckets<P> one CTA per bucket: split by key, ordered pane folds, FlatFAT leaf + path update, fired
+//                            groups (wf/flatfat_gpu.hpp:62-139, wf/ffat_replica_gpu.hpp:830-867); k_ffat_windows<P> window queries
+//   k_onesweep_pass / k_radix_ghist   LSD radix sort, 8 bits per pass, one kernel per pass: the replacement of
+//                            thrust::sort_by_key for the per-batch keyed operators and the full-sort window path
+//                            (wf/ffat_replica_gpu.hpp:751, wf/keyby_emitter_gpu.hpp:547, wf/reduce_gpu.hpp:239)
+//   k_ffat_update_lanes / k_ffat_update   full-sort window path: one thread / one warp per key
+//   k_extract_keys, k_seg_*, k_reduce_segments*, k_reduce_all, k_gather_tuples   KeyBy_Emitter_GPU grouping, Reduce_GPU
 #pragma once
 #include <type_traits>
 #include <cstdint>
@@ -638,40 +642,6 @@ __device__ __forceinline__ R shfl_rec(const R &r, uint32_t src)
     return o;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// Stable LSD radix pass over (key32, val32) pairs, 8 bits per pass, three kernels per pass:
-//   k_radix_hist    per-tile digit histogram          H[digit * num_tiles + tile]
-//   k_radix_scan    exclusive scan of H in (digit, tile) order (single CTA)
-//   k_radix_scatter stable in-tile ranks (warp match_any, warps in index order) + scatter
-// The element count lives on the device (*n_ptr): the grid covers the capacity, tiles past n do nothing.
-// Replaces thrust::sort_by_key at wf/ffat_replica_gpu.hpp:751, wf/keyby_emitter_gpu.hpp:547,
-// wf/reduce_gpu.hpp:239 (which sorts the 72-byte items themselves; here only 8-byte pairs move).
-// ------------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 2048 elements per tile
-
-template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
-                                                           uint32_t shift, uint32_t *__restrict__ H, uint32_t num_tiles)
-{
-    __shared__ uint32_t h[256];
-    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
-    const uint32_t n = n_ptr ? *n_ptr : n_host;
-    h[tid] = 0;
-    __syncthreads();
-    const uint32_t start = tile * RS_TILE;
-    if (start < n) {
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; i++) {
-            const uint32_t idx = start + i * RS_THREADS + tid;
-            if (idx < n) atomicAdd(&h[static_cast<uint32_t>(keys[idx] >> shift) & 255u], 1u);
-        }
-    }
-    __syncthreads();
-    H[tid * num_tiles + tile] = h[tid];
-}
-
 // exclusive scan of `total` uint32 counters (in may alias out), one CTA of 1024 threads
 static __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, uint32_t *out, uint32_t total, uint32_t *sum_out)
 {
@@ -698,54 +668,6 @@ static __global__ void __launch_bounds__(1024) k_scan_u32(const uint32_t *in, ui
     for (uint32_t i = begin; i < end; i++) { const uint32_t v = in[i]; out[i] = run; run += v; }
 }
 
-template <class K>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const K *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                                                              K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                                                              const uint32_t *__restrict__ n_ptr, uint32_t n_host, uint32_t shift,
-                                                              const uint32_t *__restrict__ H, uint32_t num_tiles)
-{
-    __shared__ uint32_t cntw[RS_THREADS / 32][256];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
-    const uint32_t n = n_ptr ? *n_ptr : n_host;
-    const uint32_t start = tile * RS_TILE;
-    if (start >= n) return;
-#pragma unroll
-    for (int w = 0; w < RS_THREADS / 32; w++) cntw[w][tid] = 0;
-    __syncthreads();
-    K k[RS_ITEMS];
-    uint32_t rk[RS_ITEMS];
-    // warp w owns the contiguous range [start + w*256, +256), 32 consecutive elements per round: (warp, round,
-    // lane) order == index order, so ranks are stable.
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
-        const bool valid = idx < n;
-        k[r] = valid ? keys_in[idx] : K(0);
-        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & 255u) : 256u;
-        const uint32_t mask = __match_any_sync(FULL, d);
-        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0u;
-        __syncwarp();
-        if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] += __popc(mask);
-        __syncwarp();
-    }
-    __syncthreads();
-    { // digit `tid`: exclusive prefix over the warps, on top of the tile's global base for this digit
-        uint32_t base = H[tid * num_tiles + tile];
-#pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; w++) { const uint32_t c = cntw[w][tid]; cntw[w][tid] = base; base += c; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = start + warp * (32 * RS_ITEMS) + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = static_cast<uint32_t>(k[r] >> shift) & 255u;
-            const uint32_t dst = cntw[warp][d] + rk[r];
-            keys_out[dst] = k[r];
-            vals_out[dst] = vals_in ? vals_in[idx] : idx;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // Onesweep-style stable LSD radix pass (8-bit digits): ONE kernel per pass.
@@ -1165,16 +1087,6 @@ static __global__ void k_shard_counts(const uint32_t *__restrict__ digit_counts,
     if (d == 0) counts_out[MAX_SHARDS] = over ? 1u : 0u;
 }
 
-// seg_off[slot] = first sorted position of each key present in the segment (its length is seg_cnt[slot])
-static __global__ void k_seg_starts(const uint32_t *__restrict__ sorted_slots, const uint32_t *__restrict__ n_ptr, uint32_t max_keys,
-                             uint32_t *__restrict__ seg_off)
-{
-    const uint32_t n = *n_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t s = sorted_slots[i];
-        if (s < max_keys && (i == 0 || sorted_slots[i - 1] != s)) seg_off[s] = i;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // k_ffat_update_lanes: ONE THREAD per key for the (usual) keys with few items in the segment: 65 536 keys are 65 536

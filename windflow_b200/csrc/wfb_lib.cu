@@ -272,13 +272,12 @@ struct wfb_engine {
     uint32_t cap = 0;
     uint64_t *keysA = nullptr, *keysB = nullptr;
     uint32_t *idxA = nullptr, *idxB = nullptr, *destA = nullptr, *destB = nullptr;
-    uint32_t *head = nullptr, *seg_begin = nullptr, *H = nullptr;
+    uint32_t *head = nullptr, *seg_begin = nullptr;
     // wfb_shard_lift: lifted records / destinations of one segment, tile t owns positions [t*TILE, +TILE)
     unsigned char *sh_lifted = nullptr; uint32_t *sh_dest = nullptr, *sh_ctl = nullptr; uint64_t sh_cap = 0;
     // wfb_reduce_by_key_batches: element offset of every batch, first segment of every batch, segment total
     uint32_t *rb_off = nullptr, *rb_first = nullptr, *rb_total = nullptr; uint32_t rb_cap = 0;
     uint32_t *rb_long = nullptr; uint32_t rb_long_cap = 0; // segments folded by a warp; rb_total[1] = their number
-    uint32_t h_tiles = 0;
     RadixSorter sorter;
 
     int ensure_sort(uint32_t n, cudaStream_t s)
@@ -286,14 +285,12 @@ struct wfb_engine {
         if (n <= cap) return 0;
         CK(cudaStreamSynchronize(s));
         cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
-        cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+        cudaFree(head); cudaFree(seg_begin);
         cap = std::max(n, 2 * cap);
         CK(cudaMalloc(&keysA, sizeof(uint64_t) * cap)); CK(cudaMalloc(&keysB, sizeof(uint64_t) * cap));
         CK(cudaMalloc(&idxA, sizeof(uint32_t) * cap)); CK(cudaMalloc(&idxB, sizeof(uint32_t) * cap));
         CK(cudaMalloc(&destA, sizeof(uint32_t) * cap)); CK(cudaMalloc(&destB, sizeof(uint32_t) * cap));
         CK(cudaMalloc(&head, sizeof(uint32_t) * cap)); CK(cudaMalloc(&seg_begin, sizeof(uint32_t) * (static_cast<size_t>(cap) + 1)));
-        h_tiles = (cap + RS_TILE - 1) / RS_TILE;
-        CK(cudaMalloc(&H, sizeof(uint32_t) * 256 * h_tiles));
         return 0;
     }
     // stable LSD radix sort of (keysA[i], i) by key over `key_bits` bits; returns the buffers holding the result
@@ -307,7 +304,7 @@ struct wfb_engine {
     void free_sort()
     {
         cudaFree(keysA); cudaFree(keysB); cudaFree(idxA); cudaFree(idxB); cudaFree(destA); cudaFree(destB);
-        cudaFree(head); cudaFree(seg_begin); cudaFree(H);
+        cudaFree(head); cudaFree(seg_begin);
         cudaFree(sh_lifted); cudaFree(sh_dest); cudaFree(sh_ctl);
         cudaFree(rb_off); cudaFree(rb_first); cudaFree(rb_total); cudaFree(rb_long);
         sorter.destroy();
