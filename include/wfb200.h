@@ -43,6 +43,7 @@ extern "C" {
 #define WFB_PROG_WFTEST16 1   /* reference tests/graph_tests_gpu/graph_common_gpu.hpp:40-49 {key,value}  */
 #define WFB_PROG_WFWIN24  2   /* reference tests/win_tests_gpu/win_common_gpu.hpp:40-80 {key,id,value}   */
 #define WFB_PROG_LIFTED32 3   /* already-lifted wfb_result32_t records (destination side of the multi-GPU keyby) */
+#define WFB_PROG_LIFTEDWIN24 4 /* already-lifted wfb_wfwin24_t records (pane aggregates of time-based windows of programs 1, 2) */
 
 typedef struct { uint64_t key; uint64_t id; int64_t ivalue; double fvalue; uint64_t pad[4]; } wfb_tuple64_t;
 typedef struct { uint64_t key; uint64_t id; int64_t isum; double fsum; } wfb_result32_t;
@@ -86,7 +87,7 @@ int         wfb_device_count(void);                    /* 0 => every compute ent
 int         wfb_program_info(int prog, wfb_program_info_t *info);
 /* Adds an application-defined program (record schema + functors compiled in the application's own .cu): `ops` is the
  * launch table built by wfb::register_program<P>() of windflow_b200/csrc/wfb_launch.cuh. Returns the new program id
- * (>= 4) or a negative error. For such programs every `const wfb_functors_t *` parameter below points to the program's
+ * (>= 5) or a negative error. For such programs every `const wfb_functors_t *` parameter below points to the program's
  * own params_t (its functor objects) instead. */
 int         wfb_program_register(const void *ops, size_t ops_bytes);
 
@@ -166,7 +167,8 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
  * Per-replica handle: owns the key table and, per key, the count, the open-pane accumulator and the FlatFAT
  * (pane ring + internal levels). replaces Key_Descriptor / FlatFAT_GPU allocation,
  * wf/ffat_replica_gpu.hpp:438-506, wf/flatfat_gpu.hpp:165-192.
- *   win_type: 0 count-based (win/slide in tuples), 1 time-based (win/slide/lateness in timestamp units)
+ *   win_type: 0 count-based (win/slide in tuples, wfb_ffat_process_cb), 1 time-based (win/slide/lateness in timestamp
+ *             units, wfb_ffat_process_tb)
  *   flags   : WFB_FFAT_DENSE_KEYS => keys are known to be < max_keys (slot = key, no hash probe) */
 #define WFB_FFAT_DENSE_KEYS 1u
 /*   WFB_FFAT_PIPELINED  => results are delivered one call late: wfb_ffat_process_cb(segment k) returns the results of
@@ -198,6 +200,16 @@ int wfb_ffat_set_key_shard(wfb_ffat_t *h, uint32_t num_shards, uint32_t shard);
 int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev,
                         void *stream);
+
+/* Time-based windows (handles created with win_type = 1; win / slide / lateness in timestamp units; built-in programs only).
+ * Every batch must carry its timestamps; batches are processed one after the other. Per batch: tuples are assigned to panes
+ * ts / gcd(win, slide), per-(key, pane) partials are merged into the key's pending panes, and for every key PRESENT in the
+ * batch the groups of panes the watermark has completed (panes < (watermark - lateness) / pane length; first (Nb-1)*slide+win
+ * panes, then slide*Nb) fire Nb windows each, ts = the batch watermark. Tuples of panes already consumed are dropped.
+ * replaces Ffat_Replica_GPU::process_batch_tb + process_wins_tb, PendingPanes_Queue and Lifting_Kernel_TB_Keyed,
+ * wf/ffat_replica_gpu.hpp:150-171, :214-420, :870-1047. Synchronises the stream once per batch (so does the reference, :962). */
+int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                        void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);
 
 /* Pipelined handles only: deliver the results of the last segment (a no-op with *n_out_dev = 0 otherwise). */
 int wfb_ffat_flush(wfb_ffat_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);

@@ -63,6 +63,13 @@ def lib():
         L.wfo_ffat_gpu_process_batch.restype = _u64
         L.wfo_ffat_gpu_window_linear.argtypes = [_vp, _u64, _u64, _vp]
         L.wfo_ffat_gpu_window_linear.restype = C.c_int
+        L.wfo_ffat_tb_create.argtypes = [_u64, _u64, _u64, _u64]
+        L.wfo_ffat_tb_create.restype = _vp
+        L.wfo_ffat_tb_destroy.argtypes = [_vp]
+        L.wfo_ffat_tb_ignored.argtypes = [_vp]
+        L.wfo_ffat_tb_ignored.restype = _u64
+        L.wfo_ffat_tb_process_batch.argtypes = [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _u64]
+        L.wfo_ffat_tb_process_batch.restype = _u64
         L.wfo_ffat_cpu_create.argtypes = [_u64, _u64]
         L.wfo_ffat_cpu_create.restype = _vp
         L.wfo_ffat_cpu_destroy.argtypes = [_vp]
@@ -209,6 +216,37 @@ class FfatGpuOracle:
     def close(self):
         if self.h:
             lib().wfo_ffat_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class FfatTbOracle:
+    """Ffat_Windows_GPU, time-based (wf/ffat_replica_gpu.hpp:870-1047): win / slide / lateness in timestamp units."""
+
+    def __init__(self, win, slide, lateness, nb):
+        self.win, self.slide, self.lateness, self.nb = win, slide, lateness, nb
+        self.h = lib().wfo_ffat_tb_create(win, slide, lateness, nb)
+
+    def process_batch(self, res, ts, watermark):
+        res = np.ascontiguousarray(res, dtype=RES)
+        ts = np.ascontiguousarray(ts, dtype=np.uint64)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=RES)
+            ots = np.zeros(cap, dtype=np.uint64)
+            n = lib().wfo_ffat_tb_process_batch(self.h, _p(res), _p(ts), len(res), watermark, _p(out), _p(ots), cap)
+            assert n <= cap, "oracle output capacity estimate too small (state already advanced)"
+            return out[:n], ots[:n]
+
+    @property
+    def ignored(self):
+        return int(lib().wfo_ffat_tb_ignored(self.h))
+
+    def close(self):
+        if self.h:
+            lib().wfo_ffat_tb_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -413,6 +413,158 @@ uint64_t wfo_ffat_gpu_process_batch(wfo_ffat_gpu_t *h, const wfo_res_t *res, uin
     return nout;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Ffat_Replica_GPU, time-based windows (ffat_replica_gpu.hpp:870-1047), PendingPanes_Queue (:263-420),
+ * Aggregate_Panes_Kernel (:214-260), Lifting_Kernel_TB_Keyed (:150-171).
+ * The queue is restated as a ring indexed by pane_id % capacity (the reference keeps first_pos / last_pos over the
+ * same content). Defined where the reference only asserts: a key that has fewer pending panes than a group needs
+ * (ffat_replica_gpu.hpp:1031,:1037 `assert`) gets empty panes (result_t()) for the missing ones.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t key; int used;
+    fatgpu_t fat;
+    uint64_t q_first_id, q_num, q_cap; wfo_res_t *q_buf;        /* PendingPanes_Queue */
+    uint64_t pane_id_triggerer, next_gwid; int firstWinDone;    /* Key_Descriptor :441-447, :462-464 */
+} tbkey_t;
+
+typedef struct {
+    uint64_t win_p, slide_p, pane_len, lateness, Nb, Bp;
+    tbkey_t *tab; uint64_t cap, used;
+    uint64_t ignored;                                           /* ignored_tuples_gpu */
+} wfo_ffat_tb_t;
+
+static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+wfo_ffat_tb_t *wfo_ffat_tb_create(uint64_t win, uint64_t slide, uint64_t lateness, uint64_t nb)
+{
+    wfo_ffat_tb_t *h = (wfo_ffat_tb_t *)calloc(1, sizeof(*h));
+    h->pane_len = gcd_u64(win, slide);                          /* :639-642 */
+    h->win_p = win / h->pane_len; h->slide_p = slide / h->pane_len;
+    h->lateness = lateness; h->Nb = nb;
+    h->Bp = (nb - 1) * h->slide_p + h->win_p;                   /* batchSize :657 */
+    return h;
+}
+
+void wfo_ffat_tb_destroy(wfo_ffat_tb_t *h)
+{
+    for (uint64_t i = 0; i < h->cap; i++) if (h->tab[i].used) { free(h->tab[i].fat.tree); free(h->tab[i].q_buf); }
+    free(h->tab); free(h);
+}
+
+uint64_t wfo_ffat_tb_ignored(const wfo_ffat_tb_t *h) { return h->ignored; }
+
+static tbkey_t *tb_find(wfo_ffat_tb_t *h, uint64_t key)
+{
+    if ((h->used + 1) * 2 > h->cap) {
+        uint64_t ncap = h->cap ? h->cap * 2 : 1024;
+        tbkey_t *nt = (tbkey_t *)calloc(ncap, sizeof(tbkey_t));
+        for (uint64_t i = 0; i < h->cap; i++) if (h->tab[i].used) {
+            uint64_t p = splitmix64(h->tab[i].key) & (ncap - 1);
+            while (nt[p].used) p = (p + 1) & (ncap - 1);
+            nt[p] = h->tab[i];
+        }
+        free(h->tab); h->tab = nt; h->cap = ncap;
+    }
+    uint64_t p = splitmix64(key) & (h->cap - 1);
+    while (h->tab[p].used && h->tab[p].key != key) p = (p + 1) & (h->cap - 1);
+    if (!h->tab[p].used) {
+        tbkey_t *k = &h->tab[p];
+        memset(k, 0, sizeof(*k));
+        k->used = 1; k->key = key;
+        fatgpu_init(&k->fat, h->Bp, h->Nb, h->win_p, h->slide_p);
+        k->q_cap = h->Bp; k->q_buf = (wfo_res_t *)calloc(k->q_cap, sizeof(wfo_res_t)); /* initial capacity :470 */
+        k->pane_id_triggerer = h->Bp - 1;                       /* :463 */
+        h->used++;
+    }
+    return &h->tab[p];
+}
+
+static void tbq_resize(tbkey_t *k, uint64_t ncap) /* PendingPanes_Queue::resize :326-357 (content preserved) */
+{
+    wfo_res_t *nb = (wfo_res_t *)calloc(ncap, sizeof(wfo_res_t));
+    for (uint64_t j = 0; j < k->q_num; j++) nb[(k->q_first_id + j) % ncap] = k->q_buf[(k->q_first_id + j) % k->q_cap];
+    free(k->q_buf); k->q_buf = nb; k->q_cap = ncap;
+}
+
+typedef struct { uint64_t key, pane; uint32_t idx; } wfo_kpi_t;
+static int cmp_kpi(const void *a, const void *b) /* lessThan_func_gpu_t :174-192: key ascending, pane DEscending; stable (idx) */
+{
+    const wfo_kpi_t *x = (const wfo_kpi_t *)a, *y = (const wfo_kpi_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    if (x->pane != y->pane) return x->pane > y->pane ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+/* One input batch: res[i] = lift(tuple i) with res[i].key = key of tuple i, ts[i] its timestamp, wm the batch watermark.
+ * Appends Nb results per fired group (ts of a result = wm). Returns the number of results. */
+uint64_t wfo_ffat_tb_process_batch(wfo_ffat_tb_t *h, const wfo_res_t *res, const uint64_t *ts, uint64_t n, uint64_t wm,
+                                   wfo_res_t *out, uint64_t *out_ts, uint64_t out_cap)
+{
+    if (n == 0) return 0;
+    const uint64_t F = wm >= h->lateness ? (wm - h->lateness) / h->pane_len : 0; /* first_pane_not_complete :875-881 */
+    wfo_kpi_t *ki = (wfo_kpi_t *)malloc(sizeof(wfo_kpi_t) * n);
+    for (uint64_t i = 0; i < n; i++) {
+        ki[i].key = res[i].key; ki[i].pane = ts[i] / h->pane_len; ki[i].idx = (uint32_t)i;
+        if (ki[i].pane < F) h->ignored++;                        /* :165-167 (statistic only) */
+    }
+    qsort(ki, n, sizeof(wfo_kpi_t), cmp_kpi);                   /* sort_by_key :917-921 */
+    /* reduce_by_key over equal (key, pane), arrival order inside (:925-935) */
+    wfo_res_t *pv = (wfo_res_t *)malloc(sizeof(wfo_res_t) * n);
+    uint64_t *pp = (uint64_t *)malloc(sizeof(uint64_t) * n), *pk = (uint64_t *)malloc(sizeof(uint64_t) * n);
+    uint64_t np = 0;
+    for (uint64_t i = 0; i < n; ) {
+        uint64_t j = i + 1;
+        wfo_res_t acc = res[ki[i].idx];
+        while (j < n && ki[j].key == ki[i].key && ki[j].pane == ki[i].pane) { comb(&acc, &res[ki[j].idx], &acc); j++; } /* thrust_comb_func_t: comb(acc, next, acc) */
+        pv[np] = acc; pp[np] = ki[i].pane; pk[np] = ki[i].key; np++;
+        i = j;
+    }
+    uint64_t nout = 0;
+    for (uint64_t i = 0; i < np; ) { /* one key at a time, ascending (:963-987) */
+        uint64_t j = i + 1;
+        while (j < np && pk[j] == pk[i]) j++;
+        tbkey_t *k = tb_find(h, pk[i]);
+        /* push_panes(new_panes, new_infos, num, newest_pane_id = pp[i]) :360-391 */
+        const uint64_t newest = pp[i];
+        if (newest >= k->q_first_id) {
+            const uint64_t need = newest - k->q_first_id + 2;
+            if (need > k->q_cap) tbq_resize(k, need);
+        }
+        for (uint64_t a = i; a < j; a++) { /* Aggregate_Panes_Kernel :214-260 */
+            const uint64_t pane = pp[a];
+            if (pane < k->q_first_id) continue; /* late pane */
+            wfo_res_t *slot = &k->q_buf[pane % k->q_cap];
+            if (k->q_num > 0 && pane < k->q_first_id + k->q_num) comb(slot, &pv[a], slot); /* :236 */
+            else {
+                *slot = pv[a];
+                const uint64_t lower = (a == j - 1) ? (k->q_first_id + k->q_num) : (pp[a + 1] + 1); /* first missing pane below */
+                for (uint64_t m = (lower > k->q_first_id + k->q_num ? lower : k->q_first_id + k->q_num); m < pane; m++)
+                    memset(&k->q_buf[m % k->q_cap], 0, sizeof(wfo_res_t)); /* result_t() */
+            }
+        }
+        if (newest >= k->q_first_id + k->q_num) k->q_num = newest - k->q_first_id + 1;
+        /* process_wins_tb :1022-1047 with next_pane_id = F (:985) */
+        while (k->pane_id_triggerer < F) {
+            const uint64_t need = k->firstWinDone ? h->slide_p * h->Nb : h->Bp;
+            wfo_res_t *grp = (wfo_res_t *)calloc(need, sizeof(wfo_res_t));
+            for (uint64_t m = 0; m < need; m++) /* pop_and_add :394-415; missing panes are empty */
+                if (m < k->q_num) grp[m] = k->q_buf[(k->q_first_id + m) % k->q_cap];
+            fatgpu_add_cb(&k->fat, grp, need);
+            free(grp);
+            k->q_first_id += need; k->q_num = k->q_num > need ? k->q_num - need : 0;
+            if (!k->firstWinDone) { fatgpu_build(&k->fat); k->firstWinDone = 1; }
+            else fatgpu_update(&k->fat, h->slide_p * h->Nb);
+            if (nout + h->Nb <= out_cap) fatgpu_results(&k->fat, k->key, k->next_gwid, wm, out + nout, out_ts + nout);
+            nout += h->Nb;
+            k->next_gwid += h->Nb;
+            k->pane_id_triggerer += h->slide_p * h->Nb;
+        }
+        i = j;
+    }
+    free(pk); free(pp); free(pv); free(ki);
+    return nout;
+}
+
 /* Semantic definition of window `gwid` of `key`: left fold of comb over the key's lifted
  * results [gwid*S, gwid*S+W) starting from result_t(key, gwid). Needs keep_history=1. Returns 0 if the
  * window is not complete yet. */

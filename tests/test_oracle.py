@@ -165,3 +165,31 @@ def test_reduce_by_key(oracle):
             assert r["id"] == t["id"][sel][0]
         else:
             assert r["id"] == 0
+
+
+def test_tb_oracle_matches_the_window_definition():
+    """Time-based restatement (process_batch_tb / PendingPanes_Queue): on a stream whose keys appear in every batch, window
+    gwid of key k is the fold of the key's tuples with ts in [gwid*slide, gwid*slide + win), consecutive gwids from 0, and
+    the result timestamp is the watermark of the batch that fired it."""
+    from oracle import oracle as O
+    for win, slide, nb, lateness in [(40, 10, 3, 0), (30, 45, 2, 0), (64, 16, 1, 32)]:
+        nkeys, n, B = 5, 6000, 500
+        t, _ = O.gen_tuple64(0, n, O.KEY_RR, nkeys)
+        ts = np.arange(n, dtype=np.uint64)
+        res = O.lift_tuple64(t)
+        tb = O.FfatTbOracle(win, slide, lateness, nb)
+        outs = []
+        for b in range(0, n, B):
+            o, ots = tb.process_batch(res[b:b + B], ts[b:b + B], int(ts[b]))
+            assert np.all(ots == int(ts[b]))
+            outs.append(o)
+        out = np.concatenate(outs)
+        assert len(out) > 0 and tb.ignored == 0
+        for r in out:
+            k, g = int(r["key"]), int(r["id"])
+            m = (t["key"] == k) & (ts >= g * slide) & (ts < g * slide + win)
+            assert r["isum"] == t["ivalue"][m].sum()
+            assert abs(r["fsum"] - t["fvalue"][m].sum()) <= 1e-9 * max(1.0, abs(r["fsum"]))
+        for k in range(nkeys):
+            ids = np.sort(out["id"][out["key"] == k])
+            assert np.array_equal(ids, np.arange(len(ids)))

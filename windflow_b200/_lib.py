@@ -58,6 +58,7 @@ SYMBOLS = {
     "wfb_ffat_destroy": (C.c_int, [vp]),
     "wfb_ffat_launches": (u64, [vp]),
     "wfb_ffat_state_bytes": (u64, [vp]),
+    "wfb_ffat_process_tb": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), u32, vp, vp, u32, vp, vp]),
     "wfb_ffat_process_cb": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), u32, vp, vp, u32, vp, vp]),
     "wfb_ffat_flush": (C.c_int, [vp, vp, vp, u32, vp, vp]),
     "wfb_ffat_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),

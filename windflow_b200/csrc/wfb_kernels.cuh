@@ -2102,6 +2102,221 @@ __global__ void __launch_bounds__(256) k_reduce_segments_batches(const DevBatch 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Time-based windows, front end (Ffat_Replica_GPU::process_batch_tb, wf/ffat_replica_gpu.hpp:870-1019; PendingPanes_Queue
+// :263-420; Aggregate_Panes_Kernel :214-260). Per input batch: lift + (slot, pane) composite key -> stable sort ->
+// per-(key, pane) partial in arrival order -> merged into the key's ring of pending panes -> for every key present in the
+// batch, the panes of the groups the watermark has completed are popped, in pane order, into an array of lifted records
+// that the count-based back end (a second handle over the "lifted" program, window / slide in panes) consumes as one
+// batch: it fires exactly one group of Nb windows per popped group, with ts = the batch watermark.
+// ------------------------------------------------------------------------------------------------------
+constexpr uint32_t TB_PANE_BITS = 40;
+constexpr uint64_t TB_PANE_MASK = (1ull << TB_PANE_BITS) - 1ull;
+
+struct TbDev {
+    uint64_t pane_len, Bp, group;      // pane length (timestamp units), panes of the first group, panes of every further group
+    uint32_t capq;                     // ring capacity per key (panes)
+    uint64_t *first;                   // id of the first pending pane of every key
+    uint32_t *num, *num_new;           // pending panes (before / after this batch)
+    uint64_t *trig;                    // pane_id_triggerer
+    uint32_t *done;                    // firstWinDone
+    unsigned char *ring;               // max_keys x capq results, pane p of key s at (s * capq + p % capq)
+    uint32_t *present, *n_present;     // slots of the keys of this batch
+    uint32_t *cnt;                     // panes to pop per present key -> exclusive offsets
+    uint32_t *ignored;                 // tuples older than the first incomplete pane (statistic)
+    uint32_t *need;                    // ring capacity this batch needs: max over its tuples of pane - first pending pane + 2
+    uint32_t *err;                     // bit 2: ring overflow / pane id out of range
+};
+
+template <class P>
+__global__ void k_tb_lift(const unsigned char *__restrict__ tuples, const uint64_t *__restrict__ ts, uint32_t n, const FfatDev ff,
+                          const TbDev tb, uint64_t first_incomplete, unsigned char *__restrict__ lifted, uint64_t *__restrict__ ckeys,
+                          const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    using R = typename P::result_t;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        alignas(16) T t;
+        ld_rec<T>(tuples + static_cast<size_t>(i) * sizeof(T), t);
+        P::map(t, prm);
+        uint64_t ck = ~0ull;
+        if (P::filter(t, prm)) {
+            alignas(16) R r;
+            P::lift(t, r, prm);
+            st_rec<R>(lifted + static_cast<size_t>(i) * sizeof(R), r);
+            const uint32_t slot = slot_of_key(ff, P::key(t, prm));
+            const uint64_t pane = ts[i] / tb.pane_len;                 // Lifting_Kernel_TB_Keyed :164
+            if (pane < first_incomplete) atomicAdd(tb.ignored, 1u);    // :165-167
+            if (pane > TB_PANE_MASK) atomicOr(tb.err, 4u);
+            else if (slot != INVALID_SLOT) {
+                ck = (static_cast<uint64_t>(slot) << TB_PANE_BITS) | pane;
+                const uint64_t f0 = tb.first[slot];
+                if (pane >= f0) atomicMax(tb.need, static_cast<uint32_t>(min(pane - f0 + 2, static_cast<uint64_t>(0xffffffffu)))); // push_panes :367-372
+            }
+        }
+        ckeys[i] = ck;
+    }
+}
+
+// partial of every (key, pane) of the batch: fold of the lifted results in arrival order (thrust::reduce_by_key :925-935)
+template <class P>
+__global__ void k_tb_reduce(const unsigned char *__restrict__ lifted, const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx,
+                            const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ n_segs, unsigned char *__restrict__ part,
+                            const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    const uint32_t nk = *n_segs;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
+        const uint32_t sb = seg_begin[k], se = seg_begin[k + 1];
+        if (skeys[sb] == ~0ull) continue;
+        alignas(16) R acc;
+        ld_rec<R>(lifted + static_cast<size_t>(sidx[sb]) * sizeof(R), acc);
+        for (uint32_t j = sb + 1; j < se; j++) {
+            alignas(16) R r;
+            ld_rec<R>(lifted + static_cast<size_t>(sidx[j]) * sizeof(R), r);
+            P::comb(acc, r, acc, prm);
+        }
+        st_rec<R>(part + static_cast<size_t>(k) * sizeof(R), acc);
+    }
+}
+
+// partials (ascending slot, ascending pane) -> the keys' rings of pending panes; the last partial of a key records the
+// new number of pending panes and lists the key as present
+template <class P>
+__global__ void k_tb_merge(const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ n_segs,
+                           const unsigned char *__restrict__ part, const FfatDev ff, const TbDev tb, const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    const uint32_t nk = *n_segs;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
+        const uint64_t ck = skeys[seg_begin[k]];
+        if (ck == ~0ull) continue;
+        const uint32_t slot = static_cast<uint32_t>(ck >> TB_PANE_BITS);
+        const uint64_t pane = ck & TB_PANE_MASK;
+        const uint64_t first_id = tb.first[slot];
+        const uint32_t num = tb.num[slot];
+        const uint64_t have_end = first_id + num;                      // first pane id that is not in the ring yet
+        unsigned char *ring = tb.ring + static_cast<size_t>(slot) * tb.capq * sizeof(R);
+        const uint64_t ckn = (k + 1 < nk) ? skeys[seg_begin[k + 1]] : ~0ull;
+        const bool last_of_key = ckn == ~0ull || static_cast<uint32_t>(ckn >> TB_PANE_BITS) != slot;
+        bool stored = false;
+        if (pane >= first_id) {                                        // (older: late pane, ignored -- :232-234)
+            if (pane - first_id >= tb.capq) atomicOr(tb.err, 4u);
+            else {
+                alignas(16) R v;
+                ld_rec<R>(part + static_cast<size_t>(k) * sizeof(R), v);
+                unsigned char *dst = ring + (pane % tb.capq) * sizeof(R);
+                if (pane < have_end) { alignas(16) R old; ld_rec<R>(dst, old); P::comb(old, v, old, prm); st_rec<R>(dst, old); } // :236
+                else {
+                    st_rec<R>(dst, v);
+                    uint64_t lower = have_end;                          // missing panes below this one become empty panes (:239-257)
+                    if (k > 0) {
+                        const uint64_t ckp = skeys[seg_begin[k - 1]];
+                        if (ckp != ~0ull && static_cast<uint32_t>(ckp >> TB_PANE_BITS) == slot && (ckp & TB_PANE_MASK) + 1 > lower) lower = (ckp & TB_PANE_MASK) + 1;
+                    }
+                    const uint64_t key = key_of_slot(ff, slot);
+                    for (uint64_t m = lower; m < pane; m++) {
+                        alignas(16) R e = P::make_result(key, 0, prm);
+                        st_rec<R>(ring + (m % tb.capq) * sizeof(R), e);
+                    }
+                }
+                stored = true;
+            }
+        }
+        if (last_of_key) {
+            uint32_t nn = num;
+            if (stored && pane >= have_end) nn = static_cast<uint32_t>(pane - first_id + 1);
+            tb.num_new[slot] = nn;
+            tb.present[atomicAdd(tb.n_present, 1u)] = slot;
+        }
+    }
+}
+
+// the rings grow (PendingPanes_Queue::resize :326-357): pending pane p of key s moves from p % old_cap to p % new_cap
+static __global__ void k_tb_ring_resize(const TbDev tb, const unsigned char *__restrict__ old_ring, uint32_t old_cap, unsigned char *__restrict__ new_ring,
+                                        uint32_t new_cap, uint32_t max_keys, uint32_t rbytes)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < max_keys; s += gridDim.x * blockDim.x) {
+        const uint64_t f0 = tb.first[s];
+        const uint32_t num = tb.num[s];
+        for (uint32_t j = 0; j < num; j++) {
+            const uint64_t *src = reinterpret_cast<const uint64_t *>(old_ring + (static_cast<size_t>(s) * old_cap + (f0 + j) % old_cap) * rbytes);
+            uint64_t *dst = reinterpret_cast<uint64_t *>(new_ring + (static_cast<size_t>(s) * new_cap + (f0 + j) % new_cap) * rbytes);
+            for (uint32_t q = 0; q < rbytes / 8; q++) dst[q] = src[q];
+        }
+    }
+}
+
+// panes every present key pops now: groups completed by the watermark (process_wins_tb :1029-1046), first Bp then `group` each
+static __global__ void k_tb_pop_count(const TbDev tb, uint64_t first_incomplete)
+{
+    const uint32_t np = *tb.n_present;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = tb.present[i];
+        uint64_t trig = tb.trig[slot];
+        bool done = tb.done[slot] != 0;
+        uint64_t c = 0;
+        while (trig < first_incomplete) { c += done ? tb.group : tb.Bp; done = true; trig += tb.group; }
+        tb.cnt[i] = static_cast<uint32_t>(c > 0x7fffffffull ? 0x7fffffffull : c);
+    }
+}
+
+// exclusive scan of the pop counts of the *n_present keys of the batch (one CTA), total to *total_out
+static __global__ void __launch_bounds__(1024) k_tb_scan_present(uint32_t *__restrict__ cnt, const uint32_t *__restrict__ n_present, uint32_t *__restrict__ total_out)
+{
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t total = *n_present;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (total + 1023) / 1024;
+    const uint32_t begin = min(tid * per, total), end = min(begin + per, total);
+    uint32_t sum = 0;
+    for (uint32_t i = begin; i < end; i++) sum += cnt[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, wi, o); if (lane >= static_cast<uint32_t>(o)) wi += v; }
+        warp_sums[lane] = wi - w;
+        if (lane == 31) *total_out = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - sum;
+    for (uint32_t i = begin; i < end; i++) { const uint32_t v = cnt[i]; cnt[i] = run; run += v; }
+}
+
+template <class P>
+__global__ void k_tb_pop_write(const FfatDev ff, const TbDev tb, uint64_t first_incomplete, const uint32_t *__restrict__ offs,
+                               unsigned char *__restrict__ popped, uint32_t popped_cap, const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    const uint32_t np = *tb.n_present;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = tb.present[i];
+        uint64_t trig = tb.trig[slot], first_id = tb.first[slot];
+        uint32_t num = tb.num_new[slot];
+        bool done = tb.done[slot] != 0;
+        const uint64_t key = key_of_slot(ff, slot);
+        const unsigned char *ring = tb.ring + static_cast<size_t>(slot) * tb.capq * sizeof(R);
+        uint32_t w = offs[i];
+        while (trig < first_incomplete) {
+            const uint64_t need = done ? tb.group : tb.Bp;
+            for (uint64_t m = 0; m < need; m++, w++) {                  // pop_and_add :394-415; a missing pane is an empty pane
+                alignas(16) R v;
+                if (m < num) ld_rec<R>(ring + ((first_id + m) % tb.capq) * sizeof(R), v);
+                else v = P::make_result(key, 0, prm);
+                if (w < popped_cap) st_rec<R>(popped + static_cast<size_t>(w) * sizeof(R), v);
+            }
+            first_id += need; num = num > need ? static_cast<uint32_t>(num - need) : 0u;
+            done = true; trig += tb.group;
+        }
+        tb.first[slot] = first_id; tb.num[slot] = num; tb.trig[slot] = trig; tb.done[slot] = done ? 1u : 0u;
+    }
+}
+
 // Reduce_GPU un-keyed: the whole batch folded into one item, starting from a default-constructed item
 // (thrust::reduce with init = batch_item_gpu_t<tuple_t>(), wf/reduce_gpu.hpp:264-273). One CTA of 1024 threads.
 template <class P>

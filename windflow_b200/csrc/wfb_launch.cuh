@@ -80,6 +80,15 @@ struct ProgramOps {
                       const void *params);
     int (*gather)(const unsigned char *tuples, const uint64_t *ts, const uint32_t *perm, uint32_t n, unsigned char *out_tuples,
                   uint64_t *out_ts, cudaStream_t s);
+    // time-based windows, front end
+    int (*tb_lift)(const unsigned char *tuples, const uint64_t *ts, uint32_t n, const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete,
+                   unsigned char *lifted, uint64_t *ckeys, cudaStream_t s, const void *params);
+    int (*tb_reduce)(const unsigned char *lifted, const uint64_t *skeys, const uint32_t *sidx, const uint32_t *seg_begin, const uint32_t *n_segs,
+                     unsigned char *part, uint32_t n, cudaStream_t s, const void *params);
+    int (*tb_merge)(const uint64_t *skeys, const uint32_t *seg_begin, const uint32_t *n_segs, const unsigned char *part, const FfatDev &ff,
+                    const TbDev &tb, uint32_t n, cudaStream_t s, const void *params);
+    int (*tb_pop_write)(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
+                        uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params);
     // Reduce_GPU over K queued batches
     int (*extract_keys_batches)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, uint32_t key_bits, uint64_t *keys,
                                 cudaStream_t s, const void *params);
@@ -198,6 +207,38 @@ int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, co
     return 0;
 }
 template <class P>
+int tb_lift_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete,
+                     unsigned char *lifted, uint64_t *ckeys, cudaStream_t s, const void *params)
+{
+    k_tb_lift<P><<<grid_for(n, 256), 256, 0, s>>>(tuples, ts, n, ff, tb, first_incomplete, lifted, ckeys, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int tb_reduce_dispatch(const unsigned char *lifted, const uint64_t *skeys, const uint32_t *sidx, const uint32_t *seg_begin, const uint32_t *n_segs,
+                       unsigned char *part, uint32_t n, cudaStream_t s, const void *params)
+{
+    k_tb_reduce<P><<<grid_for(n, 128), 128, 0, s>>>(lifted, skeys, sidx, seg_begin, n_segs, part, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int tb_merge_dispatch(const uint64_t *skeys, const uint32_t *seg_begin, const uint32_t *n_segs, const unsigned char *part, const FfatDev &ff,
+                      const TbDev &tb, uint32_t n, cudaStream_t s, const void *params)
+{
+    k_tb_merge<P><<<grid_for(n, 128), 128, 0, s>>>(skeys, seg_begin, n_segs, part, ff, tb, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int tb_pop_write_dispatch(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
+                          uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params)
+{
+    k_tb_pop_write<P><<<grid_for(max_present, 128), 128, 0, s>>>(ff, tb, first_incomplete, offs, popped, popped_cap, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
 int extract_keys_batches_dispatch(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, uint32_t key_bits, uint64_t *keys,
                                   cudaStream_t s, const void *params)
 {
@@ -250,13 +291,14 @@ ProgramOps make_ops()
     o.reduce_segments = &reduce_segments_dispatch<P>;
     o.reduce_all = &reduce_all_dispatch<P>;
     o.gather = &gather_dispatch<P>;
+    o.tb_lift = &tb_lift_dispatch<P>; o.tb_reduce = &tb_reduce_dispatch<P>; o.tb_merge = &tb_merge_dispatch<P>; o.tb_pop_write = &tb_pop_write_dispatch<P>;
     o.extract_keys_batches = &extract_keys_batches_dispatch<P>;
     o.reduce_segments_batches = &reduce_segments_batches_dispatch<P>;
     return o;
 }
 
 
-// registers the launch table of program P with libwfb200 and returns its program id (>= 4), or a negative error
+// registers the launch table of program P with libwfb200 and returns its program id (>= 5), or a negative error
 template <class P>
 int register_program()
 {

@@ -36,7 +36,7 @@ int device_ready()
 
 std::vector<ProgramOps> &registry()
 {
-    static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() }; table.reserve(4096); }
+    static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>(), make_ops<ProgLiftedWin24>() }; table.reserve(4096); }
     return table;
 }
 
@@ -358,6 +358,15 @@ struct wfb_ffat {
     uint64_t launches = 0;
     size_t state_bytes = 0;
     int win_type = 0;
+    // time-based windows (win_type 1): this handle is the front end (key table, rings of pending panes); the popped panes go to
+    // `cb`, a count-based handle over the lifted program with window / slide in panes
+    TbDev tb{};
+    wfb_ffat *cb = nullptr;
+    uint64_t tb_lateness = 0;
+    uint32_t tb_cap = 0, tb_pop_cap = 0;            // scratch capacities (tuples per batch, popped panes)
+    uint64_t *tb_kA = nullptr, *tb_kB = nullptr; uint32_t *tb_iA = nullptr, *tb_iB = nullptr;
+    unsigned char *tb_lifted = nullptr, *tb_part = nullptr, *tb_popped = nullptr;
+    uint32_t *tb_head = nullptr, *tb_seg = nullptr, *tb_misc = nullptr; // misc: [0] n_segs [1] first_seg dummy [2] n_present [3] popped total [4] ignored [5] ring capacity needed
     bool buckets = true;          // one wide radix pass + per-bucket CTAs (<= 65536 keys); WFB_UPDATE=lanes selects the
                                   // full sort + thread-per-key update instead
     uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
@@ -743,12 +752,174 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
 // ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------------
 static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
+// ---- time-based windows: front-end handle + count-based back end over the lifted program ------------------------------------
+static int lifted_program_of(int prog)
+{
+    switch (prog) {
+    case WFB_PROG_TUPLE64: return WFB_PROG_LIFTED32;
+    case WFB_PROG_WFTEST16: case WFB_PROG_WFWIN24: return WFB_PROG_LIFTEDWIN24;
+    default: return -1; // registered programs: not yet (they would register their lifted program as well)
+    }
+}
+
+static int tb_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uint32_t nb, uint32_t max_keys, uint64_t lateness, uint32_t flags)
+{
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    const int lp = lifted_program_of(prog);
+    if (lp < 0 || (flags & WFB_FFAT_PIPELINED)) return WFB_E_UNSUPPORTED;
+    int rc = device_ready(); if (rc) return rc;
+    const uint64_t pane_len = gcd_u64(win, slide);                   // wf/ffat_replica_gpu.hpp:639-642
+    const uint64_t win_p = win / pane_len, slide_p = slide / pane_len;
+    const uint64_t Bp = static_cast<uint64_t>(nb - 1) * slide_p + win_p, group = slide_p * nb;
+    uint64_t capq = 1; while (capq < 2 * Bp + group + lateness / pane_len + 8) capq <<= 1;
+    const size_t RB = o->result_bytes;
+    if (Bp > (1ull << 24) || capq * max_keys * RB > (32ull << 30)) return WFB_E_BADARG;
+    wfb_ffat *h = new (std::nothrow) wfb_ffat();
+    if (!h) return WFB_E_BADARG;
+    h->prog = prog; h->ops = o; h->win_type = 1; h->tb_lateness = lateness; h->pipelined = false;
+    FfatDev &ff = h->ff;
+    ff.max_keys = max_keys; ff.dense = (flags & WFB_FFAT_DENSE_KEYS) ? 1u : 0u; ff.nb = nb;
+    uint32_t cap = 1; while (cap < 2ull * max_keys) cap <<= 1;
+    ff.ht_mask = cap - 1;
+    size_t total = 0;
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)); if (e_ != cudaSuccess) { wfb_ffat_destroy(h); return static_cast<int>(e_); } total += (bytes); } while (0)
+    if (!ff.dense) {
+        ALLOC(ff.ht_keys, sizeof(uint64_t) * cap);
+        ALLOC(ff.ht_slots, sizeof(uint32_t) * cap);
+        CK(cudaMemset(ff.ht_keys, 0xff, sizeof(uint64_t) * cap));
+        CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
+    }
+    ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
+    ff.err_flags = ff.n_slots + 1;
+    CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
+    ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
+    TbDev &tb = h->tb;
+    tb.pane_len = pane_len; tb.Bp = Bp; tb.group = group; tb.capq = static_cast<uint32_t>(capq);
+    ALLOC(tb.first, sizeof(uint64_t) * max_keys); CK(cudaMemset(tb.first, 0, sizeof(uint64_t) * max_keys));
+    ALLOC(tb.num, sizeof(uint32_t) * max_keys); CK(cudaMemset(tb.num, 0, sizeof(uint32_t) * max_keys));
+    ALLOC(tb.num_new, sizeof(uint32_t) * max_keys);
+    ALLOC(tb.trig, sizeof(uint64_t) * max_keys);
+    { std::vector<uint64_t> t0(max_keys, Bp - 1); CK(cudaMemcpy(tb.trig, t0.data(), sizeof(uint64_t) * max_keys, cudaMemcpyHostToDevice)); } // :463
+    ALLOC(tb.done, sizeof(uint32_t) * max_keys); CK(cudaMemset(tb.done, 0, sizeof(uint32_t) * max_keys));
+    ALLOC(tb.ring, RB * capq * max_keys);
+    ALLOC(tb.present, sizeof(uint32_t) * max_keys);
+    ALLOC(tb.cnt, sizeof(uint32_t) * (static_cast<size_t>(max_keys) + 1));
+    ALLOC(h->tb_misc, sizeof(uint32_t) * 8); CK(cudaMemset(h->tb_misc, 0, sizeof(uint32_t) * 8));
+    tb.n_present = h->tb_misc + 2; tb.ignored = h->tb_misc + 4; tb.need = h->tb_misc + 5; tb.err = ff.err_flags;
+#undef ALLOC
+    rc = h->ts.init(); if (rc) { wfb_ffat_destroy(h); return rc; }
+    rc = wfb_ffat_create(&h->cb, lp, win_p, slide_p, nb, max_keys, 0, 0, flags & WFB_FFAT_DENSE_KEYS);
+    if (rc) { wfb_ffat_destroy(h); return rc; }
+    h->state_bytes = total + h->cb->state_bytes;
+    *hh = h;
+    return 0;
+}
+
+static int tb_ensure(wfb_ffat *h, uint32_t n, cudaStream_t s)
+{
+    if (n <= h->tb_cap) return 0;
+    CK(cudaStreamSynchronize(s));
+    cudaFree(h->tb_kA); cudaFree(h->tb_kB); cudaFree(h->tb_iA); cudaFree(h->tb_iB); cudaFree(h->tb_lifted); cudaFree(h->tb_part);
+    cudaFree(h->tb_head); cudaFree(h->tb_seg);
+    h->tb_cap = std::max(n, 2 * h->tb_cap);
+    const size_t RB = h->ops->result_bytes, c = h->tb_cap;
+    CK(cudaMalloc(&h->tb_kA, sizeof(uint64_t) * c)); CK(cudaMalloc(&h->tb_kB, sizeof(uint64_t) * c));
+    CK(cudaMalloc(&h->tb_iA, sizeof(uint32_t) * c)); CK(cudaMalloc(&h->tb_iB, sizeof(uint32_t) * c));
+    CK(cudaMalloc(&h->tb_lifted, RB * c)); CK(cudaMalloc(&h->tb_part, RB * c));
+    CK(cudaMalloc(&h->tb_head, sizeof(uint32_t) * ((c + SEGT - 1) / SEGT + 1))); CK(cudaMalloc(&h->tb_seg, sizeof(uint32_t) * (c + 1)));
+    return 0;
+}
+
+int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                        void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
+{
+    if (!h || h->win_type != 1 || !n_out_dev || (nbatches && !batches_h) || (out_capacity && !out_results)) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t RB = h->ops->result_bytes;
+    const void *prm = pre ? static_cast<const void *>(pre) : h->pp();
+    uint32_t produced = 0;
+    for (uint32_t bi = 0; bi < nbatches; bi++) {
+        const wfb_batch_t &b = batches_h[bi];
+        if (b.n == 0) continue;
+        if (!b.tuples || !b.ts) return WFB_E_BADARG;            // time-based windows need the timestamps
+        int rc = tb_ensure(h, b.n, s); if (rc) return rc;
+        const uint64_t wm = b.watermark;
+        const uint64_t F = wm >= h->tb_lateness ? (wm - h->tb_lateness) / h->tb.pane_len : 0; // first_pane_not_complete :875-881
+        uint32_t *misc = h->tb_misc;
+        CK(cudaMemsetAsync(misc, 0, sizeof(uint32_t) * 4, s));
+        CK(cudaMemsetAsync(misc + 5, 0, sizeof(uint32_t), s));
+        // 1. lift + composite (slot, pane) keys; 2. stable sort; 3. (key, pane) segments; 4. partials; 5. merge into the rings
+        rc = h->ops->tb_lift(static_cast<const unsigned char *>(b.tuples), b.ts, b.n, h->ff, h->tb, F, h->tb_lifted, h->tb_kA, s, prm); if (rc) return rc;
+        { // the rings must hold every pane from a key's first pending one to its newest (PendingPanes_Queue::push_panes :367-372)
+            uint32_t need = 0;
+            CK(cudaMemcpyAsync(&need, misc + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (need > h->tb.capq) {
+                uint64_t ncap = h->tb.capq; while (ncap < need) ncap <<= 1;
+                if (ncap * h->ff.max_keys * RB > (32ull << 30)) return WFB_E_CAPACITY;
+                unsigned char *nr = nullptr;
+                CK(cudaMalloc(&nr, RB * ncap * h->ff.max_keys));
+                k_tb_ring_resize<<<grid_for(h->ff.max_keys, 128), 128, 0, s>>>(h->tb, h->tb.ring, h->tb.capq, nr, static_cast<uint32_t>(ncap), h->ff.max_keys,
+                                                                                static_cast<uint32_t>(RB));
+                CK(cudaStreamSynchronize(s));
+                cudaFree(h->tb.ring);
+                h->tb.ring = nr; h->tb.capq = static_cast<uint32_t>(ncap);
+                h->launches++;
+            }
+        }
+        const uint64_t *skeys; const uint32_t *sidx;
+        const uint64_t before = h->sorter.launches;
+        rc = h->sorter.sort<uint64_t>(h->tb_kA, h->tb_kB, h->tb_iA, h->tb_iB, nullptr, b.n, b.n, 8, s, &skeys, &sidx); if (rc) return rc;
+        // (all 64 bits: filtered tuples carry ~0 and must sort last)
+        const uint32_t tiles = (b.n + SEGT - 1) / SEGT;
+        k_head_tile_counts<<<tiles, 256, 0, s>>>(skeys, b.n, h->tb_head);
+        k_scan_u32<<<1, 1024, 0, s>>>(h->tb_head, h->tb_head, tiles, nullptr);
+        k_seg_finish_batches<<<tiles, 256, 0, s>>>(skeys, b.n, 64u, h->tb_head, h->tb_seg, misc + 1, misc + 0);
+        CK(cudaGetLastError());
+        rc = h->ops->tb_reduce(h->tb_lifted, skeys, sidx, h->tb_seg, misc + 0, h->tb_part, b.n, s, prm); if (rc) return rc;
+        rc = h->ops->tb_merge(skeys, h->tb_seg, misc + 0, h->tb_part, h->ff, h->tb, b.n, s, prm); if (rc) return rc;
+        // 6. panes to pop per present key, offsets, total
+        const uint32_t maxp = std::min<uint32_t>(b.n, h->ff.max_keys);
+        k_tb_pop_count<<<grid_for(maxp, 128), 128, 0, s>>>(h->tb, F);
+        k_tb_scan_present<<<1, 1024, 0, s>>>(h->tb.cnt, h->tb.n_present, misc + 3);
+        CK(cudaGetLastError());
+        uint32_t total = 0;
+        CK(cudaMemcpyAsync(&total, misc + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));                           // (the reference synchronises here as well, :962)
+        if (total > h->tb_pop_cap) {
+            cudaFree(h->tb_popped);
+            h->tb_pop_cap = std::max(total, 2 * h->tb_pop_cap);
+            CK(cudaMalloc(&h->tb_popped, RB * h->tb_pop_cap));
+        }
+        rc = h->ops->tb_pop_write(h->ff, h->tb, F, h->tb.cnt, h->tb_popped, h->tb_pop_cap, maxp, s, prm); if (rc) return rc;
+        h->launches += 9 + (h->sorter.launches - before);
+        // 7. the count-based back end consumes the popped panes as one batch with this batch's watermark
+        if (total) {
+            wfb_batch_t pb; std::memset(&pb, 0, sizeof(pb));
+            pb.tuples = h->tb_popped; pb.ts = nullptr; pb.watermark = wm; pb.n = total;
+            const uint64_t lb = h->cb->launches;
+            rc = wfb_ffat_process_cb(h->cb, nullptr, &pb, 1, static_cast<unsigned char *>(out_results) + static_cast<size_t>(produced) * RB,
+                                     out_ts ? out_ts + produced : nullptr, out_capacity - produced, n_out_dev, s);
+            if (rc) return rc;
+            h->launches += h->cb->launches - lb;
+            uint32_t got = 0;
+            CK(cudaMemcpyAsync(&got, n_out_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            produced += std::min(got, out_capacity - produced);
+        }
+    }
+    CK(cudaMemcpyAsync(n_out_dev, &produced, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s)); // `produced` lives on this stack frame
+    return 0;
+}
+
 int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
                     uint32_t max_keys, int win_type, uint64_t lateness, uint32_t flags)
 {
-    (void) lateness;
     if (!hh || win == 0 || slide == 0 || wins_per_batch == 0 || max_keys == 0) return WFB_E_BADARG;
-    if (win_type != 0) return WFB_E_UNSUPPORTED; // time-based windows: see DESIGN.md (next)
+    if (win_type == 1) return tb_create(hh, prog, win, slide, wins_per_batch, max_keys, lateness, flags);
+    if (win_type != 0) return WFB_E_UNSUPPORTED;
     const ProgramOps *o = program(prog);
     if (!o) return WFB_E_NOPROG;
     int rc = device_ready(); if (rc) return rc;
@@ -847,6 +1018,11 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off); cudaFree(ff.heavy);
     for (int p = 0; p < 2; p++) h->seg[p].destroy();
     h->sorter.destroy();
+    if (h->cb) wfb_ffat_destroy(h->cb);
+    cudaFree(h->tb.first); cudaFree(h->tb.num); cudaFree(h->tb.num_new); cudaFree(h->tb.trig); cudaFree(h->tb.done); cudaFree(h->tb.ring);
+    cudaFree(h->tb.present); cudaFree(h->tb.cnt); cudaFree(h->tb_misc);
+    cudaFree(h->tb_kA); cudaFree(h->tb_kB); cudaFree(h->tb_iA); cudaFree(h->tb_iB); cudaFree(h->tb_lifted); cudaFree(h->tb_part);
+    cudaFree(h->tb_popped); cudaFree(h->tb_head); cudaFree(h->tb_seg);
     if (h->s2) cudaStreamDestroy(h->s2);
     for (auto &e : h->tev) cudaEventDestroy(e);
     h->ts.destroy();
@@ -966,7 +1142,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
 {
     if (!h || !n_out_dev || (nbatches && !batches_h) || (out_capacity && !out_results)) return WFB_E_BADARG;
-    if (h->win_type != 0) return WFB_E_UNSUPPORTED;
+    if (h->win_type != 0) return WFB_E_BADARG; // time-based handles: wfb_ffat_process_tb
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = h->ts.enter(s); if (rc) return rc;
     unsigned char *out = static_cast<unsigned char *>(out_results);
@@ -1111,6 +1287,7 @@ int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, voi
     CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     if (n_keys_h) *n_keys_h = v[0];
     if (err_flags_h) *err_flags_h = v[1];
+    if (h->cb && err_flags_h) { uint32_t e2 = 0; int rc = wfb_ffat_stats(h->cb, nullptr, &e2, stream); if (rc) return rc; *err_flags_h |= e2; }
     return 0;
 }
 

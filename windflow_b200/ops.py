@@ -15,15 +15,15 @@ from . import _lib
 from ._lib import Batch as CBatch
 from ._lib import Functors, check
 
-PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32 = 0, 1, 2, 3
+PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32, PROG_LIFTEDWIN24 = 0, 1, 2, 3, 4
 
 TUPLE64 = np.dtype([("key", "<u8"), ("id", "<u8"), ("ivalue", "<i8"), ("fvalue", "<f8"), ("pad", "<u8", (4,))])
 RESULT32 = np.dtype([("key", "<u8"), ("id", "<u8"), ("isum", "<i8"), ("fsum", "<f8")])
 WFTEST16 = np.dtype([("key", "<u8"), ("value", "<i8")])
 WFWIN24 = np.dtype([("key", "<u8"), ("id", "<u8"), ("value", "<i8")])
 
-TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
-RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
+TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32, PROG_LIFTEDWIN24: WFWIN24}
+RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32, PROG_LIFTEDWIN24: WFWIN24}
 
 KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
 SEED = 0x5EED5EED
@@ -214,6 +214,7 @@ class FfatWindowsGPU:
         if self.L.wfb_device_count() <= 0:
             raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
         self.prog, self.win, self.slide, self.nb = prog, win, slide, nb
+        self.win_type = win_type  # 0 count-based, 1 time-based (win / slide / lateness in timestamp units)
         self.h = C.c_void_p()
         self.pipelined = pipelined
         check(self.L.wfb_ffat_create(C.byref(self.h), prog, win, slide, nb, max_keys, win_type, lateness,
@@ -245,7 +246,8 @@ class FfatWindowsGPU:
         check(self.L.wfb_ffat_set_key_shard(self.h, num_shards, shard), "wfb_ffat_set_key_shard")
 
     def max_results(self, n_items):
-        """Upper bound on the results one call over n_items input items can produce."""
+        """Upper bound on the results one call over n_items input items can produce (count-based windows; time-based
+        callers size the output for the groups a watermark jump can complete)."""
         return (n_items // max(1, self.slide * self.nb) + 65536) * self.nb
 
     def process(self, batches, pre=None, out=None, out_ts=None, n_out=None, stream=None):
@@ -260,6 +262,10 @@ class FfatWindowsGPU:
         if n_out is None:
             n_out = torch.zeros(1, dtype=torch.int32, device=dev)
         arr = _cbatches(batches)
+        if self.win_type == 1:
+            check(self.L.wfb_ffat_process_tb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
+                                             _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)), "wfb_ffat_process_tb")
+            return out, out_ts, n_out
         check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                          _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
               "wfb_ffat_process_cb")
