@@ -49,10 +49,13 @@ typedef struct { uint64_t key; uint64_t id; int64_t ivalue; double fvalue; uint6
 typedef struct { uint64_t key; uint64_t id; int64_t isum; double fsum; } wfb_result32_t;
 typedef struct { uint64_t key; int64_t value; } wfb_wftest16_t;
 typedef struct { uint64_t key; uint64_t id; int64_t value; } wfb_wfwin24_t; /* tuple_t and result_t */
+typedef struct { int64_t counter; } wfb_state8_t; /* per-key state of the built-in stateful functors (map_state_t / filter_state_t of the reference's tests) */
 
 /* Parameters of the built-in functors (a user program carries its own functor objects instead).
  *   map_kind : 0 identity; 1 value += map_iadd, fvalue *= map_fscale   (Map_Functor_GPU "+2": iadd=2, fscale=1)
- *   filt_kind: 0 keep all; 1 (value & 1) == 0; 2 value % filt_mod == 0 (Filter_Functor_GPU(mod)) */
+ *   filt_kind: 0 keep all; 1 (value & 1) == 0; 2 value % filt_mod == 0 (Filter_Functor_GPU(mod))
+ * keyed-stateful variants (wfb_map_stateful / wfb_filter_stateful): a counter per key; map_kind 1: counter++, 2: counter-- on
+ * odd keys, then value += counter (Map_Functor_GPU_KB); filter: counter++, value += counter, then the filt_kind predicate. */
 typedef struct {
     int32_t map_kind;
     int32_t filt_kind;
@@ -125,6 +128,21 @@ int wfb_map_filter(wfb_engine_t *e, const wfb_functors_t *f,
  * in[i].tuples (in-place compaction of every batch). */
 int wfb_map_filter_batches(wfb_engine_t *e, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h,
                            uint32_t nbatches, uint32_t *n_out_dev, void *stream);
+
+/* ---- Map_GPU / Filter_GPU, keyed-stateful ------------------------------------------------------------------------
+ * func(tuple, state_of_key) applied in per-key arrival order; a key's state (the program's state_t, zero-initialised) lives
+ * in the handle, which the replicas of one operator share (they see disjoint keys). K queued batches per call; arrival
+ * order = batch order, then index order. replaces Stateful_MAPGPU_Kernel / Stateful_FILTERGPU_Kernel + the TBB key map,
+ * spinlock and per-key state allocation, wf/map_gpu.hpp:80-102, :212-299, wf/filter_gpu.hpp:91-117, :247-355. */
+typedef struct wfb_kstate wfb_kstate_t;
+int wfb_kstate_create(wfb_kstate_t **h, int prog, uint32_t max_keys, uint32_t flags /* WFB_FFAT_DENSE_KEYS */);
+int wfb_kstate_destroy(wfb_kstate_t *h);
+/* Map_GPU: in place. */
+int wfb_map_stateful(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_t *batches_h, uint32_t nbatches, void *stream);
+/* Filter_GPU: the functor may modify the tuple; survivors of batch i are compacted (stable) into (out[i].tuples, out[i].ts),
+ * n_out_dev[i] of them. out[i] must not alias in[i]. */
+int wfb_filter_stateful(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches,
+                        uint32_t *n_out_dev, void *stream);
 
 /* ---- Reduce_GPU, per batch -------------------------------------------------------------------------
  * keyed: one output item per distinct key, ascending key order, tuple = fold of the program's reduce functor

@@ -401,3 +401,33 @@ def sort_results(res, ts=None):
     """Canonical order for comparing window results: (key, gwid)."""
     order = np.lexsort((res["id"], res["key"]))
     return (res[order], ts[order]) if ts is not None else res[order]
+
+
+# ---------------------------------------------------------------------------------------------------
+# keyed-stateful Map / Filter (wf/map_gpu.hpp:80-102 Stateful_MAPGPU_Kernel, wf/filter_gpu.hpp:91-117): func(tuple, state)
+# in per-key arrival order; functors of tests/graph_tests_gpu/graph_common_gpu.hpp:221-231, :256-265 and
+# tests/merge_tests_gpu/merge_common_gpu_kb.hpp:153-168 (kind 2: on the key's parity). `state` maps key -> counter and
+# persists across calls. Pure-Python loops: small cases only.
+# ---------------------------------------------------------------------------------------------------
+def stateful_map(tuples, field, state, map_kind=1):
+    out = tuples.copy()
+    for i in range(len(out)):
+        k = int(out["key"][i])
+        c = state.get(k, 0)
+        c = c - 1 if (map_kind == 2 and (k & 1)) else c + 1
+        state[k] = c
+        out[field][i] += c
+    return out
+
+
+def stateful_filter(tuples, ts, field, state, filt_kind=0, mod=1):
+    out = tuples.copy()
+    keep = np.zeros(len(out), dtype=bool)
+    for i in range(len(out)):
+        k = int(out["key"][i])
+        c = state.get(k, 0) + 1
+        state[k] = c
+        out[field][i] += c
+        v = int(out[field][i])
+        keep[i] = True if filt_kind == 0 else ((v & 1) == 0 if filt_kind == 1 else (v % mod) == 0)
+    return out[keep], (ts[keep] if ts is not None else None), keep

@@ -47,6 +47,10 @@ SYMBOLS = {
     "wfb_engine_set_key_bits": (C.c_int, [vp, u32]),
     "wfb_map": (C.c_int, [vp, C.POINTER(Functors), vp, u32, vp]),
     "wfb_map_filter": (C.c_int, [vp, C.POINTER(Functors), vp, vp, u32, vp, vp, vp, vp]),
+    "wfb_kstate_create": (C.c_int, [C.POINTER(vp), C.c_int, u32, u32]),
+    "wfb_kstate_destroy": (C.c_int, [vp]),
+    "wfb_map_stateful": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), u32, vp]),
+    "wfb_filter_stateful": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), C.POINTER(Batch), u32, vp, vp]),
     "wfb_reduce_by_key_batches": (C.c_int, [vp, C.POINTER(Batch), C.POINTER(Batch), u32, vp, vp]),
     "wfb_map_filter_batches": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), C.POINTER(Batch), u32, vp, vp]),
     "wfb_reduce_by_key": (C.c_int, [vp, vp, vp, u32, vp, vp, vp, vp]),

@@ -2317,6 +2317,225 @@ __global__ void k_tb_pop_write(const FfatDev ff, const TbDev tb, uint64_t first_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Keyed-stateful Map_GPU / Filter_GPU (wf/map_gpu.hpp:80-102, :212-299; wf/filter_gpu.hpp:91-117, :247-355): the same
+// shape as the window update -- slots of the segment's tuples, ONE wide partition pass into 1024 buckets of consecutive
+// slots, one CTA per bucket splits its items by key (stable) and ONE THREAD per key walks its run in arrival order with
+// the key's state in registers. Stateful filter: keep flags, then a stable per-batch compaction.
+// ------------------------------------------------------------------------------------------------------
+template <class P>
+__global__ void k_ks_slots(const DevBatch *__restrict__ batches, const uint32_t *__restrict__ boff, uint32_t nb, uint32_t total, const FfatDev ff,
+                           uint32_t *__restrict__ slots, const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += gridDim.x * blockDim.x) {
+        const uint32_t b = batch_of(boff, nb, gi);
+        const T *t = reinterpret_cast<const T *>(batches[b].tuples + static_cast<size_t>(gi - boff[b]) * sizeof(T));
+        slots[gi] = slot_of_key(ff, P::key(*t, prm));
+    }
+}
+
+constexpr uint32_t KS_KEYS = 64, KS_THREADS = 128, KS_IT = 18, KS_CAP = KS_THREADS * KS_IT;
+
+template <class P, bool FILTER>
+__global__ void __launch_bounds__(KS_THREADS) k_ks_apply(const FfatDev ff, const DevBatch *__restrict__ batches, const uint32_t *__restrict__ boff,
+                                                         uint32_t nb, const uint32_t *__restrict__ bk_slots, const uint32_t *__restrict__ bk_pos,
+                                                         const uint32_t *__restrict__ digit_counts, uint32_t shift, unsigned char *__restrict__ states,
+                                                         unsigned char *__restrict__ keep, const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    using S = typename P::state_t;
+    constexpr uint32_t NW = KS_THREADS / 32, DPT = OSW_DIGITS / KS_THREADS, HS = KS_THREADS + 2;
+    __shared__ uint32_t s_idx[KS_CAP];                 // positions (global tuple index in the segment), key-major
+    __shared__ uint16_t hist[KS_KEYS][HS];             // private key counts of every thread -> exclusive over the threads
+    __shared__ uint32_t htot[2][KS_KEYS], kcnt[KS_KEYS], koff[KS_KEYS];
+    __shared__ uint32_t misc[NW], s_boff[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bucket = blockIdx.x;
+    const uint32_t kpc = min(KS_KEYS, 1u << shift), key_lo = bucket << shift;
+    { // bucket range = exclusive scan of the pass histogram (as in k_ffat_update_buckets)
+        uint32_t cc[DPT];
+#pragma unroll
+        for (uint32_t q = 0; q < DPT / 4; q++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(digit_counts)[tid * (DPT / 4) + q];
+            cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < DPT; q++) sum += cc[q];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+        if (lane == 31) misc[warp] = incl;
+        __syncthreads();
+        if (tid == bucket / DPT) {
+            uint32_t base = incl - sum;
+            for (uint32_t w = 0; w < warp; w++) base += misc[w];
+            uint32_t own = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < DPT; q++) { if (q < bucket % DPT) base += cc[q]; if (q == bucket % DPT) own = cc[q]; }
+            s_boff[0] = base; s_boff[1] = base + own;
+        }
+        __syncthreads();
+    }
+    uint32_t cursor = s_boff[0];
+    const uint32_t bend = s_boff[1];
+    if (cursor == bend) return;
+    // the key's state stays in registers across the chunks of the bucket
+    alignas(8) S st;
+    const bool has_key = tid < kpc && key_lo + tid < ff.max_keys;
+    bool touched = false;
+    if (has_key) st = *reinterpret_cast<const S *>(states + static_cast<size_t>(key_lo + tid) * sizeof(S));
+    while (cursor < bend) {
+        const uint32_t nsel = min(KS_CAP, bend - cursor);
+        uint32_t ek[KS_IT], ep[KS_IT];
+#pragma unroll
+        for (uint32_t r = 0; r < KS_IT; r++) {
+            const uint32_t i = tid * KS_IT + r;
+            ek[r] = KS_KEYS; ep[r] = 0;
+            if (i < nsel) {
+                const uint32_t lk = bk_slots[cursor + i] - key_lo; // slots outside the bucket's keys (invalid slots) are dropped
+                ep[r] = bk_pos[cursor + i];
+                if (lk < kpc) ek[r] = lk;
+            }
+        }
+        {
+            uint32_t *z = reinterpret_cast<uint32_t *>(&hist[0][0]);
+            for (uint32_t i = tid; i < KS_KEYS * HS / 2; i += KS_THREADS) z[i] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t r = 0; r < KS_IT; r++) if (ek[r] < KS_KEYS) hist[ek[r]][tid]++;
+        __syncthreads();
+        {
+            const uint32_t k = tid & 63u, half = tid >> 6;
+            uint16_t *row = &hist[k][half * 64];
+            uint32_t run = 0;
+#pragma unroll 16
+            for (uint32_t i = 0; i < 64; i++) { const uint32_t c = row[i]; row[i] = static_cast<uint16_t>(run); run += c; }
+            htot[half][k] = run;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t a0 = htot[0][lane] + htot[1][lane], a1 = htot[0][lane + 32] + htot[1][lane + 32];
+            uint32_t i0 = a0, i1 = a1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v0 = __shfl_up_sync(FULL, i0, o), v1 = __shfl_up_sync(FULL, i1, o);
+                if (lane >= static_cast<uint32_t>(o)) { i0 += v0; i1 += v1; }
+            }
+            const uint32_t t0 = __shfl_sync(FULL, i0, 31);
+            kcnt[lane] = a0; kcnt[lane + 32] = a1;
+            koff[lane] = i0 - a0; koff[lane + 32] = t0 + i1 - a1;
+        }
+        __syncthreads();
+        {
+            const uint32_t hb = tid >> 6;
+#pragma unroll
+            for (uint32_t r = 0; r < KS_IT; r++) {
+                const uint32_t k = ek[r];
+                if (k < KS_KEYS) {
+                    const uint32_t rank = hist[k][tid];
+                    hist[k][tid] = static_cast<uint16_t>(rank + 1);
+                    s_idx[koff[k] + (hb ? htot[0][k] : 0u) + rank] = ep[r];
+                }
+            }
+        }
+        __syncthreads();
+        if (has_key) { // one thread per key: the run in arrival order
+            const uint32_t m = kcnt[tid], off = koff[tid];
+            for (uint32_t j = 0; j < m; j++) {
+                const uint32_t gi = s_idx[off + j];
+                const uint32_t b = batch_of(boff, nb, gi);
+                unsigned char *tp = const_cast<unsigned char *>(batches[b].tuples) + static_cast<size_t>(gi - boff[b]) * sizeof(T);
+                alignas(16) T t;
+                ld_rec<T>(tp, t);
+                if constexpr (FILTER) keep[gi] = P::filter_stateful(t, st, prm) ? 1 : 0;
+                else P::map_stateful(t, st, prm);
+                st_rec<T>(tp, t);
+            }
+            touched |= m != 0;
+        }
+        cursor += nsel;
+        __syncthreads();
+    }
+    if (has_key && touched) *reinterpret_cast<S *>(states + static_cast<size_t>(key_lo + tid) * sizeof(S)) = st;
+}
+
+// stable per-batch compaction by the keep flags of a stateful filter: tile counts, scan, scatter
+static __global__ void __launch_bounds__(256) k_flag_tile_counts(const unsigned char *__restrict__ keep, uint32_t n, uint32_t *__restrict__ counts)
+{
+    __shared__ uint32_t wsum[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, base = blockIdx.x * SEGT;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) { const uint32_t i = base + r * 256 + tid; if (i < n && keep[i]) c++; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0) wsum[warp] = c;
+    __syncthreads();
+    if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; counts[blockIdx.x] = t; }
+}
+
+// rank_start[b] = survivors before batch b (global rank of its first tuple); n_out of every batch
+static __global__ void k_flag_batch_starts(const unsigned char *__restrict__ keep, const uint32_t *__restrict__ tile_base, const uint32_t *__restrict__ boff,
+                                           uint32_t nb, uint32_t n, uint32_t *__restrict__ rank_start, const DevBatch *__restrict__ batches)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    const uint32_t gi = boff[b]; // boff[nb] = n
+    uint32_t r;
+    if (gi >= n) { // total survivors
+        const uint32_t lt = (n - 1) / SEGT;
+        r = tile_base[lt];
+        for (uint32_t i = lt * SEGT; i < n; i++) r += keep[i] ? 1u : 0u;
+    } else {
+        const uint32_t t = gi / SEGT;
+        r = tile_base[t];
+        for (uint32_t i = t * SEGT; i < gi; i++) r += keep[i] ? 1u : 0u;
+    }
+    rank_start[b] = r;
+}
+static __global__ void k_flag_batch_counts(const uint32_t *__restrict__ rank_start, uint32_t nb, const DevBatch *__restrict__ batches)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb && batches[b].n_out != nullptr) *batches[b].n_out = rank_start[b + 1] - rank_start[b];
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) k_flag_scatter(const unsigned char *__restrict__ keep, const uint32_t *__restrict__ tile_base,
+                                                      const uint32_t *__restrict__ boff, uint32_t nb, uint32_t n,
+                                                      const uint32_t *__restrict__ rank_start, const DevBatch *__restrict__ batches)
+{
+    using T = typename P::tuple_t;
+    __shared__ uint32_t wsum[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t first = blockIdx.x * SEGT + tid * (SEGT / 256);
+    bool k[SEGT / 256];
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) { const uint32_t i = first + r; k[r] = i < n && keep[i]; mine += k[r] ? 1u : 0u; }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t rank = tile_base[blockIdx.x] + incl - mine;
+    for (uint32_t w = 0; w < warp; w++) rank += wsum[w];
+#pragma unroll
+    for (uint32_t r = 0; r < SEGT / 256; r++) {
+        if (k[r]) {
+            const uint32_t gi = first + r, b = batch_of(boff, nb, gi);
+            const DevBatch bt = batches[b];
+            const uint32_t li = gi - boff[b], o = rank - rank_start[b];
+            alignas(16) T t;
+            ld_rec<T>(bt.tuples + static_cast<size_t>(li) * sizeof(T), t);
+            st_rec<T>(bt.out + static_cast<size_t>(o) * sizeof(T), t);
+            if (bt.ts_out) bt.ts_out[o] = bt.ts[li];
+            rank++;
+        }
+    }
+}
+
 // Reduce_GPU un-keyed: the whole batch folded into one item, starting from a default-constructed item
 // (thrust::reduce with init = batch_item_gpu_t<tuple_t>(), wf/reduce_gpu.hpp:264-273). One CTA of 1024 threads.
 template <class P>

@@ -89,6 +89,15 @@ struct ProgramOps {
                     const TbDev &tb, uint32_t n, cudaStream_t s, const void *params);
     int (*tb_pop_write)(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
                         uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params);
+    // keyed-stateful Map_GPU / Filter_GPU (null when the program has no state_t)
+    uint32_t state_bytes, reserved2;
+    int (*ks_slots)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, const FfatDev &ff, uint32_t *slots, cudaStream_t s,
+                    const void *params);
+    int (*ks_apply)(int filter, const FfatDev &ff, const DevBatch *batches, const uint32_t *boff, uint32_t nb, const uint32_t *bk_slots,
+                    const uint32_t *bk_pos, const uint32_t *digit_counts, uint32_t shift, unsigned char *states, unsigned char *keep, cudaStream_t s,
+                    const void *params);
+    int (*flag_scatter)(const unsigned char *keep, const uint32_t *tile_base, const uint32_t *boff, uint32_t nb, uint32_t n,
+                        const uint32_t *rank_start, const DevBatch *batches, cudaStream_t s);
     // Reduce_GPU over K queued batches
     int (*extract_keys_batches)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, uint32_t key_bits, uint64_t *keys,
                                 cudaStream_t s, const void *params);
@@ -206,6 +215,39 @@ int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, co
     WFB_CK(cudaGetLastError());
     return 0;
 }
+template <class P, class = void> struct program_has_state : std::false_type {};
+template <class P> struct program_has_state<P, std::void_t<typename P::state_t>> : std::true_type {};
+
+template <class P>
+int ks_slots_dispatch(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, const FfatDev &ff, uint32_t *slots, cudaStream_t s,
+                      const void *params)
+{
+    k_ks_slots<P><<<grid_for(total, 256), 256, 0, s>>>(batches, boff, nb, total, ff, slots, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P>
+int ks_apply_dispatch(int filter, const FfatDev &ff, const DevBatch *batches, const uint32_t *boff, uint32_t nb, const uint32_t *bk_slots,
+                      const uint32_t *bk_pos, const uint32_t *digit_counts, uint32_t shift, unsigned char *states, unsigned char *keep, cudaStream_t s,
+                      const void *params)
+{
+    if constexpr (program_has_state<P>::value) {
+        if (filter) k_ks_apply<P, true><<<OSW_DIGITS, KS_THREADS, 0, s>>>(ff, batches, boff, nb, bk_slots, bk_pos, digit_counts, shift, states, keep, load_params<P>(params));
+        else k_ks_apply<P, false><<<OSW_DIGITS, KS_THREADS, 0, s>>>(ff, batches, boff, nb, bk_slots, bk_pos, digit_counts, shift, states, keep, load_params<P>(params));
+        WFB_CK(cudaGetLastError());
+        return 0;
+    } else return WFB_E_UNSUPPORTED;
+}
+template <class P>
+int flag_scatter_dispatch(const unsigned char *keep, const uint32_t *tile_base, const uint32_t *boff, uint32_t nb, uint32_t n,
+                          const uint32_t *rank_start, const DevBatch *batches, cudaStream_t s)
+{
+    k_flag_scatter<P><<<(n + SEGT - 1) / SEGT, 256, 0, s>>>(keep, tile_base, boff, nb, n, rank_start, batches);
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+template <class P> constexpr uint32_t program_state_bytes() { if constexpr (program_has_state<P>::value) return sizeof(typename P::state_t); else return 0; }
+
 template <class P>
 int tb_lift_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n, const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete,
                      unsigned char *lifted, uint64_t *ckeys, cudaStream_t s, const void *params)
@@ -291,6 +333,8 @@ ProgramOps make_ops()
     o.reduce_segments = &reduce_segments_dispatch<P>;
     o.reduce_all = &reduce_all_dispatch<P>;
     o.gather = &gather_dispatch<P>;
+    o.state_bytes = program_state_bytes<P>(); o.reserved2 = 0;
+    o.ks_slots = &ks_slots_dispatch<P>; o.ks_apply = &ks_apply_dispatch<P>; o.flag_scatter = &flag_scatter_dispatch<P>;
     o.tb_lift = &tb_lift_dispatch<P>; o.tb_reduce = &tb_reduce_dispatch<P>; o.tb_merge = &tb_merge_dispatch<P>; o.tb_pop_write = &tb_pop_write_dispatch<P>;
     o.extract_keys_batches = &extract_keys_batches_dispatch<P>;
     o.reduce_segments_batches = &reduce_segments_batches_dispatch<P>;

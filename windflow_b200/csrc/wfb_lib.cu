@@ -752,6 +752,143 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
 // ---- Ffat_Windows_GPU ------------------------------------------------------------------------------------------
 static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
 
+// ---- keyed-stateful Map_GPU / Filter_GPU ---------------------------------------------------------------------------------
+} // extern "C" (the struct below is C++)
+struct wfb_kstate {
+    int prog = 0;
+    const ProgramOps *ops = nullptr;
+    FfatDev ff{};                 // key table only (dense or open addressing)
+    unsigned char *states = nullptr;
+    RadixSorter sorter;
+    uint32_t bucket_shift = 0;
+    DevBatch *d_batches = nullptr; uint32_t *d_boff = nullptr; uint32_t batch_cap = 0;
+    uint32_t cap = 0;             // tuples per call
+    uint32_t *slotsA = nullptr, *slotsB = nullptr, *posB = nullptr, *tile_cnt = nullptr, *rank_start = nullptr;
+    unsigned char *keep = nullptr;
+    uint64_t launches = 0;
+};
+extern "C" {
+
+int wfb_kstate_create(wfb_kstate_t **hh, int prog, uint32_t max_keys, uint32_t flags)
+{
+    if (!hh || max_keys == 0) return WFB_E_BADARG;
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    if (o->state_bytes == 0) return WFB_E_UNSUPPORTED; // the program has no state_t / stateful functors
+    uint32_t bits = 0; while ((1ull << bits) < max_keys) bits++;
+    if (bits > OSW_BITS + 6) return WFB_E_UNSUPPORTED;  // 1024 buckets of at most 64 keys
+    int rc = device_ready(); if (rc) return rc;
+    wfb_kstate *h = new (std::nothrow) wfb_kstate();
+    if (!h) return WFB_E_BADARG;
+    h->prog = prog; h->ops = o; h->bucket_shift = bits > OSW_BITS ? bits - OSW_BITS : 0;
+    FfatDev &ff = h->ff;
+    ff.max_keys = max_keys; ff.dense = (flags & WFB_FFAT_DENSE_KEYS) ? 1u : 0u;
+    uint32_t cap = 1; while (cap < 2ull * max_keys) cap <<= 1;
+    ff.ht_mask = cap - 1;
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc(reinterpret_cast<void **>(&(ptr)), (bytes)); if (e_ != cudaSuccess) { wfb_kstate_destroy(h); return static_cast<int>(e_); } } while (0)
+    if (!ff.dense) {
+        ALLOC(ff.ht_keys, sizeof(uint64_t) * cap); ALLOC(ff.ht_slots, sizeof(uint32_t) * cap);
+        CK(cudaMemset(ff.ht_keys, 0xff, sizeof(uint64_t) * cap)); CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
+    }
+    ALLOC(ff.n_slots, sizeof(uint32_t) * 4); ff.err_flags = ff.n_slots + 1;
+    CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
+    ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
+    ALLOC(h->states, static_cast<size_t>(o->state_bytes) * max_keys);
+    CK(cudaMemset(h->states, 0, static_cast<size_t>(o->state_bytes) * max_keys)); // state_t(): zero-initialised
+#undef ALLOC
+    *hh = h;
+    return 0;
+}
+
+int wfb_kstate_destroy(wfb_kstate_t *h)
+{
+    if (!h) return 0;
+    cudaDeviceSynchronize();
+    cudaFree(h->ff.ht_keys); cudaFree(h->ff.ht_slots); cudaFree(h->ff.n_slots); cudaFree(h->ff.slot_key); cudaFree(h->states);
+    cudaFree(h->d_batches); cudaFree(h->d_boff); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posB); cudaFree(h->tile_cnt);
+    cudaFree(h->rank_start); cudaFree(h->keep);
+    h->sorter.destroy();
+    delete h;
+    cudaGetLastError();
+    return 0;
+}
+
+static int kstate_run(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches,
+                      uint32_t *n_out_dev, bool filter, cudaStream_t s)
+{
+    if (!h || !f || (nbatches && !in_h) || (filter && (!out_h || !n_out_dev))) return WFB_E_BADARG;
+    if (nbatches == 0) return 0;
+    if (filter) CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t) * nbatches, s));
+    std::vector<DevBatch> hb(nbatches);
+    std::vector<uint32_t> boff(nbatches + 1);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nbatches; i++) {
+        if (in_h[i].n && (!in_h[i].tuples || (filter && !out_h[i].tuples))) return WFB_E_BADARG;
+        DevBatch b; std::memset(&b, 0, sizeof(b));
+        b.tuples = static_cast<const unsigned char *>(in_h[i].tuples); b.ts = in_h[i].ts; b.n = in_h[i].n;
+        if (filter) {
+            b.out = static_cast<unsigned char *>(const_cast<void *>(out_h[i].tuples));
+            b.ts_out = in_h[i].ts ? const_cast<uint64_t *>(out_h[i].ts) : nullptr;
+            b.n_out = n_out_dev + i;
+        }
+        hb[i] = b; boff[i] = static_cast<uint32_t>(total); total += b.n;
+    }
+    boff[nbatches] = static_cast<uint32_t>(total);
+    if (total == 0) return 0;
+    if (total > 0x7fffffffull) return WFB_E_BADARG;
+    const uint32_t n = static_cast<uint32_t>(total);
+    if (nbatches > h->batch_cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(h->d_batches); cudaFree(h->d_boff); cudaFree(h->rank_start);
+        h->batch_cap = std::max(nbatches, 2 * h->batch_cap);
+        CK(cudaMalloc(&h->d_batches, sizeof(DevBatch) * h->batch_cap));
+        CK(cudaMalloc(&h->d_boff, sizeof(uint32_t) * (static_cast<size_t>(h->batch_cap) + 1)));
+        CK(cudaMalloc(&h->rank_start, sizeof(uint32_t) * (static_cast<size_t>(h->batch_cap) + 1)));
+    }
+    if (n > h->cap) {
+        CK(cudaStreamSynchronize(s));
+        cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posB); cudaFree(h->tile_cnt); cudaFree(h->keep);
+        h->cap = std::max(n, 2 * h->cap);
+        CK(cudaMalloc(&h->slotsA, sizeof(uint32_t) * h->cap)); CK(cudaMalloc(&h->slotsB, sizeof(uint32_t) * h->cap));
+        CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->cap)); CK(cudaMalloc(&h->keep, h->cap));
+        CK(cudaMalloc(&h->tile_cnt, sizeof(uint32_t) * ((h->cap + SEGT - 1) / SEGT + 1)));
+    }
+    CK(cudaMemcpyAsync(h->d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_boff, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+    // 1. slots; 2. one wide partition pass into 1024 buckets of consecutive slots; 3. per-bucket CTAs, one thread per key
+    int rc = h->ops->ks_slots(h->d_batches, h->d_boff, nbatches, n, h->ff, h->slotsA, s, f); if (rc) return rc;
+    const uint32_t *counts = nullptr;
+    const uint64_t before = h->sorter.launches;
+    rc = h->sorter.sort_wide<uint32_t>(h->slotsA, h->slotsB, h->posB, nullptr, n, n, h->bucket_shift, s, nullptr, &counts, nullptr, nullptr, 0, true);
+    if (rc) return rc;
+    rc = h->ops->ks_apply(filter ? 1 : 0, h->ff, h->d_batches, h->d_boff, nbatches, h->slotsB, h->posB, counts, h->bucket_shift, h->states,
+                          h->keep, s, f);
+    if (rc) return rc;
+    h->launches += 2 + (h->sorter.launches - before);
+    if (filter) { // stable per-batch compaction by the keep flags
+        const uint32_t tiles = (n + SEGT - 1) / SEGT;
+        k_flag_tile_counts<<<tiles, 256, 0, s>>>(h->keep, n, h->tile_cnt);
+        k_scan_u32<<<1, 1024, 0, s>>>(h->tile_cnt, h->tile_cnt, tiles, nullptr);
+        k_flag_batch_starts<<<(nbatches + 1 + 127) / 128, 128, 0, s>>>(h->keep, h->tile_cnt, h->d_boff, nbatches, n, h->rank_start, h->d_batches);
+        k_flag_batch_counts<<<(nbatches + 127) / 128, 128, 0, s>>>(h->rank_start, nbatches, h->d_batches);
+        CK(cudaGetLastError());
+        rc = h->ops->flag_scatter(h->keep, h->tile_cnt, h->d_boff, nbatches, n, h->rank_start, h->d_batches, s); if (rc) return rc;
+        h->launches += 5;
+    }
+    return 0;
+}
+
+int wfb_map_stateful(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_t *batches_h, uint32_t nbatches, void *stream)
+{
+    return kstate_run(h, f, batches_h, nullptr, nbatches, nullptr, false, static_cast<cudaStream_t>(stream));
+}
+
+int wfb_filter_stateful(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_t *in_h, const wfb_batch_t *out_h, uint32_t nbatches,
+                        uint32_t *n_out_dev, void *stream)
+{
+    return kstate_run(h, f, in_h, out_h, nbatches, n_out_dev, true, static_cast<cudaStream_t>(stream));
+}
+
 // ---- time-based windows: front-end handle + count-based back end over the lifted program ------------------------------------
 static int lifted_program_of(int prog)
 {

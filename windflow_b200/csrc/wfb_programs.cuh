@@ -55,6 +55,20 @@ struct ProgTuple64 {
         tuple_t r; r.key = a.key; r.id = 0; r.ivalue = a.ivalue + b.ivalue; r.fvalue = a.fvalue + b.fvalue;
         r.pad[0] = r.pad[1] = r.pad[2] = r.pad[3] = 0; return r;
     }
+    // keyed-stateful Map_GPU / Filter_GPU functors (API:54-56, :38-40): a running counter per key
+    using state_t = wfb_state8_t;
+    __host__ __device__ static void map_stateful(tuple_t &t, state_t &st, const params_t &p)
+    {
+        if (p.map_kind == 2 && (t.key & 1)) st.counter--; else st.counter++;
+        t.ivalue += st.counter;
+    }
+    __host__ __device__ static bool filter_stateful(tuple_t &t, state_t &st, const params_t &p)
+    {
+        st.counter++; t.ivalue += st.counter;
+        if (p.filt_kind == 1) return (t.ivalue & 1) == 0;
+        if (p.filt_kind == 2) return (t.ivalue % p.filt_mod) == 0;
+        return true;
+    }
 };
 
 // ---- program 1: reference tests/graph_tests_gpu/graph_common_gpu.hpp ({key, value}) ------------------
@@ -82,6 +96,21 @@ struct ProgWfTest16 {
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &) // Reduce_Functor_GPU :268-279
     {
         tuple_t r; r.key = a.key; r.value = a.value + b.value; return r;
+    }
+    // Map_Functor_GPU_KB :256-265 (kind 1) / tests/merge_tests_gpu/merge_common_gpu_kb.hpp:153-168 (kind 2, on the key's parity),
+    // Filter_Functor_GPU_KB :221-231 (kind 0 keeps everything, as the reference's does)
+    using state_t = wfb_state8_t;
+    __host__ __device__ static void map_stateful(tuple_t &t, state_t &st, const params_t &p)
+    {
+        if (p.map_kind == 2 && (t.key & 1)) st.counter--; else st.counter++;
+        t.value += st.counter;
+    }
+    __host__ __device__ static bool filter_stateful(tuple_t &t, state_t &st, const params_t &p)
+    {
+        st.counter++; t.value += st.counter;
+        if (p.filt_kind == 1) return (t.value & 1) == 0;
+        if (p.filt_kind == 2) return (t.value % p.filt_mod) == 0;
+        return true;
     }
 };
 

@@ -183,6 +183,39 @@ class Engine:
         return out, seg
 
 
+class KeyedState:
+    """Per-operator keyed state of a stateful Map_GPU / Filter_GPU (wf/map_gpu.hpp:212-299, wf/filter_gpu.hpp:247-355)."""
+
+    def __init__(self, prog, max_keys, dense_keys=False):
+        self.L = _lib.lib()
+        if self.L.wfb_device_count() <= 0:
+            raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
+        self.h = C.c_void_p()
+        check(self.L.wfb_kstate_create(C.byref(self.h), prog, max_keys, 1 if dense_keys else 0), "wfb_kstate_create")
+
+    def close(self):
+        if self.h:
+            self.L.wfb_kstate_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def map(self, batches, f, stream=None):
+        """func(tuple, state_of_key) in place, per-key arrival order over the queued batches."""
+        check(self.L.wfb_map_stateful(self.h, C.byref(f), _cbatches(batches), len(batches), _stream_ptr(stream)), "wfb_map_stateful")
+        return batches
+
+    def filter(self, batches, f, outs, n_out, stream=None):
+        """predicate(tuple, state_of_key); survivors of batch i compacted into outs[i], n_out[i] of them."""
+        check(self.L.wfb_filter_stateful(self.h, C.byref(f), _cbatches(batches), _cbatches(outs), len(batches), _ptr(n_out), _stream_ptr(stream)),
+              "wfb_filter_stateful")
+        return outs, n_out
+
+
 class Segment(list):
     """A list of DeviceBatch whose C descriptor array is built once: a replica that re-submits the same device buffers
     (a ring of input segments) does not pay the per-batch Python / ctypes cost on every call. Immutable by convention."""
