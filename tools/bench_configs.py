@@ -69,6 +69,43 @@ def main():
     print(json.dumps({"config": f"cfg3 Reduce_GPU keyed, 1M keys Zipf-0.8, {ring} queued batches per call (wfb_reduce_by_key_batches)", "tuples_per_s": tps,
                       "ms_per_call": ms, "distinct_fraction": float(nos.sum().item()) / (ring * BATCH), "bytes_per_tuple": bpt,
                       "achieved_gbs": tps * bpt / 1e9, "frac_of_measured_peak": tps * bpt / 1e9 / peak}))
+    # ---- keyed-stateful Map_GPU / Filter_GPU: 65536 uniform keys, 64 queued batches per call --------------------
+    kb = [ops.gen_tuple64(i * BATCH, BATCH, ops.KEY_UNIFORM, 65536) for i in range(ring)]
+    kseg = ops.Segment(kb)
+    ksm = ops.KeyedState(ops.PROG_TUPLE64, max_keys=65536, dense_keys=True)
+    ms = timed(lambda i: ksm.map(kseg, f), max(10, a.iters // 8))
+    tps = ring * BATCH / (ms * 1e-3)
+    print(json.dumps({"config": f"Map_GPU keyed-stateful (counter per key), 65536 uniform keys, {ring} queued batches per call (wfb_map_stateful)",
+                      "tuples_per_s": tps, "ms_per_call": ms, "bytes_per_tuple": 128, "achieved_gbs": tps * 128 / 1e9, "frac_of_measured_peak": tps * 128 / 1e9 / peak}))
+    ksf = ops.KeyedState(ops.PROG_TUPLE64, max_keys=65536, dense_keys=True)
+    ms = timed(lambda i: ksf.filter(kseg, ops.functors(filt_kind=1), seg_out, nos), max(10, a.iters // 8))
+    tps = ring * BATCH / (ms * 1e-3)
+    print(json.dumps({"config": f"Filter_GPU keyed-stateful, 65536 uniform keys, {ring} queued batches per call (wfb_filter_stateful)",
+                      "tuples_per_s": tps, "ms_per_call": ms, "selectivity": float(nos.sum().item()) / (ring * BATCH)}))
+    # ---- time-based windows, one batch per call: ts = tuple index, keys round-robin, so a key sees one tuple every
+    # nk timestamp units; win = 4096 nk, slide = 64 nk are the count-based config's windows (4096 / 64 tuples per key) in time units
+    for nk in (65536, 1024):
+        tbh = ops.FfatWindowsGPU(ops.PROG_TUPLE64, 4096 * nk, 64 * nk, 65, max_keys=nk, dense_keys=True, win_type=1)
+        tbb = [ops.gen_tuple64(i * BATCH, BATCH, ops.KEY_RR, nk) for i in range(ring)]
+        for i, b in enumerate(tbb):
+            b.watermark = i * BATCH
+        cap = 1 << 22
+        o = torch.empty(cap * 32, dtype=torch.uint8, device=dev); ots = torch.empty(cap, dtype=torch.int64, device=dev)
+        state = {"i": 0}
+        def tb_step(_):
+            # a fresh stretch of the stream every call (timestamps keep growing): regenerate into the ring slot
+            i = state["i"]; state["i"] += 1
+            b = tbb[i % ring]
+            ops.gen_tuple64(i * BATCH, BATCH, ops.KEY_RR, nk, tuples=b.tuples, ts=b.ts)
+            b.watermark = i * BATCH
+            tbh.process([b], out=o, out_ts=ots, n_out=n_out)
+        ms = timed(tb_step, max(20, a.iters // 4))
+        gen_ms = timed(lambda i: ops.gen_tuple64(i * BATCH, BATCH, ops.KEY_RR, nk, tuples=tbb[0].tuples, ts=tbb[0].ts), 50)
+        tps = BATCH / ((ms - gen_ms) * 1e-3)
+        print(json.dumps({"config": f"Ffat_Windows_GPU time-based, win 4096*{nk} slide 64*{nk} ts units (= 4096 / 64 tuples per key), Nb=65, {nk} round-robin keys, one batch of 65536 per call (first version, stream syncs per batch)",
+                          "tuples_per_s": tps, "ms_per_batch": ms - gen_ms, "windows_last_call": int(n_out.item())}))
+        assert tbh.stats()[1] == 0
+        tbh.close()
     # ---- cfg 4 --------------------------------------------------------------------------------------------------
     for nb in (65, 1):
         for bps in (1, 64):
