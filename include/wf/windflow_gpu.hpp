@@ -14,8 +14,8 @@
 // __host__ __device__ functors reach the kernels as a *program* registered from this translation unit
 // (wfb::register_program, windflow_b200/csrc/wfb_launch.cuh). Compile the application with nvcc, link with -lwfb200.
 //
-// Scope of this facade: linear pipelines Source(CPU) -> GPU operators -> Sink(CPU), stateless
-// Map_GPU / Filter_GPU, keyed or un-keyed Reduce_GPU, count-based Ffat_Windows_GPU, DEFAULT execution mode (the only
+// Scope of this facade: linear pipelines Source(CPU) -> GPU operators -> Sink(CPU), stateless and
+// keyed-stateful Map_GPU / Filter_GPU, keyed or un-keyed Reduce_GPU, count-based Ffat_Windows_GPU, DEFAULT execution mode (the only
 // mode the reference's GPU operators accept, wf/map_gpu.hpp:470-475). FastFlow is not required: stages run in the
 // calling thread and hand batches over by pointer, which is what MultiPipe::chain does for chained replicas
 // (wf/multipipe.hpp:538-590). Errors follow the reference convention: a red "WindFlow Error:" line and exit.
@@ -101,6 +101,27 @@ struct FacadeProgram {
     }
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &p) { RedF f = p.red; return f(a, b); }
 };
+
+// The program of a keyed-stateful Map_GPU / Filter_GPU: func(tuple_t &, state_t &) in per-key arrival order
+// (API: __host__ __device__ void(tuple_t &, state_t &) / bool(tuple_t &, state_t &), wf/map_gpu.hpp:104-310, wf/filter_gpu.hpp:120-399).
+template <class T, class S, class MapF2, class FiltF2, class KeyF>
+struct FacadeStatefulProgram {
+    using tuple_t = T; using result_t = T; using key_t = uint64_t; using state_t = S;
+    struct params_t { MapF2 map; FiltF2 filt; KeyF key; };
+    static_assert(std::is_trivially_copyable<T>::value && std::is_trivially_copyable<S>::value, "tuple_t / state_t must be trivially copyable");
+    static_assert(sizeof(T) % 8 == 0, "tuple_t size must be a multiple of 8 bytes");
+    __host__ __device__ static void map(tuple_t &, const params_t &) {}
+    __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &p) { KeyF f = p.key; return static_cast<key_t>(f(t)); }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r = t; }
+    __host__ __device__ static void comb(const result_t &, const result_t &, result_t &, const params_t &) {}
+    __host__ __device__ static result_t make_result(key_t, uint64_t, const params_t &) { return result_t(); }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &, const params_t &) { return a; }
+    __host__ __device__ static void map_stateful(tuple_t &t, state_t &st, const params_t &p) { MapF2 f = p.map; f(t, st); }
+    __host__ __device__ static bool filter_stateful(tuple_t &t, state_t &st, const params_t &p) { FiltF2 f = p.filt; return f(t, st); }
+};
+template <class T, class S> struct StatefulIdMap { __host__ __device__ void operator()(T &, S &) const {} };
+template <class T, class S> struct StatefulKeepAll { __host__ __device__ bool operator()(T &, S &) const { return true; } };
 
 // ---- Batch_GPU_t (wf/batch_gpu_t.hpp:50-243) as structure of arrays ---------------------------------------------------
 template <class tuple_t>
@@ -373,6 +394,92 @@ public:
     std::unique_ptr<Stage> make_replica() override { return std::make_unique<Replica>(func, recycle_in); }
 };
 
+// Map_GPU, keyed-stateful (wf/map_gpu.hpp:104-310): func(tuple, state_of_key) in per-key arrival order, in place. The key -> state
+// table is one wfb_kstate_t per operator, shared by its replicas (the reference's TBB map + spinlock, :551-559).
+template <class map_func_gpu_t, class keyextr_func_gpu_t>
+class Map_GPU_KB: public Basic_Operator {
+public:
+    using tuple_t = fn_arg_t<map_func_gpu_t, 0>;
+    using state_t = fn_arg_t<map_func_gpu_t, 1>;
+    using result_t = tuple_t;
+    using prog_t = FacadeStatefulProgram<tuple_t, state_t, map_func_gpu_t, StatefulKeepAll<tuple_t, state_t>, keyextr_func_gpu_t>;
+    static constexpr op_type_t op_type = op_type_t::BASIC_GPU;
+    map_func_gpu_t func; keyextr_func_gpu_t key_extr; uint32_t max_keys;
+    std::shared_ptr<wfb_kstate_t> kstate;
+    Map_GPU_KB(map_func_gpu_t f, keyextr_func_gpu_t k, size_t p, std::string n, uint32_t mk): Basic_Operator(std::move(n), p, Routing_Mode_t::KEYBY, 1), func(f), key_extr(k), max_keys(mk) {}
+    std::string getType() const override { return "Map_GPU"; }
+    keyextr_func_gpu_t getKeyExtractor() const { return key_extr; }
+    struct Replica: Stage {
+        std::shared_ptr<wfb_kstate_t> ks; typename prog_t::params_t prm;
+        Replica(std::shared_ptr<wfb_kstate_t> h, map_func_gpu_t f, keyextr_func_gpu_t k): ks(std::move(h)), prm{f, {}, k} {}
+        void *svc(void *msg) override
+        {
+            auto *in = reinterpret_cast<Batch_GPU_t<tuple_t> *>(msg);
+            if (!in->isPunct() && in->size) {
+                wfb_batch_t b{}; b.tuples = in->tuples_gpu; b.ts = in->ts_gpu; b.n = static_cast<uint32_t>(in->size);
+                wfbErrChk(wfb_map_stateful(ks.get(), reinterpret_cast<const wfb_functors_t *>(&prm), &b, 1, in->cudaStream));
+            }
+            this->ff_send_out(in);
+            return nullptr;
+        }
+    };
+    std::unique_ptr<Stage> make_replica() override
+    {
+        if (!kstate) { wfb_kstate_t *h = nullptr; wfbErrChk(wfb_kstate_create(&h, wfb::register_program<prog_t>(), max_keys, 0)); kstate.reset(h, [](wfb_kstate_t *p) { wfb_kstate_destroy(p); }); }
+        return std::make_unique<Replica>(kstate, func, key_extr);
+    }
+};
+
+// Filter_GPU, keyed-stateful (wf/filter_gpu.hpp:120-399): predicate(tuple, state_of_key); survivors compacted (stable).
+template <class filter_func_gpu_t, class keyextr_func_gpu_t>
+class Filter_GPU_KB: public Basic_Operator {
+public:
+    using tuple_t = fn_arg_t<filter_func_gpu_t, 0>;
+    using state_t = fn_arg_t<filter_func_gpu_t, 1>;
+    using result_t = tuple_t;
+    using prog_t = FacadeStatefulProgram<tuple_t, state_t, StatefulIdMap<tuple_t, state_t>, filter_func_gpu_t, keyextr_func_gpu_t>;
+    static constexpr op_type_t op_type = op_type_t::BASIC_GPU;
+    filter_func_gpu_t func; keyextr_func_gpu_t key_extr; uint32_t max_keys;
+    std::shared_ptr<wfb_kstate_t> kstate;
+    std::function<void(void *)> recycle_in;
+    Filter_GPU_KB(filter_func_gpu_t f, keyextr_func_gpu_t k, size_t p, std::string n, uint32_t mk): Basic_Operator(std::move(n), p, Routing_Mode_t::KEYBY, 1), func(f), key_extr(k), max_keys(mk) {}
+    std::string getType() const override { return "Filter_GPU"; }
+    keyextr_func_gpu_t getKeyExtractor() const { return key_extr; }
+    struct Replica: Stage {
+        std::shared_ptr<wfb_kstate_t> ks; typename prog_t::params_t prm; uint32_t *n_out_dev = nullptr; uint32_t *n_out_h = nullptr;
+        BatchPool<tuple_t> pool; std::function<void(void *)> recycle_in;
+        Replica(std::shared_ptr<wfb_kstate_t> h, filter_func_gpu_t f, keyextr_func_gpu_t k, std::function<void(void *)> r): ks(std::move(h)), prm{{}, f, k}, recycle_in(std::move(r))
+        {
+            gpuErrChk(cudaMalloc(&n_out_dev, sizeof(uint32_t))); gpuErrChk(cudaMallocHost(&n_out_h, sizeof(uint32_t)));
+        }
+        ~Replica() override { cudaFree(n_out_dev); cudaFreeHost(n_out_h); }
+        void *svc(void *msg) override
+        {
+            auto *in = reinterpret_cast<Batch_GPU_t<tuple_t> *>(msg);
+            if (in->isPunct()) { this->ff_send_out(in); return nullptr; }
+            Batch_GPU_t<tuple_t> *out = pool.get(in->original_size);
+            out->watermarks = in->watermarks;
+            wfb_batch_t bi{}, bo{};
+            bi.tuples = in->tuples_gpu; bi.ts = in->ts_gpu; bi.n = static_cast<uint32_t>(in->size);
+            bo.tuples = out->tuples_gpu; bo.ts = out->ts_gpu; bo.n = bi.n;
+            wfbErrChk(wfb_filter_stateful(ks.get(), reinterpret_cast<const wfb_functors_t *>(&prm), &bi, &bo, 1, n_out_dev, in->cudaStream));
+            gpuErrChk(cudaMemcpyAsync(n_out_h, n_out_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, in->cudaStream));
+            gpuErrChk(cudaStreamSynchronize(in->cudaStream));
+            out->size = *n_out_h;
+            if (recycle_in) recycle_in(in); else delete in;
+            if (out->size == 0) { pool.put(out); return nullptr; }
+            this->ff_send_out(out);
+            return nullptr;
+        }
+        void take_back(void *b) { pool.put(reinterpret_cast<Batch_GPU_t<tuple_t> *>(b)); }
+    };
+    std::unique_ptr<Stage> make_replica() override
+    {
+        if (!kstate) { wfb_kstate_t *h = nullptr; wfbErrChk(wfb_kstate_create(&h, wfb::register_program<prog_t>(), max_keys, 0)); kstate.reset(h, [](wfb_kstate_t *p) { wfb_kstate_destroy(p); }); }
+        return std::make_unique<Replica>(kstate, func, key_extr, recycle_in);
+    }
+};
+
 // Reduce_GPU (wf/reduce_gpu.hpp:109-289): per batch, one item per distinct key (ascending) or one item for the batch.
 template <class reduce_func_gpu_t, class keyextr_func_gpu_t>
 class Reduce_GPU: public Basic_Operator {
@@ -476,34 +583,76 @@ public:
 };
 
 // ---- builders (wf/builders_gpu.hpp) ----------------------------------------------------------------------------------------
+template <class map_func_gpu_t, class keyextr_func_gpu_t>
+class MapGPU_KB_Builder { // MapGPU_Builder(func).withKeyBy(key_extr): the keyed-stateful operator
+    map_func_gpu_t func; keyextr_func_gpu_t key; std::string name; size_t parallelism; uint32_t max_keys = 1u << 16;
+public:
+    MapGPU_KB_Builder(map_func_gpu_t f, keyextr_func_gpu_t k, std::string n, size_t p): func(f), key(k), name(std::move(n)), parallelism(p) {}
+    auto &withName(std::string n) { name = std::move(n); return *this; }
+    auto &withParallelism(size_t p) { parallelism = p; return *this; }
+    auto &withMaxKeys(uint32_t mk) { max_keys = mk; return *this; } // capacity of the device key -> state table (not in the reference: its map grows on the host)
+    auto build() { return Map_GPU_KB<map_func_gpu_t, keyextr_func_gpu_t>(func, key, parallelism, name, max_keys); }
+};
+
 template <class map_func_gpu_t>
 class MapGPU_Builder {
     map_func_gpu_t func; std::string name = "map_gpu"; size_t parallelism = 1; Routing_Mode_t mode = Routing_Mode_t::FORWARD;
+    static constexpr size_t arity = std::tuple_size<typename fn_sig<map_func_gpu_t>::args>::value;
 public:
     explicit MapGPU_Builder(map_func_gpu_t f): func(f)
     {
-        static_assert(std::tuple_size<typename fn_sig<map_func_gpu_t>::args>::value == 1,
-                      "WindFlow Compilation Error - MapGPU_Builder: only the stateless signature __host__ __device__ void(tuple_t &) is available");
+        static_assert(arity == 1 || arity == 2,
+                      "WindFlow Compilation Error - MapGPU_Builder: __host__ __device__ void(tuple_t &) or void(tuple_t &, state_t &)");
     }
     auto &withName(std::string n) { name = std::move(n); return *this; }
     auto &withParallelism(size_t p) { parallelism = p; return *this; }
     auto &withRebalancing() { mode = Routing_Mode_t::REBALANCING; return *this; }
-    auto build() { return Map_GPU<map_func_gpu_t>(func, parallelism, name, mode); }
+    template <class keyextr_t> auto withKeyBy(keyextr_t k)
+    {
+        static_assert(arity == 2, "WindFlow Compilation Error - MapGPU_Builder: withKeyBy() needs the stateful signature void(tuple_t &, state_t &)");
+        return MapGPU_KB_Builder<map_func_gpu_t, keyextr_t>(func, k, name, parallelism);
+    }
+    auto build()
+    {
+        static_assert(arity == 1, "WindFlow Compilation Error - MapGPU_Builder: a stateful functor needs withKeyBy()");
+        return Map_GPU<map_func_gpu_t>(func, parallelism, name, mode);
+    }
+};
+
+template <class filter_func_gpu_t, class keyextr_func_gpu_t>
+class FilterGPU_KB_Builder {
+    filter_func_gpu_t func; keyextr_func_gpu_t key; std::string name; size_t parallelism; uint32_t max_keys = 1u << 16;
+public:
+    FilterGPU_KB_Builder(filter_func_gpu_t f, keyextr_func_gpu_t k, std::string n, size_t p): func(f), key(k), name(std::move(n)), parallelism(p) {}
+    auto &withName(std::string n) { name = std::move(n); return *this; }
+    auto &withParallelism(size_t p) { parallelism = p; return *this; }
+    auto &withMaxKeys(uint32_t mk) { max_keys = mk; return *this; }
+    auto build() { return Filter_GPU_KB<filter_func_gpu_t, keyextr_func_gpu_t>(func, key, parallelism, name, max_keys); }
 };
 
 template <class filter_func_gpu_t>
 class FilterGPU_Builder {
     filter_func_gpu_t func; std::string name = "filter_gpu"; size_t parallelism = 1; Routing_Mode_t mode = Routing_Mode_t::FORWARD;
+    static constexpr size_t arity = std::tuple_size<typename fn_sig<filter_func_gpu_t>::args>::value;
 public:
     explicit FilterGPU_Builder(filter_func_gpu_t f): func(f)
     {
-        static_assert(std::tuple_size<typename fn_sig<filter_func_gpu_t>::args>::value == 1,
-                      "WindFlow Compilation Error - FilterGPU_Builder: only the stateless signature __host__ __device__ bool(tuple_t &) is available");
+        static_assert(arity == 1 || arity == 2,
+                      "WindFlow Compilation Error - FilterGPU_Builder: __host__ __device__ bool(tuple_t &) or bool(tuple_t &, state_t &)");
     }
     auto &withName(std::string n) { name = std::move(n); return *this; }
     auto &withParallelism(size_t p) { parallelism = p; return *this; }
     auto &withRebalancing() { mode = Routing_Mode_t::REBALANCING; return *this; }
-    auto build() { return Filter_GPU<filter_func_gpu_t>(func, parallelism, name, mode); }
+    template <class keyextr_t> auto withKeyBy(keyextr_t k)
+    {
+        static_assert(arity == 2, "WindFlow Compilation Error - FilterGPU_Builder: withKeyBy() needs the stateful signature bool(tuple_t &, state_t &)");
+        return FilterGPU_KB_Builder<filter_func_gpu_t, keyextr_t>(func, k, name, parallelism);
+    }
+    auto build()
+    {
+        static_assert(arity == 1, "WindFlow Compilation Error - FilterGPU_Builder: a stateful functor needs withKeyBy()");
+        return Filter_GPU<filter_func_gpu_t>(func, parallelism, name, mode);
+    }
 };
 
 template <class reduce_func_gpu_t, class keyextr_func_gpu_t = NoKey<fn_arg_t<reduce_func_gpu_t, 0>>>
@@ -578,6 +727,18 @@ public:
         attach(op); op.recycle_in = recycle_prev;
         auto rep = op.make_replica();
         auto *r = static_cast<typename Filter_GPU<filter_f>::Replica *>(rep.get());
+        recycle_prev = [r](void *b) { r->take_back(b); };
+        link(std::move(rep)); tail_is_gpu = true; return *this;
+    }
+    template <class map_f, class key_f> MultiPipe &chain(Map_GPU_KB<map_f, key_f> op)
+    {
+        attach(op); link(op.make_replica()); tail_is_gpu = true; return *this; // in place: the batch keeps its producer
+    }
+    template <class filter_f, class key_f> MultiPipe &chain(Filter_GPU_KB<filter_f, key_f> op)
+    {
+        attach(op); op.recycle_in = recycle_prev;
+        auto rep = op.make_replica();
+        auto *r = static_cast<typename Filter_GPU_KB<filter_f, key_f>::Replica *>(rep.get());
         recycle_prev = [r](void *b) { r->take_back(b); };
         link(std::move(rep)); tail_is_gpu = true; return *this;
     }

@@ -43,6 +43,13 @@ struct Reduce_Functor_GPU { // graph_common_gpu.hpp:268-279
     __host__ __device__ tuple_t operator()(const tuple_t &a, const tuple_t &b) { tuple_t r; r.key = a.key; r.value = a.value + b.value; return r; }
 };
 
+struct map_state_t { int64_t counter; __host__ __device__ map_state_t(): counter(0) {} };       // graph_common_gpu.hpp:52-60
+struct filter_state_t { int64_t counter; __host__ __device__ filter_state_t(): counter(0) {} }; // :63-71
+struct Map_Functor_GPU_KB { __host__ __device__ void operator()(tuple_t &t, map_state_t &state) { state.counter++; t.value += state.counter; } }; // :256-265
+struct Filter_Functor_GPU_KB { // :221-231 (with a predicate on the updated value so that the compaction is exercised)
+    __host__ __device__ bool operator()(tuple_t &t, filter_state_t &state) { state.counter++; t.value += state.counter; return (t.value & 1) == 0; }
+};
+
 static std::atomic<long> global_sum{0};
 static std::atomic<long> received{0};
 struct Sink_Functor {
@@ -110,6 +117,22 @@ int main()
         check("reduce_by_key sum", global_sum, exp);
         const long nb = (len * keys + batch - 1) / batch;
         check("reduce_by_key items", received, nb * static_cast<long>(keys)); // every batch holds all 7 keys
+    }
+    // ---- test 4: Source -> Map_GPU (keyed-stateful) -> Filter_GPU (keyed-stateful) -> Sink (test_graph_gpu / merge kb shapes) --
+    {
+        global_sum = 0; received = 0;
+        PipeGraph graph("test_stateful_gpu", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(batch).build());
+        mp.chain(MapGPU_Builder(Map_Functor_GPU_KB()).withName("mapgpu_kb").withKeyBy(Key_Functor()).withMaxKeys(64).build());
+        mp.chain(FilterGPU_Builder(Filter_Functor_GPU_KB()).withName("filtergpu_kb").withKeyBy(Key_Functor()).withMaxKeys(64).build());
+        mp.chain_sink(Sink_Builder(Sink_Functor_T()).withName("sink").build());
+        graph.run();
+        // per key: the i-th tuple (value i) gets +i from the map's counter (2i) and +i from the filter's counter (3i); kept when even
+        long exp_sum = 0, exp_cnt = 0;
+        for (size_t i = 1; i <= len; i++) { const long v = 3 * static_cast<long>(i); if ((v & 1) == 0) { exp_sum += v * keys; exp_cnt += keys; } }
+        check("stateful map -> stateful filter sum", global_sum, exp_sum);
+        check("stateful map -> stateful filter items", received, exp_cnt);
     }
     std::printf("FACADE_OK\n");
     return 0;
