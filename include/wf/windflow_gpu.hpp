@@ -15,7 +15,7 @@
 // (wfb::register_program, windflow_b200/csrc/wfb_launch.cuh). Compile the application with nvcc, link with -lwfb200.
 //
 // Scope of this facade: linear pipelines Source(CPU) -> GPU operators -> Sink(CPU), stateless and
-// keyed-stateful Map_GPU / Filter_GPU, keyed or un-keyed Reduce_GPU, count-based Ffat_Windows_GPU, DEFAULT execution mode (the only
+// keyed-stateful Map_GPU / Filter_GPU, keyed or un-keyed Reduce_GPU, count-based and time-based Ffat_Windows_GPU, DEFAULT execution mode (the only
 // mode the reference's GPU operators accept, wf/map_gpu.hpp:470-475). FastFlow is not required: stages run in the
 // calling thread and hand batches over by pointer, which is what MultiPipe::chain does for chained replicas
 // (wf/multipipe.hpp:538-590). Errors follow the reference convention: a red "WindFlow Error:" line and exit.
@@ -546,17 +546,16 @@ public:
     {
         if (win_len == 0 || slide_len == 0) wf_fatal("Ffat_Windows_GPU used with window length or slide equal to zero");
         if (numWinPerBatch == 0) wf_fatal("Ffat_Windows_GPU used with zero windows per batch");
-        if (winType != Win_Type_t::CB) wf_fatal("Ffat_Windows_GPU: time-based windows are not available in this build (DESIGN.md section 1)");
     }
     std::string getType() const override { return "Ffat_Windows_GPU"; }
     struct Replica: Stage {
         wfb_ffat_t *ffat = nullptr; typename prog_t::params_t prm; uint32_t *n_out_dev = nullptr; uint32_t *n_out_h = nullptr;
-        BatchPool<result_t> pool; std::function<void(void *)> recycle_in; uint64_t slide, nb; uint32_t max_keys;
+        BatchPool<result_t> pool; std::function<void(void *)> recycle_in; uint64_t slide, nb; uint32_t max_keys; bool tb; uint64_t last_wm = 0;
         Replica(const Ffat_Windows_GPU &op): prm{{}, {}, op.key_extr, op.lift, op.comb, {}}, recycle_in(op.recycle_in), slide(op.slide_len),
-                                             nb(op.numWinPerBatch), max_keys(op.max_keys)
+                                             nb(op.numWinPerBatch), max_keys(op.max_keys), tb(op.winType == Win_Type_t::TB)
         {
             wfbErrChk(wfb_ffat_create(&ffat, wfb::register_program<prog_t>(), op.win_len, op.slide_len, static_cast<uint32_t>(op.numWinPerBatch),
-                                      op.max_keys, 0, op.lateness, 0));
+                                      op.max_keys, tb ? 1 : 0, op.lateness, 0));
             wfbErrChk(wfb_ffat_set_params(ffat, &prm, sizeof(prm)));
             gpuErrChk(cudaMalloc(&n_out_dev, sizeof(uint32_t))); gpuErrChk(cudaMallocHost(&n_out_h, sizeof(uint32_t)));
         }
@@ -565,10 +564,16 @@ public:
         {
             auto *in = reinterpret_cast<Batch_GPU_t<tuple_t> *>(msg);
             if (in->isPunct()) { if (recycle_in) recycle_in(in); else delete in; return nullptr; }
-            const size_t cap = (in->size / (slide * nb) + max_keys + 1) * nb; // every group that can fire on this batch
+            // every group that can fire on this batch: per key, count-based one per slide*nb items; time-based one per slide*nb
+            // time units the watermark advanced (+1: the first group, B panes, may complete together with the next one)
+            const uint64_t wm = in->getWatermark();
+            const size_t per_key = tb ? static_cast<size_t>((wm > last_wm ? wm - last_wm : 0) / (slide * nb) + 2) : 1;
+            const size_t cap = tb ? static_cast<size_t>(max_keys) * per_key * nb : (in->size / (slide * nb) + max_keys + 1) * nb;
+            if (tb) last_wm = wm;
             Batch_GPU_t<result_t> *out = pool.get(cap);
-            wfb_batch_t b{in->tuples_gpu, in->ts_gpu, in->getWatermark(), static_cast<uint32_t>(in->size), 0};
-            wfbErrChk(wfb_ffat_process_cb(ffat, nullptr, &b, 1, out->tuples_gpu, out->ts_gpu, static_cast<uint32_t>(cap), n_out_dev, in->cudaStream));
+            wfb_batch_t b{in->tuples_gpu, in->ts_gpu, wm, static_cast<uint32_t>(in->size), 0};
+            if (tb) wfbErrChk(wfb_ffat_process_tb(ffat, nullptr, &b, 1, out->tuples_gpu, out->ts_gpu, static_cast<uint32_t>(cap), n_out_dev, in->cudaStream))
+            else wfbErrChk(wfb_ffat_process_cb(ffat, nullptr, &b, 1, out->tuples_gpu, out->ts_gpu, static_cast<uint32_t>(cap), n_out_dev, in->cudaStream));
             gpuErrChk(cudaMemcpyAsync(n_out_h, n_out_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, in->cudaStream));
             gpuErrChk(cudaStreamSynchronize(in->cudaStream));
             out->size = *n_out_h; out->setWatermark(in->getWatermark());

@@ -43,7 +43,6 @@ extern "C" {
 #define WFB_PROG_WFTEST16 1   /* reference tests/graph_tests_gpu/graph_common_gpu.hpp:40-49 {key,value}  */
 #define WFB_PROG_WFWIN24  2   /* reference tests/win_tests_gpu/win_common_gpu.hpp:40-80 {key,id,value}   */
 #define WFB_PROG_LIFTED32 3   /* already-lifted wfb_result32_t records (destination side of the multi-GPU keyby) */
-#define WFB_PROG_LIFTEDWIN24 4 /* already-lifted wfb_wfwin24_t records (pane aggregates of time-based windows of programs 1, 2) */
 
 typedef struct { uint64_t key; uint64_t id; int64_t ivalue; double fvalue; uint64_t pad[4]; } wfb_tuple64_t;
 typedef struct { uint64_t key; uint64_t id; int64_t isum; double fsum; } wfb_result32_t;
@@ -90,7 +89,7 @@ int         wfb_device_count(void);                    /* 0 => every compute ent
 int         wfb_program_info(int prog, wfb_program_info_t *info);
 /* Adds an application-defined program (record schema + functors compiled in the application's own .cu): `ops` is the
  * launch table built by wfb::register_program<P>() of windflow_b200/csrc/wfb_launch.cuh. Returns the new program id
- * (>= 5) or a negative error. For such programs every `const wfb_functors_t *` parameter below points to the program's
+ * (>= 4) or a negative error. For such programs every `const wfb_functors_t *` parameter below points to the program's
  * own params_t (its functor objects) instead. */
 int         wfb_program_register(const void *ops, size_t ops_bytes);
 
@@ -219,7 +218,7 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev,
                         void *stream);
 
-/* Time-based windows (handles created with win_type = 1; win / slide / lateness in timestamp units; built-in programs only).
+/* Time-based windows (handles created with win_type = 1; win / slide / lateness in timestamp units).
  * Every batch must carry its timestamps; batches are processed one after the other. Per batch: tuples are assigned to panes
  * ts / gcd(win, slide), per-(key, pane) partials are merged into the key's pending panes, and for every key PRESENT in the
  * batch the groups of panes the watermark has completed (panes < (watermark - lateness) / pane length; first (Nb-1)*slide+win

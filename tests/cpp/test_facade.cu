@@ -59,6 +59,16 @@ struct Sink_Functor_T {
     void operator()(std::optional<tuple_t> &out) { if (out) { global_sum += out->value; received++; } }
 };
 
+static long win_count[16], win_sum[16]; static bool win_order_ok = true;
+struct Sink_Functor_Win { // windows of a key must arrive with consecutive ids 0, 1, 2, ...
+    void operator()(std::optional<result_t> &out)
+    {
+        if (!out) return;
+        if (static_cast<long>(out->id) != win_count[out->key]) win_order_ok = false;
+        win_count[out->key]++; win_sum[out->key] += out->value; received++;
+    }
+};
+
 static void check(const char *what, long got, long exp)
 {
     if (got != exp) { std::printf("FAILED %s: got %ld expected %ld\n", what, got, exp); std::exit(1); }
@@ -133,6 +143,32 @@ int main()
         for (size_t i = 1; i <= len; i++) { const long v = 3 * static_cast<long>(i); if ((v & 1) == 0) { exp_sum += v * keys; exp_cnt += keys; } }
         check("stateful map -> stateful filter sum", global_sum, exp_sum);
         check("stateful map -> stateful filter items", received, exp_cnt);
+    }
+    // ---- test 5: Source -> Ffat_Windows_GPU keyed, TIME-based windows -> Sink (test_win_fat_gpu_tb shape) ------------------------
+    {
+        received = 0; win_order_ok = true;
+        for (int k = 0; k < 16; k++) { win_count[k] = 0; win_sum[k] = 0; }
+        const uint64_t win = 210, slide = 70; // microseconds; timestamps grow by 1 per tuple, so a key sees one tuple every 7 us
+        PipeGraph graph("test_win_fat_gpu_tb", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(batch).build());
+        mp.add(Ffat_WindowsGPU_Builder(Lift_Functor_GPU(), Comb_Functor_GPU()).withName("ffat_tb").withKeyBy(Key_Functor())
+                   .withTBWindows(std::chrono::microseconds(win), std::chrono::microseconds(slide)).withNumWinPerBatch(3).withMaxKeys(16).build());
+        mp.chain_sink(Sink_Builder(Sink_Functor_Win()).withName("sink").build());
+        graph.run();
+        if (!win_order_ok) { std::printf("FAILED tb windows: ids not consecutive per key\n"); return 1; }
+        long fired = 0;
+        for (size_t k = 0; k < keys; k++) { // window g of key k = sum of the values of its tuples with ts in [g*slide, g*slide + win)
+            long exp = 0;
+            for (long g = 0; g < win_count[k]; g++)
+                for (size_t i = 1; i <= len; i++) { const uint64_t ts = (i - 1) * keys + k; if (ts >= g * slide && ts < g * slide + win) exp += static_cast<long>(i); }
+            if (exp != win_sum[k]) { std::printf("FAILED tb windows of key %zu: got %ld expected %ld over %ld windows\n", k, win_sum[k], exp, win_count[k]); return 1; }
+            if (win_count[k] != win_count[0]) { std::printf("FAILED tb windows: keys fired different numbers of windows\n"); return 1; }
+            fired += win_count[k];
+        }
+        // the stream spans len*keys = 21000 us: all but the last few groups of 3 windows have fired
+        if (fired < static_cast<long>(keys) * 270 || fired % 3 != 0) { std::printf("FAILED tb windows: %ld fired\n", fired); return 1; }
+        std::printf("ffat tb windows OK (%ld windows, %ld per key)\n", fired, win_count[0]);
     }
     std::printf("FACADE_OK\n");
     return 0;

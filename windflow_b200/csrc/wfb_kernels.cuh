@@ -109,6 +109,8 @@ struct TileArgs {
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
     uint32_t sparse;           // MODE_INGEST, 1: no global compaction -- tile t owns lifted / slots [t*TILE, +TILE) (survivors first,
                                // INVALID_SLOT padding), so tiles are independent: no look-back chain, positions are tuple indices
+    const uint32_t *ext_slots; // MODE_INGEST + in-place: slot of the record at every position, given by the caller (the time-based
+                               // front end knows the key slot of every pane it pops); the program's key extractor is not used
     uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
                                // batches lie at their tile positions in one buffer: nothing is copied, only the slots are written
     uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
@@ -442,7 +444,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     P::lift(tup, res, prm);
                     if (a.nshards) slot = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); // keyby across GPUs: the "slot" is the destination
                     else {
-                        slot = slot_of_key(a.ff, P::key(tup, prm));
+                        if (a.ext_slots != nullptr) { slot = a.ext_slots[m.tile * TILE + ctid]; if (slot >= a.ff.max_keys) slot = INVALID_SLOT; }
+                        else slot = slot_of_key(a.ff, P::key(tup, prm));
                         if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
                     }
                     if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
@@ -2290,7 +2293,8 @@ static __global__ void __launch_bounds__(1024) k_tb_scan_present(uint32_t *__res
 
 template <class P>
 __global__ void k_tb_pop_write(const FfatDev ff, const TbDev tb, uint64_t first_incomplete, const uint32_t *__restrict__ offs,
-                               unsigned char *__restrict__ popped, uint32_t popped_cap, const typename P::params_t prm)
+                               unsigned char *__restrict__ popped, uint32_t *__restrict__ popped_slots, uint32_t popped_cap,
+                               const typename P::params_t prm)
 {
     using R = typename P::result_t;
     const uint32_t np = *tb.n_present;
@@ -2308,7 +2312,7 @@ __global__ void k_tb_pop_write(const FfatDev ff, const TbDev tb, uint64_t first_
                 alignas(16) R v;
                 if (m < num) ld_rec<R>(ring + ((first_id + m) % tb.capq) * sizeof(R), v);
                 else v = P::make_result(key, 0, prm);
-                if (w < popped_cap) st_rec<R>(popped + static_cast<size_t>(w) * sizeof(R), v);
+                if (w < popped_cap) { st_rec<R>(popped + static_cast<size_t>(w) * sizeof(R), v); popped_slots[w] = slot; }
             }
             first_id += need; num = num > need ? static_cast<uint32_t>(num - need) : 0u;
             done = true; trig += tb.group;

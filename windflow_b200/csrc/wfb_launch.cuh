@@ -88,7 +88,9 @@ struct ProgramOps {
     int (*tb_merge)(const uint64_t *skeys, const uint32_t *seg_begin, const uint32_t *n_segs, const unsigned char *part, const FfatDev &ff,
                     const TbDev &tb, uint32_t n, cudaStream_t s, const void *params);
     int (*tb_pop_write)(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
-                        uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params);
+                        uint32_t *popped_slots, uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params);
+    // launch table of the program's lifted variant (LiftedOf<P>: the count-based back end of time-based windows); null for lifted programs
+    const void *(*lifted_ops)();
     // keyed-stateful Map_GPU / Filter_GPU (null when the program has no state_t)
     uint32_t state_bytes, reserved2;
     int (*ks_slots)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, const FfatDev &ff, uint32_t *slots, cudaStream_t s,
@@ -274,9 +276,9 @@ int tb_merge_dispatch(const uint64_t *skeys, const uint32_t *seg_begin, const ui
 }
 template <class P>
 int tb_pop_write_dispatch(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
-                          uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params)
+                          uint32_t *popped_slots, uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params)
 {
-    k_tb_pop_write<P><<<grid_for(max_present, 128), 128, 0, s>>>(ff, tb, first_incomplete, offs, popped, popped_cap, load_params<P>(params));
+    k_tb_pop_write<P><<<grid_for(max_present, 128), 128, 0, s>>>(ff, tb, first_incomplete, offs, popped, popped_slots, popped_cap, load_params<P>(params));
     WFB_CK(cudaGetLastError());
     return 0;
 }
@@ -318,6 +320,46 @@ int gather_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint3
     return 0;
 }
 
+// The lifted variant of a program: its records are the program's results (pane aggregates), combined with the program's comb;
+// the key slot of every record comes from the caller (TileArgs::ext_slots), so the program needs no key inside result_t.
+template <class P>
+struct LiftedOf {
+    using tuple_t = typename P::result_t; using result_t = typename P::result_t; using key_t = uint64_t; using params_t = typename P::params_t;
+    static constexpr bool passthrough = true;
+    static constexpr bool is_lifted = true;
+    __host__ __device__ static void map(tuple_t &, const params_t &) {}
+    __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
+    __host__ __device__ static key_t key(const tuple_t &, const params_t &) { return 0; }
+    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r = t; }
+    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &o, const params_t &p) { P::comb(a, b, o, p); }
+    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &p) { return P::make_result(k, gwid, p); }
+    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &, const params_t &) { return a; }
+};
+template <class P, class = void> struct program_is_lifted : std::false_type {};
+template <class P> struct program_is_lifted<P, std::void_t<decltype(P::is_lifted)>> : std::integral_constant<bool, P::is_lifted> {};
+
+template <class P>
+int tile_pass_ingest_dispatch(int mode, TileArgs &a, const void *params, uint32_t want_grid, cudaStream_t s, uint32_t *grid_used,
+                              uint64_t span_begin, uint64_t span_end)
+{
+    if (mode != MODE_INGEST) return WFB_E_UNSUPPORTED;
+    return launch_tile_pass<P, MODE_INGEST>(a, params, want_grid, s, grid_used, span_begin, span_end);
+}
+template <class P>
+const void *lifted_ops_of()
+{
+    static const ProgramOps o = [] {
+        using L = LiftedOf<P>;
+        ProgramOps t; std::memset(&t, 0, sizeof(t));
+        t.tuple_bytes = sizeof(typename L::tuple_t); t.result_bytes = sizeof(typename L::result_t);
+        t.params_bytes = sizeof(typename L::params_t); t.reserved = 1u; // pass-through
+        t.tile_pass = &tile_pass_ingest_dispatch<L>;
+        t.ffat_update = &ffat_update_dispatch<L>; t.ffat_buckets = &ffat_buckets_dispatch<L>; t.ffat_windows = &ffat_windows_dispatch<L>;
+        return t;
+    }();
+    return &o;
+}
+
 template <class P>
 ProgramOps make_ops()
 {
@@ -338,11 +380,12 @@ ProgramOps make_ops()
     o.tb_lift = &tb_lift_dispatch<P>; o.tb_reduce = &tb_reduce_dispatch<P>; o.tb_merge = &tb_merge_dispatch<P>; o.tb_pop_write = &tb_pop_write_dispatch<P>;
     o.extract_keys_batches = &extract_keys_batches_dispatch<P>;
     o.reduce_segments_batches = &reduce_segments_batches_dispatch<P>;
+    if constexpr (program_is_lifted<P>::value) o.lifted_ops = nullptr; else o.lifted_ops = &lifted_ops_of<P>;
     return o;
 }
 
 
-// registers the launch table of program P with libwfb200 and returns its program id (>= 5), or a negative error
+// registers the launch table of program P with libwfb200 and returns its program id (>= 4), or a negative error
 template <class P>
 int register_program()
 {

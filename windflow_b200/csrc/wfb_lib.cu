@@ -36,7 +36,7 @@ int device_ready()
 
 std::vector<ProgramOps> &registry()
 {
-    static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>(), make_ops<ProgLiftedWin24>() }; table.reserve(4096); }
+    static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() }; table.reserve(4096); }
     return table;
 }
 
@@ -366,6 +366,9 @@ struct wfb_ffat {
     uint32_t tb_cap = 0, tb_pop_cap = 0;            // scratch capacities (tuples per batch, popped panes)
     uint64_t *tb_kA = nullptr, *tb_kB = nullptr; uint32_t *tb_iA = nullptr, *tb_iB = nullptr;
     unsigned char *tb_lifted = nullptr, *tb_part = nullptr, *tb_popped = nullptr;
+    uint32_t *tb_popped_slots = nullptr;
+    bool shares_slot_key = false;                   // back end of a time-based handle: ff.slot_key / ff.n_slots belong to the front end
+    uint32_t *own_n_slots = nullptr;                // the allocation behind ff.n_slots / ff.err_flags of this handle
     uint32_t *tb_head = nullptr, *tb_seg = nullptr, *tb_misc = nullptr; // misc: [0] n_segs [1] first_seg dummy [2] n_present [3] popped total [4] ignored [5] ring capacity needed
     bool buckets = true;          // one wide radix pass + per-bucket CTAs (<= 65536 keys); WFB_UPDATE=lanes selects the
                                   // full sort + thread-per-key update instead
@@ -889,14 +892,22 @@ int wfb_filter_stateful(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batc
     return kstate_run(h, f, in_h, out_h, nbatches, n_out_dev, true, static_cast<cudaStream_t>(stream));
 }
 
+static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_t *batches_h, uint32_t nbatches, void *out_results, uint64_t *out_ts,
+                                uint32_t out_capacity, uint32_t *n_out_dev, void *stream, const uint32_t *ext_slots);
+
 // ---- time-based windows: front-end handle + count-based back end over the lifted program ------------------------------------
+// id of the lifted variant of a program (LiftedOf<P>, registered on first use)
 static int lifted_program_of(int prog)
 {
-    switch (prog) {
-    case WFB_PROG_TUPLE64: return WFB_PROG_LIFTED32;
-    case WFB_PROG_WFTEST16: case WFB_PROG_WFWIN24: return WFB_PROG_LIFTEDWIN24;
-    default: return -1; // registered programs: not yet (they would register their lifted program as well)
-    }
+    static std::vector<int> cache; // by program id
+    const ProgramOps *o = program(prog);
+    if (!o || !o->lifted_ops) return -1;
+    if (static_cast<size_t>(prog) < cache.size() && cache[prog] > 0) return cache[prog];
+    const int id = wfb_program_register(o->lifted_ops(), sizeof(ProgramOps));
+    if (id < 0) return id;
+    if (cache.size() <= static_cast<size_t>(prog)) cache.resize(prog + 1, 0);
+    cache[prog] = id;
+    return id;
 }
 
 static int tb_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uint32_t nb, uint32_t max_keys, uint64_t lateness, uint32_t flags)
@@ -928,6 +939,7 @@ static int tb_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, ui
         CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
     }
     ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
+    h->own_n_slots = ff.n_slots;
     ff.err_flags = ff.n_slots + 1;
     CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
     ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
@@ -948,6 +960,8 @@ static int tb_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, ui
     rc = h->ts.init(); if (rc) { wfb_ffat_destroy(h); return rc; }
     rc = wfb_ffat_create(&h->cb, lp, win_p, slide_p, nb, max_keys, 0, 0, flags & WFB_FFAT_DENSE_KEYS);
     if (rc) { wfb_ffat_destroy(h); return rc; }
+    // the back end never looks keys up (the front end hands it the slot of every record): it only needs slot -> key for the results
+    if (!ff.dense) { cudaFree(h->cb->ff.slot_key); h->cb->ff.slot_key = ff.slot_key; h->cb->ff.n_slots = ff.n_slots; h->cb->shares_slot_key = true; }
     h->state_bytes = total + h->cb->state_bytes;
     *hh = h;
     return 0;
@@ -1025,19 +1039,20 @@ int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         CK(cudaMemcpyAsync(&total, misc + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));                           // (the reference synchronises here as well, :962)
         if (total > h->tb_pop_cap) {
-            cudaFree(h->tb_popped);
+            cudaFree(h->tb_popped); cudaFree(h->tb_popped_slots);
             h->tb_pop_cap = std::max(total, 2 * h->tb_pop_cap);
             CK(cudaMalloc(&h->tb_popped, RB * h->tb_pop_cap));
+            CK(cudaMalloc(&h->tb_popped_slots, sizeof(uint32_t) * ((static_cast<size_t>(h->tb_pop_cap) + TILE - 1) / TILE * TILE)));
         }
-        rc = h->ops->tb_pop_write(h->ff, h->tb, F, h->tb.cnt, h->tb_popped, h->tb_pop_cap, maxp, s, prm); if (rc) return rc;
+        rc = h->ops->tb_pop_write(h->ff, h->tb, F, h->tb.cnt, h->tb_popped, h->tb_popped_slots, h->tb_pop_cap, maxp, s, prm); if (rc) return rc;
         h->launches += 9 + (h->sorter.launches - before);
         // 7. the count-based back end consumes the popped panes as one batch with this batch's watermark
         if (total) {
             wfb_batch_t pb; std::memset(&pb, 0, sizeof(pb));
             pb.tuples = h->tb_popped; pb.ts = nullptr; pb.watermark = wm; pb.n = total;
             const uint64_t lb = h->cb->launches;
-            rc = wfb_ffat_process_cb(h->cb, nullptr, &pb, 1, static_cast<unsigned char *>(out_results) + static_cast<size_t>(produced) * RB,
-                                     out_ts ? out_ts + produced : nullptr, out_capacity - produced, n_out_dev, s);
+            rc = ffat_process_cb_impl(h->cb, prm, &pb, 1, static_cast<unsigned char *>(out_results) + static_cast<size_t>(produced) * RB,
+                                      out_ts ? out_ts + produced : nullptr, out_capacity - produced, n_out_dev, s, h->tb_popped_slots);
             if (rc) return rc;
             h->launches += h->cb->launches - lb;
             uint32_t got = 0;
@@ -1088,6 +1103,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         CK(cudaMemset(ff.ht_slots, 0xff, sizeof(uint32_t) * cap));
     }
     ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
+    h->own_n_slots = ff.n_slots;
     ff.err_flags = ff.n_slots + 1;
     CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
     ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
@@ -1151,7 +1167,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     if (!h) return 0;
     cudaDeviceSynchronize();
     FfatDev &ff = h->ff;
-    cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(ff.n_slots); cudaFree(ff.slot_key); cudaFree(ff.cnt);
+    cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(h->own_n_slots); if (!h->shares_slot_key) cudaFree(ff.slot_key); cudaFree(ff.cnt);
     cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off); cudaFree(ff.heavy);
     for (int p = 0; p < 2; p++) h->seg[p].destroy();
     h->sorter.destroy();
@@ -1159,7 +1175,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaFree(h->tb.first); cudaFree(h->tb.num); cudaFree(h->tb.num_new); cudaFree(h->tb.trig); cudaFree(h->tb.done); cudaFree(h->tb.ring);
     cudaFree(h->tb.present); cudaFree(h->tb.cnt); cudaFree(h->tb_misc);
     cudaFree(h->tb_kA); cudaFree(h->tb_kB); cudaFree(h->tb_iA); cudaFree(h->tb_iB); cudaFree(h->tb_lifted); cudaFree(h->tb_part);
-    cudaFree(h->tb_popped); cudaFree(h->tb_head); cudaFree(h->tb_seg);
+    cudaFree(h->tb_popped); cudaFree(h->tb_popped_slots); cudaFree(h->tb_head); cudaFree(h->tb_seg);
     if (h->s2) cudaStreamDestroy(h->s2);
     for (auto &e : h->tev) cudaEventDestroy(e);
     h->ts.destroy();
@@ -1174,6 +1190,7 @@ int wfb_ffat_set_params(wfb_ffat_t *h, const void *params, size_t bytes)
 {
     if (!h || !params || bytes != h->ops->params_bytes) return WFB_E_BADARG;
     h->params.assign(static_cast<const unsigned char *>(params), static_cast<const unsigned char *>(params) + bytes);
+    if (h->cb) h->cb->params = h->params; // the lifted variant shares the program's params_t (its comb / make_result)
     return 0;
 }
 uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes : 0; }
@@ -1278,6 +1295,15 @@ static int ffat_deliver(wfb_ffat *h, SegScratch &g, unsigned char *out, uint64_t
 int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
                         void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
 {
+    return ffat_process_cb_impl(h, pre, batches_h, nbatches, out_results, out_ts, out_capacity, n_out_dev, stream, nullptr);
+}
+
+// ext_slots != nullptr: the key slot of the record at every position is given (one batch, read in place; used by the
+// time-based front end, whose programs' lifted variants have no key extractor)
+static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                                void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream,
+                                const uint32_t *ext_slots)
+{
     if (!h || !n_out_dev || (nbatches && !batches_h) || (out_capacity && !out_results)) return WFB_E_BADARG;
     if (h->win_type != 0) return WFB_E_BADARG; // time-based handles: wfb_ffat_process_tb
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1344,8 +1370,9 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         const unsigned char *base = hb[0].tuples;
         bool ok = (reinterpret_cast<uintptr_t>(base) & 15u) == 0;
         for (uint32_t i = 0; ok && i < nbatches; i++) ok = hb[i].tuples == base + static_cast<size_t>(hb[i].tile_begin) * TILE * h->ops->tuple_bytes;
-        if (ok) { a.inplace = 1; g.lifted_src = base; }
+        if (ok) { a.inplace = 1; g.lifted_src = base; a.ext_slots = ext_slots; }
     }
+    if (ext_slots != nullptr && !a.inplace) return WFB_E_UNSUPPORTED; // (the front end always meets the in-place conditions)
     h->ts.next_launch(a);
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     a.l2_hints = h->l2_hints ? 1u : 0u;

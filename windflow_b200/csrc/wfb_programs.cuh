@@ -150,6 +150,7 @@ struct ProgLifted32 {
     using key_t = uint64_t;
     using params_t = wfb_functors_t;
     static constexpr int id = WFB_PROG_LIFTED32;
+    static constexpr bool is_lifted = true;    // (no lifted variant of a lifted program)
     static constexpr bool passthrough = true; // map is a no-op and lift the identity: the window operator may read the records in place
 
     __host__ __device__ static void map(tuple_t &, const params_t &) {}
@@ -161,28 +162,6 @@ struct ProgLifted32 {
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.isum = a.isum + b.isum; r.fsum = a.fsum + b.fsum; return r;
-    }
-};
-
-// ---- program 4: already-lifted {key, id, value} records: the pane aggregates a time-based window handle of programs 1 / 2
-// feeds to its count-based back end ------------------------------------------------------------------------------------
-struct ProgLiftedWin24 {
-    using tuple_t = wfb_wfwin24_t;
-    using result_t = wfb_wfwin24_t;
-    using key_t = uint64_t;
-    using params_t = wfb_functors_t;
-    static constexpr int id = WFB_PROG_LIFTEDWIN24;
-    static constexpr bool passthrough = true;
-
-    __host__ __device__ static void map(tuple_t &, const params_t &) {}
-    __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
-    __host__ __device__ static key_t key(const tuple_t &t, const params_t &) { return t.key; }
-    __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r = t; }
-    __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &p) { ProgWfWin24::comb(a, b, out, p); }
-    __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &p) { return ProgWfWin24::make_result(k, gwid, p); }
-    __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
-    {
-        tuple_t r; r.key = a.key; r.id = 0; r.value = a.value + b.value; return r;
     }
 };
 

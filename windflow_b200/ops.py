@@ -15,15 +15,15 @@ from . import _lib
 from ._lib import Batch as CBatch
 from ._lib import Functors, check
 
-PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32, PROG_LIFTEDWIN24 = 0, 1, 2, 3, 4
+PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32 = 0, 1, 2, 3
 
 TUPLE64 = np.dtype([("key", "<u8"), ("id", "<u8"), ("ivalue", "<i8"), ("fvalue", "<f8"), ("pad", "<u8", (4,))])
 RESULT32 = np.dtype([("key", "<u8"), ("id", "<u8"), ("isum", "<i8"), ("fsum", "<f8")])
 WFTEST16 = np.dtype([("key", "<u8"), ("value", "<i8")])
 WFWIN24 = np.dtype([("key", "<u8"), ("id", "<u8"), ("value", "<i8")])
 
-TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32, PROG_LIFTEDWIN24: WFWIN24}
-RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32, PROG_LIFTEDWIN24: WFWIN24}
+TUPLE_DTYPE = {PROG_TUPLE64: TUPLE64, PROG_WFTEST16: WFTEST16, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
+RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WFWIN24, PROG_LIFTED32: RESULT32}
 
 KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
 SEED = 0x5EED5EED
