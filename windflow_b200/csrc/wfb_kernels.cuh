@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
 // slots (k_ffat_update_buckets finishes the grouping inside each bucket).
 // ------------------------------------------------------------------------------------------------------
 #ifndef WFB_OSW_MINBLOCKS
-#define WFB_OSW_MINBLOCKS 4
+#define WFB_OSW_MINBLOCKS 5
 #endif
 constexpr uint32_t OSW_BITS = 10, OSW_DIGITS = 1u << OSW_BITS;
 constexpr uint32_t OSW_THREADS = 256, OSW_ITEMS = 16, OSW_TILE = OSW_THREADS * OSW_ITEMS; // 4096 elements per tile
@@ -1238,7 +1238,7 @@ constexpr uint32_t BK_THREADS = 128;
 constexpr uint32_t BK_IT = 18;        // consecutive items per thread and chunk
 constexpr uint32_t BK_CAP = BK_THREADS * BK_IT; // items per chunk
 #ifndef WFB_BK_U
-#define WFB_BK_U 8
+#define WFB_BK_U 4
 #endif
 #ifndef WFB_BK_MINBLOCKS
 #define WFB_BK_MINBLOCKS 4
