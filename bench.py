@@ -324,8 +324,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_tile_pass<ProgTuple64, MODE_INGEST>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("ingest_dram_bytes_per_launch"),
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_tile_pass<ProgTuple64, MODE_INGEST>" if world == 1 else
+                                   "whole pipeline per GPU, SURVEY 8d bytes (the kernel-level roofline is the N=1 line: at N>1 the timed handle is the destination side)",
+                         "achieved": achieved if world == 1 else value / world * PIPELINE_BYTES_PER_TUPLE / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved if world == 1 else value / world * PIPELINE_BYTES_PER_TUPLE / 1e9) / peak,
+                         "traffic": (traffic or {}).get("ingest_dram_bytes_per_launch") if world == 1 else None,
                          "peak_source": peak_src, "bytes_per_tuple": INGEST_BYTES_PER_TUPLE,
                          "avg_launch_ms": ingest_ms_avg,
                          "phase_ms_per_step": {"ingest": ing_ms / max(1, calls), "offsets+sort": sort_ms / max(1, calls),
