@@ -29,6 +29,7 @@
 namespace wfb {
 
 constexpr int TILE = 256;    // tuples per tile == threads per CTA of k_tile_pass
+constexpr uint32_t OSW_TILE_POS = 4096; // positions per tile of the wide partition pass (== OSW_TILE below)
 #ifndef WFB_STAGES
 #define WFB_STAGES 4
 #endif
@@ -109,6 +110,8 @@ struct TileArgs {
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
     uint32_t sparse;           // MODE_INGEST, 1: no global compaction -- tile t owns lifted / slots [t*TILE, +TILE) (survivors first,
                                // INVALID_SLOT padding), so tiles are independent: no look-back chain, positions are tuple indices
+    uint32_t *wide_h32;        // MODE_INGEST + sparse: per-tile digit counts of the wide partition that follows ([position / 4096][1024], 32-bit),
+                               // accumulated here so that the partition needs no counting pass of its own (null: it counts itself)
     const uint32_t *ext_slots; // MODE_INGEST + in-place: slot of the record at every position, given by the caller (the time-based
                                // front end knows the key slot of every pane it pops); the program's key extractor is not used
     uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
@@ -448,9 +451,12 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                         else slot = slot_of_key(a.ff, P::key(tup, prm));
                         if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
                     }
-                    if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
+                    if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) { // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
                             atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
+                        if (a.wide_h32 != nullptr) // (tile t owns positions [256 t, +256): wide tile t / 16)
+                            atomicAdd(&a.wide_h32[static_cast<size_t>(m.tile / (OSW_TILE_POS / TILE)) * 1024u + ((slot >> a.sort_shift) & 1023u)], 1u);
+                    }
                 }
             }
             if constexpr (MODE == MODE_MAP) {
@@ -848,6 +854,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
 #endif
 constexpr uint32_t OSW_BITS = 10, OSW_DIGITS = 1u << OSW_BITS;
 constexpr uint32_t OSW_THREADS = 256, OSW_ITEMS = 16, OSW_TILE = OSW_THREADS * OSW_ITEMS; // 4096 elements per tile
+static_assert(OSW_TILE == OSW_TILE_POS, "the tile pass files its digit counts per wide tile");
 
 template <class K>
 __global__ void __launch_bounds__(OSW_THREADS) k_wide_tile_hist(const K *__restrict__ keys, const uint32_t *__restrict__ n_ptr, uint32_t n_host,
@@ -884,6 +891,18 @@ __global__ void __launch_bounds__(OSW_THREADS) k_wide_tile_hist(const K *__restr
     }
 }
 
+// C[chunk][digit] = sum of the 32-bit per-tile rows of the chunk (when the tile pass filled them: no counting pass)
+static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums(const uint32_t *__restrict__ H32, uint32_t tiles, uint32_t chunk_shift, uint32_t *__restrict__ C)
+{
+    const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+    const uint32_t t0 = chunk << chunk_shift, t1 = min(tiles, t0 + (1u << chunk_shift));
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint4 *row = reinterpret_cast<const uint4 *>(H32) + tid;
+#pragma unroll 8
+    for (uint32_t t = t0; t < t1; t++) { const uint4 v = row[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    reinterpret_cast<uint4 *>(C + static_cast<size_t>(chunk) * OSW_DIGITS)[tid] = acc;
+}
+
 // RBYTES: bytes of the payload record that travels with each element (payload_out[dst] = payload_in[index]); 0 = none,
 // -1 = run-time size `payload_bytes` (multiple of 8)
 template <class K, int RBYTES>
@@ -892,8 +911,10 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
                                                               uint32_t chunk_shift, const uint16_t *__restrict__ H, const uint32_t *__restrict__ C,
                                                               const uint32_t *__restrict__ ctl_counts,
                                                               const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
-                                                              uint32_t payload_bytes, uint32_t skip_invalid, uint32_t region_stride)
+                                                              uint32_t payload_bytes, uint32_t skip_invalid, uint32_t region_stride,
+                                                              const uint32_t *__restrict__ H32)
 {
+    // H32 != nullptr: the per-tile counts are 32-bit rows filled by the producer of the keys (the tile pass) instead of H
     // region_stride != 0: bin d starts at d * region_stride (fixed-capacity regions; elements beyond the capacity are dropped)
     constexpr uint32_t NW = OSW_THREADS / 32;
     __shared__ __align__(16) uint16_t cntw[NW][OSW_DIGITS]; // per-warp digit counts -> exclusive offsets over the warps
@@ -914,9 +935,15 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
         const uint4 *crow = reinterpret_cast<const uint4 *>(C) + tid;
 #pragma unroll 8
         for (uint32_t c = 0; c < chunk; c++) { const uint4 v = crow[static_cast<size_t>(c) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
-        const ushort4 *hrow = reinterpret_cast<const ushort4 *>(H) + tid;
+        if (H32 != nullptr) {
+            const uint4 *hrow = reinterpret_cast<const uint4 *>(H32) + tid;
 #pragma unroll 8
-        for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const ushort4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+            for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const uint4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+        } else {
+            const ushort4 *hrow = reinterpret_cast<const ushort4 *>(H) + tid;
+#pragma unroll 8
+            for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const ushort4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+        }
     }
     const uint4 g4 = reinterpret_cast<const uint4 *>(ctl_counts)[tid];
     const uint32_t gsum = g4.x + g4.y + g4.z + g4.w;

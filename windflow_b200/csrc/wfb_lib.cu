@@ -120,7 +120,7 @@ struct RadixSorter {
         }
         return 0;
     }
-    void destroy() { cudaFree(ctl); cudaFree(state); cudaFree(wideH); cudaFree(wideC); }
+    void destroy() { cudaFree(ctl); cudaFree(state); cudaFree(wideH); cudaFree(wideC); cudaFree(wideH32); }
 
     // stable sort of (kA[i], i) by the low 8*passes bits; n on the device (n_ptr) or the host (n_host), cap = upper bound
     template <class K, int ITEMS>
@@ -150,18 +150,34 @@ struct RadixSorter {
     // ONE stable partition pass of (kin[i], i) on the digit (key >> shift) & 1023 into (kout, vout): per-tile counts, then
     // the scatter (no chained scan). *counts = the 1024 digit counts (ready_ctl if the producer of the keys made them).
     uint16_t *wideH = nullptr; uint32_t *wideC = nullptr; uint32_t wide_tiles = 0, wide_chunks = 0;
+    uint32_t *wideH32 = nullptr; uint32_t wide32_tiles = 0; // per-tile counts filled by the producer of the keys (32-bit rows)
+    // rows for `cap` positions, zeroed on stream s: the producer adds its digit counts, sort_wide(..., h32_ready) consumes them
+    int prepare_h32(uint32_t cap, cudaStream_t s, uint32_t **rows)
+    {
+        const uint32_t tiles = std::max(1u, (cap + OSW_TILE - 1) / OSW_TILE);
+        if (tiles > wide32_tiles) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(wideH32);
+            wide32_tiles = std::max(tiles, 2 * wide32_tiles);
+            CK(cudaMalloc(&wideH32, sizeof(uint32_t) * OSW_DIGITS * wide32_tiles));
+        }
+        CK(cudaMemsetAsync(wideH32, 0, sizeof(uint32_t) * OSW_DIGITS * tiles, s));
+        *rows = wideH32;
+        return 0;
+    }
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
                              uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
-                             uint32_t skip_invalid, uint32_t region_stride)
+                             uint32_t skip_invalid, uint32_t region_stride, const uint32_t *h32)
     {
-        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride);
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride, h32);
     }
     // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
     template <class K>
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
-                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0)
+                  unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0,
+                  bool h32_ready = false)
     {
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
@@ -178,8 +194,14 @@ struct RadixSorter {
         }
         uint32_t *c = ready_ctl ? ready_ctl : ctl;
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
-        CK(cudaMemsetAsync(wideC, 0, sizeof(uint32_t) * OSW_DIGITS * chunks, s));
-        k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c, skip_invalid ? 1u : 0u);
+        const uint32_t *h32 = nullptr;
+        if (h32_ready && ready_ctl && !few_bins) { // the producer of the keys counted the digits per tile: only the chunk sums are missing
+            k_wide_chunk_sums<<<chunks, OSW_THREADS, 0, s>>>(wideH32, tiles, chunk_shift, wideC);
+            h32 = wideH32;
+        } else {
+            CK(cudaMemsetAsync(wideC, 0, sizeof(uint32_t) * OSW_DIGITS * chunks, s));
+            k_wide_tile_hist<K><<<tiles, OSW_THREADS, 0, s>>>(kin, n_ptr, n_host, shift, chunk_shift, wideH, wideC, ready_ctl ? nullptr : c, skip_invalid ? 1u : 0u);
+        }
         if (region_stride && few_bins && payload_in && few_bins <= 32 && (payload_bytes == 16 || payload_bytes == 24 || payload_bytes == 32 || payload_bytes == 64)) {
             // a few fixed-capacity regions (destination GPUs): ranks from ballots, records leave in runs
             const uint32_t *d32 = reinterpret_cast<const uint32_t *>(kin);
@@ -197,7 +219,7 @@ struct RadixSorter {
                 return 0;
             }
         }
-#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride)
+#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride, h32)
         if (!payload_in) WFB_WS(0);
         else switch (payload_bytes) {
             case 8: WFB_WS(8); break;   case 16: WFB_WS(16); break; case 24: WFB_WS(24); break; case 32: WFB_WS(32); break;
@@ -321,6 +343,7 @@ struct SegScratch {
     DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
     uint32_t *n_total = nullptr;
     bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
+    bool h32_ready = false;       // the streaming pass filed the per-tile digit counts of the wide partition (sorter.wideH32)
     const unsigned char *lifted_src = nullptr; // records of this segment: `lifted`, or the caller's buffer (in-place ingest)
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
@@ -375,6 +398,8 @@ struct wfb_ffat {
     uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
     bool bucket_move = false;     // WFB_BUCKET_MOVE=1: the wide pass also moves the lifted records into their buckets
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
+    bool fuse_tile_hist = false;  // WFB_FUSE_TILE_HIST=1: the tile pass also files the per-tile digit counts of the wide partition (one more
+                                  // global RED per survivor: measured +17 us on the tile pass against -8 us on the partition, so off)
     bool inplace_ok = true;       // WFB_INPLACE=0: always copy the records of a pass-through program
     bool sparse_ingest = true;    // WFB_SPARSE=0: the bucket path also compacts the survivors over the whole segment
     uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
@@ -1142,6 +1167,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     { const char *e = std::getenv("WFB_L2_HINTS"); h->l2_hints = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_SPARSE"); h->sparse_ingest = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_INPLACE"); h->inplace_ok = !(e && std::atoi(e) == 0); }
+    { const char *e = std::getenv("WFB_FUSE_TILE_HIST"); h->fuse_tile_hist = e && std::atoi(e) != 0; }
     { // WFB_L2_PERSIST=<MB>: L2 set-aside for evict-last lines (the lifted records between the ingest pass and the update)
         const char *e = std::getenv("WFB_L2_PERSIST");
         if (e && std::atoi(e) > 0) {
@@ -1247,7 +1273,7 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         const uint32_t *counts = nullptr;
         rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.sparse ? nullptr : g.n_total, g.total, g.total, h->bucket_shift, s,
                                            g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
-                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse);
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
@@ -1377,6 +1403,12 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     a.l2_hints = h->l2_hints ? 1u : 0u;
     a.sparse = sparse ? 1u : 0u;
+    g.h32_ready = false;
+    if (sparse && fuse_hist && h->fuse_tile_hist && !h->pipelined) { // (pipelined: the rows would be shared by two segments in flight)
+        // the tile pass also files its digit counts per tile of the wide partition
+        rc = h->sorter.prepare_h32(g.total, s, &a.wide_h32); if (rc) return rc;
+        g.h32_ready = true;
+    }
     uint32_t grid = 0;
     rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
     h->ts.launched(tiles, grid);
