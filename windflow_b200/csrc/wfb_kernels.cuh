@@ -110,6 +110,7 @@ struct TileArgs {
     uint32_t max_ctas_per_sm;  // host-side launch hint (0 = no limit), not read by the kernel
     uint32_t sparse;           // MODE_INGEST, 1: no global compaction -- tile t owns lifted / slots [t*TILE, +TILE) (survivors first,
                                // INVALID_SLOT padding), so tiles are independent: no look-back chain, positions are tuple indices
+    uint32_t count_keys;       // MODE_INGEST: 1 = per-key item counts of the segment (ff.seg_cnt) for the full-sort update kernels
     uint32_t *wide_h32;        // MODE_INGEST + sparse: per-tile digit counts of the wide partition that follows ([position / 4096][1024], 32-bit),
                                // accumulated here so that the partition needs no counting pass of its own (null: it counts itself)
     const uint32_t *ext_slots; // MODE_INGEST + in-place: slot of the record at every position, given by the caller (the time-based
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     else {
                         if (a.ext_slots != nullptr) { slot = a.ext_slots[m.tile * TILE + ctid]; if (slot >= a.ff.max_keys) slot = INVALID_SLOT; }
                         else slot = slot_of_key(a.ff, P::key(tup, prm));
-                        if (slot != INVALID_SLOT) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                        if (slot != INVALID_SLOT && a.count_keys) atomicAdd(&a.ff.seg_cnt[slot], 1u); // (full-sort path only)
                     }
                     if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) { // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
@@ -1323,10 +1324,10 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
     const bool has_key = tid < kpc && key_lo + tid < ff.max_keys;
     if (has_key) {
         const uint32_t slot = key_lo + tid;
-        my_total = ff.seg_cnt[slot];
         st_c = ff.cnt[slot];
         ld_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, st_acc);
     }
+    if (tid < BK_KEYS) kleft[tid] = 0;
     // ---- bucket range = exclusive scan of the pass histogram --------------------------------------------------------------
     {
         uint32_t cc[DPT];
@@ -1351,9 +1352,18 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
             for (uint32_t q = 0; q < DPT; q++) { if (q < bucket % DPT) base += cc[q]; if (q == bucket % DPT) own = cc[q]; }
             s_boff[0] = base; s_boff[1] = base + own;
         }
+        __syncthreads();
     }
+    // items of every key in this stream segment (the whole bucket, all chunks): the deferral of fired groups needs them. Counting
+    // them here instead of one global RED per survivor in the streaming pass is what that pass is sensitive to (+17 us per RED).
+    for (uint32_t i = s_boff[0] + tid; i < s_boff[1]; i += BK_THREADS) {
+        const uint32_t lk = bk_slots[i] - key_lo;
+        if (lk < kpc) atomicAdd(&kleft[lk], 1u);
+    }
+    __syncthreads();
     if (tid < BK_KEYS) {
-        const uint32_t m = my_total;
+        const uint32_t m = has_key ? kleft[tid] : 0u;
+        my_total = m;
         const uint64_t c = st_c;
         uint64_t g = 0, tt = 0; uint32_t cp = 0, leaf = 0;
         if (m) {
@@ -1671,7 +1681,6 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
         const uint32_t slot = key_lo + tid;
         ff.cnt[slot] = kc[tid];
         if (kcp[tid]) { alignas(16) R a; ld_rec<R>(kacc + tid * RB, a); st_rec<R>(ff.acc + static_cast<size_t>(slot) * RB, a); }
-        ff.seg_cnt[slot] = 0;
     }
     BK_MARK(6);
 }

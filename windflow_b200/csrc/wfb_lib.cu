@@ -1403,6 +1403,7 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
     a.max_ctas_per_sm = h->ingest_ctas_per_sm;
     a.l2_hints = h->l2_hints ? 1u : 0u;
     a.sparse = sparse ? 1u : 0u;
+    a.count_keys = h->buckets ? 0u : 1u;
     g.h32_ready = false;
     if (sparse && fuse_hist && h->fuse_tile_hist && !h->pipelined) { // (pipelined: the rows would be shared by two segments in flight)
         // the tile pass also files its digit counts per tile of the wide partition
