@@ -2149,12 +2149,12 @@ __global__ void __launch_bounds__(256) k_reduce_segments_batches(const DevBatch 
 // that the count-based back end (a second handle over the "lifted" program, window / slide in panes) consumes as one
 // batch: it fires exactly one group of Nb windows per popped group, with ts = the batch watermark.
 // ------------------------------------------------------------------------------------------------------
-constexpr uint32_t TB_PANE_BITS = 40;
-constexpr uint64_t TB_PANE_MASK = (1ull << TB_PANE_BITS) - 1ull;
 
 struct TbDev {
     uint64_t pane_len, Bp, group;      // pane length (timestamp units), panes of the first group, panes of every further group
     uint32_t capq;                     // ring capacity per key (panes)
+    uint32_t kbits;                    // this batch: sort key = (slot << kbits) | (pane - first pending pane of the key); 2^kbits - 1 = late
+                                       // pane (already consumed), slot >= max_keys = no tuple (filtered out)
     uint64_t *first;                   // id of the first pending pane of every key
     uint32_t *num, *num_new;           // pending panes (before / after this batch)
     uint64_t *trig;                    // pane_id_triggerer
@@ -2186,14 +2186,29 @@ __global__ void k_tb_lift(const unsigned char *__restrict__ tuples, const uint64
             const uint32_t slot = slot_of_key(ff, P::key(t, prm));
             const uint64_t pane = ts[i] / tb.pane_len;                 // Lifting_Kernel_TB_Keyed :164
             if (pane < first_incomplete) atomicAdd(tb.ignored, 1u);    // :165-167
-            if (pane > TB_PANE_MASK) atomicOr(tb.err, 4u);
-            else if (slot != INVALID_SLOT) {
-                ck = (static_cast<uint64_t>(slot) << TB_PANE_BITS) | pane;
+            if (slot != INVALID_SLOT) { // raw key: slot, pane relative to the key's first pending pane (0xffffffff: older = late)
                 const uint64_t f0 = tb.first[slot];
-                if (pane >= f0) atomicMax(tb.need, static_cast<uint32_t>(min(pane - f0 + 2, static_cast<uint64_t>(0xffffffffu)))); // push_panes :367-372
+                uint32_t rel = 0xffffffffu;
+                if (pane >= f0) {
+                    if (pane - f0 >= 0xfffffff0ull) atomicOr(tb.err, 4u);
+                    else { rel = static_cast<uint32_t>(pane - f0); atomicMax(tb.need, rel + 2u); } // push_panes :367-372
+                }
+                ck = (static_cast<uint64_t>(slot) << 32) | rel;
             }
         }
         ckeys[i] = ck;
+    }
+}
+
+// sort keys of the batch once the number of pane bits it needs is known: (slot << kbits) | relative pane
+static __global__ void k_tb_pack(uint64_t *__restrict__ ckeys, uint32_t n, uint32_t kbits, uint32_t invalid_slot)
+{
+    const uint64_t late = (1ull << kbits) - 1ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t c = ckeys[i];
+        if (c == ~0ull) { ckeys[i] = static_cast<uint64_t>(invalid_slot) << kbits; continue; }
+        const uint32_t rel = static_cast<uint32_t>(c);
+        ckeys[i] = ((c >> 32) << kbits) | (rel == 0xffffffffu ? late : static_cast<uint64_t>(rel));
     }
 }
 
@@ -2201,13 +2216,13 @@ __global__ void k_tb_lift(const unsigned char *__restrict__ tuples, const uint64
 template <class P>
 __global__ void k_tb_reduce(const unsigned char *__restrict__ lifted, const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx,
                             const uint32_t *__restrict__ seg_begin, const uint32_t *__restrict__ n_segs, unsigned char *__restrict__ part,
-                            const typename P::params_t prm)
+                            uint32_t kbits, uint32_t max_keys, const typename P::params_t prm)
 {
     using R = typename P::result_t;
     const uint32_t nk = *n_segs;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
         const uint32_t sb = seg_begin[k], se = seg_begin[k + 1];
-        if (skeys[sb] == ~0ull) continue;
+        if ((skeys[sb] >> kbits) >= max_keys || (skeys[sb] & ((1ull << kbits) - 1ull)) == (1ull << kbits) - 1ull) continue; // no tuple / late pane
         alignas(16) R acc;
         ld_rec<R>(lifted + static_cast<size_t>(sidx[sb]) * sizeof(R), acc);
         for (uint32_t j = sb + 1; j < se; j++) {
@@ -2229,17 +2244,19 @@ __global__ void k_tb_merge(const uint64_t *__restrict__ skeys, const uint32_t *_
     const uint32_t nk = *n_segs;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nk; k += gridDim.x * blockDim.x) {
         const uint64_t ck = skeys[seg_begin[k]];
-        if (ck == ~0ull) continue;
-        const uint32_t slot = static_cast<uint32_t>(ck >> TB_PANE_BITS);
-        const uint64_t pane = ck & TB_PANE_MASK;
+        const uint64_t relmask = (1ull << tb.kbits) - 1ull;
+        if ((ck >> tb.kbits) >= ff.max_keys) continue;                // filtered tuples
+        const uint32_t slot = static_cast<uint32_t>(ck >> tb.kbits);
         const uint64_t first_id = tb.first[slot];
+        const bool late = (ck & relmask) == relmask;                  // pane already consumed (:232-234)
+        const uint64_t pane = late ? 0 : first_id + (ck & relmask);
         const uint32_t num = tb.num[slot];
         const uint64_t have_end = first_id + num;                      // first pane id that is not in the ring yet
         unsigned char *ring = tb.ring + static_cast<size_t>(slot) * tb.capq * sizeof(R);
         const uint64_t ckn = (k + 1 < nk) ? skeys[seg_begin[k + 1]] : ~0ull;
-        const bool last_of_key = ckn == ~0ull || static_cast<uint32_t>(ckn >> TB_PANE_BITS) != slot;
+        const bool last_of_key = (ckn >> tb.kbits) != slot; // (ckn = ~0 past the end: never a slot)
         bool stored = false;
-        if (pane >= first_id) {                                        // (older: late pane, ignored -- :232-234)
+        if (!late) {
             if (pane - first_id >= tb.capq) atomicOr(tb.err, 4u);
             else {
                 alignas(16) R v;
@@ -2251,7 +2268,7 @@ __global__ void k_tb_merge(const uint64_t *__restrict__ skeys, const uint32_t *_
                     uint64_t lower = have_end;                          // missing panes below this one become empty panes (:239-257)
                     if (k > 0) {
                         const uint64_t ckp = skeys[seg_begin[k - 1]];
-                        if (ckp != ~0ull && static_cast<uint32_t>(ckp >> TB_PANE_BITS) == slot && (ckp & TB_PANE_MASK) + 1 > lower) lower = (ckp & TB_PANE_MASK) + 1;
+                        if ((ckp >> tb.kbits) == slot && first_id + (ckp & relmask) + 1 > lower) lower = first_id + (ckp & relmask) + 1;
                     }
                     const uint64_t key = key_of_slot(ff, slot);
                     for (uint64_t m = lower; m < pane; m++) {

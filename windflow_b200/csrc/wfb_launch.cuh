@@ -84,7 +84,7 @@ struct ProgramOps {
     int (*tb_lift)(const unsigned char *tuples, const uint64_t *ts, uint32_t n, const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete,
                    unsigned char *lifted, uint64_t *ckeys, cudaStream_t s, const void *params);
     int (*tb_reduce)(const unsigned char *lifted, const uint64_t *skeys, const uint32_t *sidx, const uint32_t *seg_begin, const uint32_t *n_segs,
-                     unsigned char *part, uint32_t n, cudaStream_t s, const void *params);
+                     unsigned char *part, uint32_t n, uint32_t kbits, uint32_t max_keys, cudaStream_t s, const void *params);
     int (*tb_merge)(const uint64_t *skeys, const uint32_t *seg_begin, const uint32_t *n_segs, const unsigned char *part, const FfatDev &ff,
                     const TbDev &tb, uint32_t n, cudaStream_t s, const void *params);
     int (*tb_pop_write)(const FfatDev &ff, const TbDev &tb, uint64_t first_incomplete, const uint32_t *offs, unsigned char *popped,
@@ -260,9 +260,9 @@ int tb_lift_dispatch(const unsigned char *tuples, const uint64_t *ts, uint32_t n
 }
 template <class P>
 int tb_reduce_dispatch(const unsigned char *lifted, const uint64_t *skeys, const uint32_t *sidx, const uint32_t *seg_begin, const uint32_t *n_segs,
-                       unsigned char *part, uint32_t n, cudaStream_t s, const void *params)
+                       unsigned char *part, uint32_t n, uint32_t kbits, uint32_t max_keys, cudaStream_t s, const void *params)
 {
-    k_tb_reduce<P><<<grid_for(n, 128), 128, 0, s>>>(lifted, skeys, sidx, seg_begin, n_segs, part, load_params<P>(params));
+    k_tb_reduce<P><<<grid_for(n, 128), 128, 0, s>>>(lifted, skeys, sidx, seg_begin, n_segs, part, kbits, max_keys, load_params<P>(params));
     WFB_CK(cudaGetLastError());
     return 0;
 }

@@ -1027,10 +1027,12 @@ int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
         CK(cudaMemsetAsync(misc + 5, 0, sizeof(uint32_t), s));
         // 1. lift + composite (slot, pane) keys; 2. stable sort; 3. (key, pane) segments; 4. partials; 5. merge into the rings
         rc = h->ops->tb_lift(static_cast<const unsigned char *>(b.tuples), b.ts, b.n, h->ff, h->tb, F, h->tb_lifted, h->tb_kA, s, prm); if (rc) return rc;
+        uint32_t tb_need_bits = 2;
         { // the rings must hold every pane from a key's first pending one to its newest (PendingPanes_Queue::push_panes :367-372)
             uint32_t need = 0;
             CK(cudaMemcpyAsync(&need, misc + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
+            tb_need_bits = std::max(2u, need);
             if (need > h->tb.capq) {
                 uint64_t ncap = h->tb.capq; while (ncap < need) ncap <<= 1;
                 if (ncap * h->ff.max_keys * RB > (32ull << 30)) return WFB_E_CAPACITY;
@@ -1044,16 +1046,20 @@ int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
                 h->launches++;
             }
         }
+        // sort keys (slot << kbits) | relative pane, with just the bits this batch needs; filtered tuples sort behind every slot
+        uint32_t sbits = 0; while ((1ull << sbits) < static_cast<uint64_t>(h->ff.max_keys) + 1) sbits++;
+        uint32_t kbits = 1; while ((1ull << kbits) < tb_need_bits) kbits++;
+        h->tb.kbits = kbits;
+        k_tb_pack<<<grid_for(b.n, 256), 256, 0, s>>>(h->tb_kA, b.n, kbits, h->ff.max_keys);
         const uint64_t *skeys; const uint32_t *sidx;
         const uint64_t before = h->sorter.launches;
-        rc = h->sorter.sort<uint64_t>(h->tb_kA, h->tb_kB, h->tb_iA, h->tb_iB, nullptr, b.n, b.n, 8, s, &skeys, &sidx); if (rc) return rc;
-        // (all 64 bits: filtered tuples carry ~0 and must sort last)
+        rc = h->sorter.sort<uint64_t>(h->tb_kA, h->tb_kB, h->tb_iA, h->tb_iB, nullptr, b.n, b.n, (kbits + sbits + 7) / 8, s, &skeys, &sidx); if (rc) return rc;
         const uint32_t tiles = (b.n + SEGT - 1) / SEGT;
         k_head_tile_counts<<<tiles, 256, 0, s>>>(skeys, b.n, h->tb_head);
         k_scan_u32<<<1, 1024, 0, s>>>(h->tb_head, h->tb_head, tiles, nullptr);
         k_seg_finish_batches<<<tiles, 256, 0, s>>>(skeys, b.n, 64u, h->tb_head, h->tb_seg, misc + 1, misc + 0);
         CK(cudaGetLastError());
-        rc = h->ops->tb_reduce(h->tb_lifted, skeys, sidx, h->tb_seg, misc + 0, h->tb_part, b.n, s, prm); if (rc) return rc;
+        rc = h->ops->tb_reduce(h->tb_lifted, skeys, sidx, h->tb_seg, misc + 0, h->tb_part, b.n, kbits, h->ff.max_keys, s, prm); if (rc) return rc;
         rc = h->ops->tb_merge(skeys, h->tb_seg, misc + 0, h->tb_part, h->ff, h->tb, b.n, s, prm); if (rc) return rc;
         // 6. panes to pop per present key, offsets, total
         const uint32_t maxp = std::min<uint32_t>(b.n, h->ff.max_keys);
@@ -1070,7 +1076,7 @@ int wfb_ffat_process_tb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
             CK(cudaMalloc(&h->tb_popped_slots, sizeof(uint32_t) * ((static_cast<size_t>(h->tb_pop_cap) + TILE - 1) / TILE * TILE)));
         }
         rc = h->ops->tb_pop_write(h->ff, h->tb, F, h->tb.cnt, h->tb_popped, h->tb_popped_slots, h->tb_pop_cap, maxp, s, prm); if (rc) return rc;
-        h->launches += 9 + (h->sorter.launches - before);
+        h->launches += 10 + (h->sorter.launches - before);
         // 7. the count-based back end consumes the popped panes as one batch with this batch's watermark
         if (total) {
             wfb_batch_t pb; std::memset(&pb, 0, sizeof(pb));
