@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 #include <algorithm>
 #include <new>
@@ -34,6 +35,8 @@ int device_ready()
     return 0;
 }
 
+std::mutex &registry_mutex() { static std::mutex m; return m; } // replicas of different operators may register programs concurrently
+
 std::vector<ProgramOps> &registry()
 {
     static std::vector<ProgramOps> table; if (table.empty()) { table.reserve(4096); table = { make_ops<ProgTuple64>(), make_ops<ProgWfTest16>(), make_ops<ProgWfWin24>(), make_ops<ProgLifted32>() }; table.reserve(4096); }
@@ -42,6 +45,7 @@ std::vector<ProgramOps> &registry()
 
 const ProgramOps *program(int prog)
 {
+    std::lock_guard<std::mutex> lock(registry_mutex());
     std::vector<ProgramOps> &t = registry();
     if (prog < 0 || prog >= static_cast<int>(t.size())) return nullptr;
     return &t[prog];
@@ -444,6 +448,7 @@ int wfb_device_count(void)
 int wfb_program_register(const void *ops, size_t ops_bytes)
 {
     if (!ops || ops_bytes != sizeof(ProgramOps)) return WFB_E_BADARG;
+    std::lock_guard<std::mutex> lock(registry_mutex());
     std::vector<ProgramOps> &t = registry();
     if (t.size() >= 4096) return WFB_E_CAPACITY;
     t.reserve(4096); // handles keep pointers into the table: never reallocate it
@@ -925,8 +930,10 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
 static int lifted_program_of(int prog)
 {
     static std::vector<int> cache; // by program id
+    static std::mutex cache_mutex;
     const ProgramOps *o = program(prog);
     if (!o || !o->lifted_ops) return -1;
+    std::lock_guard<std::mutex> lock(cache_mutex);
     if (static_cast<size_t>(prog) < cache.size() && cache[prog] > 0) return cache[prog];
     const int id = wfb_program_register(o->lifted_ops(), sizeof(ProgramOps));
     if (id < 0) return id;
