@@ -840,6 +840,51 @@ __global__ void __launch_bounds__(OS_THREADS) k_onesweep_pass(const K *__restric
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_slots_inplace: the streaming pass of a pass-through program whose records already sit at their tile positions
+// (TileArgs::inplace): nothing is staged or copied, so a plain grid-stride kernel replaces k_tile_pass -- key -> slot (or the
+// caller's slot), INVALID_SLOT padding, the digit counts of the wide partition (shared-memory counts, one flush per CTA).
+// 32-byte records make 8-KB tiles, too small to amortise the tile pass's per-tile machinery (measured 1.2 TB/s there).
+// ------------------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(256) k_slots_inplace(const TileArgs a, const typename P::params_t prm)
+{
+    using T = typename P::tuple_t;
+    __shared__ uint32_t s_h[1024];
+    const uint32_t tid = threadIdx.x;
+    const bool hist = a.sort_ctl != nullptr;
+    if (hist) for (uint32_t i = tid; i < 1024; i += blockDim.x) s_h[i] = 0;
+    if (blockIdx.x == 0 && tid == 0 && a.ff.n_trig != nullptr) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists of the update kernels
+    __syncthreads();
+    const uint32_t npos = a.num_tiles * TILE;
+    const uint32_t dmask = (1u << a.sort_dbits) - 1u;
+    for (uint32_t p = blockIdx.x * blockDim.x + tid; p < npos; p += gridDim.x * blockDim.x) {
+        const uint32_t t = p / TILE;
+        uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= t
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (a.batches[mid].tile_begin <= t) lo = mid; else hi = mid - 1; }
+        const DevBatch &b = a.batches[lo];
+        const uint32_t local = p - b.tile_begin * TILE;
+        uint32_t slot = INVALID_SLOT;
+        if (local < b.n) {
+            if (a.ext_slots != nullptr) { slot = a.ext_slots[p]; if (slot >= a.ff.max_keys) slot = INVALID_SLOT; }
+            else {
+                const T *rec = reinterpret_cast<const T *>(b.tuples + static_cast<size_t>(local) * sizeof(T));
+                slot = slot_of_key(a.ff, P::key(*rec, prm));
+            }
+            if (slot != INVALID_SLOT) {
+                if (a.count_keys) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+                if (hist) atomicAdd(&s_h[(slot >> a.sort_shift) & dmask], 1u);
+                if (a.wide_h32 != nullptr) atomicAdd(&a.wide_h32[static_cast<size_t>(t / (OSW_TILE_POS / TILE)) * 1024u + ((slot >> a.sort_shift) & 1023u)], 1u);
+            }
+        }
+        a.slots[p] = slot;
+    }
+    if (hist) {
+        __syncthreads();
+        for (uint32_t i = tid; i < (1u << a.sort_dbits) && i < 1024; i += blockDim.x) { const uint32_t c = s_h[i]; if (c) atomicAdd(&a.sort_ctl[i], c); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Wide partition: ONE stable pass on a 10-bit digit (1024 bins) without a chained scan -- with 1024 bins a tile holds
 // only a few elements per bin, so the look-back chains of k_onesweep_pass are long and cheap to avoid:
 //   k_wide_tile_hist  per-tile digit counts H[tile][1024] (16-bit) + their sums over chunks of 2^chunk_shift tiles

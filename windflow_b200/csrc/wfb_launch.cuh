@@ -91,6 +91,8 @@ struct ProgramOps {
                         uint32_t *popped_slots, uint32_t popped_cap, uint32_t max_present, cudaStream_t s, const void *params);
     // launch table of the program's lifted variant (LiftedOf<P>: the count-based back end of time-based windows); null for lifted programs
     const void *(*lifted_ops)();
+    // streaming pass of a pass-through program whose records are read in place (TileArgs::inplace)
+    int (*slots_inplace)(const TileArgs &a, const void *params, cudaStream_t s);
     // keyed-stateful Map_GPU / Filter_GPU (null when the program has no state_t)
     uint32_t state_bytes, reserved2;
     int (*ks_slots)(const DevBatch *batches, const uint32_t *boff, uint32_t nb, uint32_t total, const FfatDev &ff, uint32_t *slots, cudaStream_t s,
@@ -217,6 +219,15 @@ int reduce_segments_dispatch(const unsigned char *tuples, const uint64_t *ts, co
     WFB_CK(cudaGetLastError());
     return 0;
 }
+template <class P>
+int slots_inplace_dispatch(const TileArgs &a, const void *params, cudaStream_t s)
+{
+    const uint32_t npos = a.num_tiles * TILE;
+    k_slots_inplace<P><<<std::max(1u, std::min((npos + 2047u) / 2048u, static_cast<uint32_t>(wfb::num_sms()) * 8u)), 256, 0, s>>>(a, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
 template <class P, class = void> struct program_has_state : std::false_type {};
 template <class P> struct program_has_state<P, std::void_t<typename P::state_t>> : std::true_type {};
 
@@ -353,7 +364,7 @@ const void *lifted_ops_of()
         ProgramOps t; std::memset(&t, 0, sizeof(t));
         t.tuple_bytes = sizeof(typename L::tuple_t); t.result_bytes = sizeof(typename L::result_t);
         t.params_bytes = sizeof(typename L::params_t); t.reserved = 1u; // pass-through
-        t.tile_pass = &tile_pass_ingest_dispatch<L>;
+        t.tile_pass = &tile_pass_ingest_dispatch<L>; t.slots_inplace = &slots_inplace_dispatch<L>;
         t.ffat_update = &ffat_update_dispatch<L>; t.ffat_buckets = &ffat_buckets_dispatch<L>; t.ffat_windows = &ffat_windows_dispatch<L>;
         return t;
     }();
@@ -375,6 +386,7 @@ ProgramOps make_ops()
     o.reduce_segments = &reduce_segments_dispatch<P>;
     o.reduce_all = &reduce_all_dispatch<P>;
     o.gather = &gather_dispatch<P>;
+    o.slots_inplace = &slots_inplace_dispatch<P>;
     o.state_bytes = program_state_bytes<P>(); o.reserved2 = 0;
     o.ks_slots = &ks_slots_dispatch<P>; o.ks_apply = &ks_apply_dispatch<P>; o.flag_scatter = &flag_scatter_dispatch<P>;
     o.tb_lift = &tb_lift_dispatch<P>; o.tb_reduce = &tb_reduce_dispatch<P>; o.tb_merge = &tb_merge_dispatch<P>; o.tb_pop_write = &tb_pop_write_dispatch<P>;

@@ -404,6 +404,7 @@ struct wfb_ffat {
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
     bool fuse_tile_hist = false;  // WFB_FUSE_TILE_HIST=1: the tile pass also files the per-tile digit counts of the wide partition (one more
                                   // global RED per survivor: measured +17 us on the tile pass against -8 us on the partition, so off)
+    bool inplace_kernel = true;   // WFB_INPLACE_KERNEL=0: the in-place case also goes through the tile pass
     bool inplace_ok = true;       // WFB_INPLACE=0: always copy the records of a pass-through program
     bool sparse_ingest = true;    // WFB_SPARSE=0: the bucket path also compacts the survivors over the whole segment
     uint32_t ingest_ctas_per_sm = 0; // 0: as many as fit; pipelined handles leave room for the concurrent sort/update kernels
@@ -1180,6 +1181,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     { const char *e = std::getenv("WFB_L2_HINTS"); h->l2_hints = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_SPARSE"); h->sparse_ingest = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_INPLACE"); h->inplace_ok = !(e && std::atoi(e) == 0); }
+    { const char *e = std::getenv("WFB_INPLACE_KERNEL"); h->inplace_kernel = !(e && std::atoi(e) == 0); }
     { const char *e = std::getenv("WFB_FUSE_TILE_HIST"); h->fuse_tile_hist = e && std::atoi(e) != 0; }
     { // WFB_L2_PERSIST=<MB>: L2 set-aside for evict-last lines (the lifted records between the ingest pass and the update)
         const char *e = std::getenv("WFB_L2_PERSIST");
@@ -1423,9 +1425,14 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
         rc = h->sorter.prepare_h32(g.total, s, &a.wide_h32); if (rc) return rc;
         g.h32_ready = true;
     }
-    uint32_t grid = 0;
-    rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
-    h->ts.launched(tiles, grid);
+    if (a.inplace && a.sort_passes <= 1 && h->ops->slots_inplace && h->inplace_kernel) {
+        // records read in place: only the slots (and the digit counts) are produced -- no tiles to stage, a plain kernel does it
+        rc = h->ops->slots_inplace(a, pre ? static_cast<const void *>(pre) : h->pp(), s); if (rc) return rc;
+    } else {
+        uint32_t grid = 0;
+        rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
+        h->ts.launched(tiles, grid);
+    }
     h->launches++;
     h->mark(1, s);
 
