@@ -77,7 +77,8 @@ struct FfatDev {
     uint64_t *cnt;             // lifted results appended so far (Key_Descriptor::count)
     unsigned char *acc;        // open-pane accumulator, result_t per slot
     unsigned char *tree;       // FlatFAT per slot: (2*n_leaves-1) result_t, leaves first (level 0), root last
-    uint32_t *seg_cnt;         // items of the current stream segment per slot (zeroed by k_ffat_update)
+    uint32_t *seg_cnt;         // full-sort path only: items of the current stream segment per slot (TileArgs::count_keys; zeroed by the
+                               // update kernels). The bucket path counts per key inside the bucket CTA instead.
     uint32_t *seg_off;         // exclusive offsets into the sorted segment, max_keys+1
     struct Trigger *trig;      // deferred window groups of the current segment (evaluated by k_ffat_windows)
     uint32_t *n_trig;          // number of deferred groups
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     uint64_t *staged = full + STAGES;                            // STAGES  consumers -> epilogue
     uint64_t *empty = staged + STAGES;                           // STAGES  epilogue -> producer
     StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);  // STAGES
-    uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 [x MAX_SHARDS] (double-buffered by iteration parity)
+    uint32_t *warp_tot = reinterpret_cast<uint32_t *>(meta + STAGES); // 2 x 8 warp totals (double-buffered by iteration parity)
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(ctl + 1024);      // MODE_INGEST: [pass][1 << sort_dbits] digit counts of this CTA (1024 words)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
