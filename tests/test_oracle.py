@@ -193,3 +193,86 @@ def test_tb_oracle_matches_the_window_definition():
         for k in range(nkeys):
             ids = np.sort(out["id"][out["key"] == k])
             assert np.array_equal(ids, np.arange(len(ids)))
+
+
+def _tb_model(batches, win, slide, lateness, nb):
+    """Second, independent restatement of Ffat_Replica_GPU::process_batch_tb / process_wins_tb (wf/ffat_replica_gpu.hpp:870-1047)
+    with plain Python containers: per key a dict pane -> (isum, fsum) of pending panes, the id of the first pending pane, the
+    triggering pane and the list of panes already handed to the FlatFAT (windows are folds over that list). Pure model: no ring,
+    no tree."""
+    from math import gcd
+    pane_len = gcd(win, slide)
+    wp, sp = win // pane_len, slide // pane_len
+    bp, group = (nb - 1) * sp + wp, sp * nb
+    keys = {}
+    out = []
+    for res, ts, wm in batches:
+        first_incomplete = (wm - lateness) // pane_len if wm >= lateness else 0
+        present = []
+        parts = {}
+        for r, t in zip(res, ts):  # arrival order inside a (key, pane)
+            k, p = int(r["key"]), int(t) // pane_len
+            if k not in parts:
+                parts[k] = {}
+                present.append(k)
+            a = parts[k].get(p)
+            parts[k][p] = (int(r["isum"]), float(r["fsum"])) if a is None else (a[0] + int(r["isum"]), a[1] + float(r["fsum"]))
+        for k in sorted(present):
+            st = keys.setdefault(k, {"first": 0, "pend": {}, "end": 0, "trig": bp - 1, "done": False, "fed": [], "gwid": 0})
+            for p in sorted(parts[k], reverse=True):  # the reference walks them newest first
+                if p < st["first"]:
+                    continue  # pane already consumed: dropped
+                if p < st["end"]:
+                    a = st["pend"].get(p, (0, 0.0))
+                    st["pend"][p] = (a[0] + parts[k][p][0], a[1] + parts[k][p][1])
+                else:
+                    st["pend"][p] = parts[k][p]
+            newest = max(parts[k])
+            if newest >= st["end"]:
+                st["end"] = newest + 1
+            while st["trig"] < first_incomplete:
+                need = group if st["done"] else bp
+                for p in range(st["first"], st["first"] + need):
+                    st["fed"].append(st["pend"].pop(p, (0, 0.0)))  # a missing pane is an empty pane
+                st["first"] += need
+                st["end"] = max(st["end"], st["first"])
+                st["done"] = True
+                for i in range(nb):
+                    g = st["gwid"] + i
+                    panes = st["fed"][g * sp:g * sp + wp]
+                    isum, fsum = 0, 0.0
+                    for a in panes:
+                        isum += a[0]; fsum += a[1]
+                    out.append((k, g, isum, fsum, wm))
+                st["gwid"] += nb
+                st["trig"] += group
+    return out
+
+
+@pytest.mark.parametrize("cfg", [(40, 10, 0, 3), (64, 16, 100, 2), (30, 45, 0, 2), (96, 32, 64, 4)])
+def test_tb_oracle_vs_independent_model(cfg):
+    """The C restatement of the time-based path against a second restatement with Python containers, on streams with
+    out-of-order timestamps, idle periods and tuples far behind the watermark."""
+    from oracle import oracle as O
+    win, slide, lateness, nb = cfg
+    rng = np.random.default_rng(7)
+    nkeys, n, B = 6, 9000, 750
+    t, _ = O.gen_tuple64(3, n, O.KEY_RR, nkeys)
+    ts = np.arange(n, dtype=np.int64) * 2 + rng.integers(-30, 31, n) + (np.arange(n) // 1500) * 400
+    late = rng.random(n) < 0.02
+    ts = np.maximum(np.where(late, ts - rng.integers(300, 2500, n), ts), 0).astype(np.uint64)
+    res = O.lift_tuple64(t)
+    tb = O.FfatTbOracle(win, slide, lateness, nb)
+    got, batches = [], []
+    for b in range(0, n, B):
+        wm = int(ts[b:b + B].min())
+        r, rt = tb.process_batch(res[b:b + B], ts[b:b + B], wm)
+        assert np.all(rt == wm)
+        got.extend((int(x["key"]), int(x["id"]), int(x["isum"]), float(x["fsum"]), wm) for x in r)
+        batches.append((res[b:b + B], ts[b:b + B], wm))
+    exp = _tb_model(batches, win, slide, lateness, nb)
+    assert len(got) == len(exp) > 0
+    got.sort(key=lambda x: (x[0], x[1])); exp.sort(key=lambda x: (x[0], x[1]))
+    for a, e in zip(got, exp):
+        assert a[0] == e[0] and a[1] == e[1] and a[2] == e[2] and a[4] == e[4], (a, e)
+        assert abs(a[3] - e[3]) <= 1e-9 * max(1.0, abs(e[3]))
