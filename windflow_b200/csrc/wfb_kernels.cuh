@@ -114,6 +114,10 @@ struct TileArgs {
     uint32_t count_keys;       // MODE_INGEST: 1 = per-key item counts of the segment (ff.seg_cnt) for the full-sort update kernels
     uint32_t *wide_h32;        // MODE_INGEST + sparse: per-tile digit counts of the wide partition that follows ([position / 4096][1024], 32-bit),
                                // accumulated here so that the partition needs no counting pass of its own (null: it counts itself)
+    uint16_t *wide_h16;        // MODE_INGEST + sparse: per-tile digit counts of the wide partition ([position / 4096][1024], 16-bit rows), filed by
+                               // the tile pass itself: with tiles_per_ticket = 16 a CTA owns whole wide tiles, counts their digits in shared
+                               // memory and writes each row once -- the partition then needs no counting pass (k_wide_tile_hist) of its own
+    uint32_t tiles_per_ticket; // consecutive tiles a producer claims per ticket (0 or 1: one; 16 with wide_h16)
     const uint32_t *ext_slots; // MODE_INGEST + in-place: slot of the record at every position, given by the caller (the time-based
                                // front end knows the key slot of every pane it pops); the program's key extractor is not used
     uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
@@ -279,11 +283,11 @@ __device__ __forceinline__ uint32_t slot_of_key(const FfatDev &ff, uint64_t key)
 // ------------------------------------------------------------------------------------------------------
 constexpr uint32_t TP_THREADS = TILE + 64;         // producer warp + 8 consumer warps + epilogue warp
 constexpr uint32_t TILE_SENTINEL = 0x7fffffffu;
-enum { TF_SWZ = 1u, TF_FALLBACK = 2u, TF_TS_SMEM = 4u };
+enum { TF_SWZ = 1u, TF_FALLBACK = 2u, TF_TS_SMEM = 4u, TF_WIDE_LAST = 8u };
 
 struct StageMeta {
     uint32_t tile, batch, first, cnt, flags, count; // count: survivors (written by the consumers)
-    uint32_t pad[2];
+    uint32_t wide, pad;                             // wide: ticket (= wide tile when tiles_per_ticket = 16)
 };
 
 template <class P, int MODE>
@@ -294,7 +298,7 @@ struct TilePassSmem {
     static constexpr uint32_t tile_bytes = (TILE * rec_bytes + 1023u) & ~1023u; // swizzled stages need 512-B alignment
     static constexpr uint32_t aux_bytes = (MODE == MODE_INGEST) ? TILE * 4u : (MODE == MODE_FILTER ? TILE * 16u : 0u); // slots | ts in + ts out
     static constexpr uint32_t stage_bytes = tile_bytes + aux_bytes;
-    static constexpr uint32_t hist_bytes = (MODE == MODE_INGEST) ? 4u * 256u * 4u : 0u; // up to 4 sort passes
+    static constexpr uint32_t hist_bytes = (MODE == MODE_INGEST) ? 4u * 256u * 4u : 0u; // up to 4 sort passes of 8 bits or one of 10 | two buffers of 1024 packed 16-bit per-wide-tile counts
     static constexpr uint32_t total = STAGES * stage_bytes + 1024 /*alignment slack*/ + 1024 /*barriers, meta, scan*/ + hist_bytes;
 };
 
@@ -358,13 +362,20 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             const uint64_t pol_first = l2_policy_evict_first();
             DevBatch b = a.one; uint32_t bi = 0, b_end = 0; // batch of the previous tile, first tile after it
             bool have_batch = false;
+            const uint32_t tpt = a.tiles_per_ticket ? a.tiles_per_ticket : 1u;
+            uint32_t t_next = 0, t_end = 0, claim = 0; // tiles [t_next, t_end) of the current claim are still to load
             for (uint32_t it = 0;; it++) {
                 const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
                 mbar_wait(&empty[s], par ^ 1u); // a fresh barrier passes the wait on parity 1
                 // claim only now: a claimed tile is loaded at once, so the look-backs of its successors never wait on a stalled ring
-                const uint32_t t = atomicAdd(a.ticket, 1u) - a.ticket_base;
                 StageMeta &m = meta[s];
-                if (t >= a.num_tiles) { m.tile = TILE_SENTINEL; mbar_arrive(&full[s]); break; }
+                if (t_next == t_end) {
+                    claim = atomicAdd(a.ticket, 1u) - a.ticket_base;
+                    t_next = claim * tpt; // (claim <= (num_tiles + grid) / tpt: no overflow)
+                    if (claim >= (a.num_tiles + tpt - 1) / tpt) { m.tile = TILE_SENTINEL; mbar_arrive(&full[s]); break; }
+                    t_end = min(t_next + tpt, a.num_tiles);
+                }
+                const uint32_t t = t_next++;
                 if (a.batches != nullptr && !(have_batch && t >= b.tile_begin && t < b_end)) {
                     uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= t
                     while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (a.batches[mid].tile_begin <= t) lo = mid; else hi = mid - 1; }
@@ -382,7 +393,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 if (!(flags & TF_FALLBACK)) tx += cnt * TB;
                 const uint64_t *tsp = (MODE == MODE_FILTER && b.ts != nullptr) ? b.ts + first : nullptr;
                 if (tsp != nullptr && bulk_ok(tsp, cnt * 8u)) { flags |= TF_TS_SMEM; tx += cnt * 8u; }
-                m.tile = t; m.batch = bi; m.first = first; m.cnt = cnt; m.flags = flags;
+                if (t_next == t_end) flags |= TF_WIDE_LAST;
+                m.tile = t; m.batch = bi; m.first = first; m.cnt = cnt; m.flags = flags; m.wide = claim;
                 if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
                 if (a.l2_hints) { // read-once stream: first in line for eviction
                     if (flags & TF_SWZ) tma_load_2d_hint(stage_buf(s), &tmap, 0, static_cast<int32_t>(off >> 6), &full[s], pol_first);
@@ -395,6 +407,7 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
     } else if (warp <= TILE / 32) {
         // ================================= CONSUMERS =================================
         const uint32_t ctid = tid - 32, cwarp = warp - 1;
+        uint32_t wpar = 0; // which of the two digit-count buffers the current wide tile uses
         for (uint32_t it = 0;; it++) {
             const uint32_t s = it % STAGES, par = (it / STAGES) & 1u;
             unsigned char *buf = stage_buf(s);
@@ -453,7 +466,12 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                         else slot = slot_of_key(a.ff, P::key(tup, prm));
                         if (slot != INVALID_SLOT && a.count_keys) atomicAdd(&a.ff.seg_cnt[slot], 1u); // (full-sort path only)
                     }
-                    if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) { // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
+                    if (a.wide_h16 != nullptr) { // digit counts of this wide tile (the CTA owns all of its tiles)
+                        if (slot != INVALID_SLOT) { // two 16-bit counters per word (a wide tile holds 4096 positions: no carry)
+                            const uint32_t d = (slot >> a.sort_shift) & 1023u;
+                            atomicAdd(&s_hist[wpar * 512u + (d >> 1)], 1u << ((d & 1u) * 16u));
+                        }
+                    } else if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) { // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
                             atomicAdd(&s_hist[(ps << a.sort_dbits) + ((slot >> (a.sort_shift + a.sort_dbits * ps)) & ((1u << a.sort_dbits) - 1u))], 1u);
                         if (a.wide_h32 != nullptr) // (tile t owns positions [256 t, +256): wide tile t / 16)
@@ -481,6 +499,15 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                 uint32_t *wt = warp_tot + (it & 1u) * (TILE / 32);
                 if (lane == 0) wt[cwarp] = __popc(bal);
                 consumer_bar(); // totals visible; every consumer has read its tuple (stage re-usable for staging)
+                if constexpr (MODE == MODE_INGEST) {
+                    if (a.wide_h16 != nullptr && (m.flags & TF_WIDE_LAST)) { // last tile of the wide tile: file its row, clear the buffer for the
+                        uint32_t *hrow = s_hist + wpar * 512u;                 // wide tile after the next (a barrier per tile lies in between)
+                        const uint2 c = reinterpret_cast<const uint2 *>(hrow)[ctid];
+                        reinterpret_cast<uint2 *>(hrow)[ctid] = make_uint2(0, 0);
+                        reinterpret_cast<uint2 *>(a.wide_h16 + static_cast<size_t>(m.wide) * 1024u)[ctid] = c; // (little endian: the packed words are the row)
+                        wpar ^= 1u;
+                    }
+                }
                 uint32_t wbase = 0, total = 0;
 #pragma unroll
                 for (uint32_t w = 0; w < TILE / 32; w++) { const uint32_t c = wt[w]; if (w < cwarp) wbase += c; total += c; }
@@ -950,6 +977,46 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums(const ui
     reinterpret_cast<uint4 *>(C + static_cast<size_t>(chunk) * OSW_DIGITS)[tid] = acc;
 }
 
+// the same for the 16-bit rows the tile pass files (TileArgs::wide_h16)
+static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums16(const uint16_t *__restrict__ H, uint32_t tiles, uint32_t chunk_shift, uint32_t *__restrict__ C)
+{
+    const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+    const uint32_t t0 = chunk << chunk_shift, t1 = min(tiles, t0 + (1u << chunk_shift));
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const ushort4 *row = reinterpret_cast<const ushort4 *>(H) + tid;
+#pragma unroll 16
+    for (uint32_t t = t0; t < t1; t++) { const ushort4 v = row[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    reinterpret_cast<uint4 *>(C + static_cast<size_t>(chunk) * OSW_DIGITS)[tid] = acc;
+}
+
+// C[chunk][digit] (chunk sums) -> first output position of (chunk, digit): exclusive scan over the digits of the totals + exclusive
+// scan over the chunks, in place; ctl_counts[digit] = total of the digit. One CTA, one thread per digit, every load independent.
+static __global__ void __launch_bounds__(OSW_DIGITS) k_wide_chunk_scan(uint32_t *__restrict__ C, uint32_t chunks, uint32_t *__restrict__ ctl_counts)
+{
+    __shared__ uint32_t wsum[32];
+    const uint32_t d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    uint32_t total = 0;
+#pragma unroll 16
+    for (uint32_t c = 0; c < chunks; c++) total += C[static_cast<size_t>(c) * OSW_DIGITS + d];
+    ctl_counts[d] = total;
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = wsum[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, wi, o); if (lane >= static_cast<uint32_t>(o)) wi += v; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + incl - total;
+#pragma unroll 16
+    for (uint32_t c = 0; c < chunks; c++) { uint32_t *p = C + static_cast<size_t>(c) * OSW_DIGITS + d; const uint32_t v = *p; *p = run; run += v; }
+}
+
 // RBYTES: bytes of the payload record that travels with each element (payload_out[dst] = payload_in[index]); 0 = none,
 // -1 = run-time size `payload_bytes` (multiple of 8)
 template <class K, int RBYTES>
@@ -959,8 +1026,9 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
                                                               const uint32_t *__restrict__ ctl_counts,
                                                               const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out,
                                                               uint32_t payload_bytes, uint32_t skip_invalid, uint32_t region_stride,
-                                                              const uint32_t *__restrict__ H32)
+                                                              const uint32_t *__restrict__ H32, uint32_t cx)
 {
+    // cx != 0: C holds the first output position of every (chunk, digit) already (k_wide_chunk_scan); ctl_counts is not read
     // H32 != nullptr: the per-tile counts are 32-bit rows filled by the producer of the keys (the tile pass) instead of H
     // region_stride != 0: bin d starts at d * region_stride (fixed-capacity regions; elements beyond the capacity are dropped)
     constexpr uint32_t NW = OSW_THREADS / 32;
@@ -980,19 +1048,22 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
     {
         const uint32_t chunk = tile >> chunk_shift;
         const uint4 *crow = reinterpret_cast<const uint4 *>(C) + tid;
+        if (cx) { const uint4 v = crow[static_cast<size_t>(chunk) * (OSW_DIGITS / 4)]; acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w; }
+        else {
 #pragma unroll 8
-        for (uint32_t c = 0; c < chunk; c++) { const uint4 v = crow[static_cast<size_t>(c) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+            for (uint32_t c = 0; c < chunk; c++) { const uint4 v = crow[static_cast<size_t>(c) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+        }
         if (H32 != nullptr) {
             const uint4 *hrow = reinterpret_cast<const uint4 *>(H32) + tid;
 #pragma unroll 8
             for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const uint4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
         } else {
             const ushort4 *hrow = reinterpret_cast<const ushort4 *>(H) + tid;
-#pragma unroll 8
+#pragma unroll 16
             for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const ushort4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
         }
     }
-    const uint4 g4 = reinterpret_cast<const uint4 *>(ctl_counts)[tid];
+    const uint4 g4 = cx ? make_uint4(0, 0, 0, 0) : reinterpret_cast<const uint4 *>(ctl_counts)[tid];
     const uint32_t gsum = g4.x + g4.y + g4.z + g4.w;
     uint32_t incl = gsum;
 #pragma unroll
@@ -1012,12 +1083,16 @@ __global__ void __launch_bounds__(OSW_THREADS, WFB_OSW_MINBLOCKS) k_wide_scatter
     for (uint32_t r = 0; r < OSW_ITEMS; r++) {
         const uint32_t idx = start + warp * (32 * OSW_ITEMS) + r * 32 + lane;
         const bool valid = idx < n && !(skip_invalid && k[r] == static_cast<K>(~K(0)));
-        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u)) : OSW_DIGITS;
+        rk[r] = 0xffffffffu; // 0xffffffff: not an element
+        if (!__any_sync(FULL, valid)) continue; // (the survivors of the streaming pass sit at the front of every 256-position tile: half of the rounds are padding)
+        const uint32_t d = valid ? (static_cast<uint32_t>(k[r] >> shift) & (OSW_DIGITS - 1u)) : OSW_DIGITS + lane;
         const uint32_t mask = __match_any_sync(FULL, d);
-        rk[r] = valid ? (cntw[warp][d] + __popc(mask & lanemask_lt())) : 0xffffffffu; // 0xffffffff: not an element
-        __syncwarp();
-        if (valid && lane == static_cast<uint32_t>(__ffs(mask) - 1)) cntw[warp][d] = static_cast<uint16_t>(cntw[warp][d] + __popc(mask));
-        __syncwarp();
+        const uint32_t leader = static_cast<uint32_t>(__ffs(mask) - 1);
+        uint32_t before = 0;
+        if (valid && lane == leader) { before = cntw[warp][d]; cntw[warp][d] = static_cast<uint16_t>(before + __popc(mask)); } // one lane per digit and round
+        before = __shfl_sync(FULL, before, leader);
+        if (valid) rk[r] = before + __popc(mask & lanemask_lt());
+        __syncwarp(); // the next round's leaders read what this round's leaders wrote
     }
     __syncthreads();
     {
@@ -1732,6 +1807,256 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_ffat_update_stream: the window update as a STREAM per warp -- no in-bucket sort, no per-key runs, no block barriers in the
+// loop. One CTA (2 warps) per bucket of the wide partition; warp w owns the bucket's keys [32 w, 32 w + 32) and LANE k OF THE WARP
+// IS KEY 32 w + k: the key's count, open pane (accumulator in registers), next leaf and next trigger live in that lane's
+// registers for the whole kernel. Every warp reads the bucket's (slot, position) pairs in arrival order (128 per step, coalesced,
+// prefetched one step ahead; the two warps share the lines through L1), keeps the items of its own keys in a small shared-memory
+// queue and, whenever 32 are queued, takes them one per lane:
+//   - the 32 records are gathered straight away (32 independent 32-byte loads per warp in flight) and folded ONE STEP LATER, so the
+//     gather of batch j+1 overlaps the fold of batch j and the next pair reads;
+//   - five ballots turn the 32 item keys into one bit mask per key lane (the items of my key, ascending lane = arrival order);
+//     every key lane then pulls its items one per round with warp shuffles and folds them in order -- a batch of 32 items over 32
+//     keys takes 3-4 rounds of eight shuffles and one comb, with no shared-memory traffic at all;
+//   - a lane that completes a pane writes the FlatFAT leaf and recomputes the root path -- with the siblings of the first leaf each
+//     key completes staged in shared memory at kernel start (cp.async by the key's own lane), so the usual completion issues no
+//     dependent global load;
+//   - a fired group is deferred to k_ffat_windows; should the same key complete ANOTHER pane later in this call (it would
+//     overwrite ring leaves the deferred windows still read), the pending group is evaluated first by the whole warp and its list
+//     entry voided. No per-key item counts of the segment are needed for that decision (the bucket kernel counts them first).
+// Built for panes of at least a few items (a pane per item would make every round a path update): the host selects
+// k_ffat_update_buckets otherwise.
+// ------------------------------------------------------------------------------------------------------
+#ifndef WFB_ST_MINBLOCKS
+#define WFB_ST_MINBLOCKS 8
+#endif
+constexpr uint32_t ST_THREADS = 64, ST_WARPS = ST_THREADS / 32, ST_Q = 64;
+constexpr uint32_t ST_NONE = 0xffffffffu;
+static_assert(ST_WARPS * 32 == BK_KEYS, "one key per lane");
+
+template <class P>
+__global__ void __launch_bounds__(ST_THREADS, WFB_ST_MINBLOCKS) k_ffat_update_stream(const FfatDev ff, const unsigned char *__restrict__ lifted,
+                                                                     const uint32_t *__restrict__ bk_slots, const uint32_t *__restrict__ bk_pos,
+                                                                     const uint32_t *__restrict__ digit_counts, uint32_t shift,
+                                                                     const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
+                                                                     uint32_t nbatches, unsigned char *__restrict__ out_res,
+                                                                     uint64_t *__restrict__ out_ts, uint32_t out_cap, uint32_t *__restrict__ n_out,
+                                                                     const typename P::params_t prm)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    constexpr uint32_t DPT = OSW_DIGITS / ST_THREADS;
+    constexpr uint32_t CPB = (RB % 16 == 0) ? 16 : 8;
+    constexpr uint32_t SIBL = RB <= 32 ? 8 : (RB <= 64 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged
+    static_assert(DPT % 4 == 0 && RB % 8 == 0, "layout");
+    __shared__ __align__(16) unsigned char s_sib[BK_KEYS * SIBL * RB];  // siblings of the leaf key k completes first (private to the key's lane)
+    __shared__ uint32_t q_lk[ST_WARPS][ST_Q], q_pos[ST_WARPS][ST_Q];
+    __shared__ uint32_t misc[ST_WARPS], s_boff[2];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t bucket = blockIdx.x;
+    const uint32_t kpc = min(BK_KEYS, 1u << shift);
+    const uint32_t key_lo = bucket << shift;
+    const uint32_t n = ff.n_leaves, logn = ff.log_leaves;
+    const uint32_t P32 = static_cast<uint32_t>(ff.pane);
+    const uint64_t group_items = ff.slide * ff.nb;
+    const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
+
+    // ---- my key's state (loads first: they overlap the scan below) ------------------------------------------------------------------
+    const uint32_t my_k = tid; // local key of this lane
+    const bool has_key = my_k < kpc && key_lo + my_k < ff.max_keys;
+    const uint32_t my_slot = key_lo + my_k;
+    unsigned char *const my_tree = ff.tree + static_cast<size_t>(has_key ? my_slot : 0u) * tree_stride;
+    uint64_t st_c = 0;
+    alignas(16) R acc;
+    if (has_key) {
+        st_c = ff.cnt[my_slot];
+        ld_rec<R>(ff.acc + static_cast<size_t>(my_slot) * RB, acc);
+    }
+    // ---- bucket range = exclusive scan of the pass histogram ------------------------------------------------------------------------
+    {
+        uint32_t cc[DPT];
+#pragma unroll
+        for (uint32_t q = 0; q < DPT / 4; q++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(digit_counts)[tid * (DPT / 4) + q];
+            cc[4 * q] = v.x; cc[4 * q + 1] = v.y; cc[4 * q + 2] = v.z; cc[4 * q + 3] = v.w;
+        }
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < DPT; q++) sum += cc[q];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+        if (lane == 31) misc[warp] = incl;
+        __syncthreads();
+        if (tid == bucket / DPT) {
+            uint32_t base = incl - sum;
+            for (uint32_t w = 0; w < warp; w++) base += misc[w];
+            uint32_t own = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < DPT; q++) { if (q < bucket % DPT) base += cc[q]; if (q == bucket % DPT) own = cc[q]; }
+            s_boff[0] = base; s_boff[1] = base + own;
+        }
+    }
+    uint64_t g = 0, tt = 0;          // groups fired | ordinal (1-based, among the key's items of this call) of the item that fires the next group
+    uint32_t cp = 0, leaf = 0, cons = 0, pend = ST_NONE; // items in the open pane | leaf it becomes | items consumed in this call | deferred group of this call
+    bool staged = false;
+    if (has_key) {
+        const uint64_t c = st_c;
+        cp = static_cast<uint32_t>(c % P32); leaf = static_cast<uint32_t>((c / P32) & (n - 1));
+        if (c < ff.B) { g = 0; tt = ff.B - c; }
+        else { g = 1 + (c - ff.B) / group_items; tt = ff.B + g * group_items - c; }
+        for (uint32_t l = 0; l < min(logn, SIBL); l++) {
+            const unsigned char *src = my_tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB;
+            unsigned char *dst = s_sib + (my_k * SIBL + l) * RB;
+#pragma unroll
+            for (uint32_t q = 0; q < RB / CPB; q++) cp_async<CPB>(dst + q * CPB, src + q * CPB);
+        }
+        staged = true;
+    }
+    __syncthreads();
+    const uint32_t b0 = s_boff[0], b1 = s_boff[1];
+    cp_async_wait_all(); // (the siblings are read by the lane that copied them)
+    if (b0 == b1) return;
+
+    // the whole warp evaluates the Nb windows of one fired group
+    auto eval_group = [&](uint32_t e_slot, uint64_t e_key, uint64_t e_g, uint32_t e_pos, uint32_t e_obase) {
+        const unsigned char *e_tree = ff.tree + static_cast<size_t>(e_slot) * tree_stride;
+        const uint64_t wm = batch_watermark(batch_off, batches, nbatches, e_pos);
+        for (uint32_t i = lane; i < ff.nb; i += 32)
+            ffat_eval_window<P>(ff, e_tree, e_key, e_g * ff.nb + i, wm, e_obase + i, out_res, out_ts, out_cap, prm);
+    };
+
+    // one batch of at most 32 queued items, one per lane (act: this lane holds one; lk: its key lane)
+    auto process = [&](bool act, uint32_t lk, uint32_t pos, const R &rec) {
+        uint32_t m = __ballot_sync(FULL, act);
+#pragma unroll
+        for (uint32_t b = 0; b < 5; b++) { const uint32_t B = __ballot_sync(FULL, act && ((lk >> b) & 1u)); m &= ((lane >> b) & 1u) ? B : ~B; }
+        // m: the lanes holding the items of MY key, ascending lane = arrival order
+        while (__any_sync(FULL, m != 0)) {
+            const bool has = m != 0;
+            const uint32_t j = has ? static_cast<uint32_t>(__ffs(m) - 1) : 0u;
+            m &= m - 1;
+            const R it = shfl_rec<R>(rec, j);
+            const uint32_t it_pos = __shfl_sync(FULL, pos, j);
+            const bool completes = has && cp + 1 == P32;
+            // a key about to complete a pane while a group of it is still deferred: evaluate that group before its leaves are overwritten
+            uint32_t ev = __ballot_sync(FULL, completes && pend != ST_NONE);
+            while (ev) {
+                const int src = __ffs(ev) - 1;
+                ev &= ev - 1;
+                const uint32_t ti = __shfl_sync(FULL, pend, src);
+                const Trigger tr = ff.trig[ti];
+                eval_group(tr.slot, tr.key, tr.g, tr.last_pos, tr.obase);
+                if (lane == static_cast<uint32_t>(src)) { ff.trig[ti].slot = INVALID_SLOT; pend = ST_NONE; } // k_ffat_windows skips voided entries
+                __syncwarp();
+            }
+            bool eval_now = false;
+            uint32_t ev_obase = 0; uint64_t ev_g = 0;
+            if (has) {
+                if (cp == 0) acc = it; else P::comb(acc, it, acc, prm);
+                cons++;
+                if (!completes) cp++;
+                else {
+                    cp = 0;
+                    const uint32_t lf = leaf;
+                    leaf = (leaf + 1) & (n - 1);
+                    st_rec<R>(my_tree + static_cast<size_t>(lf) * RB, acc);
+                    alignas(16) R cur = acc;
+                    for (uint32_t l = 0; l < logn; l++) {
+                        alignas(16) R sb;
+                        if (staged && l < SIBL) ld_rec<R>(s_sib + (my_k * SIBL + l) * RB, sb);
+                        else ld_rec<R>(my_tree + static_cast<size_t>(level_off(n, l) + ((lf >> l) ^ 1u)) * RB, sb);
+                        alignas(16) R parent = cur;
+                        if ((lf >> l) & 1u) P::comb(sb, cur, parent, prm); else P::comb(cur, sb, parent, prm);
+                        cur = parent;
+                        st_rec<R>(my_tree + static_cast<size_t>(level_off(n, l + 1) + (lf >> (l + 1))) * RB, cur);
+                    }
+                    staged = false; // the next pane of the key reads the tree this one has just written
+                    if (cons == tt) { // the group fires: Nb windows, evaluated after the update (k_ffat_windows)
+                        const uint32_t obase = atomicAdd(n_out, ff.nb);
+                        const uint32_t ti = atomicAdd(ff.n_trig, 1u);
+                        if (ti < ff.trig_cap) {
+                            Trigger tr; tr.key = key_of_slot(ff, my_slot); tr.g = g; tr.slot = my_slot; tr.last_pos = it_pos; tr.obase = obase; tr.pad = 0;
+                            ff.trig[ti] = tr;
+                            pend = ti;
+                        } else { eval_now = true; ev_obase = obase; ev_g = g; } // list full: evaluate here
+                        g++; tt += group_items;
+                    }
+                }
+            }
+            uint32_t pd = __ballot_sync(FULL, eval_now);
+            while (pd) {
+                const int src = __ffs(pd) - 1;
+                pd &= pd - 1;
+                const uint32_t e_obase = __shfl_sync(FULL, ev_obase, src), e_pos = __shfl_sync(FULL, it_pos, src);
+                const uint64_t e_g = __shfl_sync(FULL, ev_g, src);
+                const uint32_t e_slot = key_lo + warp * 32u + static_cast<uint32_t>(src);
+                __syncwarp(); // the path nodes the source lane has just written
+                eval_group(e_slot, key_of_slot(ff, e_slot), e_g, e_pos, e_obase);
+                __syncwarp();
+            }
+        }
+    };
+
+    uint32_t q_head = 0, q_tail = 0; // warp-uniform
+    bool have = false;
+    uint32_t p_lk = 0, p_pos = 0;
+    alignas(16) R p_rec;
+    uint32_t sl[4], ps[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {
+        const uint32_t i = b0 + u * 32 + lane;
+        sl[u] = i < b1 ? bk_slots[i] : INVALID_SLOT;
+        ps[u] = i < b1 ? bk_pos[i] : 0u;
+    }
+    for (uint32_t base = b0; base < b1; base += 128) {
+        uint32_t nsl[4], nps[4]; // the next step's pairs fly while this step's are queued and folded
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t i = base + 128 + u * 32 + lane;
+            nsl[u] = i < b1 ? bk_slots[i] : INVALID_SLOT;
+            nps[u] = i < b1 ? bk_pos[i] : 0u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) {
+            const uint32_t lk = sl[u] - key_lo; // (slots outside the bucket's keys, the padding included, wrap to large values)
+            const bool mine = lk < kpc && (lk >> 5) == warp;
+            const uint32_t bal = __ballot_sync(FULL, mine);
+            if (mine) { const uint32_t qi = (q_tail + __popc(bal & lanemask_lt())) % ST_Q; q_lk[warp][qi] = lk & 31u; q_pos[warp][qi] = ps[u]; }
+            q_tail += __popc(bal);
+            __syncwarp();
+            if (q_tail - q_head >= 32) {
+                const uint32_t qi = (q_head + lane) % ST_Q;
+                const uint32_t n_lk = q_lk[warp][qi], n_pos = q_pos[warp][qi];
+                q_head += 32;
+                alignas(16) R n_rec;
+                ld_rec<R>(lifted + static_cast<size_t>(n_pos) * RB, n_rec); // the gather of this batch flies while the previous one is folded
+                if (have) process(true, p_lk, p_pos, p_rec);
+                p_lk = n_lk; p_pos = n_pos; p_rec = n_rec; have = true;
+                __syncwarp(); // the popped queue entries may be overwritten now
+            }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++) { sl[u] = nsl[u]; ps[u] = nps[u]; }
+    }
+    if (have) process(true, p_lk, p_pos, p_rec);
+    if (q_tail != q_head) { // the last, partial batch
+        const bool act = lane < q_tail - q_head;
+        const uint32_t qi = (q_head + lane) % ST_Q;
+        const uint32_t n_lk = act ? q_lk[warp][qi] : 0u, n_pos = act ? q_pos[warp][qi] : 0u;
+        alignas(16) R n_rec;
+        if (act) ld_rec<R>(lifted + static_cast<size_t>(n_pos) * RB, n_rec);
+        process(act, n_lk, n_pos, n_rec);
+    }
+    // ---- my key's state back -----------------------------------------------------------------------------------------------------------
+    if (has_key && cons != 0) {
+        ff.cnt[my_slot] = st_c + cons;
+        if (cp) st_rec<R>(ff.acc + static_cast<size_t>(my_slot) * RB, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_ffat_update: one warp per key that received items in this stream segment.
 //   items of the key, in arrival order: lifted[sorted_pos[seg_off[slot] .. +seg_cnt[slot])] (gather = 1), or, when the last
 //   sort pass also moved the records (gather = 0), lifted[seg_off[slot] .. +seg_cnt[slot])
@@ -1797,6 +2122,7 @@ __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const ui
     for (uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; w < total; w += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
         const uint32_t ti = static_cast<uint32_t>(w / ff.nb), i = static_cast<uint32_t>(w % ff.nb);
         const Trigger tr = ff.trig[ti];
+        if (tr.slot == INVALID_SLOT) continue; // evaluated inside the update kernel (k_ffat_update_stream)
         const uint64_t wm = batch_watermark(batch_off, batches, nbatches, tr.last_pos);
         ffat_eval_window<P>(ff, ff.tree + static_cast<size_t>(tr.slot) * tree_stride, tr.key, tr.g * ff.nb + i, wm, tr.obase + i,
                             out_res, out_ts, out_cap, prm);

@@ -108,6 +108,11 @@ struct ProgramOps {
     int (*reduce_segments_batches)(const DevBatch *batches, const uint32_t *boff, const uint64_t *skeys, const uint32_t *sidx,
                                    const uint32_t *seg_begin, const uint32_t *first_seg, const uint32_t *n_segs, uint32_t key_bits,
                                    uint32_t total, uint32_t *long_list, uint32_t *n_long, cudaStream_t s, const void *params);
+    // window update after the wide partition, streaming variant (k_ffat_update_stream): same contract as ffat_buckets, records gathered
+    int (*ffat_stream)(const FfatDev &ff, const unsigned char *lifted, const uint32_t *bk_slots, const uint32_t *bk_pos,
+                       const uint32_t *digit_counts, uint32_t shift, const uint32_t *batch_off, const DevBatch *batches,
+                       uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s,
+                       const void *params);
 };
 
 // P::passthrough (optional): map is a no-op and lift the identity (tuple_t == result_t)
@@ -187,6 +192,18 @@ int ffat_buckets_dispatch(const FfatDev &ff, const unsigned char *lifted, const 
 {
     k_ffat_update_buckets<P><<<OSW_DIGITS, BK_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, moved, batch_off, batches,
                                                                nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
+    WFB_CK(cudaGetLastError());
+    return 0;
+}
+
+template <class P>
+int ffat_stream_dispatch(const FfatDev &ff, const unsigned char *lifted, const uint32_t *bk_slots, const uint32_t *bk_pos,
+                         const uint32_t *digit_counts, uint32_t shift, const uint32_t *batch_off, const DevBatch *batches,
+                         uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s,
+                         const void *params)
+{
+    k_ffat_update_stream<P><<<OSW_DIGITS, ST_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, batch_off, batches,
+                                                              nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
     WFB_CK(cudaGetLastError());
     return 0;
 }
@@ -366,6 +383,7 @@ const void *lifted_ops_of()
         t.params_bytes = sizeof(typename L::params_t); t.reserved = 1u; // pass-through
         t.tile_pass = &tile_pass_ingest_dispatch<L>; t.slots_inplace = &slots_inplace_dispatch<L>;
         t.ffat_update = &ffat_update_dispatch<L>; t.ffat_buckets = &ffat_buckets_dispatch<L>; t.ffat_windows = &ffat_windows_dispatch<L>;
+        t.ffat_stream = &ffat_stream_dispatch<L>;
         return t;
     }();
     return &o;
@@ -381,6 +399,7 @@ ProgramOps make_ops()
     o.tile_pass = &tile_pass_dispatch<P>;
     o.ffat_update = &ffat_update_dispatch<P>;
     o.ffat_buckets = &ffat_buckets_dispatch<P>;
+    o.ffat_stream = &ffat_stream_dispatch<P>;
     o.ffat_windows = &ffat_windows_dispatch<P>;
     o.extract_keys = &extract_keys_dispatch<P>;
     o.reduce_segments = &reduce_segments_dispatch<P>;

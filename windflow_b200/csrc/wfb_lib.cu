@@ -98,7 +98,7 @@ struct TileScratch {
         return 0;
     }
     void next_launch(TileArgs &a) { epoch = (epoch + 1) & 0x3fffffffu; if (epoch == 0) epoch = 1; a.epoch = epoch; a.ticket = ticket; a.ticket_base = ticket_base; a.tile_state = tile_state; }
-    void launched(uint32_t num_tiles, uint32_t grid) { ticket_base += num_tiles + grid; } // one failing claim per CTA
+    void launched(uint32_t num_claims, uint32_t grid) { ticket_base += num_claims + grid; } // one failing claim per CTA
 };
 
 inline uint32_t tiles_of(uint32_t n) { return (n + TILE - 1) / TILE; }
@@ -169,26 +169,51 @@ struct RadixSorter {
         *rows = wideH32;
         return 0;
     }
+    // tiles of the wide pass over `cap` positions and their chunks. prefix = false: about sqrt(tiles) chunks of >= 16 tiles, every
+    // scatter CTA sums the rows of the earlier chunks itself; true (rows filed by the tile pass): chunks of 16 tiles whose first
+    // output positions one small kernel computes (k_wide_chunk_scan), so a scatter CTA reads one chunk row and < 16 tile rows
+    static void wide_geometry(uint32_t cap, bool prefix, uint32_t *tiles, uint32_t *chunk_shift, uint32_t *chunks)
+    {
+        *tiles = std::max(1u, (cap + OSW_TILE - 1) / OSW_TILE);
+        uint32_t cs = 4;
+        if (!prefix) while ((1u << (2 * cs)) < *tiles) cs++;
+        *chunk_shift = cs;
+        *chunks = (*tiles + (1u << cs) - 1) >> cs;
+    }
+    // rows of the wide partition for `cap` positions, allocated before the producer of the keys files them (TileArgs::wide_h16)
+    int ensure_wide(uint32_t cap, cudaStream_t s, uint16_t **rows)
+    {
+        uint32_t tiles, chunk_shift, chunks;
+        wide_geometry(cap, true, &tiles, &chunk_shift, &chunks);
+        if (tiles > wide_tiles || chunks > wide_chunks) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(wideH); cudaFree(wideC);
+            wide_tiles = std::max(tiles, wide_tiles); wide_chunks = std::max(chunks, wide_chunks);
+            CK(cudaMalloc(&wideH, sizeof(uint16_t) * OSW_DIGITS * wide_tiles));
+            CK(cudaMalloc(&wideC, sizeof(uint32_t) * OSW_DIGITS * wide_chunks));
+        }
+        *rows = wideH;
+        return 0;
+    }
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
                              uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
-                             uint32_t skip_invalid, uint32_t region_stride, const uint32_t *h32)
+                             uint32_t skip_invalid, uint32_t region_stride, const uint32_t *h32, uint32_t cx)
     {
-        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride, h32);
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride, h32, cx);
     }
     // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
     template <class K>
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
                   unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0,
-                  bool h32_ready = false)
+                  bool h32_ready = false, bool h16_ready = false)
     {
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
-        const uint32_t tiles = std::max(1u, (cap + OSW_TILE - 1) / OSW_TILE);
-        uint32_t chunk_shift = 4; // chunks of >= 16 tiles, about sqrt(tiles) of them
-        while ((1u << (2 * chunk_shift)) < tiles) chunk_shift++;
-        const uint32_t chunks = (tiles + (1u << chunk_shift) - 1) >> chunk_shift;
+        const bool prefix = h16_ready && ready_ctl && !few_bins;
+        uint32_t tiles, chunk_shift, chunks;
+        wide_geometry(cap, prefix, &tiles, &chunk_shift, &chunks);
         if (tiles > wide_tiles || chunks > wide_chunks) {
             CK(cudaStreamSynchronize(s));
             cudaFree(wideH); cudaFree(wideC);
@@ -199,7 +224,11 @@ struct RadixSorter {
         uint32_t *c = ready_ctl ? ready_ctl : ctl;
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
         const uint32_t *h32 = nullptr;
-        if (h32_ready && ready_ctl && !few_bins) { // the producer of the keys counted the digits per tile: only the chunk sums are missing
+        if (prefix) { // the tile pass filed the 16-bit rows (wideH): chunk sums, then first output position of every (chunk, digit) + digit counts
+            k_wide_chunk_sums16<<<chunks, OSW_THREADS, 0, s>>>(wideH, tiles, chunk_shift, wideC);
+            k_wide_chunk_scan<<<1, OSW_DIGITS, 0, s>>>(wideC, chunks, c);
+            launches++;
+        } else if (h32_ready && ready_ctl && !few_bins) { // the producer of the keys counted the digits per tile: only the chunk sums are missing
             k_wide_chunk_sums<<<chunks, OSW_THREADS, 0, s>>>(wideH32, tiles, chunk_shift, wideC);
             h32 = wideH32;
         } else {
@@ -223,7 +252,7 @@ struct RadixSorter {
                 return 0;
             }
         }
-#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride, h32)
+#define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride, h32, prefix ? 1u : 0u)
         if (!payload_in) WFB_WS(0);
         else switch (payload_bytes) {
             case 8: WFB_WS(8); break;   case 16: WFB_WS(16); break; case 24: WFB_WS(24); break; case 32: WFB_WS(32); break;
@@ -348,6 +377,7 @@ struct SegScratch {
     uint32_t *n_total = nullptr;
     bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
     bool h32_ready = false;       // the streaming pass filed the per-tile digit counts of the wide partition (sorter.wideH32)
+    bool h16_ready = false;       // the tile pass filed them per wide tile as 16-bit rows (sorter.wideH), claiming 16 tiles per ticket
     const unsigned char *lifted_src = nullptr; // records of this segment: `lifted`, or the caller's buffer (in-place ingest)
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
@@ -404,6 +434,8 @@ struct wfb_ffat {
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
     bool fuse_tile_hist = false;  // WFB_FUSE_TILE_HIST=1: the tile pass also files the per-tile digit counts of the wide partition (one more
                                   // global RED per survivor: measured +17 us on the tile pass against -8 us on the partition, so off)
+    bool stream_update = true;    // bucket path: k_ffat_update_stream (warp streams, panes of >= 8 items) instead of k_ffat_update_buckets; WFB_UPDATE=buckets|stream forces one
+    bool tile_h16 = true;         // the tile pass claims whole wide tiles and files their digit counts itself (no k_wide_tile_hist); WFB_TILE_H16=0: off
     bool inplace_kernel = true;   // WFB_INPLACE_KERNEL=0: the in-place case also goes through the tile pass
     bool inplace_ok = true;       // WFB_INPLACE=0: always copy the records of a pass-through program
     bool sparse_ingest = true;    // WFB_SPARSE=0: the bucket path also compacts the survivors over the whole segment
@@ -1197,6 +1229,10 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     { // bucket path: every bucket holds at most BK_KEYS keys and the pane length fits 32 bits
         const char *e = std::getenv("WFB_UPDATE");
         h->buckets = !(e && std::strcmp(e, "lanes") == 0) && (1u << h->bucket_shift) <= BK_KEYS && ff.pane < (1ull << 32);
+        // streaming update: one path update per completed pane inside the item loop, so panes of a few items at least
+        h->stream_update = h->buckets && !h->bucket_move && (e && std::strcmp(e, "stream") == 0 ? true : (e && std::strcmp(e, "buckets") == 0 ? false : ff.pane >= 8));
+        const char *t = std::getenv("WFB_TILE_H16");
+        h->tile_h16 = h->buckets && !h->pipelined && !(t && std::atoi(t) == 0); // (pipelined: the rows would be shared by two segments in flight)
     }
     h->state_bytes = total;
     *hh = h;
@@ -1288,13 +1324,16 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         const uint32_t *counts = nullptr;
         rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.sparse ? nullptr : g.n_total, g.total, g.total, h->bucket_shift, s,
                                            g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
-                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready);
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready, g.h16_ready);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
         // ... then one CTA per bucket finishes the job (local split by key, per-key ordered fold, FlatFAT update)
-        rc = h->ops->ffat_buckets(ff, h->bucket_move ? g.lifted_sorted : g.lifted_src, g.slotsB, g.posB, counts, h->bucket_shift, h->bucket_move ? 1u : 0u, g.batch_off, g.d_batches, g.nbatches, out, out_ts,
-                                  out_cap, n_out, s, h->pp());
+        if (h->stream_update && h->ops->ffat_stream)
+            rc = h->ops->ffat_stream(ff, g.lifted_src, g.slotsB, g.posB, counts, h->bucket_shift, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, n_out, s, h->pp());
+        else
+            rc = h->ops->ffat_buckets(ff, h->bucket_move ? g.lifted_sorted : g.lifted_src, g.slotsB, g.posB, counts, h->bucket_shift, h->bucket_move ? 1u : 0u, g.batch_off, g.d_batches, g.nbatches, out, out_ts,
+                                      out_cap, n_out, s, h->pp());
         if (rc) return rc;
         h->launches += 1;
     } else {
@@ -1425,13 +1464,24 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
         rc = h->sorter.prepare_h32(g.total, s, &a.wide_h32); if (rc) return rc;
         g.h32_ready = true;
     }
+    g.h16_ready = false;
     if (a.inplace && a.sort_passes <= 1 && h->ops->slots_inplace && h->inplace_kernel) {
         // records read in place: only the slots (and the digit counts) are produced -- no tiles to stage, a plain kernel does it
         rc = h->ops->slots_inplace(a, pre ? static_cast<const void *>(pre) : h->pp(), s); if (rc) return rc;
     } else {
+        uint32_t claims = tiles;
+        if (sparse && fuse_hist && h->tile_h16 && !g.h32_ready) {
+            // a CTA claims the 16 tiles of a wide tile at once, counts its digits in shared memory and files the row itself:
+            // the partition that follows needs neither a counting pass nor the per-CTA global digit counts
+            rc = h->sorter.ensure_wide(g.total, s, &a.wide_h16); if (rc) return rc;
+            a.tiles_per_ticket = OSW_TILE_POS / TILE;
+            a.sort_ctl = nullptr; // (the chunk-sum kernel accumulates the global counts into g.sort_ctl, cleared above)
+            claims = (tiles + a.tiles_per_ticket - 1) / a.tiles_per_ticket;
+            g.h16_ready = true;
+        }
         uint32_t grid = 0;
-        rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
-        h->ts.launched(tiles, grid);
+        rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), claims, s, &grid, span_begin, span_end); if (rc) return rc;
+        h->ts.launched(claims, grid);
     }
     h->launches++;
     h->mark(1, s);
