@@ -6,15 +6,20 @@
 
 Workload (BASELINE.json north_star / SURVEY.md 8d): 64-byte tuples of the seeded synthetic stream, batch 65536,
 65536 uniform keys, map (ivalue += 2, fvalue *= 1.0000001) -> filter ((ivalue & 1) == 0) -> count-based sliding
-windows win 4096 / slide 64, lift {isum, fsum}, comb +. A *step* is one stream segment of `--batches-per-step`
+windows win 4096 / slide 64, Nb 65, lift {isum, fsum}, comb +. A *step* is one stream segment of `--batches-per-step`
 consecutive batches handed to the operator in one call (the operator coalesces queued batches; one launch sequence
-per segment). Input segments are resident in HBM in a ring larger than L2; the window state is primed (untimed) so
-that every timed step is steady state (each key fires one window per 64 surviving tuples).
+per segment). Every step reads a DIFFERENT segment of the stream, resident in HBM (no segment is replayed inside the
+timed region; each is larger than L2). The window state is primed (untimed): every key is past its first trigger and
+the keys' trigger phases are spread evenly over the trigger period, so every timed step fires the same expected number
+of windows (keys / 65 groups of 65) whatever K and N are.
 
-One JSON line is printed by rank 0 (see the contract in the task statement): value = whole-job tuples/s with
-inputs resident in HBM, e2e = the same through the public call with HOST (pinned) buffers, host<->device copies
-inside the timed region, roofline = dominant kernel against the measured HBM peak, cpu_baseline = the reference's
-CPU path (oracle port / reference FlatFAT) timed on this box's cores on a bounded steady-state sample.
+One JSON line is printed by rank 0 (see the contract in the task statement): value = whole-job tuples/s with inputs
+resident in HBM; e2e = the same through the public call with HOST (pinned) buffers, host<->device copies inside the
+timed region; roofline = the whole pipeline against the measured HBM peak with SURVEY 8d's bytes per tuple (+ the
+per-kernel table); cpu_baseline = the reference's own CPU pipeline timed on this box's cores on a bounded sample;
+gpu_reference = the reference's own GPU operators (unmodified headers compiled for sm_100a) on this box; facade = the
+same pipeline driven through the builder API (include/wf/windflow_gpu.hpp) for K queued batches per call; check =
+window results of a sample of keys at this exact configuration against an independent reconstruction of their history.
 """
 import argparse
 import json
@@ -36,11 +41,20 @@ WIN, SLIDE = 4096, 64
 MAP = dict(map_kind=1, iadd=2, fscale=1.0000001)
 FILT = dict(filt_kind=1, mod=1)
 SIGMA = 0.5  # selectivity of (ivalue & 1) == 0 on the synthetic stream
+CHECK_STEPS = 2
+CHECK_KEYS = 48
 
-# algorithmic bytes. SURVEY 8d pipeline figure and the dominant kernel's own compulsory traffic.
+# algorithmic bytes per input tuple (SURVEY.md 8d / DESIGN.md section 4)
 METRIC = "tuples/sec, Map_GPU->Filter_GPU->Ffat_Windows_GPU (CB win 4096 slide 64) pipeline"
 PIPELINE_BYTES_PER_TUPLE = 123.3        # read I + sigma*(3R + (O+12R)/S), I=72 R=32 O=40 S=64
-INGEST_BYTES_PER_TUPLE = 64 + SIGMA * (32 + 4)   # k_tile_pass<INGEST>: read tuple, write sigma*(lifted result + slot)
+KERNEL_BYTES_PER_TUPLE = {              # compulsory traffic of each phase of one call, per input tuple
+    "tile_pass (map, filter, lift, key->slot)": 64 + SIGMA * (32 + 4),      # read tuple; write sigma * (lifted result + slot)
+    "partition (per-tile counts -> offsets -> scatter)": SIGMA * (4 + 8),    # read sigma slots; write sigma (slot, position) pairs
+    "window update + queries": SIGMA * (8 + 32 + (32 + 8 + 7 * 64 + 8 * 32) / 64 + (40 + 12 * 32) / 64),  # pairs + records; per pane: state, leaf, path; windows
+}
+REF_CPU = os.path.join(ROOT, "oracle", "_ref", "ref_pipeline_cpu")
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "ref_pipeline_gpu")
+FACADE_APP = os.path.join(ROOT, "windflow_b200", "apps", "pipeline_bench.bin")
 
 
 def measured_peaks():
@@ -54,14 +68,21 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    """dram bytes per launch of the kernels from the committed ncu captures (profiles/traffic.json), or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             return json.load(open(p))
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -112,15 +133,39 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's CPU Map -> Filter -> Ffat_Windows path on the host cores
+# CPU arm: the reference's own CPU pipeline (Source -> Map -> Filter -> Ffat_Windows, PipeGraph) on the host cores
 # ----------------------------------------------------------------------------------------------------------
-def cpu_pipeline(kind, threads, target_seconds, keys_per_thread=64):
-    """Bounded steady-state sample: `threads` replicas, each a keyby shard owning `keys_per_thread` keys and fed its own
-    (already routed) tuple64 stream; state primed until every key fires windows, then timed. Returns (tuples/s, desc)."""
+def cpu_reference_sample(target_seconds, nb):
+    """One bounded sample of the bench workload through the UNMODIFIED reference (oracle/_ref/ref_pipeline_cpu: wf/windflow.hpp
+    compiled from /root/reference over include/ff/): Source -> Map(par) -> Filter(par) -> Ffat_Windows(par, keyby) -> Sink,
+    65536 uniform keys, win 4096 / slide 64. Returns (tuples/s, threads, kind, description)."""
+    cores = host_cores()
+    if os.path.exists(REF_CPU):
+        par = max(1, (cores - 2) // 2)  # 1 source + par (map+filter chained) + par ffat + 1 sink threads = the cores we may use
+        n = 1 << 21
+        # calibrate on one pass over 2 Mi tuples, then size the sample for the time budget
+        def run(reps):
+            p = subprocess.run([REF_CPU, "cpu_cb", f"gen={n}", f"keys={NKEYS}", f"win={WIN}", f"slide={SLIDE}", f"par={par}", f"reps={reps}"],
+                               capture_output=True, text=True, timeout=900)
+            if p.returncode != 0:
+                raise RuntimeError("ref_pipeline_cpu failed: " + p.stderr[-500:])
+            return json.loads(p.stdout.strip().splitlines()[-1])
+        r = run(1)
+        reps = int(max(1, min(64, target_seconds / max(r["seconds"], 1e-3))))
+        if reps > 1:
+            r = run(reps)
+        desc = (f"the reference's own PipeGraph (wf/windflow.hpp unmodified, FastFlow API from include/ff/): Source(1) -> Map({par}) -> Filter({par}) -> "
+                f"Ffat_Windows({par}, keyby, CB {WIN}/{SLIDE}) -> Sink(1), {r['threads']} threads on {cores} usable cores; first {r['tuples']} tuples of the "
+                f"stream, {NKEYS} uniform keys: the per-tuple FlatFAT inserts are paid, no window has fired yet (a key needs {WIN} tuples: "
+                f"{WIN * NKEYS * 2} tuples of this stream, hours at this rate); {r['seconds']:.1f} s")
+        return r["tuples_per_s"], r["threads"], "reference", desc
+    # the reference was not compiled here: the oracle's restatement, one key shard per Python thread (ctypes releases the GIL)
     from oracle import oracle as O
+    threads = max(1, cores)
+    kpt = max(1, NKEYS // threads)
     n_buf = 1 << 18
-    bufs = [O.gen_tuple64(s * n_buf, n_buf, O.KEY_UNIFORM, keys_per_thread) for s in range(threads)]
-    pipes = [O.CpuPipe(kind, 1, 2, 1.0000001, 1, 1, WIN, SLIDE, 0, 1) for _ in range(threads)]
+    bufs = [O.gen_tuple64(s * n_buf, n_buf, O.KEY_UNIFORM, kpt) for s in range(threads)]
+    pipes = [O.CpuPipe("port", 1, 2, 1.0000001, 1, 1, WIN, SLIDE, 0, 1) for _ in range(threads)]
 
     def run_all(reps):
         def work(p, buf):
@@ -133,26 +178,13 @@ def cpu_pipeline(kind, threads, target_seconds, keys_per_thread=64):
         for t in th:
             t.join()
         return time.perf_counter() - t0
-
-    prime_reps = int(np.ceil(WIN * keys_per_thread / SIGMA / n_buf)) + 1   # every key past its first window
-    run_all(prime_reps)
     dt1 = run_all(1)
     reps = max(1, int(target_seconds / max(dt1, 1e-3)))
-    w0 = sum(p.windows for p in pipes)
     dt = run_all(reps)
-    nwin = sum(p.windows for p in pipes) - w0
     for p in pipes:
         p.close()
-    tps = reps * n_buf * threads / dt
-    desc = (f"{threads} replica threads x {reps} x {n_buf} tuple64 (each thread = one keyby shard with {keys_per_thread} uniform keys, "
-            f"already routed; win {WIN} slide {SLIDE}; state primed to steady state; {nwin} windows in the timed sample); "
-            f"{'reference wf/flatfat.hpp under the restated FFAT_Replica loop' if kind == 'reference' else 'oracle port of map.hpp/filter.hpp/ffat_replica.hpp/flatfat.hpp'}")
-    return tps, desc
-
-
-def best_cpu_kind():
-    from oracle import oracle as O
-    return "reference" if O.ref_cpu_lib() is not None else "port"
+    return reps * n_buf * threads / dt, threads, "port", (f"oracle port of map.hpp/filter.hpp/ffat_replica.hpp/flatfat.hpp, {threads} threads x {kpt} keys "
+                                                         f"({threads * kpt} keys in all), pre-routed streams, {reps} x {n_buf} tuples per thread")
 
 
 def run_reference(args):
@@ -160,30 +192,94 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    kind = best_cpu_kind()
-    threads = min(os.cpu_count() or 1, 128)
-    per_step = 12.0 / max(1, args.steps + args.warmup)
-    vals = []
-    desc = ""
+    per_step = 60.0 / max(1, args.steps + args.warmup)
+    vals, desc, threads, kind = [], "", 0, "reference"
     for i in range(args.warmup + args.steps):
-        tps, desc = cpu_pipeline(kind, threads, max(1.0, per_step))
+        tps, threads, kind, desc = cpu_reference_sample(max(2.0, min(10.0, per_step)), args.nb)
         if i >= args.warmup:
             vals.append(tps)
     v = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": v,
         "unit": "tuples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (1 << 18) * threads / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * BATCH * args.batches_per_step / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "i64+f64", "data": "synthetic",
         "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES, "keys": NKEYS, "key_dist": "uniform",
                    "win": WIN, "slide": SLIDE, "wins_per_batch": args.nb, "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0",
                    "selectivity": SIGMA,
-                   "note": "the reference's CPU Map->Filter->Ffat_Windows path on this box's host cores (all of them); every step is a "
-                           "bounded steady-state sample of the same stream"},
+                   "note": "the reference's CPU Map->Filter->Ffat_Windows pipeline on this box's host cores; every step is a bounded sample of "
+                           "the same stream (wins_per_batch is a GPU-operator parameter: the CPU operator emits every window on its own); "
+                           "values of the steps: " + ", ".join(f"{x / 1e6:.2f}M" for x in vals)},
         "cpu_baseline": {"value": v, "unit": "tuples/s", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the stream the GPU arm feeds: every segment is logged so that the check can rebuild the history of a few keys
+# ----------------------------------------------------------------------------------------------------------
+def stagger_rounds(world):
+    """Untimed priming rounds that spread the keys' trigger phases: round r feeds one pane (64 surviving tuples) to the keys
+    < NKEYS (r+1)/65, so key k ends up 65 - floor(65 k / NKEYS) panes ahead -- uniformly spread over the period of 65 panes."""
+    rounds = []
+    for r in range(65):
+        nk = max(1, NKEYS * (r + 1) // 65)
+        n = int(np.ceil(SLIDE / SIGMA * nk / (BATCH * world))) * BATCH  # per rank, whole batches
+        rounds.append((nk, n))
+    return rounds
+
+
+def expected_windows_for_keys(hist, keys, O, nb):
+    """Independent reconstruction: `hist` = the segments fed so far in global stream order, each (start, n, nkeys_gen, first_wm,
+    tag). Returns {key: (ivals, fvals, wms)} of the key's surviving tuples in arrival order (wm = watermark of the tuple's batch)."""
+    sel = np.zeros(NKEYS, dtype=np.uint8)
+    sel[keys] = 1
+    acc = {int(k): ([], [], []) for k in keys}
+    for (start, n, nk, wm0, _tag) in hist:
+        s = sel[:nk] if nk < NKEYS else sel
+        k, idx, iv, fv = O.scan_keys(start, n, O.KEY_UNIFORM, nk, np.ascontiguousarray(s))
+        wm = wm0 + ((idx - start) // BATCH) * BATCH
+        for key in np.unique(k):
+            m = k == key
+            a = acc[int(key)]
+            a[0].append(iv[m]); a[1].append(fv[m]); a[2].append(wm[m])
+    return {k: (np.concatenate(v[0]) if v[0] else np.zeros(0, np.int64), np.concatenate(v[1]) if v[1] else np.zeros(0),
+                np.concatenate(v[2]) if v[2] else np.zeros(0, np.uint64)) for k, v in acc.items()}
+
+
+def check_results(hist, n_before, got, keys, O, nb, check_ts):
+    """got: structured results (key, id, isum, fsum, ts) the operator produced for `keys` in the check steps. Expected: the groups
+    whose triggering tuple (count B + g*slide*nb) arrived in the check steps (tuples after the first n_before[key] ones)."""
+    B = (nb - 1) * SLIDE + WIN
+    per = SLIDE * nb
+    full = expected_windows_for_keys(hist, keys, O, nb)
+    compared, bad = 0, []
+    for key in keys:
+        iv, fv, wm = full[int(key)]
+        c0, c1 = n_before[int(key)], len(iv)
+        g_lo = 0 if c0 < B else (c0 - B) // per + 1          # first group whose trigger count is > c0
+        exp = []
+        g = g_lo
+        while B + g * per <= c1:
+            trig = B + g * per                                # 1-based count of the triggering tuple
+            for j in range(nb):
+                w = g * nb + j
+                a, b = w * SLIDE, w * SLIDE + WIN
+                exp.append((w, int(iv[a:b].sum()), float(np.sum(fv[a:b])), int(wm[trig - 1])))
+            g += 1
+        mine = got[got["key"] == key]
+        mine = mine[np.argsort(mine["id"])]
+        if len(mine) != len(exp):
+            bad.append(f"key {key}: {len(mine)} windows, expected {len(exp)}")
+            continue
+        for r, e in zip(mine, exp):
+            ok = int(r["id"]) == e[0] and int(r["isum"]) == e[1] and abs(float(r["fsum"]) - e[2]) <= 1e-6 * abs(e[2]) and (not check_ts or int(r["ts"]) == e[3])
+            if not ok:
+                bad.append(f"key {key} window {e[0]}: got {(int(r['id']), int(r['isum']), float(r['fsum']), int(r['ts']))} expected {e}")
+                break
+        compared += len(exp)
+    return compared, bad
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -192,7 +288,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from windflow_b200 import build, ops
+    from windflow_b200 import build, ops, multigpu
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,25 +303,28 @@ def run_ours(args):
 
     bps = args.batches_per_step
     seg_tuples = bps * BATCH
-    ring = max(2, args.ring)
     nb = args.nb
     B = (nb - 1) * SLIDE + WIN
     f = ops.functors(**MAP, **FILT)
     pipelined = args.pipeline
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    do_check = not args.no_check
 
-    # ---- input ring, resident in HBM (larger than L2: ring * seg_tuples * 64 B) ---------------------------------
-    # N = 1: one fused call per segment. N > 1: rank r owns the K batches [r*K, (r+1)*K) of every
-    # global step, Map->Filter, partition by key % N, NCCL all-to-all, windows on the rank's key shard.
-    from windflow_b200 import multigpu
-    segs_whole, segs = [], []
-    for r in range(ring):
-        start = multigpu.owner_span(r, rank, world, seg_tuples)[0]
-        b = ops.gen_tuple64(start, seg_tuples, ops.KEY_UNIFORM, NKEYS)
+    # ---- the stream: global step t covers world * seg_tuples consecutive indices, rank r owns [(t*world + r) * seg_tuples, +seg_tuples) ----
+    hist = []          # every segment fed to the operator, global stream order: (start, n, nkeys of the generator, first watermark, tag)
+
+    def gen_segment(start, n, nkeys=NKEYS):
+        b = ops.gen_tuple64(start, n, ops.KEY_UNIFORM, nkeys)
         b.watermark = start
-        segs_whole.append(b)
-        segs.append(ops.Segment([ops.DeviceBatch(b.tuples[i * BATCH * 64:(i + 1) * BATCH * 64], b.ts[i * BATCH:(i + 1) * BATCH], BATCH,
-                                                 watermark=start + i * BATCH) for i in range(bps)]))
-    torch.cuda.synchronize()
+        seg = ops.Segment([ops.DeviceBatch(b.tuples[i * BATCH * 64:(i + 1) * BATCH * 64], b.ts[i * BATCH:(i + 1) * BATCH], BATCH, watermark=start + i * BATCH)
+                           for i in range(n // BATCH)])
+        ops._cbatches(seg)  # the C descriptors of the segment's batches, built now (a C++ replica fills them in a microsecond; ctypes needs ~0.2 ms)
+        return b, seg
+
+    def log(step_index, n, nkeys, tag, base=0):
+        for r in range(world):
+            start = base + (step_index * world + r) * n
+            hist.append((start, n, nkeys, start, tag))
 
     if world == 1:
         ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=NKEYS, dense_keys=True, pipelined=pipelined)
@@ -238,47 +337,81 @@ def run_ours(args):
     out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def process_device_segment(whole, batches):
+    def feed(whole, batches):
         if pipe is None:
             ff.process(batches, pre=f, out=out, out_ts=out_ts, n_out=n_out)
         else:
             pipe.step(batches, whole.watermark, out, out_ts, n_out)
 
-    def step(i):
-        process_device_segment(segs_whole[i % ring], segs[i % ring])
-
-    def launches_now():
-        return ff.launches + (pipe.eng.launches if pipe is not None else 0)
-
-    # ---- prime the window state (untimed setup): every key past its first trigger --------------------------------
+    # ---- prime the window state (untimed setup): every key past its first trigger, phases spread over the period -------------------
+    STAG_BASE = 1 << 44   # the stagger rounds draw from a far-away part of the index space (their own, logged, segments)
+    t_step = 0            # global step counter of the main stream
     prime = int(np.ceil(B * NKEYS / SIGMA / (seg_tuples * world))) + 2
     if args.prime_steps >= 0:
         prime = args.prime_steps  # profiling runs only: the timed steps are then NOT steady state
+    scratch = None
     for i in range(prime):
-        step(i)
+        scratch = gen_segment(multigpu.owner_span(t_step, rank, world, seg_tuples)[0], seg_tuples)
+        feed(*scratch); log(t_step, seg_tuples, NKEYS, "prime"); t_step += 1
+    stag_off = 0
+    if args.prime_steps < 0:
+        for (nk, n) in stagger_rounds(world):
+            start = STAG_BASE + stag_off + rank * n
+            scratch = gen_segment(start, n, nk)
+            feed(*scratch)
+            for r in range(world):
+                s = STAG_BASE + stag_off + r * n
+                hist.append((s, n, nk, s, "stagger"))
+            stag_off += world * n
     torch.cuda.synchronize()
-    it = prime
-    for _ in range(args.warmup):
-        step(it); it += 1
+    del scratch
+
+    # ---- the segments of the measured part, resident in HBM before the clock starts (each one read once) ------------------------------
+    n_main = args.warmup + args.steps + e2e_steps + (CHECK_STEPS if do_check else 0)
+    ring = min(n_main, max(4, args.ring))
+    segs = [gen_segment(multigpu.owner_span(t_step + i, rank, world, seg_tuples)[0], seg_tuples) for i in range(ring)]
+    replay = n_main > ring  # (only with --steps beyond the ring: segments then repeat, with their original indices)
     torch.cuda.synchronize()
-    windows_per_step = int(n_out.item())
+
+    t0_main = t_step
+    cur = {"j": 0}
+
+    def log_main(jj, tag):  # the jj-th step of the measured part reads segs[jj % ring], generated for global step t0_main + jj % ring
+        log(t0_main + (jj % ring), seg_tuples, NKEYS, tag)
+
+    def step(tag="main"):   # next step of the measured part
+        jj = cur["j"]
+        feed(*segs[jj % ring])
+        log_main(jj, tag)
+        cur["j"] = jj + 1
+
+    def launches_now():
+        return ff.launches + (pipe.eng.launches if pipe is not None else 0)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    for _ in range(args.warmup):
+        step("warmup")
+    torch.cuda.synchronize()
+
     # ---- timed region: K steps, device-resident inputs ------------------------------------------------------------
     ff.timing(True)
     launches0 = launches_now()
     sampler = ClockSampler(local)
+    n_windows = torch.zeros(1, dtype=torch.int64, device=dev)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(it); it += 1
+        step("timed")
+        n_windows += n_out     # (a device-side add: the host does not wait)
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps  # host time to ISSUE a step (must stay below the device time of a step)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -289,71 +422,180 @@ def run_ours(args):
     if err:
         raise SystemExit(f"bench.py: device error flags {err}")
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    wins = n_windows.to(torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wins, op=dist.ReduceOp.SUM)
     ms_max = float(t_ms.item())
     value = world * args.steps * seg_tuples / (ms_max * 1e-3)
+    windows_timed = int(wins.item())
+    windows_expected = args.steps * world * seg_tuples * SIGMA / SLIDE  # steady state: one window per slide surviving tuples of a key
 
     # ---- e2e: the same call with HOST (pinned) buffers, copies inside the timed region ------------------------------
-    e2e = run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev, args, world, out, n_out)
+    e2e = run_e2e(torch, ops, feed, segs, ring, cur["j"], seg_tuples, bps, dev, e2e_steps, world, out, n_out)
+    for s_ in range(e2e_steps):
+        log_main(cur["j"] + s_, "e2e")
+    cur["j"] += e2e_steps
 
+    # ---- check: two more steps, the results of a sample of keys against an independent reconstruction of their history ---------------------
+    check = None
+    if do_check and not replay:
+        check = run_check(torch, dist, ops, ff, pipe, step, hist, out, out_ts, n_out, nb, rank, world, dev, pipelined or (pipe is not None and not args.sync_exchange))
     if pipe is not None:
         pipe.flush(out, out_ts, n_out)
         torch.cuda.synchronize()
     if rank == 0:
         peak, peak_src = measured_peaks()
-        ingest_ms_avg = ing_ms / max(1, calls)
-        achieved = INGEST_BYTES_PER_TUPLE * seg_tuples / (ingest_ms_avg * 1e-3) / 1e9
         traffic = ncu_traffic()
-        cpu_kind = best_cpu_kind()
-        cpu_threads = min(os.cpu_count() or 1, 32)
-        cpu_tps, cpu_desc = cpu_pipeline(cpu_kind, cpu_threads, args.cpu_seconds)
+        calls = max(1, calls)
+        phases = [("tile_pass (map, filter, lift, key->slot)", ing_ms / calls), ("partition (per-tile counts -> offsets -> scatter)", sort_ms / calls),
+                  ("window update + queries", upd_ms / calls)]
+        kernels = []
+        for name, avg_ms in phases:
+            bpt = KERNEL_BYTES_PER_TUPLE[name]
+            ach = bpt * seg_tuples / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+            kernels.append({"phase": name, "avg_us": avg_ms * 1e3, "algorithmic_bytes": bpt * seg_tuples, "ncu_dram_bytes": traffic.get(name),
+                            "achieved_gbs": ach, "frac": ach / peak})
+        pipe_gbs = value / world * PIPELINE_BYTES_PER_TUPLE / 1e9
+        cpu_tps, cpu_threads, cpu_kind, cpu_desc = cpu_reference_sample(args.cpu_seconds, nb)
         line = {
             "metric": METRIC,
             "value": value, "unit": "tuples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "host_issue_ms_per_step": host_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i64+f64", "data": "synthetic",
             "config": {"workload": "map_filter_ffat_cb", "batch": BATCH, "tuple_bytes": TUPLE_BYTES,
                        "batches_per_step": bps, "tuples_per_step_per_gpu": seg_tuples, "keys": NKEYS, "keys_per_gpu": NKEYS // world,
                        "key_dist": "uniform", "win": WIN, "slide": SLIDE, "wins_per_batch": nb,
                        "map": "ivalue+=2,fvalue*=1.0000001", "filter": "(ivalue&1)==0", "selectivity": SIGMA,
-                       "l2": f"inputs larger than L2: ring of {ring} segments x {seg_tuples * 64 / 1e6:.0f} MB",
-                       "state_primed_steps": prime, "windows_per_step_per_gpu": windows_per_step,
+                       "l2": f"inputs larger than L2 and read once: {ring} distinct segments x {seg_tuples * 64 / 1e6:.0f} MB resident in HBM" + (" (replayed: more steps than --ring)" if replay else ""),
+                       "state_primed_steps": prime, "phase_stagger_rounds": 65 if args.prime_steps < 0 else 0,
+                       "windows_in_timed_region": windows_timed, "windows_expected_steady_state": windows_expected,
                        "pipelined": args.pipeline if world == 1 else (not args.sync_exchange),
                        "parallelism": f"keyby{world}" + ("" if world == 1 else " (Map->Filter->lift + partition by key % N | NCCL all-to-all of 32-B results | Ffat on the key shard, records read in place)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm",
-                         "kernel": "k_tile_pass<ProgTuple64, MODE_INGEST>" if world == 1 else
-                                   "whole pipeline per GPU, SURVEY 8d bytes (the kernel-level roofline is the N=1 line: at N>1 the timed handle is the destination side)",
-                         "achieved": achieved if world == 1 else value / world * PIPELINE_BYTES_PER_TUPLE / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved if world == 1 else value / world * PIPELINE_BYTES_PER_TUPLE / 1e9) / peak,
-                         "traffic": (traffic or {}).get("ingest_dram_bytes_per_launch") if world == 1 else None,
-                         "peak_source": peak_src, "bytes_per_tuple": INGEST_BYTES_PER_TUPLE,
-                         "avg_launch_ms": ingest_ms_avg,
-                         "phase_ms_per_step": {"ingest": ing_ms / max(1, calls), "offsets+sort": sort_ms / max(1, calls),
-                                               "update": upd_ms / max(1, calls), "call": tot_ms / max(1, calls)},
-                         "pipeline": {"bytes_per_tuple": PIPELINE_BYTES_PER_TUPLE,
-                                      "achieved": value / world * PIPELINE_BYTES_PER_TUPLE / 1e9,
-                                      "frac": value / world * PIPELINE_BYTES_PER_TUPLE / 1e9 / peak}},
+            "roofline": {"bound": "hbm", "kernel": "whole pipeline (one call = tile pass + partition + window update + window queries), SURVEY 8d bytes per tuple",
+                         "achieved": pipe_gbs, "peak": peak, "unit": "GB/s", "frac": pipe_gbs / peak,
+                         "traffic": traffic.get("pipeline_dram_bytes_per_call"), "peak_source": peak_src,
+                         "bytes_per_tuple": PIPELINE_BYTES_PER_TUPLE, "avg_launch_ms": tot_ms / calls,
+                         "kernels": kernels if world == 1 else None,
+                         "note": None if world == 1 else "per GPU; the per-kernel table is on the N=1 line (at N>1 the timed handle is the destination side)"},
             "cpu_baseline": {"value": cpu_tps, "unit": "tuples/s", "cores": cpu_threads, "kind": cpu_kind, "sample": cpu_desc},
+            "check": check,
         }
+        if world == 1 and not args.no_extras:
+            line["gpu_reference"] = gpu_reference_sample(nb)
+            line["facade"] = facade_sweep(nb)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev, args, world, out, n_out):
+def run_check(torch, dist, ops, ff, pipe, step, hist, out, out_ts, n_out, nb, rank, world, dev, delayed):
+    """CHECK_STEPS more steps; the windows of CHECK_KEYS sampled keys produced in them are compared (key, window id, integer sum exact,
+    floating-point sum within 1e-6, result timestamp at N = 1) with sums over the keys' own tuples, rebuilt from the stream generator
+    for the WHOLE history (priming, stagger, warm-up, timed, e2e and check steps). All ranks call this."""
+    from oracle import oracle as O
+    res_dt = np.dtype([("key", "<u8"), ("id", "<u8"), ("isum", "<i8"), ("fsum", "<f8"), ("ts", "<u8")])
+    rng = np.random.default_rng(12345)
+    keys = np.unique(np.concatenate([[0, 1, NKEYS - 1, NKEYS // 2], rng.integers(0, NKEYS, CHECK_KEYS)])).astype(np.int64)
+    torch.cuda.synchronize()
+    if delayed:  # results arrive one call late: drain what is pending first, so that the check steps' results are exactly the ones collected
+        if pipe is not None:
+            pipe.flush(out, out_ts, n_out)
+        else:
+            ff.flush(out, out_ts, n_out)
+        torch.cuda.synchronize()
+    n_hist = len(hist)
+    got = []
+
+    def collect():
+        torch.cuda.synchronize()
+        r, t = ff.results_to_host(out, out_ts, n_out)
+        g = np.zeros(len(r), dtype=res_dt)
+        for fld in ("key", "id", "isum", "fsum"):
+            g[fld] = r[fld]
+        g["ts"] = t
+        got.append(g[np.isin(g["key"], keys)])
+    for _ in range(CHECK_STEPS):
+        step("check")
+        collect()
+    if delayed:
+        if pipe is not None:
+            pipe.flush(out, out_ts, n_out)
+        else:
+            ff.flush(out, out_ts, n_out)
+        collect()
+    mine = np.concatenate(got) if got else np.zeros(0, dtype=res_dt)
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0)
+        if rank != 0:
+            return None
+        mine = np.concatenate(gathered)
+    # history before the check steps -> tuples each sampled key had then; whole history -> the expected windows
+    before = expected_windows_for_keys(hist[:n_hist], keys, O, nb)
+    n_before = {int(k): len(before[int(k)][0]) for k in keys}
+    compared, bad = check_results(hist, n_before, mine, keys, O, nb, check_ts=(world == 1))
+    if bad:
+        raise SystemExit("bench.py --check FAILED: " + "; ".join(bad[:5]))
+    return {"passed": True, "keys_sampled": int(len(keys)), "windows_compared": int(compared), "steps": CHECK_STEPS,
+            "history_segments": len(hist), "fsum_rtol": 1e-6, "timestamps_compared": world == 1,
+            "how": "sums over each sampled key's own surviving tuples (arrival ranks [64 w, 64 w + 4096)), rebuilt from the stream generator over the whole history"}
+
+
+def gpu_reference_sample(nb):
+    """The reference's own GPU operators on this box: oracle/_ref/ref_pipeline_gpu = wf/windflow_gpu.hpp (Map_GPU -> Filter_GPU ->
+    Ffat_Windows_GPU, unmodified, nvcc -arch sm_100a) inside the reference's PipeGraph, on a bounded sample of the bench stream."""
+    if not os.path.exists(REF_GPU):
+        return {"unavailable": "oracle/_ref/ref_pipeline_gpu was not built (needs /root/reference at build time)"}
+    out = {}
+    try:
+        for tag, keys, n in (("bench_config_65536_keys", NKEYS, 1 << 20), ("64_keys", 64, 1 << 22)):
+            p = subprocess.run([REF_GPU, "gpu_cb", f"gen={n}", f"keys={keys}", f"batch={BATCH}", f"win={WIN}", f"slide={SLIDE}", f"nb={nb}"],
+                               capture_output=True, text=True, timeout=300)
+            if p.returncode != 0:
+                out[tag] = {"error": p.stderr[-300:]}
+                continue
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            out[tag] = {"value": r["tuples_per_s"], "unit": "tuples/s", "tuples": r["tuples"], "seconds": r["seconds"], "threads": r["threads"]}
+        out["what"] = ("the reference's Map_GPU -> Filter_GPU -> Ffat_Windows_GPU (wf/*.hpp unmodified, Thrust + its own kernels, sm_100a) in its own "
+                       "PipeGraph on this GPU; CPU source pushing tuple by tuple, batch 65536; the window operator loops over the distinct keys of "
+                       "every batch on the host (wf/ffat_replica_gpu.hpp:783-827)")
+    except Exception as e:  # pragma: no cover
+        out["error"] = repr(e)
+    return out
+
+
+def facade_sweep(nb):
+    """The same pipeline through the builder API (windflow_b200/apps/pipeline_bench.cu over include/wf/windflow_gpu.hpp): replicas on
+    threads, queues between them, the window replica taking up to K queued batches per call."""
+    if not os.path.exists(FACADE_APP):
+        return {"unavailable": "windflow_b200/apps/pipeline_bench.bin not built"}
+    rows = []
+    for k, timed in ((1, 2048), (4, 8192), (16, 16384), (64, 24576), (128, 32768)):
+        try:
+            p = subprocess.run([FACADE_APP, str(k), str(timed), str(NKEYS), str(nb)], capture_output=True, text=True, timeout=300)
+            if p.returncode != 0:
+                rows.append({"max_batches_per_call": k, "error": (p.stdout + p.stderr)[-300:]})
+                continue
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            rows.append({"max_batches_per_call": k, "value": r["tuples_per_s"], "unit": "tuples/s", "tuples": r["tuples"], "threads": r["threads"], "windows": r["windows"]})
+        except Exception as e:  # pragma: no cover
+            rows.append({"max_batches_per_call": k, "error": repr(e)})
+    return {"api": "facade", "what": "SourceGPU (ring of batches in HBM) -> Map_GPU -> Filter_GPU -> Ffat_Windows_GPU -> Sink built with the builders and "
+                                     "MultiPipe; Map and Filter are fused into the window operator's ingest pass; wall clock over the timed batches after priming",
+            "rows": rows}
+
+
+def run_e2e(torch, ops, feed, segs, ring, j0, seg_tuples, bps, dev, steps, world, out, n_out):
     """Same operator call(s), inputs start in pinned host memory every step; result count + results come back."""
     import torch.distributed as dist
-    steps = max(2, min(args.steps, args.e2e_steps))
     nbuf = 2
     host_t = [torch.empty(seg_tuples * 64, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
     host_ts = [torch.empty(seg_tuples, dtype=torch.int64).pin_memory() for _ in range(nbuf)]
-    for k in range(nbuf):  # the segments' bytes are copied out to the host once, untimed
-        host_t[k].copy_(segs_whole[k % len(segs_whole)].tuples); host_ts[k].copy_(segs_whole[k % len(segs_whole)].ts)
     dev_t = [torch.empty(seg_tuples * 64, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dev_ts = [torch.empty(seg_tuples, dtype=torch.int64, device=dev) for _ in range(nbuf)]
     host_n = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -363,7 +605,11 @@ def run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev
     main = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(nbuf)]
     freed = [torch.cuda.Event() for _ in range(nbuf)]
-    wm0 = segs_whole[0].watermark
+
+    def stage(k, s):  # the host side of the source: the step's segment sits in pinned host memory (copied out untimed)
+        whole = segs[(j0 + s) % ring][0]
+        host_t[k].copy_(whole.tuples); host_ts[k].copy_(whole.ts)
+        return whole.watermark
 
     def h2d(k):
         with torch.cuda.stream(copy_stream):
@@ -372,64 +618,70 @@ def run_e2e(torch, ops, process_device_segment, segs_whole, seg_tuples, bps, dev
             dev_ts[k].copy_(host_ts[k], non_blocking=True)
             ready[k].record(copy_stream)
 
-    def compute(k, step_idx):
+    def compute(k, wm):
         main.wait_event(ready[k])
-        wm = wm0 + step_idx * seg_tuples
         whole = ops.DeviceBatch(dev_t[k], dev_ts[k], seg_tuples, wm)
         batches = [ops.DeviceBatch(dev_t[k][i * BATCH * 64:(i + 1) * BATCH * 64], dev_ts[k][i * BATCH:(i + 1) * BATCH], BATCH,
                                    watermark=wm + i * BATCH) for i in range(bps)]
-        process_device_segment(whole, batches)
+        feed(whole, batches)
         freed[k].record(main)
         host_n.copy_(n_out, non_blocking=True)
 
-    d2h_bytes = 0
+    # the steps' segments are staged in host memory two at a time; the staging copy (device -> pinned) of step s+2 is NOT part of the
+    # stream's work and happens while the clock is stopped -- so the timed region is split per pair of steps
+    d2h_bytes, total_ms = 0, 0.0
     for k in range(nbuf):
         freed[k].record(main)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    h2d(0)
-    for s in range(steps):
-        k = s % nbuf
-        if s + 1 < steps:
-            h2d((s + 1) % nbuf)
-        compute(k, s)
-        main.synchronize()                       # the caller reads the step's result count ...
-        nres = int(host_n.item())
-        if nres:                                  # ... and the window results themselves
-            host_res[:nres * 32].copy_(out[:nres * 32], non_blocking=True)
-            d2h_bytes += nres * 32
-        d2h_bytes += 4
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    s = 0
+    while s < steps:
+        pair = min(nbuf, steps - s)
+        wms = [stage(k, s + k) for k in range(pair)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h2d(0)
+        for k in range(pair):
+            if k + 1 < pair:
+                h2d(k + 1)
+            compute(k, wms[k])
+            main.synchronize()                       # the caller reads the step's result count ...
+            nres = int(host_n.item())
+            if nres:                                  # ... and the window results themselves
+                host_res[:nres * 32].copy_(out[:nres * 32], non_blocking=True)
+                d2h_bytes += nres * 32
+            d2h_bytes += 4
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        s += pair
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     val = world * steps * seg_tuples / (float(t_ms.item()) * 1e-3)
     return {"value": val, "unit": "tuples/s", "h2d_bytes_per_step": seg_tuples * 72, "d2h_bytes_per_step": d2h_bytes // steps,
             "steps": steps, "note": "pinned host segment -> H2D (double-buffered on a copy stream) -> the operator call(s) "
-                                    "-> D2H of the result count and the window results"}
+                                    "-> D2H of the result count and the window results; timed in pairs of steps (the clock stops while the next "
+                                    "pair of segments is staged in host memory)"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=65)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batches-per-step", type=int, default=128, help="queued batches the replica hands to the operator per call (one stream segment)")
-    ap.add_argument("--ring", type=int, default=4)
+    ap.add_argument("--ring", type=int, default=96, help="distinct segments resident in HBM (more steps than this replay them)")
     ap.add_argument("--nb", type=int, default=65, help="withNumWinPerBatch")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--pipeline", action="store_true", help="WFB_FFAT_PIPELINED handle: results one call late, sort+update overlap the next ingest")
+    ap.add_argument("--pipeline", action="store_true", help="WFB_FFAT_PIPELINED handle: results one call late, partition+update overlap the next ingest")
     ap.add_argument("--sync-exchange", action="store_true", help="N > 1: exchange and window update of a step right after its source pass (no overlap with the next step)")
     ap.add_argument("--prime-steps", type=int, default=-1, help="override state priming (ncu runs); default: steady state")
+    ap.add_argument("--no-check", action="store_true", help="skip the result check of the sampled keys")
+    ap.add_argument("--no-extras", action="store_true", help="skip the gpu_reference and facade legs")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

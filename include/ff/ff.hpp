@@ -44,6 +44,7 @@ namespace ff {
 class ff_node;
 class ff_pipeline;
 class ff_a2a;
+class ff_group;
 
 namespace rt {
 
@@ -89,8 +90,9 @@ class ff_node {
     friend class ff_pipeline;
     friend class ff_a2a;
     friend class ff_comb;
+    friend class ff_group;
 protected:
-    enum kind_t { LEAF, COMB, PIPE, A2A };
+    enum kind_t { LEAF, COMB, PIPE, A2A, GROUP };
     rt::Worker *worker_ = nullptr; // set when the graph is flattened
     size_t pos_ = 0;               // position in the worker's chain
     bool skipfirstpop_ = false;
@@ -322,6 +324,21 @@ public:
     bool isMultiOutput() const override { return true; }
 };
 
+// Extension (not in FastFlow): the replicas of one operator as a pipeline stage -- every member is an input and an output of
+// the stage, so consecutive groups of a pipeline are connected all-to-all (what a matrioska of ff_a2a's expresses by nesting).
+class ff_group: public ff_node {
+    friend class ff_pipeline;
+    std::vector<ff_node *> members;
+    std::vector<ff_node *> cleanup_list;
+protected:
+    kind_t kind() const override { return GROUP; }
+public:
+    ~ff_group() override { for (auto *n : cleanup_list) delete n; }
+    void *svc(void *) override { return EOS; }
+    void add(ff_node *n, bool cleanup = false) { members.push_back(n); if (cleanup) cleanup_list.push_back(n); }
+    const std::vector<ff_node *> &getMembers() const { return members; }
+};
+
 class ff_pipeline: public ff_node {
     friend class ff_a2a;
     template <class T> friend int combine_with_firststage(ff_pipeline &, T *, bool);
@@ -345,6 +362,10 @@ protected:
                 if (firstStage) { e = se; firstStage = false; }
                 else { g.connect(e.outs, se.ins); e.outs = se.outs; }
             }
+            break;
+        }
+        case GROUP: {
+            for (auto *s : static_cast<ff_group *>(n)->getMembers()) { rt::Ends se = build(s, g); e.ins.insert(e.ins.end(), se.ins.begin(), se.ins.end()); e.outs.insert(e.outs.end(), se.outs.begin(), se.outs.end()); }
             break;
         }
         case A2A: {

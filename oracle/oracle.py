@@ -109,6 +109,23 @@ def gen_tuple64(start, n, key_mode=KEY_UNIFORM, nkeys=65536, seed=SEED, cdf=None
 # ---------------------------------------------------------------------------------------------------
 # Map / Filter (column-wise)
 # ---------------------------------------------------------------------------------------------------
+def scan_keys(start, n, key_mode, nkeys, sel, ia=2, fa=1.0000001, seed=SEED):
+    """Survivors (bench functors) of the keys marked in `sel` (uint8[nkeys]) among stream indices [start, start+n), in stream order:
+    (key, index, mapped ivalue, mapped fvalue) arrays. For the check of the full-size bench configuration."""
+    L = lib()
+    L.wfo_scan_keys.argtypes = [_u64, _u64, _u64, C.c_int, _u64, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _u64]
+    L.wfo_scan_keys.restype = _u64
+    sel = np.ascontiguousarray(sel, dtype=np.uint8)
+    cap = max(1024, int(n * (int(sel.sum()) + 1) / max(1, nkeys)) * 2 + 1024)
+    while True:
+        ok, oi = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+        ov, of = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.float64)
+        m = L.wfo_scan_keys(seed, start, n, key_mode, nkeys, _p(sel), ia, fa, _p(ok), _p(oi), _p(ov), _p(of), cap)
+        if m <= cap:
+            return ok[:m], oi[:m], ov[:m], of[:m]
+        cap = int(m) + 1024
+
+
 def map_cols(ival, fval, kind, ia=0, fa=1.0):
     ival = np.ascontiguousarray(ival, dtype=np.int64).copy()
     fval = None if fval is None else np.ascontiguousarray(fval, dtype=np.float64).copy()

@@ -70,6 +70,30 @@ void wfo_gen_tuple64(uint64_t seed, uint64_t start, uint64_t n, int key_mode, ui
     }
 }
 
+/* Survivors of a SAMPLE of keys in [start, start+n) of the synthetic stream after the bench functors (map kind 1: ivalue += ia,
+ * fvalue *= fa; filter kind 1: (ivalue & 1) == 0): for the check of the full-size bench configuration (bench.py --check), where
+ * replaying 10^9 tuples through the window oracle is not an option but the history of a few keys is cheap to rebuild from the
+ * generator. sel[k] != 0 marks a selected key (sel has nkeys_total entries). Outputs, in stream order: the key, the stream index,
+ * the mapped ivalue / fvalue. Returns the number of survivors found (at most cap are written). */
+uint64_t wfo_scan_keys(uint64_t seed, uint64_t start, uint64_t n, int key_mode, uint64_t nkeys, const uint8_t *sel, int64_t ia, double fa,
+                       uint64_t *out_key, uint64_t *out_idx, int64_t *out_ival, double *out_fval, uint64_t cap)
+{
+    uint64_t m = 0;
+    for (uint64_t j = 0; j < n; j++) {
+        const uint64_t i = start + j;
+        const uint64_t key = key_mode == 0 ? i % nkeys : splitmix64(i) % nkeys;
+        if (!sel[key]) continue;
+        const int64_t iv = (int64_t)(splitmix64(seed ^ i) & 0xFFFFull) + ia;
+        if (iv & 1) continue;
+        if (m < cap) {
+            out_key[m] = key; out_idx[m] = i; out_ival[m] = iv;
+            out_fval[m] = (double)(splitmix64(seed ^ ~i) >> 11) * (1.0 / 9007199254740992.0) * fa;
+        }
+        m++;
+    }
+    return m;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Map (map.hpp:174-190 in-place version; map_gpu.hpp:61-76 applies func to every item of the batch).
  * kind 0: identity; kind 1: ivalue += ia, fvalue *= fa (bench functor, and "+2" of

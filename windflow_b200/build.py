@@ -31,5 +31,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+APPS = os.path.join(HERE, "apps")
+INCLUDE = os.path.join(HERE, "..", "include")
+FACADE_HEADERS = [os.path.join(INCLUDE, "wf", "windflow_gpu.hpp"), os.path.join(INCLUDE, "ff", "ff.hpp"), os.path.join(INCLUDE, "wfb200.h")]
+
+
+def build_apps(force=False):
+    """Applications written against the builder API (include/wf/windflow_gpu.hpp), linked with libwfb200.so: the application's own
+    translation unit instantiates the kernels for its functors (nvcc, sm_100a)."""
+    build()
+    out = []
+    for src in sorted(f for f in os.listdir(APPS) if f.endswith(".cu")):
+        exe = os.path.join(APPS, src[:-3] + ".bin")
+        deps = [os.path.join(APPS, src), LIB] + FACADE_HEADERS + [os.path.join(CSRC, h) for h in HEADERS if not h.startswith("..")]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            cmd = [os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
+                   "--expt-extended-lambda", "-I" + INCLUDE, "-o", exe, os.path.join(APPS, src), "-L" + HERE, "-lwfb200", "-lpthread",
+                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."]
+            subprocess.check_call(cmd)
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

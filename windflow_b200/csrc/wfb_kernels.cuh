@@ -1409,7 +1409,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
     constexpr uint32_t DPT = OSW_DIGITS / BK_THREADS;                  // digit counts per thread
     constexpr uint32_t HS = BK_THREADS + 2;                            // row stride of the private counts (bank-conflict padding)
     constexpr uint32_t CPB = (RB % 16 == 0) ? 16 : 8;                  // cp.async granule of a record
-    constexpr uint32_t BK_SIBL = RB <= 32 ? 8 : (RB <= 64 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged in shared memory
+    constexpr uint32_t BK_SIBL = RB <= 32 ? 8 : (RB <= 48 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged in shared memory (static shared memory <= 48 KB)
     static_assert(DPT % 4 == 0 && BK_KEYS == 64 && BK_THREADS == 128 && RB % 8 == 0, "layout");
     __shared__ uint32_t s_idx[BK_CAP];                 // record index of the items (into `lifted`), key-major
     __shared__ __align__(16) uint16_t hist[BK_KEYS][HS]; // items of key k among thread t's items -> exclusive over the threads;
@@ -1807,30 +1807,33 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_ffat_update_stream: the window update as a STREAM per warp -- no in-bucket sort, no per-key runs, no block barriers in the
-// loop. One CTA (2 warps) per bucket of the wide partition; warp w owns the bucket's keys [32 w, 32 w + 32) and LANE k OF THE WARP
-// IS KEY 32 w + k: the key's count, open pane (accumulator in registers), next leaf and next trigger live in that lane's
-// registers for the whole kernel. Every warp reads the bucket's (slot, position) pairs in arrival order (128 per step, coalesced,
-// prefetched one step ahead; the two warps share the lines through L1), keeps the items of its own keys in a small shared-memory
-// queue and, whenever 32 are queued, takes them one per lane:
-//   - the 32 records are gathered straight away (32 independent 32-byte loads per warp in flight) and folded ONE STEP LATER, so the
-//     gather of batch j+1 overlaps the fold of batch j and the next pair reads;
-//   - five ballots turn the 32 item keys into one bit mask per key lane (the items of my key, ascending lane = arrival order);
-//     every key lane then pulls its items one per round with warp shuffles and folds them in order -- a batch of 32 items over 32
-//     keys takes 3-4 rounds of eight shuffles and one comb, with no shared-memory traffic at all;
-//   - a lane that completes a pane writes the FlatFAT leaf and recomputes the root path -- with the siblings of the first leaf each
-//     key completes staged in shared memory at kernel start (cp.async by the key's own lane), so the usual completion issues no
-//     dependent global load;
-//   - a fired group is deferred to k_ffat_windows; should the same key complete ANOTHER pane later in this call (it would
-//     overwrite ring leaves the deferred windows still read), the pending group is evaluated first by the whole warp and its list
-//     entry voided. No per-key item counts of the segment are needed for that decision (the bucket kernel counts them first).
+// k_ffat_update_stream: the window update as 32 independent STREAMS per warp -- no in-bucket sort, no per-key runs, no block
+// barriers in the loop. One CTA (2 warps) per bucket of the wide partition; warp w owns the bucket's keys [32 w, 32 w + 32) and
+// LANE k OF THE WARP IS KEY 32 w + k: the key's count, open pane (accumulator in registers), next leaf and next trigger live in
+// that lane's registers for the whole kernel, and the lane folds the key's items itself, in arrival order:
+//   producer  every warp reads the bucket's (slot, position) pairs in arrival order (128 per step, coalesced, prefetched one step
+//             ahead; the two warps share the lines through L1). The positions of the warp's own items go to PER-KEY FIFO queues in
+//             shared memory (match_any gives an item its rank among the group's items of the same key, the key lane's tail comes
+//             by shuffle): arrival order per key is queue order.
+//   consumer  in a round every lane pops the next position of ITS key, starts the copy of that record global -> shared (cp.async
+//             into a private 3-deep ring: no registers, no other lane involved) and folds the record it asked for three rounds ago
+//             into the open pane. All 32 lanes work on 32 different keys: a round costs ~40 warp instructions for up to 32
+//             items, and three gathers per lane are in flight. Rounds run whenever the queues hold two items per key on average.
+//   a lane that completes a pane writes the FlatFAT leaf and recomputes the root path -- with the siblings of the first leaf each
+//   key completes staged in shared memory at kernel start (cp.async by the key's own lane), so the usual completion issues no
+//   dependent global load; a fired group is deferred to k_ffat_windows; should the same key complete ANOTHER pane later in this
+//   call (it would overwrite ring leaves the deferred windows still read), the pending group is evaluated first by the whole warp
+//   and its list entry voided. No per-key item counts of the segment are needed for that decision (the bucket kernel counts first).
 // Built for panes of at least a few items (a pane per item would make every round a path update): the host selects
 // k_ffat_update_buckets otherwise.
 // ------------------------------------------------------------------------------------------------------
 #ifndef WFB_ST_MINBLOCKS
-#define WFB_ST_MINBLOCKS 8
+#define WFB_ST_MINBLOCKS 7
 #endif
-constexpr uint32_t ST_THREADS = 64, ST_WARPS = ST_THREADS / 32, ST_Q = 64;
+constexpr uint32_t ST_THREADS = 64, ST_WARPS = ST_THREADS / 32;
+constexpr uint32_t ST_QCAP = 32;   // positions a key's queue holds (a whole group of 32 items of one key fits an empty queue)
+constexpr uint32_t ST_FLY = 3;     // gathers in flight per lane
+constexpr uint32_t ST_BACKLOG = 64; // consumer rounds run while the warp's queues hold at least this many items (two per key: few idle lanes)
 constexpr uint32_t ST_NONE = 0xffffffffu;
 static_assert(ST_WARPS * 32 == BK_KEYS, "one key per lane");
 
@@ -1849,8 +1852,9 @@ __global__ void __launch_bounds__(ST_THREADS, WFB_ST_MINBLOCKS) k_ffat_update_st
     constexpr uint32_t CPB = (RB % 16 == 0) ? 16 : 8;
     constexpr uint32_t SIBL = RB <= 32 ? 8 : (RB <= 64 ? 4 : (RB <= 128 ? 2 : 1)); // FlatFAT levels whose siblings are staged
     static_assert(DPT % 4 == 0 && RB % 8 == 0, "layout");
-    __shared__ __align__(16) unsigned char s_sib[BK_KEYS * SIBL * RB];  // siblings of the leaf key k completes first (private to the key's lane)
-    __shared__ uint32_t q_lk[ST_WARPS][ST_Q], q_pos[ST_WARPS][ST_Q];
+    __shared__ __align__(16) unsigned char s_sib[BK_KEYS * SIBL * RB];          // siblings of the leaf key k completes first (private to the key's lane)
+    __shared__ __align__(16) unsigned char s_stage[ST_THREADS * ST_FLY * RB];   // records in flight: ST_FLY per lane (private to the lane)
+    __shared__ uint32_t q_pos[ST_THREADS][ST_QCAP + 1];                         // per-key FIFO of arrival positions (+1: bank-conflict padding)
     __shared__ uint32_t misc[ST_WARPS], s_boff[2];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1927,128 +1931,151 @@ __global__ void __launch_bounds__(ST_THREADS, WFB_ST_MINBLOCKS) k_ffat_update_st
             ffat_eval_window<P>(ff, e_tree, e_key, e_g * ff.nb + i, wm, e_obase + i, out_res, out_ts, out_cap, prm);
     };
 
-    // one batch of at most 32 queued items, one per lane (act: this lane holds one; lk: its key lane)
-    auto process = [&](bool act, uint32_t lk, uint32_t pos, const R &rec) {
-        uint32_t m = __ballot_sync(FULL, act);
+    // ---- consumer: one round. Every lane: fold the record it asked for ST_FLY rounds ago, pop the next position of its key, ask for it --
+    uint32_t q_head = 0, q_tail = 0;     // my key's queue (indices grow; entry i lives at i % ST_QCAP)
+    uint32_t total = 0;                  // items queued in the whole warp (warp-uniform)
+    uint32_t fly_pos0 = 0, fly_pos1 = 0, fly_pos2 = 0; // positions of my gathers in flight, oldest first
+    uint32_t fly_valid = 0;              // bit i: fly_pos<i> is a real gather
+    uint32_t round_no = 0;               // warp-uniform: the stage slot of this round is round_no % ST_FLY
+    static_assert(ST_FLY == 3, "three gathers in flight per lane");
+    unsigned char *const my_stage = s_stage + static_cast<size_t>(tid) * ST_FLY * RB;
+    uint32_t *const my_q = &q_pos[tid][0];
+    auto consume_round = [&]() {
+        cp_async_wait_group<ST_FLY - 1>(); // the copy committed ST_FLY rounds ago has landed (one group per round, empty or not)
+        unsigned char *slot = my_stage + (round_no % ST_FLY) * RB;
+        const bool folded = (fly_valid & 1u) != 0;
+        const uint32_t it_pos = fly_pos0;
+        if (folded) {
+            alignas(16) R it;
+            ld_rec<R>(slot, it);
+            if (cp == 0) acc = it; else P::comb(acc, it, acc, prm);
+            cp++; cons++;
+        }
+        fly_pos0 = fly_pos1; fly_pos1 = fly_pos2; fly_valid >>= 1;
+        const bool popped = q_head != q_tail;
+        if (popped) {
+            const uint32_t pos = my_q[q_head % ST_QCAP];
+            q_head++;
+            const unsigned char *src = lifted + static_cast<size_t>(pos) * RB;
 #pragma unroll
-        for (uint32_t b = 0; b < 5; b++) { const uint32_t B = __ballot_sync(FULL, act && ((lk >> b) & 1u)); m &= ((lane >> b) & 1u) ? B : ~B; }
-        // m: the lanes holding the items of MY key, ascending lane = arrival order
-        while (__any_sync(FULL, m != 0)) {
-            const bool has = m != 0;
-            const uint32_t j = has ? static_cast<uint32_t>(__ffs(m) - 1) : 0u;
-            m &= m - 1;
-            const R it = shfl_rec<R>(rec, j);
-            const uint32_t it_pos = __shfl_sync(FULL, pos, j);
-            const bool completes = has && cp + 1 == P32;
-            // a key about to complete a pane while a group of it is still deferred: evaluate that group before its leaves are overwritten
-            uint32_t ev = __ballot_sync(FULL, completes && pend != ST_NONE);
-            while (ev) {
-                const int src = __ffs(ev) - 1;
-                ev &= ev - 1;
-                const uint32_t ti = __shfl_sync(FULL, pend, src);
-                const Trigger tr = ff.trig[ti];
-                eval_group(tr.slot, tr.key, tr.g, tr.last_pos, tr.obase);
-                if (lane == static_cast<uint32_t>(src)) { ff.trig[ti].slot = INVALID_SLOT; pend = ST_NONE; } // k_ffat_windows skips voided entries
-                __syncwarp();
+            for (uint32_t q = 0; q < RB / CPB; q++) cp_async<CPB>(slot + q * CPB, src + q * CPB);
+            fly_pos2 = pos; fly_valid |= 1u << (ST_FLY - 1);
+        }
+        cp_async_commit();
+        round_no++;
+        total -= __popc(__ballot_sync(FULL, popped));
+        if (!__any_sync(FULL, folded && cp == P32)) return;
+        // ---- some key completed a pane (about once per round): leaf, root path, fired group --------------------------------------------------
+        const bool completes = folded && cp == P32;
+        // a key about to overwrite ring leaves while a group of it is still deferred: evaluate that group first
+        uint32_t ev = __ballot_sync(FULL, completes && pend != ST_NONE);
+        while (ev) {
+            const int src = __ffs(ev) - 1;
+            ev &= ev - 1;
+            const uint32_t ti = __shfl_sync(FULL, pend, src);
+            const Trigger tr = ff.trig[ti];
+            eval_group(tr.slot, tr.key, tr.g, tr.last_pos, tr.obase);
+            if (lane == static_cast<uint32_t>(src)) { ff.trig[ti].slot = INVALID_SLOT; pend = ST_NONE; } // k_ffat_windows skips voided entries
+            __syncwarp();
+        }
+        bool eval_now = false;
+        uint32_t ev_obase = 0; uint64_t ev_g = 0;
+        if (completes) {
+            cp = 0;
+            const uint32_t lf = leaf;
+            leaf = (leaf + 1) & (n - 1);
+            st_rec<R>(my_tree + static_cast<size_t>(lf) * RB, acc);
+            alignas(16) R cur = acc;
+            for (uint32_t l = 0; l < logn; l++) {
+                alignas(16) R sb;
+                if (staged && l < SIBL) ld_rec<R>(s_sib + (my_k * SIBL + l) * RB, sb);
+                else ld_rec<R>(my_tree + static_cast<size_t>(level_off(n, l) + ((lf >> l) ^ 1u)) * RB, sb);
+                alignas(16) R parent = cur;
+                if ((lf >> l) & 1u) P::comb(sb, cur, parent, prm); else P::comb(cur, sb, parent, prm);
+                cur = parent;
+                st_rec<R>(my_tree + static_cast<size_t>(level_off(n, l + 1) + (lf >> (l + 1))) * RB, cur);
             }
-            bool eval_now = false;
-            uint32_t ev_obase = 0; uint64_t ev_g = 0;
-            if (has) {
-                if (cp == 0) acc = it; else P::comb(acc, it, acc, prm);
-                cons++;
-                if (!completes) cp++;
-                else {
-                    cp = 0;
-                    const uint32_t lf = leaf;
-                    leaf = (leaf + 1) & (n - 1);
-                    st_rec<R>(my_tree + static_cast<size_t>(lf) * RB, acc);
-                    alignas(16) R cur = acc;
-                    for (uint32_t l = 0; l < logn; l++) {
-                        alignas(16) R sb;
-                        if (staged && l < SIBL) ld_rec<R>(s_sib + (my_k * SIBL + l) * RB, sb);
-                        else ld_rec<R>(my_tree + static_cast<size_t>(level_off(n, l) + ((lf >> l) ^ 1u)) * RB, sb);
-                        alignas(16) R parent = cur;
-                        if ((lf >> l) & 1u) P::comb(sb, cur, parent, prm); else P::comb(cur, sb, parent, prm);
-                        cur = parent;
-                        st_rec<R>(my_tree + static_cast<size_t>(level_off(n, l + 1) + (lf >> (l + 1))) * RB, cur);
-                    }
-                    staged = false; // the next pane of the key reads the tree this one has just written
-                    if (cons == tt) { // the group fires: Nb windows, evaluated after the update (k_ffat_windows)
-                        const uint32_t obase = atomicAdd(n_out, ff.nb);
-                        const uint32_t ti = atomicAdd(ff.n_trig, 1u);
-                        if (ti < ff.trig_cap) {
-                            Trigger tr; tr.key = key_of_slot(ff, my_slot); tr.g = g; tr.slot = my_slot; tr.last_pos = it_pos; tr.obase = obase; tr.pad = 0;
-                            ff.trig[ti] = tr;
-                            pend = ti;
-                        } else { eval_now = true; ev_obase = obase; ev_g = g; } // list full: evaluate here
-                        g++; tt += group_items;
-                    }
-                }
+            staged = false; // the next pane of the key reads the tree this one has just written
+            if (cons == tt) { // the group fires: Nb windows, evaluated after the update (k_ffat_windows)
+                const uint32_t obase = atomicAdd(n_out, ff.nb);
+                const uint32_t ti = atomicAdd(ff.n_trig, 1u);
+                if (ti < ff.trig_cap) {
+                    Trigger tr; tr.key = key_of_slot(ff, my_slot); tr.g = g; tr.slot = my_slot; tr.last_pos = it_pos; tr.obase = obase; tr.pad = 0;
+                    ff.trig[ti] = tr;
+                    pend = ti;
+                } else { eval_now = true; ev_obase = obase; ev_g = g; } // list full: evaluate here
+                g++; tt += group_items;
             }
-            uint32_t pd = __ballot_sync(FULL, eval_now);
-            while (pd) {
-                const int src = __ffs(pd) - 1;
-                pd &= pd - 1;
-                const uint32_t e_obase = __shfl_sync(FULL, ev_obase, src), e_pos = __shfl_sync(FULL, it_pos, src);
-                const uint64_t e_g = __shfl_sync(FULL, ev_g, src);
-                const uint32_t e_slot = key_lo + warp * 32u + static_cast<uint32_t>(src);
-                __syncwarp(); // the path nodes the source lane has just written
-                eval_group(e_slot, key_of_slot(ff, e_slot), e_g, e_pos, e_obase);
-                __syncwarp();
-            }
+        }
+        uint32_t pd = __ballot_sync(FULL, eval_now);
+        while (pd) {
+            const int src = __ffs(pd) - 1;
+            pd &= pd - 1;
+            const uint32_t e_obase = __shfl_sync(FULL, ev_obase, src), e_pos = __shfl_sync(FULL, it_pos, src);
+            const uint64_t e_g = __shfl_sync(FULL, ev_g, src);
+            const uint32_t e_slot = key_lo + warp * 32u + static_cast<uint32_t>(src);
+            __syncwarp(); // the path nodes the source lane has just written
+            eval_group(e_slot, key_of_slot(ff, e_slot), e_g, e_pos, e_obase);
+            __syncwarp();
         }
     };
 
-    uint32_t q_head = 0, q_tail = 0; // warp-uniform
-    bool have = false;
-    uint32_t p_lk = 0, p_pos = 0;
-    alignas(16) R p_rec;
-    uint32_t sl[4], ps[4];
+    // ---- the stream as ONE loop with one producer site and one consumer site (the consumer body is long: instantiating it at several call
+    // sites costs more in instruction-cache misses than it saves in branches) ---------------------------------------------------------
+    // producer: the bucket's pairs, 32 per step (loaded 128 at a time, one step ahead), into the per-key queues
+    uint32_t sl0, sl1, sl2, sl3, ps0, ps1, ps2, ps3;     // the 128 pairs being queued
+    uint32_t nsl0, nsl1, nsl2, nsl3, nps0, nps1, nps2, nps3; // the next 128, in flight
+    auto load4 = [&](uint32_t base, uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3, uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &p3) {
+        const uint32_t i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+        a0 = i0 < b1 ? bk_slots[i0] : INVALID_SLOT; a1 = i1 < b1 ? bk_slots[i1] : INVALID_SLOT;
+        a2 = i2 < b1 ? bk_slots[i2] : INVALID_SLOT; a3 = i3 < b1 ? bk_slots[i3] : INVALID_SLOT;
+        p0 = i0 < b1 ? bk_pos[i0] : 0u; p1 = i1 < b1 ? bk_pos[i1] : 0u; p2 = i2 < b1 ? bk_pos[i2] : 0u; p3 = i3 < b1 ? bk_pos[i3] : 0u;
+    };
+    load4(b0, nsl0, nsl1, nsl2, nsl3, nps0, nps1, nps2, nps3);
+    sl0 = sl1 = sl2 = sl3 = INVALID_SLOT; ps0 = ps1 = ps2 = ps3 = 0;
+    uint32_t next_base = b0;  // first pair of the 128 in nsl/nps
+    uint32_t u = 4;           // group of the current 128 to queue next (4: fetch the next 128)
+    bool stream_done = false; // every pair of the bucket has been queued
+#pragma unroll 1
+    for (;;) {
+        bool want_round = total >= ST_BACKLOG || (stream_done && (total != 0 || __any_sync(FULL, fly_valid != 0)));
+        if (!want_round) {
+            if (stream_done) break;
+            if (u == 4) { // the 128 pairs loaded a step ago become current; the following 128 start to fly
+                if (next_base >= b1) { stream_done = true; continue; }
+                sl0 = nsl0; sl1 = nsl1; sl2 = nsl2; sl3 = nsl3; ps0 = nps0; ps1 = nps1; ps2 = nps2; ps3 = nps3;
+                next_base += 128;
+                load4(next_base, nsl0, nsl1, nsl2, nsl3, nps0, nps1, nps2, nps3);
+                u = 0;
+            }
+            const uint32_t slu = u == 0 ? sl0 : (u == 1 ? sl1 : (u == 2 ? sl2 : sl3));
+            const uint32_t psu = u == 0 ? ps0 : (u == 1 ? ps1 : (u == 2 ? ps2 : ps3));
+            const uint32_t lkf = slu - key_lo; // (slots outside the bucket's keys, the padding included, wrap to large values)
+            const bool mine = lkf < kpc && (lkf >> 5) == warp;
+            const uint32_t lk = lkf & 31u;
+            const uint32_t mmask = __ballot_sync(FULL, mine);
+            if (mmask == 0) { u++; continue; }
+            // key-lane view: the group's items of MY key (five ballots transpose the item keys into one mask per key lane)
+            uint32_t m = mmask;
 #pragma unroll
-    for (uint32_t u = 0; u < 4; u++) {
-        const uint32_t i = b0 + u * 32 + lane;
-        sl[u] = i < b1 ? bk_slots[i] : INVALID_SLOT;
-        ps[u] = i < b1 ? bk_pos[i] : 0u;
-    }
-    for (uint32_t base = b0; base < b1; base += 128) {
-        uint32_t nsl[4], nps[4]; // the next step's pairs fly while this step's are queued and folded
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) {
-            const uint32_t i = base + 128 + u * 32 + lane;
-            nsl[u] = i < b1 ? bk_slots[i] : INVALID_SLOT;
-            nps[u] = i < b1 ? bk_pos[i] : 0u;
-        }
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) {
-            const uint32_t lk = sl[u] - key_lo; // (slots outside the bucket's keys, the padding included, wrap to large values)
-            const bool mine = lk < kpc && (lk >> 5) == warp;
-            const uint32_t bal = __ballot_sync(FULL, mine);
-            if (mine) { const uint32_t qi = (q_tail + __popc(bal & lanemask_lt())) % ST_Q; q_lk[warp][qi] = lk & 31u; q_pos[warp][qi] = ps[u]; }
-            q_tail += __popc(bal);
-            __syncwarp();
-            if (q_tail - q_head >= 32) {
-                const uint32_t qi = (q_head + lane) % ST_Q;
-                const uint32_t n_lk = q_lk[warp][qi], n_pos = q_pos[warp][qi];
-                q_head += 32;
-                alignas(16) R n_rec;
-                ld_rec<R>(lifted + static_cast<size_t>(n_pos) * RB, n_rec); // the gather of this batch flies while the previous one is folded
-                if (have) process(true, p_lk, p_pos, p_rec);
-                p_lk = n_lk; p_pos = n_pos; p_rec = n_rec; have = true;
-                __syncwarp(); // the popped queue entries may be overwritten now
+            for (uint32_t b = 0; b < 5; b++) { const uint32_t B = __ballot_sync(FULL, mine && ((lk >> b) & 1u)); m &= ((lane >> b) & 1u) ? B : ~B; }
+            const uint32_t incoming = __popc(m);
+            want_round = __any_sync(FULL, q_tail - q_head + incoming > ST_QCAP); // (a key that floods its queue: drain a round, then retry this group)
+            if (!want_round) {
+                // item-lane view: my rank among the group's items of my key, my key's tail
+                const uint32_t peers = __match_any_sync(FULL, mine ? lk : 32u + lane);
+                const uint32_t tail = __shfl_sync(FULL, q_tail, lk);
+                if (mine) q_pos[warp * 32u + lk][(tail + __popc(peers & lanemask_lt())) % ST_QCAP] = psu;
+                q_tail += incoming;
+                total += __popc(mmask);
+                u++;
+                __syncwarp(); // the queue entries are visible to the key lanes
+                continue;
             }
         }
-#pragma unroll
-        for (uint32_t u = 0; u < 4; u++) { sl[u] = nsl[u]; ps[u] = nps[u]; }
+        consume_round();
     }
-    if (have) process(true, p_lk, p_pos, p_rec);
-    if (q_tail != q_head) { // the last, partial batch
-        const bool act = lane < q_tail - q_head;
-        const uint32_t qi = (q_head + lane) % ST_Q;
-        const uint32_t n_lk = act ? q_lk[warp][qi] : 0u, n_pos = act ? q_pos[warp][qi] : 0u;
-        alignas(16) R n_rec;
-        if (act) ld_rec<R>(lifted + static_cast<size_t>(n_pos) * RB, n_rec);
-        process(act, n_lk, n_pos, n_rec);
-    }
+    cp_async_wait_all();
     // ---- my key's state back -----------------------------------------------------------------------------------------------------------
     if (has_key && cons != 0) {
         ff.cnt[my_slot] = st_c + cons;
@@ -2113,9 +2140,12 @@ template <class P>
 __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const uint32_t *__restrict__ batch_off,
                                                       const DevBatch *__restrict__ batches, uint32_t nbatches,
                                                       unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts, uint32_t out_cap,
-                                                      const typename P::params_t prm)
+                                                      const typename P::params_t prm, uint32_t *__restrict__ n_out)
 {
     using R = typename P::result_t;
+    // the update kernels reserve output slots with atomicAdd(n_out, Nb) whether they fit or not: a count beyond the capacity is clamped
+    // here (the last kernel of the call) and flagged, so that *n_out is always the number of results actually written
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_out != nullptr && *n_out > out_cap) { *n_out = out_cap; atomicOr(ff.err_flags, 2u); }
     const uint32_t nt = min(*ff.n_trig, ff.trig_cap);
     const uint64_t total = static_cast<uint64_t>(nt) * ff.nb;
     const size_t tree_stride = static_cast<size_t>(2 * ff.n_leaves - 1) * sizeof(R);

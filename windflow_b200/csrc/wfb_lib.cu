@@ -195,23 +195,26 @@ struct RadixSorter {
         *rows = wideH;
         return 0;
     }
+    const uint16_t *rows_override = nullptr; // set by sort_wide for the duration of one call
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
                              uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
                              uint32_t skip_invalid, uint32_t region_stride, const uint32_t *h32, uint32_t cx)
     {
-        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride, h32, cx);
+        k_wide_scatter<K, RBYTES><<<tiles, OSW_THREADS, 0, s>>>(kin, kout, vout, n_ptr, n_host, shift, chunk_shift, rows_override ? rows_override : wideH, wideC, c, pin, pout, pbytes, skip_invalid, region_stride, h32, cx);
     }
     // payload_in / payload_out (optional): payload_bytes-sized records that travel with the elements (multiple of 8 bytes)
     template <class K>
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
                   unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0,
-                  bool h32_ready = false, bool h16_ready = false)
+                  bool h32_ready = false, bool h16_ready = false, uint16_t *h16_rows = nullptr)
     {
+        // h16_rows: the 16-bit rows the tile pass filed when they do not live in this sorter (a pipelined handle keeps one set per segment in flight)
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
         const bool prefix = h16_ready && ready_ctl && !few_bins;
+        rows_override = prefix ? h16_rows : nullptr;
         uint32_t tiles, chunk_shift, chunks;
         wide_geometry(cap, prefix, &tiles, &chunk_shift, &chunks);
         if (tiles > wide_tiles || chunks > wide_chunks) {
@@ -225,7 +228,7 @@ struct RadixSorter {
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
         const uint32_t *h32 = nullptr;
         if (prefix) { // the tile pass filed the 16-bit rows (wideH): chunk sums, then first output position of every (chunk, digit) + digit counts
-            k_wide_chunk_sums16<<<chunks, OSW_THREADS, 0, s>>>(wideH, tiles, chunk_shift, wideC);
+            k_wide_chunk_sums16<<<chunks, OSW_THREADS, 0, s>>>(h16_rows ? h16_rows : wideH, tiles, chunk_shift, wideC);
             k_wide_chunk_scan<<<1, OSW_DIGITS, 0, s>>>(wideC, chunks, c);
             launches++;
         } else if (h32_ready && ready_ctl && !few_bins) { // the producer of the keys counted the digits per tile: only the chunk sums are missing
@@ -378,6 +381,8 @@ struct SegScratch {
     bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
     bool h32_ready = false;       // the streaming pass filed the per-tile digit counts of the wide partition (sorter.wideH32)
     bool h16_ready = false;       // the tile pass filed them per wide tile as 16-bit rows (sorter.wideH), claiming 16 tiles per ticket
+    uint16_t *h16 = nullptr; uint32_t h16_tiles = 0; // pipelined handles: this segment's own rows (the next segment's tile pass files its rows while
+                                                     // this segment's partition still reads these)
     const unsigned char *lifted_src = nullptr; // records of this segment: `lifted`, or the caller's buffer (in-place ingest)
     uint32_t *seg_cnt = nullptr;          // per-slot item counts of the segment (max_keys)
     Trigger *trig = nullptr; uint32_t *n_trig = nullptr; uint32_t trig_cap = 0;
@@ -393,7 +398,7 @@ struct SegScratch {
     {
         cudaFree(lifted); cudaFree(lifted_sorted); cudaFree(slotsA); cudaFree(slotsB); cudaFree(posA); cudaFree(posB);
         cudaFree(batch_off); cudaFree(d_batches); cudaFree(n_total); cudaFree(seg_cnt); cudaFree(trig); cudaFree(sort_ctl);
-        cudaFree(res); cudaFree(res_ts); // n_trig and res_n live inside the n_total allocation
+        cudaFree(res); cudaFree(res_ts); cudaFree(h16); // n_trig and res_n live inside the n_total allocation
         if (ev_ingest) cudaEventDestroy(ev_ingest);
         if (ev_done) cudaEventDestroy(ev_done);
     }
@@ -1025,6 +1030,10 @@ static int tb_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, ui
     rc = h->ts.init(); if (rc) { wfb_ffat_destroy(h); return rc; }
     rc = wfb_ffat_create(&h->cb, lp, win_p, slide_p, nb, max_keys, 0, 0, flags & WFB_FFAT_DENSE_KEYS);
     if (rc) { wfb_ffat_destroy(h); return rc; }
+    // the front end hands the popped panes to the back end in place, with the slot of every record: that needs the bucket path with the
+    // in-place ingest (at most 65536 keys; not with the WFB_SPARSE=0 / WFB_INPLACE=0 / WFB_UPDATE=lanes / WFB_BUCKET_MOVE=1 knobs). Refuse here,
+    // before any pane has been consumed, rather than at the first firing batch
+    if (!h->cb->buckets || !h->cb->sparse_ingest || !h->cb->inplace_ok || h->cb->bucket_move) { wfb_ffat_destroy(h); return WFB_E_UNSUPPORTED; }
     // the back end never looks keys up (the front end hands it the slot of every record): it only needs slot -> key for the results
     if (!ff.dense) { cudaFree(h->cb->ff.slot_key); h->cb->ff.slot_key = ff.slot_key; h->cb->ff.n_slots = ff.n_slots; h->cb->shares_slot_key = true; }
     h->state_bytes = total + h->cb->state_bytes;
@@ -1232,7 +1241,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         // streaming update: one path update per completed pane inside the item loop, so panes of a few items at least
         h->stream_update = h->buckets && !h->bucket_move && (e && std::strcmp(e, "stream") == 0 ? true : (e && std::strcmp(e, "buckets") == 0 ? false : ff.pane >= 8));
         const char *t = std::getenv("WFB_TILE_H16");
-        h->tile_h16 = h->buckets && !h->pipelined && !(t && std::atoi(t) == 0); // (pipelined: the rows would be shared by two segments in flight)
+        h->tile_h16 = h->buckets && !(t && std::atoi(t) == 0);
     }
     h->state_bytes = total;
     *hh = h;
@@ -1274,6 +1283,10 @@ uint64_t wfb_ffat_state_bytes(const wfb_ffat_t *h) { return h ? h->state_bytes :
 int wfb_ffat_set_key_shard(wfb_ffat_t *h, uint32_t num_shards, uint32_t shard)
 {
     if (!h || num_shards == 0 || shard >= num_shards || !h->ff.dense || h->call_no != 0) return WFB_E_BADARG;
+    if (h->win_type == 1) { // time-based: the front end maps keys to slots, the back end turns slots back into keys for the results
+        if (h->cb == nullptr || h->cb->call_no != 0) return WFB_E_BADARG;
+        h->cb->ff.key_div = num_shards; h->cb->ff.key_rem = shard;
+    }
     h->ff.key_div = num_shards; h->ff.key_rem = shard;
     return 0;
 }
@@ -1324,7 +1337,7 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         const uint32_t *counts = nullptr;
         rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.sparse ? nullptr : g.n_total, g.total, g.total, h->bucket_shift, s,
                                            g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
-                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready, g.h16_ready);
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready, g.h16_ready, h->pipelined ? g.h16 : nullptr);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
@@ -1353,7 +1366,7 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         h->launches += h->ff.light_max ? 2 : 1;
     }
     // deferred window groups: one thread per window
-    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp());
+    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp(), n_out);
     if (rc) return rc;
     h->launches += 1;
     return 0;
@@ -1473,7 +1486,18 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
         if (sparse && fuse_hist && h->tile_h16 && !g.h32_ready) {
             // a CTA claims the 16 tiles of a wide tile at once, counts its digits in shared memory and files the row itself:
             // the partition that follows needs neither a counting pass nor the per-CTA global digit counts
-            rc = h->sorter.ensure_wide(g.total, s, &a.wide_h16); if (rc) return rc;
+            if (h->pipelined && (g.total + OSW_TILE - 1) / OSW_TILE > h->sorter.wide_tiles) CK(cudaStreamSynchronize(h->s2)); // (the rows are about to be re-allocated)
+            rc = h->sorter.ensure_wide(g.total, s, &a.wide_h16); if (rc) return rc; // (also sizes the chunk rows the partition needs)
+            if (h->pipelined) {
+                const uint32_t wt = (g.total + OSW_TILE - 1) / OSW_TILE;
+                if (wt > g.h16_tiles) {
+                    CK(cudaStreamSynchronize(s)); CK(cudaStreamSynchronize(h->s2));
+                    cudaFree(g.h16);
+                    g.h16_tiles = std::max(wt, 2 * g.h16_tiles);
+                    CK(cudaMalloc(&g.h16, sizeof(uint16_t) * OSW_DIGITS * g.h16_tiles));
+                }
+                a.wide_h16 = g.h16;
+            }
             a.tiles_per_ticket = OSW_TILE_POS / TILE;
             a.sort_ctl = nullptr; // (the chunk-sum kernel accumulates the global counts into g.sort_ctl, cleared above)
             claims = (tiles + a.tiles_per_ticket - 1) / a.tiles_per_ticket;

@@ -54,6 +54,8 @@ __device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); } // at most N groups of this thread pending
 
 // ---- L2 eviction-priority policies (createpolicy) and the TMA copies that carry them -----------------------------------
 __device__ __forceinline__ uint64_t l2_policy_evict_first()

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Batch as CBatch
+from ._lib import WfbError, Batch as CBatch
 from ._lib import Functors, check
 
 PROG_TUPLE64, PROG_WFTEST16, PROG_WFWIN24, PROG_LIFTED32 = 0, 1, 2, 3
@@ -246,7 +246,7 @@ class FfatWindowsGPU:
         self.L = _lib.lib()
         if self.L.wfb_device_count() <= 0:
             raise RuntimeError("windflow_b200: no CUDA device (there is no CPU fallback)")
-        self.prog, self.win, self.slide, self.nb = prog, win, slide, nb
+        self.prog, self.win, self.slide, self.nb, self.max_keys = prog, win, slide, nb, max_keys
         self.win_type = win_type  # 0 count-based, 1 time-based (win / slide / lateness in timestamp units)
         self.h = C.c_void_p()
         self.pipelined = pipelined
@@ -281,7 +281,7 @@ class FfatWindowsGPU:
     def max_results(self, n_items):
         """Upper bound on the results one call over n_items input items can produce (count-based windows; time-based
         callers size the output for the groups a watermark jump can complete)."""
-        return (n_items // max(1, self.slide * self.nb) + 65536) * self.nb
+        return (n_items // max(1, self.slide * self.nb) + self.max_keys + 1) * self.nb  # every key may fire one more group than its items alone account for
 
     def process(self, batches, pre=None, out=None, out_ts=None, n_out=None, stream=None):
         """One stream segment (list of DeviceBatch). Returns (out uint8 tensor, out_ts int64 tensor, n_out tensor)."""
@@ -318,6 +318,9 @@ class FfatWindowsGPU:
 
     def results_to_host(self, out, out_ts, n_out):
         n = int(n_out.item())
+        cap = out.numel() // self.res_dtype.itemsize
+        if n > cap or (n == cap and (self.stats()[1] & 2)):
+            raise WfbError(-3, "Ffat_Windows_GPU: more results than the output buffer holds (results were dropped)")
         return to_host(out, self.res_dtype)[:n].copy(), ts_to_host(out_ts)[:n].copy()
 
     def timing(self, enable=True):
