@@ -492,7 +492,11 @@ public:
             b->transfer2CPU(stream);
             for (size_t i = 0; i < b->size; i++) { std::optional<tuple_t> o(b->getTupleAtPos(i)); func(o); }
         }
-        if (wm_probe) { b->getSize(); wm_probe->store(b->getWatermark(), std::memory_order_release); }
+        if (wm_probe) { // the highest watermark finished so far (several sink replicas finish batches out of order)
+            b->getSize();
+            uint64_t wm = b->getWatermark(), cur = wm_probe->load(std::memory_order_relaxed);
+            while (cur < wm && !wm_probe->compare_exchange_weak(cur, wm, std::memory_order_release)) { }
+        }
         recycleBatch(b);
         return this->GO_ON;
     }

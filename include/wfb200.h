@@ -239,6 +239,10 @@ int wfb_ffat_timing(wfb_ffat_t *h, int enable, float *ms_h, uint32_t *calls_h);
 
 /* Number of distinct keys seen so far / error flags raised on the device (synchronises the stream). */
 int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, void *stream);
+/* Window results delivered by the handle since it was created (summed on the device by the last kernel of every call; synchronises
+ * the stream). Lets a caller account for results without reading *n_out_dev back after every call (the role of the
+ * outputs_sent counter of wf/stats_record.hpp:80-82). */
+int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream);
 
 /* ---- synthetic stream, generated on the device for tests and bench --------------------------
  * key_mode: 0 i % nkeys, 1 splitmix64(i) % nkeys, 2 zipf via zipf_cdf (device, nkeys doubles) */

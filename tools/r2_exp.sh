@@ -13,8 +13,6 @@ T stream WFB_UPDATE=stream
 T old WFB_UPDATE=buckets WFB_TILE_H16=0
 fi
 B default
-BARGS="--no-check" B buckets WFB_UPDATE=buckets
-BARGS="--no-check --ring 4" B ring4
-BARGS="--no-check --prime-steps 4" B noprime
-bash tools/prof_kernel.sh k_ffat_update_stream r2c_stream
-for K in 128 16 1; do timeout 300 windflow_b200/apps/pipeline_bench.bin $K $((K>8?20480:2048)) 2>&1 | tail -1; done
+BARGS="--no-check" B stream WFB_UPDATE=stream
+BARGS="--no-check --pipeline" B pipelined
+BARGS="--no-check --pipeline" B pipelined_ctas1 WFB_INGEST_CTAS_PER_SM=1

@@ -67,6 +67,7 @@ SYMBOLS = {
     "wfb_ffat_flush": (C.c_int, [vp, vp, vp, u32, vp, vp]),
     "wfb_ffat_timing": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(u32)]),
     "wfb_ffat_stats": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), vp]),
+    "wfb_ffat_results_total": (C.c_int, [vp, C.POINTER(C.c_uint64), vp]),
     "wfb_gen_tuple64": (C.c_int, [u64, u64, u32, C.c_int, u64, vp, vp, vp, vp]),
 }
 

@@ -7,7 +7,7 @@
 // built with the builders, wired with MultiPipe, every replica a thread of the runtime with a queue in front of it. The window
 // replica takes up to K queued batches per svc() (withMaxBatchesPerCall): K = 1 is the reference's one-batch-per-svc behaviour,
 // larger K is what a replica finds queued when the source is faster than one launch sequence.
-//   usage: pipeline_bench.bin [K=128] [timed_batches=40960] [keys=65536] [nb=65] [ring_batches=512]
+//   usage: pipeline_bench.bin [K=128] [timed_batches=40960] [keys=65536] [nb=65] [ring_batches=512] [sink_replicas=2]
 // prints one JSON line. Build: nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr
 //        --expt-extended-lambda -I include windflow_b200/apps/pipeline_bench.cu -L windflow_b200 -lwfb200
 #include <atomic>
@@ -35,6 +35,15 @@ struct KeyF { __host__ __device__ uint64_t operator()(const tuple64_t &t) { retu
 static std::atomic<uint64_t> g_seen_wm{0};      // watermark (= index of the last input batch) of the newest result batch the sink has seen
 static std::atomic<uint64_t> g_windows{0};
 static std::atomic<long long> g_isum{0};
+// every sink replica keeps its own totals and adds them to the global ones at end of stream (the reference's sinks are per-tuple functors too)
+struct SinkF {
+    uint64_t windows = 0; long long isum = 0;
+    void operator()(std::optional<result32_t> &r)
+    {
+        if (r) { windows++; isum += r->isum; }
+        else { g_windows.fetch_add(windows); g_isum.fetch_add(isum); }
+    }
+};
 
 int main(int argc, char **argv)
 {
@@ -43,6 +52,7 @@ int main(int argc, char **argv)
     const uint64_t nkeys = argc > 3 ? std::strtoull(argv[3], nullptr, 10) : 65536;
     const size_t nb = argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 65;
     const uint64_t ring = argc > 5 ? std::strtoull(argv[5], nullptr, 10) : 512; // 512 x 4 MiB = 2 GiB of input, far larger than L2
+    const size_t sinks = argc > 6 ? std::strtoull(argv[6], nullptr, 10) : 2;
     const uint64_t BATCH = 65536, WIN = 4096, SLIDE = 64;
     const uint64_t B = (nb - 1) * SLIDE + WIN;
     // every key past its first trigger before the clock starts: B surviving tuples per key at selectivity 0.5
@@ -67,7 +77,6 @@ int main(int argc, char **argv)
         drained(prime + timed);
         t1 = std::chrono::steady_clock::now();
     };
-    auto sink = [](std::optional<result32_t> &r) { if (r) { g_windows.fetch_add(1, std::memory_order_relaxed); g_isum.fetch_add(r->isum, std::memory_order_relaxed); } };
 
     size_t threads = 0;
     {
@@ -78,7 +87,7 @@ int main(int argc, char **argv)
         mp.add(Ffat_WindowsGPU_Builder(LiftF(), CombF()).withName("ffat").withKeyBy(KeyF()).withCBWindows(WIN, SLIDE).withNumWinPerBatch(nb)
                    .withMaxKeys(static_cast<uint32_t>(nkeys)).withDenseKeys().withMaxBatchesPerCall(K).build());
         // the sink also publishes how far the stream has been processed (the watermark of every result batch = its last input batch)
-        mp.chain_sink(Sink_Builder(sink).withName("sink").withWatermarkProbe(&g_seen_wm).build());
+        mp.chain_sink(Sink_Builder(SinkF()).withName("sink").withParallelism(sinks).withWatermarkProbe(&g_seen_wm).build());
         threads = graph.getNumThreads();
         graph.run();
     }

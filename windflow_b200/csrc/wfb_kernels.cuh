@@ -70,6 +70,7 @@ struct FfatDev {
     uint32_t max_keys;
     uint32_t *n_slots;         // number of keys inserted so far
     uint32_t *err_flags;       // bit0: key table full, bit1: output capacity exceeded
+    unsigned long long *results_total; // window results delivered so far (added by the last kernel of every call)
     uint32_t dense;            // 1: slot = key (keys < max_keys), or key / key_div for one shard of a keyby
     uint32_t key_div, key_rem; // dense: the handle owns the keys with key % key_div == key_rem (key_div <= 1: all keys)
     // per-slot state
@@ -93,6 +94,10 @@ struct FfatDev {
     uint32_t wp, sp;           // window / slide in panes
     uint32_t n_leaves;         // power of two >= B / P
     uint32_t log_leaves;
+    uint32_t lazy;             // 1: the update kernels only write the pane LEAVES of the key's FlatFAT; the internal levels a group of windows needs
+                               // are built in shared memory when the group is evaluated (k_ffat_windows_lazy). A pane completes once per
+                               // `pane` items but fires windows only once per slide * Nb items: maintaining log2(n) path nodes per pane in
+                               // global memory costs more than rebuilding n - 1 nodes on chip per fired group.
 };
 constexpr uint64_t EMPTY_KEY = 0xffffffffffffffffull;
 constexpr uint32_t INVALID_SLOT = 0xffffffffu;
@@ -118,6 +123,9 @@ struct TileArgs {
                                // the tile pass itself: with tiles_per_ticket = 16 a CTA owns whole wide tiles, counts their digits in shared
                                // memory and writes each row once -- the partition then needs no counting pass (k_wide_tile_hist) of its own
     uint32_t tiles_per_ticket; // consecutive tiles a producer claims per ticket (0 or 1: one; 16 with wide_h16)
+    uint32_t pack_rank;        // with wide_h16 and at most 65536 slots: slots[pos] = slot | rank << 16, rank = what the digit counter of the wide
+                               // tile held when this survivor was counted (any order among the survivors of one digit): k_wide_scatter_ranked
+                               // places the pairs with it and then restores arrival order inside every (wide tile, digit) cell
     const uint32_t *ext_slots; // MODE_INGEST + in-place: slot of the record at every position, given by the caller (the time-based
                                // front end knows the key slot of every pane it pops); the program's key extractor is not used
     uint32_t inplace;          // MODE_INGEST + sparse, 1: the program passes records through unchanged (lift = identity, no map) and the
@@ -469,7 +477,8 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
                     if (a.wide_h16 != nullptr) { // digit counts of this wide tile (the CTA owns all of its tiles)
                         if (slot != INVALID_SLOT) { // two 16-bit counters per word (a wide tile holds 4096 positions: no carry)
                             const uint32_t d = (slot >> a.sort_shift) & 1023u;
-                            atomicAdd(&s_hist[wpar * 512u + (d >> 1)], 1u << ((d & 1u) * 16u));
+                            const uint32_t before = atomicAdd(&s_hist[wpar * 512u + (d >> 1)], 1u << ((d & 1u) * 16u));
+                            if (a.pack_rank) slot |= ((before >> ((d & 1u) * 16u)) & 0xffffu) << 16; // (slot < 65536: the rank rides in the upper half)
                         }
                     } else if (a.sort_ctl != nullptr && !(a.sparse && slot == INVALID_SLOT)) { // digit counts for the radix passes over the slots (invalid slots sort last / are skipped)
                         for (uint32_t ps = 0; ps < a.sort_passes; ps++)
@@ -879,13 +888,9 @@ __global__ void __launch_bounds__(256) k_slots_inplace(const TileArgs a, const t
     using T = typename P::tuple_t;
     __shared__ uint32_t s_h[1024];
     const uint32_t tid = threadIdx.x;
-    const bool hist = a.sort_ctl != nullptr;
-    if (hist) for (uint32_t i = tid; i < 1024; i += blockDim.x) s_h[i] = 0;
-    if (blockIdx.x == 0 && tid == 0 && a.ff.n_trig != nullptr) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists of the update kernels
-    __syncthreads();
     const uint32_t npos = a.num_tiles * TILE;
-    const uint32_t dmask = (1u << a.sort_dbits) - 1u;
-    for (uint32_t p = blockIdx.x * blockDim.x + tid; p < npos; p += gridDim.x * blockDim.x) {
+    if (blockIdx.x == 0 && tid == 0 && a.ff.n_trig != nullptr) { *a.ff.n_trig = 0; *a.ff.n_heavy = 0; } // per-segment lists of the update kernels
+    auto slot_at = [&](uint32_t p) -> uint32_t {
         const uint32_t t = p / TILE;
         uint32_t lo = 0, hi = a.nbatches - 1; // last batch with tile_begin <= t
         while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (a.batches[mid].tile_begin <= t) lo = mid; else hi = mid - 1; }
@@ -898,11 +903,41 @@ __global__ void __launch_bounds__(256) k_slots_inplace(const TileArgs a, const t
                 const T *rec = reinterpret_cast<const T *>(b.tuples + static_cast<size_t>(local) * sizeof(T));
                 slot = slot_of_key(a.ff, P::key(*rec, prm));
             }
-            if (slot != INVALID_SLOT) {
-                if (a.count_keys) atomicAdd(&a.ff.seg_cnt[slot], 1u);
-                if (hist) atomicAdd(&s_h[(slot >> a.sort_shift) & dmask], 1u);
-                if (a.wide_h32 != nullptr) atomicAdd(&a.wide_h32[static_cast<size_t>(t / (OSW_TILE_POS / TILE)) * 1024u + ((slot >> a.sort_shift) & 1023u)], 1u);
+            if (slot != INVALID_SLOT && a.count_keys) atomicAdd(&a.ff.seg_cnt[slot], 1u);
+        }
+        return slot;
+    };
+    if (a.wide_h16 != nullptr) {
+        // a CTA owns whole wide tiles (4096 positions): digit counts in shared memory (two 16-bit counters per word), one row per wide tile,
+        // and -- TileArgs::pack_rank -- every slot leaves with the count its digit had when it was counted (k_wide_scatter_ranked)
+        const uint32_t nwide = (npos + OSW_TILE_POS - 1) / OSW_TILE_POS;
+        for (uint32_t wt = blockIdx.x; wt < nwide; wt += gridDim.x) {
+            for (uint32_t i = tid; i < 512; i += blockDim.x) s_h[i] = 0;
+            __syncthreads();
+            for (uint32_t p = wt * OSW_TILE_POS + tid; p < min(npos, (wt + 1) * OSW_TILE_POS); p += blockDim.x) {
+                uint32_t slot = slot_at(p);
+                if (slot != INVALID_SLOT) {
+                    const uint32_t d = (slot >> a.sort_shift) & 1023u;
+                    const uint32_t before = atomicAdd(&s_h[d >> 1], 1u << ((d & 1u) * 16u));
+                    if (a.pack_rank) slot |= ((before >> ((d & 1u) * 16u)) & 0xffffu) << 16;
+                }
+                a.slots[p] = slot;
             }
+            __syncthreads();
+            for (uint32_t i = tid; i < 512; i += blockDim.x) reinterpret_cast<uint32_t *>(a.wide_h16 + static_cast<size_t>(wt) * 1024u)[i] = s_h[i];
+            __syncthreads();
+        }
+        return;
+    }
+    const bool hist = a.sort_ctl != nullptr;
+    if (hist) for (uint32_t i = tid; i < 1024; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    const uint32_t dmask = (1u << a.sort_dbits) - 1u;
+    for (uint32_t p = blockIdx.x * blockDim.x + tid; p < npos; p += gridDim.x * blockDim.x) {
+        const uint32_t slot = slot_at(p);
+        if (slot != INVALID_SLOT) {
+            if (hist) atomicAdd(&s_h[(slot >> a.sort_shift) & dmask], 1u);
+            if (a.wide_h32 != nullptr) atomicAdd(&a.wide_h32[static_cast<size_t>(p / OSW_TILE_POS) * 1024u + ((slot >> a.sort_shift) & 1023u)], 1u);
         }
         a.slots[p] = slot;
     }
@@ -978,8 +1013,10 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums(const ui
 }
 
 // the same for the 16-bit rows the tile pass files (TileArgs::wide_h16)
-static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums16(const uint16_t *__restrict__ H, uint32_t tiles, uint32_t chunk_shift, uint32_t *__restrict__ C)
+static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums16(const uint16_t *__restrict__ H, uint32_t tiles, uint32_t chunk_shift, uint32_t *__restrict__ C,
+                                                                          uint32_t *__restrict__ ctl_counts = nullptr)
 {
+    // ctl_counts (optional): the global digit counts are accumulated there as well (callers that do not run k_wide_chunk_scan)
     const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
     const uint32_t t0 = chunk << chunk_shift, t1 = min(tiles, t0 + (1u << chunk_shift));
     uint4 acc = make_uint4(0, 0, 0, 0);
@@ -987,6 +1024,12 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_chunk_sums16(const 
 #pragma unroll 16
     for (uint32_t t = t0; t < t1; t++) { const ushort4 v = row[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     reinterpret_cast<uint4 *>(C + static_cast<size_t>(chunk) * OSW_DIGITS)[tid] = acc;
+    if (ctl_counts != nullptr) {
+        if (acc.x) atomicAdd(ctl_counts + tid * 4 + 0, acc.x);
+        if (acc.y) atomicAdd(ctl_counts + tid * 4 + 1, acc.y);
+        if (acc.z) atomicAdd(ctl_counts + tid * 4 + 2, acc.z);
+        if (acc.w) atomicAdd(ctl_counts + tid * 4 + 3, acc.w);
+    }
 }
 
 // C[chunk][digit] (chunk sums) -> first output position of (chunk, digit): exclusive scan over the digits of the totals + exclusive
@@ -1015,6 +1058,75 @@ static __global__ void __launch_bounds__(OSW_DIGITS) k_wide_chunk_scan(uint32_t 
     uint32_t run = wsum[warp] + incl - total;
 #pragma unroll 16
     for (uint32_t c = 0; c < chunks; c++) { uint32_t *p = C + static_cast<size_t>(c) * OSW_DIGITS + d; const uint32_t v = *p; *p = run; run += v; }
+}
+
+// The scatter of the wide partition when the tile pass packed a rank with every slot (TileArgs::pack_rank): word = slot | rank << 16,
+// rank = any numbering 0 .. count-1 of the survivors of one (wide tile, digit) cell. One CTA per wide tile, everything on chip:
+//   1. first output position of every digit for this tile (chunk row of k_wide_chunk_scan + the rows of the earlier tiles of the chunk)
+//      and the tile's own cells laid out back to back in shared memory (exclusive scan of the tile's digit counts),
+//   2. every item files its position within the tile at cell start + rank -- no ranking rounds, no per-warp counters,
+//   3. ARRIVAL order inside a cell (the count windows need every key's items in stream order, and two items of one key may share a
+//      cell): an item's place = number of the cell's entries with a smaller position; a cell holds a few entries, read from shared memory,
+//   4. one write of (slot, position) per item to its final place.
+// Output: keys_out[i] = slot, vals_out[i] = arrival position, stable by (digit, position) -- what k_wide_scatter produces.
+static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(const uint32_t *__restrict__ packed, uint32_t *__restrict__ keys_out,
+                                                                            uint32_t *__restrict__ vals_out, uint32_t n, uint32_t shift, uint32_t chunk_shift,
+                                                                            const uint16_t *__restrict__ H, const uint32_t *__restrict__ Cx)
+{
+    constexpr uint32_t NW = OSW_THREADS / 32;
+    __shared__ __align__(16) uint32_t bin_base[OSW_DIGITS];
+    __shared__ __align__(8) uint16_t cnt_row[OSW_DIGITS], cell_start[OSW_DIGITS];
+    __shared__ uint16_t lpos[OSW_TILE];
+    __shared__ uint32_t wsum[NW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+    const uint32_t start = tile * OSW_TILE;
+    if (start >= n) return;
+    uint32_t w[OSW_ITEMS];
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) { const uint32_t idx = start + r * OSW_THREADS + tid; w[r] = idx < n ? packed[idx] : INVALID_SLOT; }
+    {
+        const uint32_t chunk = tile >> chunk_shift;
+        uint4 acc = reinterpret_cast<const uint4 *>(Cx)[static_cast<size_t>(chunk) * (OSW_DIGITS / 4) + tid];
+        const ushort4 *hrow = reinterpret_cast<const ushort4 *>(H) + tid;
+#pragma unroll 16
+        for (uint32_t t = chunk << chunk_shift; t < tile; t++) { const ushort4 v = hrow[static_cast<size_t>(t) * (OSW_DIGITS / 4)]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        reinterpret_cast<uint4 *>(bin_base)[tid] = acc;
+        const ushort4 c = hrow[static_cast<size_t>(tile) * (OSW_DIGITS / 4)];
+        reinterpret_cast<ushort4 *>(cnt_row)[tid] = c;
+        // the tile's cells back to back: exclusive scan of its 1024 digit counts (thread tid owns digits 4 tid .. 4 tid + 3)
+        const uint32_t sum = static_cast<uint32_t>(c.x) + c.y + c.z + c.w;
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t base = incl - sum;
+#pragma unroll
+        for (uint32_t q = 0; q < NW; q++) if (q < warp) base += wsum[q];
+        reinterpret_cast<ushort4 *>(cell_start)[tid] = make_ushort4(static_cast<uint16_t>(base), static_cast<uint16_t>(base + c.x), static_cast<uint16_t>(base + c.x + c.y),
+                                                                     static_cast<uint16_t>(base + c.x + c.y + c.z));
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        if (w[r] != INVALID_SLOT) {
+            const uint32_t d = ((w[r] & 0xffffu) >> shift) & (OSW_DIGITS - 1u);
+            lpos[cell_start[d] + (w[r] >> 16)] = static_cast<uint16_t>(r * OSW_THREADS + tid);
+        }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (uint32_t r = 0; r < OSW_ITEMS; r++) {
+        if (w[r] != INVALID_SLOT) {
+            const uint32_t slot = w[r] & 0xffffu, d = (slot >> shift) & (OSW_DIGITS - 1u);
+            const uint32_t cnt = cnt_row[d], cs = cell_start[d], mine = r * OSW_THREADS + tid;
+            uint32_t less = 0;
+            for (uint32_t e = 0; e < cnt; e++) less += (lpos[cs + e] < mine) ? 1u : 0u;
+            const uint32_t dst = bin_base[d] + less;
+            keys_out[dst] = slot;
+            vals_out[dst] = start + mine;
+        }
+    }
 }
 
 // RBYTES: bytes of the payload record that travels with each element (payload_out[dst] = payload_in[index]); 0 = none,
@@ -1316,11 +1428,12 @@ __global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, con
             // ---- phase 2 (warp-converged): new leaf, root path, fired groups -----------------------------------------------
             if (completed) {
                 const uint32_t leaf = static_cast<uint32_t>((c / P_ - 1) & (n - 1));
-                for (uint32_t l = 0; l < logn; l++) // siblings towards L2 first: the sequential walk below then hits
+                const uint32_t plev = ff.lazy ? 0u : logn; // (lazy: only the leaf is written)
+                for (uint32_t l = 0; l < plev; l++) // siblings towards L2 first: the sequential walk below then hits
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB));
                 alignas(16) R cur = acc;
                 st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
-                for (uint32_t l = 0; l < logn; l++) {
+                for (uint32_t l = 0; l < plev; l++) {
                     alignas(16) R s;
                     ld_rec<R>(tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB, s);
                     alignas(16) R parent = cur;
@@ -1589,7 +1702,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
             if (m != 0) {
                 const uint32_t cp0 = kcp[tid], first = min(m, P32 - cp0), ns = 1u + (m - first + P32 - 1) / P32, sb = ksegb[tid];
                 for (uint32_t j = 0; j < ns; j++) seg_desc[sb + j] = tid | (j << 8);
-                if (cp0 + first == P32) {
+                if (cp0 + first == P32 && !ff.lazy) {
                     const uint32_t leaf = kleaf[tid];
                     const unsigned char *tr = ff.tree + static_cast<size_t>(key_lo + tid) * tree_stride;
                     for (uint32_t l = 0; l < min(logn, BK_SIBL); l++) {
@@ -1656,7 +1769,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                         leafi = (leafi + 1) & (n - 1);
                         st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
                         if (sib_staged) cp_async_wait_all();
-                        for (uint32_t l0 = 0; l0 < logn; l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
+                        for (uint32_t l0 = 0; l0 < (ff.lazy ? 0u : logn); l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
                             alignas(16) R sbl[4];
 #pragma unroll
                             for (uint32_t q = 0; q < 4; q++) {
@@ -1748,10 +1861,11 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                             const uint32_t leaf = leafi;
                             leafi = (leafi + 1) & (n - 1);
                             alignas(16) R sib;
-                            if (lane < logn) ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + ((leaf >> lane) ^ 1u)) * RB, sib);
+                            const uint32_t plev = ff.lazy ? 0u : logn; // (lazy: only the leaf is written)
+                            if (lane < plev) ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + ((leaf >> lane) ^ 1u)) * RB, sib);
                             alignas(16) R cur = acc;
                             if (lane == 0) st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
-                            for (uint32_t l = 0; l < logn; l++) {
+                            for (uint32_t l = 0; l < plev; l++) {
                                 const R sb = shfl_rec<R>(sib, l);
                                 alignas(16) R parent = cur;
                                 if ((leaf >> l) & 1u) P::comb(sb, cur, parent, prm); else P::comb(cur, sb, parent, prm);
@@ -1910,7 +2024,7 @@ __global__ void __launch_bounds__(ST_THREADS, WFB_ST_MINBLOCKS) k_ffat_update_st
         cp = static_cast<uint32_t>(c % P32); leaf = static_cast<uint32_t>((c / P32) & (n - 1));
         if (c < ff.B) { g = 0; tt = ff.B - c; }
         else { g = 1 + (c - ff.B) / group_items; tt = ff.B + g * group_items - c; }
-        for (uint32_t l = 0; l < min(logn, SIBL); l++) {
+        for (uint32_t l = 0; l < (ff.lazy ? 0u : min(logn, SIBL)); l++) {
             const unsigned char *src = my_tree + static_cast<size_t>(level_off(n, l) + ((leaf >> l) ^ 1u)) * RB;
             unsigned char *dst = s_sib + (my_k * SIBL + l) * RB;
 #pragma unroll
@@ -1986,7 +2100,7 @@ __global__ void __launch_bounds__(ST_THREADS, WFB_ST_MINBLOCKS) k_ffat_update_st
             leaf = (leaf + 1) & (n - 1);
             st_rec<R>(my_tree + static_cast<size_t>(lf) * RB, acc);
             alignas(16) R cur = acc;
-            for (uint32_t l = 0; l < logn; l++) {
+            for (uint32_t l = 0; l < (ff.lazy ? 0u : logn); l++) { // (lazy: only the leaf is written)
                 alignas(16) R sb;
                 if (staged && l < SIBL) ld_rec<R>(s_sib + (my_k * SIBL + l) * RB, sb);
                 else ld_rec<R>(my_tree + static_cast<size_t>(level_off(n, l) + ((lf >> l) ^ 1u)) * RB, sb);
@@ -2118,6 +2232,15 @@ __device__ __forceinline__ void ffat_eval_window(const FfatDev &ff, const unsign
     alignas(16) R res = P::make_result(key, gwid, prm);
     uint32_t ws = static_cast<uint32_t>((gwid * ff.sp) & (n - 1));
     uint32_t remaining = ff.wp;
+    if (ff.lazy) { // only the leaves are kept in global memory: fold them in order (the rare in-kernel evaluations; the deferred groups go
+                   // through k_ffat_windows_lazy, which builds the levels on chip)
+        for (; remaining > 0; remaining--) {
+            alignas(16) R node;
+            ld_rec<R>(tree + static_cast<size_t>(ws) * RB, node);
+            P::comb(res, node, res, prm);
+            ws = (ws + 1) & (n - 1);
+        }
+    }
     while (remaining > 0) {
         uint32_t range = (ws == 0) ? n : (ws & (0u - ws));
         const uint32_t pw = 1u << (31 - __clz(remaining));
@@ -2145,7 +2268,10 @@ __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const ui
     using R = typename P::result_t;
     // the update kernels reserve output slots with atomicAdd(n_out, Nb) whether they fit or not: a count beyond the capacity is clamped
     // here (the last kernel of the call) and flagged, so that *n_out is always the number of results actually written
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n_out != nullptr && *n_out > out_cap) { *n_out = out_cap; atomicOr(ff.err_flags, 2u); }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_out != nullptr) {
+        if (*n_out > out_cap) { *n_out = out_cap; atomicOr(ff.err_flags, 2u); }
+        if (ff.results_total != nullptr) *ff.results_total += *n_out;
+    }
     const uint32_t nt = min(*ff.n_trig, ff.trig_cap);
     const uint64_t total = static_cast<uint64_t>(nt) * ff.nb;
     const size_t tree_stride = static_cast<size_t>(2 * ff.n_leaves - 1) * sizeof(R);
@@ -2156,6 +2282,54 @@ __global__ void __launch_bounds__(256) k_ffat_windows(const FfatDev ff, const ui
         const uint64_t wm = batch_watermark(batch_off, batches, nbatches, tr.last_pos);
         ffat_eval_window<P>(ff, ff.tree + static_cast<size_t>(tr.slot) * tree_stride, tr.key, tr.g * ff.nb + i, wm, tr.obase + i,
                             out_res, out_ts, out_cap, prm);
+    }
+}
+
+// deferred window groups of a handle that keeps only the pane leaves (FfatDev::lazy): ONE WARP per fired group. The warp copies the key's
+// n leaves to shared memory (coalesced), builds the n - 1 internal nodes level by level -- the nodes of a level are independent: lanes take
+// them round-robin, one __syncwarp per level ("the FlatFAT levels with warp-level primitives") -- and then every lane evaluates its share of
+// the group's Nb windows with the same greedy aligned-node walk over the on-chip tree. Dynamic shared memory: warps per block x 2 n x sizeof(R).
+template <class P>
+__global__ void __launch_bounds__(128) k_ffat_windows_lazy(const FfatDev ff, const uint32_t *__restrict__ batch_off,
+                                                           const DevBatch *__restrict__ batches, uint32_t nbatches,
+                                                           unsigned char *__restrict__ out_res, uint64_t *__restrict__ out_ts, uint32_t out_cap,
+                                                           const typename P::params_t prm, uint32_t *__restrict__ n_out)
+{
+    using R = typename P::result_t;
+    constexpr uint32_t RB = sizeof(R);
+    extern __shared__ __align__(16) unsigned char lazy_smem[];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_out != nullptr) {
+        if (*n_out > out_cap) { *n_out = out_cap; atomicOr(ff.err_flags, 2u); }
+        if (ff.results_total != nullptr) *ff.results_total += *n_out;
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const uint32_t n = ff.n_leaves, logn = ff.log_leaves;
+    unsigned char *t = lazy_smem + static_cast<size_t>(warp) * 2u * n * RB; // (2 n - 1) nodes, levels back to back as in the global layout
+    const uint32_t nt = min(*ff.n_trig, ff.trig_cap);
+    const size_t tree_stride = static_cast<size_t>(2 * n - 1) * RB;
+    FfatDev fs = ff; fs.lazy = 0; // the on-chip tree has every level: the ordinary walk
+    for (uint32_t ti = blockIdx.x * wpb + warp; ti < nt; ti += gridDim.x * wpb) {
+        const Trigger tr = ff.trig[ti];
+        if (tr.slot == INVALID_SLOT) continue; // evaluated inside the update kernel
+        const unsigned char *leaves = ff.tree + static_cast<size_t>(tr.slot) * tree_stride;
+        for (uint32_t i = lane; i < n * (RB / 8); i += 32) reinterpret_cast<uint64_t *>(t)[i] = reinterpret_cast<const uint64_t *>(leaves)[i];
+        __syncwarp();
+        for (uint32_t l = 0; l < logn; l++) {
+            const unsigned char *src = t + static_cast<size_t>(level_off(n, l)) * RB;
+            unsigned char *dst = t + static_cast<size_t>(level_off(n, l + 1)) * RB;
+            for (uint32_t i = lane; i < (n >> (l + 1)); i += 32) {
+                alignas(16) R a, b, o;
+                ld_rec<R>(src + static_cast<size_t>(2 * i) * RB, a); ld_rec<R>(src + static_cast<size_t>(2 * i + 1) * RB, b);
+                o = a;
+                P::comb(a, b, o, prm);
+                st_rec<R>(dst + static_cast<size_t>(i) * RB, o);
+            }
+            __syncwarp();
+        }
+        const uint64_t wm = batch_watermark(batch_off, batches, nbatches, tr.last_pos);
+        for (uint32_t i = lane; i < ff.nb; i += 32)
+            ffat_eval_window<P>(fs, t, tr.key, tr.g * ff.nb + i, wm, tr.obase + i, out_res, out_ts, out_cap, prm);
+        __syncwarp(); // the next group overwrites the on-chip tree
     }
 }
 
@@ -2220,13 +2394,14 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
             if (c % P_ == 0) { // pane complete -> leaf + root path
                 const uint32_t leaf = static_cast<uint32_t>((c / P_ - 1) & (n - 1));
                 alignas(16) R sib;
-                if (lane < logn) { // lane l fetches the sibling of the path node at level l
+                const uint32_t plev = ff.lazy ? 0u : logn; // (lazy: only the leaf is written)
+                if (lane < plev) { // lane l fetches the sibling of the path node at level l
                     const uint32_t idx = (leaf >> lane) ^ 1u;
                     ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + idx) * RB, sib);
                 }
                 alignas(16) R cur = acc;
                 if (lane == 0) st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
-                for (uint32_t l = 0; l < logn; l++) {
+                for (uint32_t l = 0; l < plev; l++) {
                     const R s = shfl_rec<R>(sib, l);
                     alignas(16) R parent = cur; // key/id fields are don't-care in internal nodes
                     if ((leaf >> l) & 1u) P::comb(s, cur, parent, prm); else P::comb(cur, s, parent, prm);

@@ -212,6 +212,11 @@ template <class P>
 int ffat_windows_dispatch(const FfatDev &ff, const uint32_t *batch_off, const DevBatch *batches, uint32_t nbatches,
                           unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t grid, cudaStream_t s, const void *params, uint32_t *n_out)
 {
+    if (ff.lazy) { // one warp per fired group, the internal levels built on chip: warps per block x 2 n x sizeof(result_t) of dynamic shared memory
+        const size_t per_warp = static_cast<size_t>(2) * ff.n_leaves * sizeof(typename P::result_t);
+        const uint32_t wpb = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (32u << 10) / per_warp)));
+        k_ffat_windows_lazy<P><<<grid, 32 * wpb, wpb * per_warp, s>>>(ff, batch_off, batches, nbatches, out_res, out_ts, out_cap, load_params<P>(params), n_out);
+    } else
     k_ffat_windows<P><<<grid, 256, 0, s>>>(ff, batch_off, batches, nbatches, out_res, out_ts, out_cap, load_params<P>(params), n_out);
     WFB_CK(cudaGetLastError());
     return 0;

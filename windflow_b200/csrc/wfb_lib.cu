@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <vector>
 #include <algorithm>
@@ -51,8 +52,29 @@ const ProgramOps *program(int prog)
     return &t[prog];
 }
 
+// ---- host -> device staging of the small per-call tables (batch descriptors, offsets): a ring of pinned buffers, so that the
+// copy is a real asynchronous DMA (a cudaMemcpyAsync from pageable memory is staged by the driver and serialises with the stream) ----
+struct PinnedStage {
+    static constexpr int SLOTS = 8;
+    unsigned char *buf[SLOTS] = {}; size_t cap[SLOTS] = {}; cudaEvent_t ev[SLOTS] = {}; bool used[SLOTS] = {}; int next = 0;
+    int h2d(void *dst, const void *src, size_t bytes, cudaStream_t s)
+    {
+        if (bytes == 0) return 0;
+        const int i = next; next = (next + 1) % SLOTS;
+        if (used[i]) CK(cudaEventSynchronize(ev[i])); // the copy that used this slot SLOTS calls ago has long finished
+        if (cap[i] < bytes) { if (buf[i]) cudaFreeHost(buf[i]); cap[i] = std::max<size_t>(bytes, 4096) * 2; CK(cudaMallocHost(reinterpret_cast<void **>(&buf[i]), cap[i])); }
+        if (!ev[i]) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        std::memcpy(buf[i], src, bytes);
+        CK(cudaMemcpyAsync(dst, buf[i], bytes, cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(ev[i], s)); used[i] = true;
+        return 0;
+    }
+    void destroy() { for (int i = 0; i < SLOTS; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); buf[i] = nullptr; ev[i] = nullptr; } }
+};
+
 // ---- scratch shared by the tile passes: ticket counter, epoch-tagged tile states, batch descriptors -----------
 struct TileScratch {
+    PinnedStage stage;
     uint64_t *tile_state = nullptr; uint32_t tile_cap = 0;
     uint32_t *ticket = nullptr; uint32_t ticket_base = 0; uint32_t epoch = 0;
     DevBatch *d_batches = nullptr; uint32_t batch_cap = 0;
@@ -68,6 +90,7 @@ struct TileScratch {
     void destroy()
     {
         cudaFree(tile_state); cudaFree(ticket); cudaFree(d_batches);
+        stage.destroy();
         if (ev) cudaEventDestroy(ev);
     }
     // scratch is shared by consecutive launches: order them when the caller hops between streams
@@ -170,12 +193,12 @@ struct RadixSorter {
         return 0;
     }
     // tiles of the wide pass over `cap` positions and their chunks. prefix = false: about sqrt(tiles) chunks of >= 16 tiles, every
-    // scatter CTA sums the rows of the earlier chunks itself; true (rows filed by the tile pass): chunks of 16 tiles whose first
-    // output positions one small kernel computes (k_wide_chunk_scan), so a scatter CTA reads one chunk row and < 16 tile rows
+    // scatter CTA sums the rows of the earlier chunks itself; true (rows filed by the tile pass): chunks of 32 tiles whose first
+    // output positions one small kernel computes (k_wide_chunk_scan), so a scatter CTA reads one chunk row and < 32 tile rows
     static void wide_geometry(uint32_t cap, bool prefix, uint32_t *tiles, uint32_t *chunk_shift, uint32_t *chunks)
     {
         *tiles = std::max(1u, (cap + OSW_TILE - 1) / OSW_TILE);
-        uint32_t cs = 4;
+        uint32_t cs = prefix ? 5 : 4; // (prefix: 32 tiles per chunk -- the one-CTA scan over the chunks stays short, a scatter CTA adds < 32 rows)
         if (!prefix) while ((1u << (2 * cs)) < *tiles) cs++;
         *chunk_shift = cs;
         *chunks = (*tiles + (1u << cs) - 1) >> cs;
@@ -196,6 +219,7 @@ struct RadixSorter {
         return 0;
     }
     const uint16_t *rows_override = nullptr; // set by sort_wide for the duration of one call
+    template <class K> static bool keys_out_ok(K *kout, uint32_t *vout) { return kout != nullptr && vout != nullptr; }
     template <class K, int RBYTES>
     void launch_wide_scatter(uint32_t tiles, const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t shift,
                              uint32_t chunk_shift, const uint32_t *c, cudaStream_t s, const unsigned char *pin, unsigned char *pout, uint32_t pbytes,
@@ -208,8 +232,9 @@ struct RadixSorter {
     int sort_wide(const K *kin, K *kout, uint32_t *vout, const uint32_t *n_ptr, uint32_t n_host, uint32_t cap, uint32_t shift,
                   cudaStream_t s, uint32_t *ready_ctl, const uint32_t **counts, const unsigned char *payload_in = nullptr,
                   unsigned char *payload_out = nullptr, uint32_t payload_bytes = 0, bool skip_invalid = false, uint32_t region_stride = 0, uint32_t few_bins = 0,
-                  bool h32_ready = false, bool h16_ready = false, uint16_t *h16_rows = nullptr)
+                  bool h32_ready = false, bool h16_ready = false, uint16_t *h16_rows = nullptr, bool ranked = false)
     {
+        // ranked: the keys carry a rank in their upper half (TileArgs::pack_rank): k_wide_scatter_ranked
         // h16_rows: the 16-bit rows the tile pass filed when they do not live in this sorter (a pipelined handle keeps one set per segment in flight)
         if (payload_in && (payload_bytes == 0 || (payload_bytes & 7u))) return WFB_E_BADARG;
         if (!ctl) CK(cudaMalloc(&ctl, sizeof(uint32_t) * CTL_WORDS));
@@ -227,7 +252,9 @@ struct RadixSorter {
         uint32_t *c = ready_ctl ? ready_ctl : ctl;
         if (!ready_ctl) { int rc = prepare_wide(c, s); if (rc) return rc; }
         const uint32_t *h32 = nullptr;
-        if (prefix) { // the tile pass filed the 16-bit rows (wideH): chunk sums, then first output position of every (chunk, digit) + digit counts
+        if (h16_ready && ready_ctl && few_bins) { // a few bins (destinations), rows filed by the tile pass: chunk sums + the global counts (c was cleared by the caller)
+            k_wide_chunk_sums16<<<chunks, OSW_THREADS, 0, s>>>(h16_rows ? h16_rows : wideH, tiles, chunk_shift, wideC, c);
+        } else if (prefix) { // the tile pass filed the 16-bit rows (wideH): chunk sums, then first output position of every (chunk, digit) + digit counts
             k_wide_chunk_sums16<<<chunks, OSW_THREADS, 0, s>>>(h16_rows ? h16_rows : wideH, tiles, chunk_shift, wideC);
             k_wide_chunk_scan<<<1, OSW_DIGITS, 0, s>>>(wideC, chunks, c);
             launches++;
@@ -254,6 +281,14 @@ struct RadixSorter {
                 *counts = c;
                 return 0;
             }
+        }
+        if (prefix && ranked && sizeof(K) == 4 && !payload_in && keys_out_ok(kout, vout)) {
+            k_wide_scatter_ranked<<<tiles, OSW_THREADS, 0, s>>>(reinterpret_cast<const uint32_t *>(kin), reinterpret_cast<uint32_t *>(kout), vout, n_host, shift, chunk_shift,
+                                                                h16_rows ? h16_rows : wideH, wideC);
+            CK(cudaGetLastError());
+            launches += 2;
+            *counts = c;
+            return 0;
         }
 #define WFB_WS(RB_) launch_wide_scatter<K, RB_>(tiles, kin, kout, vout, n_ptr, n_host, shift, chunk_shift, c, s, payload_in, payload_out, payload_bytes, skip_invalid ? 1u : 0u, region_stride, h32, prefix ? 1u : 0u)
         if (!payload_in) WFB_WS(0);
@@ -381,6 +416,7 @@ struct SegScratch {
     bool sparse = false;          // this segment was ingested without global compaction (positions = tuple indices)
     bool h32_ready = false;       // the streaming pass filed the per-tile digit counts of the wide partition (sorter.wideH32)
     bool h16_ready = false;       // the tile pass filed them per wide tile as 16-bit rows (sorter.wideH), claiming 16 tiles per ticket
+    bool ranked = false;          // ... and packed a rank with every slot (TileArgs::pack_rank)
     uint16_t *h16 = nullptr; uint32_t h16_tiles = 0; // pipelined handles: this segment's own rows (the next segment's tile pass files its rows while
                                                      // this segment's partition still reads these)
     const unsigned char *lifted_src = nullptr; // records of this segment: `lifted`, or the caller's buffer (in-place ingest)
@@ -439,7 +475,8 @@ struct wfb_ffat {
     bool l2_hints = true;         // WFB_L2_HINTS=0: no eviction-priority hints on the ingest pass
     bool fuse_tile_hist = false;  // WFB_FUSE_TILE_HIST=1: the tile pass also files the per-tile digit counts of the wide partition (one more
                                   // global RED per survivor: measured +17 us on the tile pass against -8 us on the partition, so off)
-    bool stream_update = true;    // bucket path: k_ffat_update_stream (warp streams, panes of >= 8 items) instead of k_ffat_update_buckets; WFB_UPDATE=buckets|stream forces one
+    bool stream_update = false;   // WFB_UPDATE=stream: k_ffat_update_stream (lane = key, per-key queues) instead of k_ffat_update_buckets
+    bool rank_scatter = true;     // with tile_h16: the tile pass also packs a rank with every slot and the partition places the pairs by it (k_wide_scatter_ranked); WFB_RANK_SCATTER=0: off
     bool tile_h16 = true;         // the tile pass claims whole wide tiles and files their digit counts itself (no k_wide_tile_hist); WFB_TILE_H16=0: off
     bool inplace_kernel = true;   // WFB_INPLACE_KERNEL=0: the in-place case also goes through the tile pass
     bool inplace_ok = true;       // WFB_INPLACE=0: always copy the records of a pass-through program
@@ -600,7 +637,7 @@ int wfb_map_filter_batches(wfb_engine_t *e, const wfb_functors_t *f, const wfb_b
     if (hb.empty()) return 0;
     rc = e->ts.ensure_tiles(tiles); if (rc) return rc;
     rc = e->ts.ensure_batches(static_cast<uint32_t>(hb.size())); if (rc) return rc;
-    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * hb.size(), cudaMemcpyHostToDevice, s));
+    { int rc_ = e->ts.stage.h2d(e->ts.d_batches, hb.data(), sizeof(DevBatch) * hb.size(), s); if (rc_) return rc_; }
     TileArgs a; std::memset(&a, 0, sizeof(a));
     a.batches = e->ts.d_batches; a.nbatches = static_cast<uint32_t>(hb.size()); a.num_tiles = tiles; a.l2_hints = 1;
     e->ts.next_launch(a);
@@ -689,8 +726,8 @@ int wfb_reduce_by_key_batches(wfb_engine_t *e, const wfb_batch_t *in_h, const wf
         CK(cudaMalloc(&e->rb_first, sizeof(uint32_t) * e->rb_cap));
         if (!e->rb_total) CK(cudaMalloc(&e->rb_total, sizeof(uint32_t) * 2));
     }
-    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->rb_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+    { int rc_ = e->ts.stage.h2d(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, s); if (rc_) return rc_; }
+    { int rc_ = e->ts.stage.h2d(e->rb_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), s); if (rc_) return rc_; }
     CK(cudaMemsetAsync(e->rb_first, 0xff, sizeof(uint32_t) * nbatches, s));
     CK(cudaMemsetAsync(e->rb_total, 0, sizeof(uint32_t) * 2, s));
     if (n / RB_LONG + 1 > e->rb_long_cap) {
@@ -797,22 +834,30 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
     if (!e->sh_ctl) CK(cudaMalloc(&e->sh_ctl, sizeof(uint32_t) * RadixSorter::CTL_WORDS));
     rc = e->ts.ensure_tiles(tiles); if (rc) return rc;
     rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
-    CK(cudaMemcpyAsync(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    { int rc_ = e->ts.stage.h2d(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, s); if (rc_) return rc_; }
     rc = RadixSorter::prepare_wide(e->sh_ctl, s); if (rc) return rc;
     TileArgs a; std::memset(&a, 0, sizeof(a));
     a.batches = e->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
     a.lifted = e->sh_lifted; a.slots = e->sh_dest; a.nshards = num_shards; a.sparse = 1; a.l2_hints = 1;
     a.sort_ctl = e->sh_ctl; a.sort_passes = 1; a.sort_shift = 0; a.sort_dbits = OSW_BITS;
+    // the tile pass claims whole wide tiles and files the per-tile destination counts itself (no counting pass in the partition)
+    static const bool h16 = !(std::getenv("WFB_TILE_H16") && std::atoi(std::getenv("WFB_TILE_H16")) == 0);
+    uint32_t claims = tiles;
+    if (h16) {
+        rc = e->sorter.ensure_wide(static_cast<uint32_t>(positions), s, &a.wide_h16); if (rc) return rc;
+        a.tiles_per_ticket = OSW_TILE_POS / TILE; a.sort_ctl = nullptr;
+        claims = (tiles + a.tiles_per_ticket - 1) / a.tiles_per_ticket;
+    }
     e->ts.next_launch(a);
     uint32_t grid = 0;
-    rc = e->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : e->pp(), tiles, s, &grid, span_begin, span_end); if (rc) return rc;
-    e->ts.launched(tiles, grid);
+    rc = e->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : e->pp(), claims, s, &grid, span_begin, span_end); if (rc) return rc;
+    e->ts.launched(claims, grid);
     e->launches++;
     const uint32_t *counts = nullptr;
     const uint64_t before = e->sorter.launches;
     rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, nullptr, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), 0, s,
                                        e->sh_ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
-                                       region_capacity, num_shards);
+                                       region_capacity, num_shards, false, h16);
     if (rc) return rc;
     k_shard_counts<<<1, 32, 0, s>>>(counts, num_shards, region_capacity, counts_dev);
     CK(cudaGetLastError());
@@ -837,6 +882,7 @@ struct wfb_kstate {
     uint32_t *slotsA = nullptr, *slotsB = nullptr, *posB = nullptr, *tile_cnt = nullptr, *rank_start = nullptr;
     unsigned char *keep = nullptr;
     uint64_t launches = 0;
+    PinnedStage stage;
 };
 extern "C" {
 
@@ -878,7 +924,7 @@ int wfb_kstate_destroy(wfb_kstate_t *h)
     cudaFree(h->ff.ht_keys); cudaFree(h->ff.ht_slots); cudaFree(h->ff.n_slots); cudaFree(h->ff.slot_key); cudaFree(h->states);
     cudaFree(h->d_batches); cudaFree(h->d_boff); cudaFree(h->slotsA); cudaFree(h->slotsB); cudaFree(h->posB); cudaFree(h->tile_cnt);
     cudaFree(h->rank_start); cudaFree(h->keep);
-    h->sorter.destroy();
+    h->sorter.destroy(); h->stage.destroy();
     delete h;
     cudaGetLastError();
     return 0;
@@ -924,8 +970,8 @@ static int kstate_run(wfb_kstate_t *h, const wfb_functors_t *f, const wfb_batch_
         CK(cudaMalloc(&h->posB, sizeof(uint32_t) * h->cap)); CK(cudaMalloc(&h->keep, h->cap));
         CK(cudaMalloc(&h->tile_cnt, sizeof(uint32_t) * ((h->cap + SEGT - 1) / SEGT + 1)));
     }
-    CK(cudaMemcpyAsync(h->d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_boff, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+    { int rc_ = h->stage.h2d(h->d_batches, hb.data(), sizeof(DevBatch) * nbatches, s); if (rc_) return rc_; }
+    { int rc_ = h->stage.h2d(h->d_boff, boff.data(), sizeof(uint32_t) * (nbatches + 1), s); if (rc_) return rc_; }
     // 1. slots; 2. one wide partition pass into 1024 buckets of consecutive slots; 3. per-bucket CTAs, one thread per key
     int rc = h->ops->ks_slots(h->d_batches, h->d_boff, nbatches, n, h->ff, h->slotsA, s, f); if (rc) return rc;
     const uint32_t *counts = nullptr;
@@ -1185,6 +1231,7 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     ALLOC(ff.n_slots, sizeof(uint32_t) * 4);
     h->own_n_slots = ff.n_slots;
     ff.err_flags = ff.n_slots + 1;
+    ff.results_total = reinterpret_cast<unsigned long long *>(ff.n_slots + 2);
     CK(cudaMemset(ff.n_slots, 0, sizeof(uint32_t) * 4));
     ALLOC(ff.slot_key, sizeof(uint64_t) * max_keys);
     ALLOC(ff.cnt, sizeof(uint64_t) * max_keys);
@@ -1239,9 +1286,14 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         const char *e = std::getenv("WFB_UPDATE");
         h->buckets = !(e && std::strcmp(e, "lanes") == 0) && (1u << h->bucket_shift) <= BK_KEYS && ff.pane < (1ull << 32);
         // streaming update: one path update per completed pane inside the item loop, so panes of a few items at least
-        h->stream_update = h->buckets && !h->bucket_move && (e && std::strcmp(e, "stream") == 0 ? true : (e && std::strcmp(e, "buckets") == 0 ? false : ff.pane >= 8));
+        // lazy FlatFAT levels (FfatDev::lazy): bucket path, and the on-chip tree of one group must fit 32 KB
+        { const char *lz = std::getenv("WFB_LAZY_TREE");
+          ff.lazy = (h->buckets && !(lz && std::atoi(lz) == 0) && static_cast<size_t>(2) * ff.n_leaves * RB <= (32u << 10)) ? 1u : 0u; }
+        h->stream_update = h->buckets && !h->bucket_move && e && std::strcmp(e, "stream") == 0; // (measured: 173 us against 153 us for the bucket kernel at the bench configuration)
         const char *t = std::getenv("WFB_TILE_H16");
         h->tile_h16 = h->buckets && !(t && std::atoi(t) == 0);
+        const char *rs = std::getenv("WFB_RANK_SCATTER");
+        h->rank_scatter = !(rs && std::atoi(rs) == 0);
     }
     h->state_bytes = total;
     *hh = h;
@@ -1291,6 +1343,9 @@ int wfb_ffat_set_key_shard(wfb_ffat_t *h, uint32_t num_shards, uint32_t shard)
     return 0;
 }
 
+static double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
+static double g_sec[8]; static double g_sec_t = 0; static bool g_sec_on = false;
+#define SEC(i) do { if (g_sec_on) { const double n_ = host_now_us(); g_sec[i] += n_ - g_sec_t; g_sec_t = n_; } } while (0)
 static int ffat_ensure_segment(wfb_ffat *h, SegScratch &g, uint32_t total, uint32_t nbatches, cudaStream_t s)
 {
     if (total > g.cap) {
@@ -1337,10 +1392,11 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         const uint32_t *counts = nullptr;
         rc = h->sorter.sort_wide<uint32_t>(g.slotsA, g.slotsB, g.posB, g.sparse ? nullptr : g.n_total, g.total, g.total, h->bucket_shift, s,
                                            g.hist_ready ? g.sort_ctl : nullptr, &counts, h->bucket_move ? g.lifted : nullptr,
-                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready, g.h16_ready, h->pipelined ? g.h16 : nullptr);
+                                           h->bucket_move ? g.lifted_sorted : nullptr, static_cast<uint32_t>(h->ops->result_bytes), g.sparse, 0, 0, g.h32_ready, g.h16_ready, h->pipelined ? g.h16 : nullptr, g.ranked);
         if (rc) return rc;
         h->launches += h->sorter.launches - before;
         h->mark(2, s);
+        SEC(3);
         // ... then one CTA per bucket finishes the job (local split by key, per-key ordered fold, FlatFAT update)
         if (h->stream_update && h->ops->ffat_stream)
             rc = h->ops->ffat_stream(ff, g.lifted_src, g.slotsB, g.posB, counts, h->bucket_shift, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, n_out, s, h->pp());
@@ -1365,6 +1421,7 @@ static int ffat_window_phase(wfb_ffat *h, SegScratch &g, const FfatDev &ff, unsi
         if (rc) return rc;
         h->launches += h->ff.light_max ? 2 : 1;
     }
+    SEC(4);
     // deferred window groups: one thread per window
     rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, g.nbatches, out, out_ts, out_cap, static_cast<uint32_t>(g_num_sms) * 4u, s, h->pp(), n_out);
     if (rc) return rc;
@@ -1393,9 +1450,30 @@ int wfb_ffat_process_cb(wfb_ffat_t *h, const wfb_functors_t *pre, const wfb_batc
 
 // ext_slots != nullptr: the key slot of the record at every position is given (one batch, read in place; used by the
 // time-based front end, whose programs' lifted variants have no key extractor)
+static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                                 void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream,
+                                 const uint32_t *ext_slots);
 static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
                                 void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream,
                                 const uint32_t *ext_slots)
+{
+    static const bool prof = std::getenv("WFB_HOST_PROFILE") != nullptr; // host time spent issuing a call (tuning aid)
+    if (!prof) return ffat_process_cb_impl2(h, pre, batches_h, nbatches, out_results, out_ts, out_capacity, n_out_dev, stream, ext_slots);
+    static double acc = 0; static uint64_t calls = 0;
+    const double t0 = host_now_us();
+    g_sec_on = true; g_sec_t = t0;
+    const int rc = ffat_process_cb_impl2(h, pre, batches_h, nbatches, out_results, out_ts, out_capacity, n_out_dev, stream, ext_slots);
+    acc += host_now_us() - t0;
+    if (++calls % 64 == 0) {
+        std::fprintf(stderr, "[wfb] process_cb host issue: %.1f us/call over the last 64 calls; sections:", acc / 64); acc = 0;
+        for (int i = 0; i < 8; i++) { std::fprintf(stderr, " %.1f", g_sec[i] / 64); g_sec[i] = 0; }
+        std::fprintf(stderr, "\n");
+    }
+    return rc;
+}
+static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch_t *batches_h, uint32_t nbatches,
+                                 void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream,
+                                 const uint32_t *ext_slots)
 {
     if (!h || !n_out_dev || (nbatches && !batches_h) || (out_capacity && !out_results)) return WFB_E_BADARG;
     if (h->win_type != 0) return WFB_E_BADARG; // time-based handles: wfb_ffat_process_tb
@@ -1428,21 +1506,23 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
         return 0;
     }
     nbatches = static_cast<uint32_t>(hb.size());
+    SEC(0);
     // bucket path: no global compaction in the streaming pass -- tile t owns positions [t*TILE, +TILE) of the segment
     const bool sparse = h->buckets && h->sparse_ingest;
     const uint64_t seg_cap = sparse ? static_cast<uint64_t>(tiles) * TILE : total;
     if (seg_cap > 0x7fffffffull) return WFB_E_BADARG;
     rc = ffat_ensure_segment(h, g, static_cast<uint32_t>(seg_cap), nbatches, s); if (rc) return rc;
     rc = h->ts.ensure_tiles(tiles); if (rc) return rc;
-    CK(cudaMemcpyAsync(g.d_batches, hb.data(), sizeof(DevBatch) * nbatches, cudaMemcpyHostToDevice, s));
+    { int rc_ = h->ts.stage.h2d(g.d_batches, hb.data(), sizeof(DevBatch) * nbatches, s); if (rc_) return rc_; }
     g.nbatches = nbatches; g.total = static_cast<uint32_t>(seg_cap); g.sparse = sparse;
     if (sparse) { // first position of every batch (the compacting pass writes the compact offsets itself)
         std::vector<uint32_t> boff(nbatches + 1);
         for (uint32_t i = 0; i < nbatches; i++) boff[i] = hb[i].tile_begin * TILE;
         boff[nbatches] = tiles * TILE;
-        CK(cudaMemcpyAsync(g.batch_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), cudaMemcpyHostToDevice, s));
+        { int rc_ = h->ts.stage.h2d(g.batch_off, boff.data(), sizeof(uint32_t) * (nbatches + 1), s); if (rc_) return rc_; }
     }
 
+    SEC(1);
     FfatDev ff = h->ff; // this call's view of the state: per-segment buffers of parity `par`
     ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap; ff.n_heavy = g.n_heavy;
 
@@ -1477,9 +1557,16 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
         rc = h->sorter.prepare_h32(g.total, s, &a.wide_h32); if (rc) return rc;
         g.h32_ready = true;
     }
-    g.h16_ready = false;
+    g.h16_ready = false; g.ranked = false;
     if (a.inplace && a.sort_passes <= 1 && h->ops->slots_inplace && h->inplace_kernel) {
         // records read in place: only the slots (and the digit counts) are produced -- no tiles to stage, a plain kernel does it
+        if (sparse && fuse_hist && h->tile_h16 && !h->pipelined && !g.h32_ready) { // whole wide tiles per CTA: rows + ranks for the partition, as the tile pass does
+            rc = h->sorter.ensure_wide(g.total, s, &a.wide_h16); if (rc) return rc;
+            a.sort_ctl = nullptr;
+            g.h16_ready = true;
+            a.pack_rank = (h->rank_scatter && ff.max_keys <= 65536u) ? 1u : 0u;
+            g.ranked = a.pack_rank != 0;
+        }
         rc = h->ops->slots_inplace(a, pre ? static_cast<const void *>(pre) : h->pp(), s); if (rc) return rc;
     } else {
         uint32_t claims = tiles;
@@ -1502,6 +1589,8 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
             a.sort_ctl = nullptr; // (the chunk-sum kernel accumulates the global counts into g.sort_ctl, cleared above)
             claims = (tiles + a.tiles_per_ticket - 1) / a.tiles_per_ticket;
             g.h16_ready = true;
+            a.pack_rank = (h->rank_scatter && ff.max_keys <= 65536u) ? 1u : 0u;
+            g.ranked = a.pack_rank != 0;
         }
         uint32_t grid = 0;
         rc = h->ops->tile_pass(MODE_INGEST, a, pre ? static_cast<const void *>(pre) : h->pp(), claims, s, &grid, span_begin, span_end); if (rc) return rc;
@@ -1509,11 +1598,13 @@ static int ffat_process_cb_impl(wfb_ffat_t *h, const void *pre, const wfb_batch_
     }
     h->launches++;
     h->mark(1, s);
+    SEC(2);
 
     if (!h->pipelined) {
         CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
         rc = ffat_window_phase(h, g, ff, out, out_ts, out_capacity, n_out_dev, s); if (rc) return rc;
         h->mark(3, s);
+        SEC(5);
     } else {
         // the ingest pass of this segment is queued: now hand over the previous segment's results, then start this
         // segment's sort + update on the internal stream, where it overlaps the NEXT call's ingest pass
@@ -1579,6 +1670,19 @@ int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, voi
     if (n_keys_h) *n_keys_h = v[0];
     if (err_flags_h) *err_flags_h = v[1];
     if (h->cb && err_flags_h) { uint32_t e2 = 0; int rc = wfb_ffat_stats(h->cb, nullptr, &e2, stream); if (rc) return rc; *err_flags_h |= e2; }
+    return 0;
+}
+
+int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream)
+{
+    if (!h || !total_h) return WFB_E_BADARG;
+    const wfb_ffat *src = h->cb ? h->cb : h; // time-based handles: the count-based back end emits the results
+    unsigned long long v = 0;
+    if (src->s2) CK(cudaStreamSynchronize(src->s2));
+    if (src->ff.results_total == nullptr) { *total_h = 0; return 0; }
+    CK(cudaMemcpyAsync(&v, src->ff.results_total, sizeof(v), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    *total_h = v;
     return 0;
 }
 

@@ -7,6 +7,7 @@ Naming follows the reference operators: Map_GPU (wf/map_gpu.hpp), Filter_GPU (wf
 (wf/reduce_gpu.hpp), Ffat_Windows_GPU (wf/ffat_windows_gpu.hpp), KeyBy_Emitter_GPU (wf/keyby_emitter_gpu.hpp).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -27,6 +28,9 @@ RESULT_DTYPE = {PROG_TUPLE64: RESULT32, PROG_WFTEST16: WFWIN24, PROG_WFWIN24: WF
 
 KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
 SEED = 0x5EED5EED
+
+
+_PROF = [0.0, 0.0, 0] if os.environ.get("WFB_BENCH_VERBOSE") else None  # host-side timing of the window call (args, C call, calls)
 
 
 def functors(map_kind=0, iadd=0, fscale=1.0, filt_kind=0, mod=1):
@@ -254,6 +258,7 @@ class FfatWindowsGPU:
                                      (1 if dense_keys else 0) | (2 if pipelined else 0)), "wfb_ffat_create")
         self.res_dtype = RESULT_DTYPE[prog]
         self._keep = None
+        self._max_items = 0  # largest segment seen: a pipelined handle delivers the previous call's results into this call's buffer
 
     def close(self):
         if self.h:
@@ -281,14 +286,16 @@ class FfatWindowsGPU:
     def max_results(self, n_items):
         """Upper bound on the results one call over n_items input items can produce (count-based windows; time-based
         callers size the output for the groups a watermark jump can complete)."""
-        return (n_items // max(1, self.slide * self.nb) + self.max_keys + 1) * self.nb  # every key may fire one more group than its items alone account for
+        keys = self.max_keys if self.win_type == 0 else max(self.max_keys * 8, 65536)  # (time-based: a watermark jump completes several groups per key)
+        return (n_items // max(1, self.slide * self.nb) + keys + 1) * self.nb  # every key may fire one more group than its items alone account for
 
     def process(self, batches, pre=None, out=None, out_ts=None, n_out=None, stream=None):
         """One stream segment (list of DeviceBatch). Returns (out uint8 tensor, out_ts int64 tensor, n_out tensor)."""
         dev = batches[0].tuples.device
         total = batches.total if isinstance(batches, Segment) else sum(b.n for b in batches)
+        self._max_items = max(self._max_items, total)
         if out is None:
-            cap = self.max_results(total)
+            cap = self.max_results(self._max_items)
             out = torch.empty(cap * self.res_dtype.itemsize, dtype=torch.uint8, device=dev)
             out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
         cap = out.numel() // self.res_dtype.itemsize
@@ -299,6 +306,16 @@ class FfatWindowsGPU:
             check(self.L.wfb_ffat_process_tb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                              _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)), "wfb_ffat_process_tb")
             return out, out_ts, n_out
+        if _PROF is not None:
+            import time
+            t0 = time.perf_counter()
+            a = (self.h, C.byref(pre) if pre is not None else None, arr, len(batches), _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream))
+            t1 = time.perf_counter()
+            rc = self.L.wfb_ffat_process_cb(*a)
+            t2 = time.perf_counter()
+            _PROF[0] += t1 - t0; _PROF[1] += t2 - t1; _PROF[2] += 1
+            check(rc, "wfb_ffat_process_cb")
+            return out, out_ts, n_out
         check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                          _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
               "wfb_ffat_process_cb")
@@ -307,7 +324,7 @@ class FfatWindowsGPU:
     def flush(self, out=None, out_ts=None, n_out=None, stream=None, device="cuda"):
         """Pipelined handles: the results of the last segment (count 0 otherwise)."""
         if out is None:
-            cap = self.max_results(1 << 22)
+            cap = self.max_results(max(1 << 16, self._max_items))
             out = torch.empty(cap * self.res_dtype.itemsize, dtype=torch.uint8, device=device)
             out_ts = torch.empty(cap, dtype=torch.int64, device=device)
         if n_out is None:
@@ -329,6 +346,12 @@ class FfatWindowsGPU:
         calls = C.c_uint32(0)
         check(self.L.wfb_ffat_timing(self.h, 1 if enable else 0, ms, C.byref(calls)), "wfb_ffat_timing")
         return ms[0], ms[1], ms[2], ms[3], calls.value
+
+    def results_total(self, stream=None):
+        """Window results delivered since the handle was created (device-side counter; synchronises the stream)."""
+        t = C.c_uint64(0)
+        check(self.L.wfb_ffat_results_total(self.h, C.byref(t), _stream_ptr(stream)), "wfb_ffat_results_total")
+        return t.value
 
     def stats(self, stream=None):
         nk, ef = C.c_uint32(0), C.c_uint32(0)
