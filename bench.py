@@ -327,11 +327,17 @@ def run_ours(args):
             start = base + (step_index * world + r) * n
             hist.append((start, n, nkeys, start, tag))
 
-    if world == 1:
+    if world == 1 and not args.mg_path:
         ff = ops.FfatWindowsGPU(ops.PROG_TUPLE64, WIN, SLIDE, nb, max_keys=NKEYS, dense_keys=True, pipelined=pipelined)
         pipe = None
+    elif world == 1:  # profiling aid: the N>1 step (source pass -> exchange buffers -> update on records) with one rank, no NCCL
+        pipe = multigpu.KeyShardedPipelineC(ops, f, WIN, SLIDE, nb, NKEYS, 0, 1, dev)
+        ff = pipe.ff
     else:
-        pipe = multigpu.KeyShardedPipeline(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=not args.sync_exchange)
+        if args.py_exchange or args.sync_exchange:  # the torch.distributed version of the step (windflow_b200/multigpu.py)
+            pipe = multigpu.KeyShardedPipeline(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev, pipelined=not args.sync_exchange)
+        else:                                        # the whole step under the C ABI (wfb_mg_step: NCCL send/recv groups issued from C)
+            pipe = multigpu.KeyShardedPipelineC(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev)
         ff = pipe.ff
     cap = ff.max_results(seg_tuples * (2 if world > 1 else 1))
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
@@ -419,6 +425,8 @@ def run_ours(args):
     launches = launches_now() - launches0
     results1 = ff.results_total()
     # per-phase device times (CUDA events inside the call) on PHASE_STEPS further steps, outside the timed region: the event records cost ~10 us per step
+    for _ in range(2):
+        step("phases")   # (re-fill the queue after the read-back above before the event-timed steps)
     ff.timing(True)
     for _ in range(PHASE_STEPS):
         step("phases")
@@ -544,11 +552,11 @@ def run_check(torch, dist, ops, ff, pipe, step, hist, out, out_ts, n_out, nb, ra
     # history before the check steps -> tuples each sampled key had then; whole history -> the expected windows
     before = expected_windows_for_keys(hist[:n_hist], keys, O, nb)
     n_before = {int(k): len(before[int(k)][0]) for k in keys}
-    compared, bad = check_results(hist, n_before, mine, keys, O, nb, check_ts=(world == 1))
+    compared, bad = check_results(hist, n_before, mine, keys, O, nb, check_ts=(world == 1 and pipe is None))
     if bad:
         raise SystemExit("bench.py --check FAILED: " + "; ".join(bad[:5]))
     return {"passed": True, "keys_sampled": int(len(keys)), "windows_compared": int(compared), "steps": CHECK_STEPS,
-            "history_segments": len(hist), "fsum_rtol": 1e-6, "timestamps_compared": world == 1,
+            "history_segments": len(hist), "fsum_rtol": 1e-6, "timestamps_compared": world == 1 and pipe is None,
             "how": "sums over each sampled key's own surviving tuples (arrival ranks [64 w, 64 w + 4096)), rebuilt from the stream generator over the whole history"}
 
 
@@ -685,6 +693,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pipeline", action="store_true", help="WFB_FFAT_PIPELINED handle: results one call late, partition+update overlap the next ingest")
     ap.add_argument("--sync-exchange", action="store_true", help="N > 1: exchange and window update of a step right after its source pass (no overlap with the next step)")
+    ap.add_argument("--mg-path", action="store_true", help="N = 1 only, profiling aid: run the N>1 step (wfb_mg_step) with a single rank")
+    ap.add_argument("--py-exchange", action="store_true", help="N > 1: drive the exchange from Python (torch.distributed) instead of wfb_mg_step")
     ap.add_argument("--prime-steps", type=int, default=-1, help="override state priming (ncu runs); default: steady state")
     ap.add_argument("--no-check", action="store_true", help="skip the result check of the sampled keys")
     ap.add_argument("--no-extras", action="store_true", help="skip the gpu_reference and facade legs")

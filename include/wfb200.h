@@ -244,6 +244,29 @@ int wfb_ffat_stats(wfb_ffat_t *h, uint32_t *n_keys_h, uint32_t *err_flags_h, voi
  * outputs_sent counter of wf/stats_record.hpp:80-82). */
 int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream);
 
+/* ---- the pipeline sharded by key across the GPUs of one box (no counterpart in the reference: it drives one device) ----------------
+ * One process (or thread) per GPU, `nranks` of them. Global step t of the stream covers nranks * K consecutive batches; rank r
+ * ingests the K batches [r K, (r+1) K) of that span. Per step and rank: [Map_GPU -> Filter_GPU ->] lift and a stable partition
+ * of the lifted results by key % nranks (wf/keyby_emitter.hpp:215-217), an all-to-all of the partitions (NCCL send/recv over
+ * NVLink), and the rank's Ffat_Windows_GPU replica on the keys with key % nranks == rank, fed the received chunks in source-rank
+ * order = global stream order (every count window equals the single-GPU one). Stands in for KeyBy_Emitter_GPU between the
+ * replicas of different devices. NCCL is looked up at run time (dlopen "libnccl.so.2"): WFB_E_UNSUPPORTED when it is missing.
+ * The exchange and the window update of step t are issued behind the source pass of step t+1, so results arrive one step late
+ * (wfb_mg_flush delivers the last ones) and the host never waits for the GPU: the sizes NCCL needs on the host are a step old. */
+typedef struct wfb_mg wfb_mg_t;
+int wfb_mg_unique_id(void *id128_h);   /* rank 0: an ncclUniqueId (128 bytes) to hand to the other ranks (broadcast it with the launcher's means) */
+int wfb_mg_create(wfb_mg_t **h, int prog, int nranks, int rank, const void *id128_h, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
+                  uint32_t max_keys_total /* keys 0 .. max_keys_total-1 over all ranks */);
+int wfb_mg_destroy(wfb_mg_t *h);
+/* this rank's K batches of the next global step; the window results of the PREVIOUS step go to out_results / out_ts (none on the first call).
+ * `watermark`: the watermark of the segment (result timestamps carry the watermark of the source segment that held the triggering item). */
+int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark,
+                void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);
+int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);
+/* launches so far (source engine + window operator) / device error flags of the window operator and results delivered (synchronises) */
+uint64_t wfb_mg_launches(const wfb_mg_t *h);
+int wfb_mg_stats(wfb_mg_t *h, uint32_t *err_flags_h, uint64_t *results_total_h, void *stream);
+
 /* ---- synthetic stream, generated on the device for tests and bench --------------------------
  * key_mode: 0 i % nkeys, 1 splitmix64(i) % nkeys, 2 zipf via zipf_cdf (device, nkeys doubles) */
 int wfb_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys,

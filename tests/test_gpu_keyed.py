@@ -237,3 +237,37 @@ def test_key_sharded_pipeline_world1_nccl(wfb, oracle, pipelined):
     assert np.array_equal(g["key"], e["key"]) and np.array_equal(g["id"], e["id"]) and np.array_equal(g["isum"], e["isum"])
     assert np.allclose(g["fsum"], e["fsum"], rtol=1e-6, atol=0)
     assert np.array_equal(g["ts"], e["ts"]) if "ts" in g.dtype.names and "ts" in e.dtype.names else True
+
+
+def test_mg_pipeline_c_abi_world1(wfb, oracle):
+    """The same pipeline with the whole step under the C ABI (wfb_mg_step / wfb_mg_flush): one rank, so the all-to-all is a device copy,
+    everything else -- shard_lift, size bookkeeping on the communication stream, chunks read in place, results one step late -- is the
+    code every rank runs. (bench.py's check covers the NCCL exchange itself at N > 1.)"""
+    import torch
+    from windflow_b200 import multigpu
+    O, ops = oracle, wfb
+    win, slide, nb, nkeys, n, batch = 64, 16, 2, 40, 60000, 4096
+    t, ts = O.gen_tuple64(0, n, O.KEY_UNIFORM, nkeys)
+    f = ops.functors(map_kind=1, iadd=2, fscale=1.0000001, filt_kind=1)
+    pipe = multigpu.KeyShardedPipelineC(ops, f, win, slide, nb, 64, 0, 1, torch.device("cuda", 0))
+    go = O.FfatGpuOracle(win, slide, nb)
+    cap = pipe.max_results(n)
+    out = torch.empty(cap * 32, dtype=torch.uint8, device="cuda"); out_ts = torch.empty(cap, dtype=torch.int64, device="cuda")
+    n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got, exp = [], []
+    step = 3 * batch
+    for s0 in range(0, n, step):
+        bs = [ops.DeviceBatch.from_host(t[b:b + batch], ts[b:b + batch]) for b in range(s0, min(n, s0 + step), batch)]
+        pipe.step(bs, int(ts[s0]), out, out_ts, n_out)
+        torch.cuda.synchronize()
+        got.append(pipe.results_to_host(out, out_ts, n_out)[0])
+        surv, _, _ = O.map_filter_tuple64(t[s0:s0 + step], ts[s0:s0 + step], 1, 2, 1.0000001, 1)
+        exp.append(go.process_batch(O.lift_tuple64(surv), int(ts[s0]))[0])
+    pipe.flush(out, out_ts, n_out)
+    torch.cuda.synchronize()
+    got.append(pipe.results_to_host(out, out_ts, n_out)[0])
+    assert pipe.stats()[1] == 0 and pipe.results_total() == sum(len(x) for x in got)
+    g = O.sort_results(np.concatenate(got)); e = O.sort_results(np.concatenate(exp))
+    assert len(g) == len(e) > 0
+    assert np.array_equal(g["key"], e["key"]) and np.array_equal(g["id"], e["id"]) and np.array_equal(g["isum"], e["isum"])
+    assert np.allclose(g["fsum"], e["fsum"], rtol=1e-6, atol=0)

@@ -69,6 +69,13 @@ SYMBOLS = {
     "wfb_ffat_stats": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), vp]),
     "wfb_ffat_results_total": (C.c_int, [vp, C.POINTER(C.c_uint64), vp]),
     "wfb_gen_tuple64": (C.c_int, [u64, u64, u32, C.c_int, u64, vp, vp, vp, vp]),
+    "wfb_mg_unique_id": (C.c_int, [vp]),
+    "wfb_mg_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, u64, u64, u32, u32]),
+    "wfb_mg_destroy": (C.c_int, [vp]),
+    "wfb_mg_step": (C.c_int, [vp, C.POINTER(Functors), C.POINTER(Batch), u32, u64, vp, vp, u32, vp, vp]),
+    "wfb_mg_flush": (C.c_int, [vp, vp, vp, u32, vp, vp]),
+    "wfb_mg_launches": (u64, [vp]),
+    "wfb_mg_stats": (C.c_int, [vp, C.POINTER(u32), C.POINTER(C.c_uint64), vp]),
 }
 
 

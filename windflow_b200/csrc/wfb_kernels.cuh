@@ -333,7 +333,7 @@ __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" 
 
 template <class P, int MODE>
 __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant__ CUtensorMap tmap, const TileArgs a,
-                                                          const typename P::params_t prm)
+                                                          const __grid_constant__ typename P::params_t prm)
 {
     using T = typename P::tuple_t;
     using R = typename P::result_t;
@@ -1076,7 +1076,10 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
     constexpr uint32_t NW = OSW_THREADS / 32;
     __shared__ __align__(16) uint32_t bin_base[OSW_DIGITS];
     __shared__ __align__(8) uint16_t cnt_row[OSW_DIGITS], cell_start[OSW_DIGITS];
-    __shared__ uint16_t lpos[OSW_TILE];
+    constexpr uint32_t LPOS = OSW_TILE + 3u * OSW_DIGITS;  // every cell padded to a multiple of four entries (8-byte loads in the repair loop)
+    constexpr uint32_t LPAD = 0x0fffu;                     // padding entry: never below a position of the tile (positions are < 4096)
+    static_assert(OSW_TILE <= 4096 && LPOS % (2 * OSW_THREADS) == 0, "16-bit packed position compare");
+    __shared__ __align__(8) uint16_t lpos[LPOS];
     __shared__ uint32_t wsum[NW];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
     const uint32_t start = tile * OSW_TILE;
@@ -1094,17 +1097,20 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
         const ushort4 c = hrow[static_cast<size_t>(tile) * (OSW_DIGITS / 4)];
         reinterpret_cast<ushort4 *>(cnt_row)[tid] = c;
         // the tile's cells back to back: exclusive scan of its 1024 digit counts (thread tid owns digits 4 tid .. 4 tid + 3)
-        const uint32_t sum = static_cast<uint32_t>(c.x) + c.y + c.z + c.w;
+        const uint32_t p0 = (c.x + 3u) & ~3u, p1 = (c.y + 3u) & ~3u, p2 = (c.z + 3u) & ~3u, p3 = (c.w + 3u) & ~3u; // padded cell sizes
+        const uint32_t sum = p0 + p1 + p2 + p3;
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += v; }
         if (lane == 31) wsum[warp] = incl;
+#pragma unroll
+        for (uint32_t i = 0; i < LPOS / (2 * OSW_THREADS); i++) reinterpret_cast<uint32_t *>(lpos)[i * OSW_THREADS + tid] = LPAD | (LPAD << 16);
         __syncthreads();
         uint32_t base = incl - sum;
 #pragma unroll
         for (uint32_t q = 0; q < NW; q++) if (q < warp) base += wsum[q];
-        reinterpret_cast<ushort4 *>(cell_start)[tid] = make_ushort4(static_cast<uint16_t>(base), static_cast<uint16_t>(base + c.x), static_cast<uint16_t>(base + c.x + c.y),
-                                                                     static_cast<uint16_t>(base + c.x + c.y + c.z));
+        reinterpret_cast<ushort4 *>(cell_start)[tid] = make_ushort4(static_cast<uint16_t>(base), static_cast<uint16_t>(base + p0), static_cast<uint16_t>(base + p0 + p1),
+                                                                     static_cast<uint16_t>(base + p0 + p1 + p2));
     }
     __syncthreads();
 #pragma unroll
@@ -1120,8 +1126,12 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
         if (w[r] != INVALID_SLOT) {
             const uint32_t slot = w[r] & 0xffffu, d = (slot >> shift) & (OSW_DIGITS - 1u);
             const uint32_t cnt = cnt_row[d], cs = cell_start[d], mine = r * OSW_THREADS + tid;
+            // entries of the cell below `mine`, four per load: per 16-bit half, bit 15 of (0x8000 + mine - 1 - entry) says entry < mine
+            // (all values are < 4096, so the halves never borrow from each other; padding entries are never below)
+            const uint32_t mm = (mine | (mine << 16)) + 0x7fff7fffu;
+            const uint2 *cell = reinterpret_cast<const uint2 *>(lpos + cs);
             uint32_t less = 0;
-            for (uint32_t e = 0; e < cnt; e++) less += (lpos[cs + e] < mine) ? 1u : 0u;
+            for (uint32_t e = 0; e < cnt; e += 4) { const uint2 v = cell[e >> 2]; less += __popc((mm - v.x) & 0x80008000u) + __popc((mm - v.y) & 0x80008000u); }
             const uint32_t dst = bin_base[d] + less;
             keys_out[dst] = slot;
             vals_out[dst] = start + mine;
@@ -1505,10 +1515,13 @@ constexpr uint32_t BK_CAP = BK_THREADS * BK_IT; // items per chunk
 #ifndef WFB_BK_MINBLOCKS
 #define WFB_BK_MINBLOCKS 4
 #endif
+#ifndef WFB_BK_MINBLOCKS_LAZY
+#define WFB_BK_MINBLOCKS_LAZY 5   // lazy FlatFAT levels: no sibling staging (32 KB of shared memory instead of 48), no path code
+#endif
 constexpr uint32_t BK_U = WFB_BK_U;   // record loads in flight per thread
 
-template <class P>
-__global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_buckets(const FfatDev ff, const unsigned char *__restrict__ lifted,
+template <class P, bool LAZY>
+__global__ void __launch_bounds__(BK_THREADS, LAZY ? WFB_BK_MINBLOCKS_LAZY : WFB_BK_MINBLOCKS) k_ffat_update_buckets(const FfatDev ff, const unsigned char *__restrict__ lifted,
                                                                        const uint32_t *__restrict__ bk_slots, const uint32_t *__restrict__ bk_pos,
                                                                        const uint32_t *__restrict__ digit_counts, uint32_t shift, uint32_t moved,
                                                                        const uint32_t *__restrict__ batch_off, const DevBatch *__restrict__ batches,
@@ -1533,7 +1546,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
     __shared__ uint32_t kcp[BK_KEYS], kleaf[BK_KEYS];  // items in the open pane, leaf the open pane will be written to
     __shared__ uint64_t kc[BK_KEYS], kg[BK_KEYS], ktt[BK_KEYS]; // count, groups fired, items until the next trigger
     __shared__ __align__(16) unsigned char kacc[BK_KEYS * RB];   // open-pane accumulator of key k
-    __shared__ __align__(16) unsigned char s_sib[BK_KEYS * BK_SIBL * RB]; // siblings of the leaf key k completes in this chunk
+    __shared__ __align__(16) unsigned char s_sib[LAZY ? 16 : BK_KEYS * BK_SIBL * RB]; // siblings of the leaf key k completes in this chunk (lazy levels: none)
     __shared__ uint32_t s_heavy[BK_KEYS];              // keys folded by a warp in this chunk
     __shared__ uint32_t ksegb[BK_KEYS];                // first segment of key k (a segment = the items of a run that fall into one pane)
     __shared__ uint32_t misc[NW], s_boff[2], s_nheavy, s_nseg;
@@ -1702,7 +1715,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
             if (m != 0) {
                 const uint32_t cp0 = kcp[tid], first = min(m, P32 - cp0), ns = 1u + (m - first + P32 - 1) / P32, sb = ksegb[tid];
                 for (uint32_t j = 0; j < ns; j++) seg_desc[sb + j] = tid | (j << 8);
-                if (cp0 + first == P32 && !ff.lazy) {
+                if (!LAZY && cp0 + first == P32) {
                     const uint32_t leaf = kleaf[tid];
                     const unsigned char *tr = ff.tree + static_cast<size_t>(key_lo + tid) * tree_stride;
                     for (uint32_t l = 0; l < min(logn, BK_SIBL); l++) {
@@ -1769,7 +1782,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                         leafi = (leafi + 1) & (n - 1);
                         st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);
                         if (sib_staged) cp_async_wait_all();
-                        for (uint32_t l0 = 0; l0 < (ff.lazy ? 0u : logn); l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
+                        for (uint32_t l0 = 0; l0 < (LAZY ? 0u : logn); l0 += 4) { // siblings of four levels per round trip (none of them is on the path)
                             alignas(16) R sbl[4];
 #pragma unroll
                             for (uint32_t q = 0; q < 4; q++) {
@@ -1861,7 +1874,7 @@ __global__ void __launch_bounds__(BK_THREADS, WFB_BK_MINBLOCKS) k_ffat_update_bu
                             const uint32_t leaf = leafi;
                             leafi = (leafi + 1) & (n - 1);
                             alignas(16) R sib;
-                            const uint32_t plev = ff.lazy ? 0u : logn; // (lazy: only the leaf is written)
+                            const uint32_t plev = LAZY ? 0u : logn; // (lazy: only the leaf is written)
                             if (lane < plev) ld_rec<R>(tree + static_cast<size_t>(level_off(n, lane) + ((leaf >> lane) ^ 1u)) * RB, sib);
                             alignas(16) R cur = acc;
                             if (lane == 0) st_rec<R>(tree + static_cast<size_t>(leaf) * RB, cur);

@@ -190,8 +190,10 @@ int ffat_buckets_dispatch(const FfatDev &ff, const unsigned char *lifted, const 
                           uint32_t nbatches, unsigned char *out_res, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out, cudaStream_t s,
                           const void *params)
 {
-    k_ffat_update_buckets<P><<<OSW_DIGITS, BK_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, moved, batch_off, batches,
-                                                               nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
+    if (ff.lazy) k_ffat_update_buckets<P, true><<<OSW_DIGITS, BK_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, moved, batch_off, batches,
+                                                                                 nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
+    else k_ffat_update_buckets<P, false><<<OSW_DIGITS, BK_THREADS, 0, s>>>(ff, lifted, bk_slots, bk_pos, digit_counts, shift, moved, batch_off, batches,
+                                                                          nbatches, out_res, out_ts, out_cap, n_out, load_params<P>(params));
     WFB_CK(cudaGetLastError());
     return 0;
 }
@@ -355,6 +357,9 @@ int gather_dispatch(const unsigned char *tuples, const uint64_t *ts, const uint3
 
 // The lifted variant of a program: its records are the program's results (pane aggregates), combined with the program's comb;
 // the key slot of every record comes from the caller (TileArgs::ext_slots), so the program needs no key inside result_t.
+template <class P, class = void> struct program_has_result_key : std::false_type {};
+template <class P> struct program_has_result_key<P, std::void_t<decltype(P::result_key(std::declval<const typename P::result_t &>(), std::declval<const typename P::params_t &>()))>> : std::true_type {};
+
 template <class P>
 struct LiftedOf {
     using tuple_t = typename P::result_t; using result_t = typename P::result_t; using key_t = uint64_t; using params_t = typename P::params_t;
@@ -362,7 +367,12 @@ struct LiftedOf {
     static constexpr bool is_lifted = true;
     __host__ __device__ static void map(tuple_t &, const params_t &) {}
     __host__ __device__ static bool filter(tuple_t &, const params_t &) { return true; }
-    __host__ __device__ static key_t key(const tuple_t &, const params_t &) { return 0; }
+    // the key of a lifted record: P::result_key where the program names it (the destination side of the multi-GPU keyby reads it);
+    // the time-based front end hands the slots over itself (TileArgs::ext_slots) and never asks
+    __host__ __device__ static key_t key(const tuple_t &t, const params_t &p)
+    {
+        if constexpr (program_has_result_key<P>::value) return P::result_key(t, p); else return 0;
+    }
     __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r = t; }
     __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &o, const params_t &p) { P::comb(a, b, o, p); }
     __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &p) { return P::make_result(k, gwid, p); }
@@ -389,6 +399,7 @@ const void *lifted_ops_of()
         t.tile_pass = &tile_pass_ingest_dispatch<L>; t.slots_inplace = &slots_inplace_dispatch<L>;
         t.ffat_update = &ffat_update_dispatch<L>; t.ffat_buckets = &ffat_buckets_dispatch<L>; t.ffat_windows = &ffat_windows_dispatch<L>;
         t.ffat_stream = &ffat_stream_dispatch<L>;
+        t.reserved2 = program_has_result_key<P>::value ? 1u : 0u; // bit 0: the lifted records carry their key (usable behind an exchange)
         return t;
     }();
     return &o;

@@ -1686,6 +1686,244 @@ int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream)
     return 0;
 }
 
+// ---- key-sharded pipeline across GPUs ------------------------------------------------------------------------------------------------
+} // extern "C"
+#include <dlfcn.h>
+namespace {
+// the few NCCL entry points used, resolved at run time (the library a torch process has already loaded, or the system one)
+struct Nccl {
+    struct Id { char b[128]; }; // ncclUniqueId (passed by value)
+    typedef int (*GetUniqueId_t)(void *);
+    typedef int (*CommInitRank_t)(void **, int, Id, int);
+    typedef int (*CommDestroy_t)(void *);
+    typedef int (*SendRecv_t)(void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*Group_t)();
+    typedef const char *(*ErrStr_t)(int);
+    void *lib = nullptr;
+    GetUniqueId_t GetUniqueId = nullptr; CommInitRank_t CommInitRank = nullptr; CommDestroy_t CommDestroy = nullptr;
+    SendRecv_t Send = nullptr, Recv = nullptr; Group_t GroupStart = nullptr, GroupEnd = nullptr;
+    bool ok = false;
+    Nccl()
+    {
+        const char *names[] = {std::getenv("WFB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { if (n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (!lib) return;
+        GetUniqueId = reinterpret_cast<GetUniqueId_t>(dlsym(lib, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<CommInitRank_t>(dlsym(lib, "ncclCommInitRank"));
+        CommDestroy = reinterpret_cast<CommDestroy_t>(dlsym(lib, "ncclCommDestroy"));
+        Send = reinterpret_cast<SendRecv_t>(dlsym(lib, "ncclSend")); Recv = reinterpret_cast<SendRecv_t>(dlsym(lib, "ncclRecv"));
+        GroupStart = reinterpret_cast<Group_t>(dlsym(lib, "ncclGroupStart")); GroupEnd = reinterpret_cast<Group_t>(dlsym(lib, "ncclGroupEnd"));
+        ok = GetUniqueId && CommInitRank && CommDestroy && Send && Recv && GroupStart && GroupEnd;
+    }
+};
+Nccl &nccl() { static Nccl n; return n; }
+constexpr int NCCL_UINT8 = 1; // ncclUint8
+#define NK(call) do { int r__ = (call); if (r__ != 0) return 1000 + r__; } while (0) // (NCCL errors: 1000 + ncclResult_t)
+
+__global__ void k_mg_meta(const uint32_t *__restrict__ counts, uint64_t watermark, uint32_t nranks, uint64_t *__restrict__ send_meta)
+{
+    const uint32_t d = threadIdx.x;
+    if (d < nranks) { send_meta[2 * d] = counts[d]; send_meta[2 * d + 1] = watermark; }
+}
+
+struct MgSlot { // buffers of one step in flight (two: the exchange of step i-1 overlaps the source pass of step i)
+    unsigned char *regions = nullptr; uint32_t region_cap = 0;
+    uint32_t *counts = nullptr;                // MAX_SHARDS + 1 (device)
+    uint64_t *send_meta = nullptr, *recv_meta = nullptr; // [nranks][2] (device)
+    uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
+    unsigned char *recv = nullptr; size_t recv_bytes = 0;
+    cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr;
+    bool used = false, done_recorded = false;
+};
+} // namespace
+
+struct wfb_mg {
+    int nranks = 1, rank = 0;
+    void *comm = nullptr;
+    wfb_engine_t *eng = nullptr;
+    wfb_ffat_t *ffat = nullptr;
+    size_t rb = 0;
+    MgSlot slot[2];
+    cudaStream_t cs = nullptr; // communication stream
+    uint64_t step_no = 0;
+    MgSlot *pending = nullptr;
+    std::vector<wfb_batch_t> chunks;
+};
+
+extern "C" {
+
+int wfb_mg_unique_id(void *id128_h)
+{
+    if (!id128_h) return WFB_E_BADARG;
+    if (!nccl().ok) return WFB_E_UNSUPPORTED;
+    NK(nccl().GetUniqueId(id128_h));
+    return 0;
+}
+
+int wfb_mg_destroy(wfb_mg_t *h)
+{
+    if (!h) return 0;
+    cudaDeviceSynchronize();
+    if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+    if (h->eng) wfb_engine_destroy(h->eng);
+    if (h->ffat) wfb_ffat_destroy(h->ffat);
+    for (MgSlot &sl : h->slot) {
+        cudaFree(sl.regions); cudaFree(sl.counts); cudaFree(sl.send_meta); cudaFree(sl.recv_meta); cudaFree(sl.recv);
+        if (sl.h_counts) cudaFreeHost(sl.h_counts);
+        if (sl.h_recv) cudaFreeHost(sl.h_recv);
+        for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done}) if (e) cudaEventDestroy(e);
+    }
+    if (h->cs) cudaStreamDestroy(h->cs);
+    delete h;
+    cudaGetLastError();
+    return 0;
+}
+
+int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id128_h, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
+                  uint32_t max_keys_total)
+{
+    if (!hh || nranks < 1 || nranks > static_cast<int>(MAX_SHARDS) || rank < 0 || rank >= nranks || (nranks > 1 && !id128_h) || max_keys_total == 0) return WFB_E_BADARG;
+    const ProgramOps *o = program(prog);
+    if (!o) return WFB_E_NOPROG;
+    const int lp = lifted_program_of(prog);
+    if (lp < 0 || !(program(lp)->reserved2 & 1u)) return WFB_E_UNSUPPORTED; // the lifted records must carry their key (Program::result_key)
+    int rc = device_ready(); if (rc) return rc;
+    if (nranks > 1 && !nccl().ok) return WFB_E_UNSUPPORTED;
+    wfb_mg *h = new (std::nothrow) wfb_mg();
+    if (!h) return WFB_E_BADARG;
+    h->nranks = nranks; h->rank = rank; h->rb = o->result_bytes;
+#define MGCK(call) do { int r__ = (call); if (r__) { wfb_mg_destroy(h); return r__; } } while (0)
+    MGCK(wfb_engine_create(&h->eng, prog));
+    // the rank's replica owns the keys with key % nranks == rank: compact slots key / nranks, records read in place
+    MGCK(wfb_ffat_create(&h->ffat, lp, win, slide, wins_per_batch, (max_keys_total + nranks - 1) / nranks, 0, 0, WFB_FFAT_DENSE_KEYS));
+    if (nranks > 1) MGCK(wfb_ffat_set_key_shard(h->ffat, static_cast<uint32_t>(nranks), static_cast<uint32_t>(rank)));
+    MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)));
+    for (MgSlot &sl : h->slot) {
+        MGCK(static_cast<int>(cudaMalloc(&sl.counts, sizeof(uint32_t) * (MAX_SHARDS + 1))));
+        MGCK(static_cast<int>(cudaMalloc(&sl.send_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
+        MGCK(static_cast<int>(cudaMalloc(&sl.recv_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
+        MGCK(static_cast<int>(cudaMallocHost(&sl.h_counts, sizeof(uint32_t) * (MAX_SHARDS + 1))));
+        MGCK(static_cast<int>(cudaMallocHost(&sl.h_recv, sizeof(uint64_t) * 2 * MAX_SHARDS)));
+        for (cudaEvent_t *e : {&sl.ev_src, &sl.ev_meta, &sl.ev_a2a, &sl.ev_done}) MGCK(static_cast<int>(cudaEventCreateWithFlags(e, cudaEventDisableTiming)));
+    }
+    if (nranks > 1) {
+        Nccl::Id id; std::memcpy(id.b, id128_h, sizeof(id.b));
+        int r = nccl().CommInitRank(&h->comm, nranks, id, rank);
+        if (r != 0) { wfb_mg_destroy(h); return 1000 + r; }
+    }
+#undef MGCK
+    *hh = h;
+    return 0;
+}
+
+// source side of a step: fused pass + partition by destination; the sizes travel (and reach the host a step later)
+static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark, cudaStream_t s)
+{
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < nbatches; i++) n += batches_h[i].n;
+    if (n > 0x7fffffffull) return WFB_E_BADARG;
+    if (sl.region_cap < n) { // worst case: every item of the segment survives and goes to one shard
+        if (sl.used) CK(cudaDeviceSynchronize());
+        cudaFree(sl.regions);
+        sl.region_cap = static_cast<uint32_t>(n);
+        CK(cudaMalloc(&sl.regions, static_cast<size_t>(h->nranks) * sl.region_cap * h->rb));
+    }
+    int rc = wfb_shard_lift(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s);
+    if (rc) return rc;
+    k_mg_meta<<<1, 32, 0, s>>>(sl.counts, watermark, static_cast<uint32_t>(h->nranks), sl.send_meta);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(sl.ev_src, s));
+    CK(cudaStreamWaitEvent(h->cs, sl.ev_src, 0));
+    if (h->nranks > 1) {
+        NK(nccl().GroupStart());
+        for (int p = 0; p < h->nranks; p++) {
+            NK(nccl().Send(sl.send_meta + 2 * p, 16, NCCL_UINT8, p, h->comm, h->cs));
+            NK(nccl().Recv(sl.recv_meta + 2 * p, 16, NCCL_UINT8, p, h->comm, h->cs));
+        }
+        NK(nccl().GroupEnd());
+    } else CK(cudaMemcpyAsync(sl.recv_meta, sl.send_meta, 16, cudaMemcpyDeviceToDevice, h->cs));
+    CK(cudaMemcpyAsync(sl.h_counts, sl.counts, sizeof(uint32_t) * (MAX_SHARDS + 1), cudaMemcpyDeviceToHost, h->cs));
+    CK(cudaMemcpyAsync(sl.h_recv, sl.recv_meta, sizeof(uint64_t) * 2 * h->nranks, cudaMemcpyDeviceToHost, h->cs));
+    CK(cudaEventRecord(sl.ev_meta, h->cs));
+    sl.used = true;
+    return 0;
+}
+
+// exchange of the records of a step (communication stream), then the window update on the received chunks (caller's stream)
+static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out_dev, cudaStream_t s)
+{
+    CK(cudaEventSynchronize(sl.ev_meta)); // the sizes of this step on the host (a step old: no stall)
+    if (sl.h_counts[MAX_SHARDS]) return WFB_E_CAPACITY; // a shard region overflowed
+    const int n = h->nranks;
+    size_t offs[MAX_SHARDS + 1]; size_t tiles = 0; // every source's chunk at its tile position of the receive buffer (read in place)
+    for (int p = 0; p < n; p++) { offs[p] = tiles * TILE; tiles += (static_cast<size_t>(sl.h_recv[2 * p]) + TILE - 1) / TILE; }
+    const size_t need = std::max<size_t>(1, tiles * TILE) * h->rb;
+    if (sl.recv_bytes < need) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(sl.recv);
+        sl.recv_bytes = need * 5 / 4;
+        CK(cudaMalloc(&sl.recv, sl.recv_bytes));
+    }
+    if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs, sl.ev_done, 0)); // the window update that read this receive buffer two steps ago
+    if (n > 1) {
+        NK(nccl().GroupStart());
+        for (int p = 0; p < n; p++) {
+            NK(nccl().Send(sl.regions + static_cast<size_t>(p) * sl.region_cap * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+            NK(nccl().Recv(sl.recv + offs[p] * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+        }
+        NK(nccl().GroupEnd());
+    } else CK(cudaMemcpyAsync(sl.recv, sl.regions, static_cast<size_t>(sl.h_counts[0]) * h->rb, cudaMemcpyDeviceToDevice, h->cs));
+    CK(cudaEventRecord(sl.ev_a2a, h->cs));
+    CK(cudaStreamWaitEvent(s, sl.ev_a2a, 0));
+    h->chunks.resize(n);
+    for (int p = 0; p < n; p++) { // source-rank order = global stream order
+        wfb_batch_t &b = h->chunks[p];
+        b.tuples = sl.recv + offs[p] * h->rb; b.ts = nullptr; b.watermark = sl.h_recv[2 * p + 1]; b.n = static_cast<uint32_t>(sl.h_recv[2 * p]); b.reserved = 0;
+    }
+    int rc = wfb_ffat_process_cb(h->ffat, nullptr, h->chunks.data(), static_cast<uint32_t>(n), out, out_ts, out_cap, n_out_dev, s);
+    if (rc) return rc;
+    CK(cudaEventRecord(sl.ev_done, s));
+    sl.done_recorded = true;
+    return 0;
+}
+
+int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark,
+                void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
+{
+    if (!h || !n_out_dev || (nbatches && !batches_h)) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MgSlot &cur = h->slot[h->step_no & 1];
+    h->step_no++;
+    MgSlot *prev = h->pending;
+    // the source pass of this step is issued first; the exchange of the previous step runs on the communication stream next to it
+    int rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
+    h->pending = &cur;
+    if (prev == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    return mg_exchange_update(h, *prev, out_results, out_ts, out_capacity, n_out_dev, s);
+}
+
+int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
+{
+    if (!h || !n_out_dev) return WFB_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MgSlot *prev = h->pending; h->pending = nullptr;
+    if (prev == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    return mg_exchange_update(h, *prev, out_results, out_ts, out_capacity, n_out_dev, s);
+}
+
+uint64_t wfb_mg_launches(const wfb_mg_t *h) { return h ? wfb_engine_launches(h->eng) + wfb_ffat_launches(h->ffat) : 0; }
+
+int wfb_mg_stats(wfb_mg_t *h, uint32_t *err_flags_h, uint64_t *results_total_h, void *stream)
+{
+    if (!h) return WFB_E_BADARG;
+    uint32_t nk = 0, ef = 0; uint64_t tot = 0;
+    int rc = wfb_ffat_stats(h->ffat, &nk, &ef, stream); if (rc) return rc;
+    rc = wfb_ffat_results_total(h->ffat, &tot, stream); if (rc) return rc;
+    if (err_flags_h) *err_flags_h = ef;
+    if (results_total_h) *results_total_h = tot;
+    return 0;
+}
+
 int wfb_gen_tuple64(uint64_t seed, uint64_t start, uint32_t n, int key_mode, uint64_t nkeys, const double *zipf_cdf,
                     void *tuples, uint64_t *ts, void *stream)
 {

@@ -50,6 +50,7 @@ struct ProgTuple64 {
     {
         result_t r; r.key = k; r.id = gwid; r.isum = 0; r.fsum = 0.0; return r;
     }
+    __host__ __device__ static key_t result_key(const result_t &r, const params_t &) { return r.key; } // (optional: lets lifted records travel, wfb_mg_*)
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.ivalue = a.ivalue + b.ivalue; r.fvalue = a.fvalue + b.fvalue;
@@ -93,6 +94,7 @@ struct ProgWfTest16 {
     __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r.key = t.key; r.id = 0; r.value = t.value; }
     __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &) { out.value = a.value + b.value; }
     __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
+    __host__ __device__ static key_t result_key(const result_t &r, const params_t &) { return r.key; }
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &) // Reduce_Functor_GPU :268-279
     {
         tuple_t r; r.key = a.key; r.value = a.value + b.value; return r;
@@ -136,6 +138,7 @@ struct ProgWfWin24 {
     __host__ __device__ static void lift(const tuple_t &t, result_t &r, const params_t &) { r.key = t.key; r.id = 0; r.value = t.value; } // :295-303
     __host__ __device__ static void comb(const result_t &a, const result_t &b, result_t &out, const params_t &) { out.value = a.value + b.value; } // :306-314
     __host__ __device__ static result_t make_result(key_t k, uint64_t gwid, const params_t &) { result_t r; r.key = k; r.id = gwid; r.value = 0; return r; }
+    __host__ __device__ static key_t result_key(const result_t &r, const params_t &) { return r.key; }
     __host__ __device__ static tuple_t reduce(const tuple_t &a, const tuple_t &b, const params_t &)
     {
         tuple_t r; r.key = a.key; r.id = 0; r.value = a.value + b.value; return r;

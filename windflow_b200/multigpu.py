@@ -203,3 +203,91 @@ class KeyShardedPipeline:
             n_out.zero_()
             return 0
         return self._update(prev, *self._exchange(prev), out, out_ts, n_out)
+
+
+
+class KeyShardedPipelineC:
+    """The same pipeline with the whole step under the C ABI (wfb_mg_*): source pass, size exchange, NCCL all-to-all and window update
+    are issued by ONE library call per step (NCCL send/recv groups from C on a communication stream; nothing of torch on the per-step
+    path). Only the communicator's unique id travels through torch.distributed, once. Same interface as KeyShardedPipeline (always
+    pipelined: results arrive one step late, flush() delivers the last)."""
+
+    def __init__(self, ops, functors, win, slide, nb, max_keys, rank, world, device, prog=None):
+        import ctypes as C
+        from . import _lib
+        self.ops, self.f, self.rank, self.world, self.dev = ops, functors, rank, world, device
+        self.L = _lib.lib()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if world > 1:
+            if rank == 0:
+                buf = (C.c_char * 128)()
+                _lib.check(self.L.wfb_mg_unique_id(buf), "wfb_mg_unique_id")
+                ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            t = ident.to(device)
+            dist.broadcast(t, src=0)
+            ident = t.cpu()
+        self._id = (C.c_char * 128).from_buffer_copy(bytes(ident.numpy().tobytes()))
+        self.h = C.c_void_p()
+        _lib.check(self.L.wfb_mg_create(C.byref(self.h), ops.PROG_TUPLE64 if prog is None else prog, world, rank, self._id, win, slide, nb, max_keys), "wfb_mg_create")
+        self.res_dtype = ops.RESULT_DTYPE[ops.PROG_TUPLE64 if prog is None else prog]
+        self.max_keys, self.slide, self.nb = max_keys, slide, nb
+        self.ff = self  # (bench.py talks to `pipe.ff` for launches / stats / results)
+        self.eng = _NoLaunches()
+
+    # ---- the interface bench.py and the tests use ----------------------------------------------------------------------
+    def step(self, batches, watermark, out, out_ts, n_out):
+        import ctypes as C
+        from . import _lib
+        arr = self.ops._cbatches(batches)
+        _lib.check(self.L.wfb_mg_step(self.h, C.byref(self.f) if self.f is not None else None, arr, len(batches), int(watermark),
+                                      self.ops._ptr(out), self.ops._ptr(out_ts), out.numel() // self.res_dtype.itemsize, self.ops._ptr(n_out),
+                                      self.ops._stream_ptr(None)), "wfb_mg_step")
+
+    def flush(self, out, out_ts, n_out):
+        from . import _lib
+        _lib.check(self.L.wfb_mg_flush(self.h, self.ops._ptr(out), self.ops._ptr(out_ts), out.numel() // self.res_dtype.itemsize, self.ops._ptr(n_out),
+                                       self.ops._stream_ptr(None)), "wfb_mg_flush")
+
+    @property
+    def launches(self):
+        return int(self.L.wfb_mg_launches(self.h))
+
+    def max_results(self, n_items):
+        keys = (self.max_keys + self.world - 1) // self.world
+        return (n_items // max(1, self.slide * self.nb) + keys + 1) * self.nb
+
+    def stats(self):
+        import ctypes as C
+        from . import _lib
+        ef, tot = C.c_uint32(0), C.c_uint64(0)
+        _lib.check(self.L.wfb_mg_stats(self.h, C.byref(ef), C.byref(tot), self.ops._stream_ptr(None)), "wfb_mg_stats")
+        return 0, ef.value
+
+    def results_total(self):
+        import ctypes as C
+        from . import _lib
+        ef, tot = C.c_uint32(0), C.c_uint64(0)
+        _lib.check(self.L.wfb_mg_stats(self.h, C.byref(ef), C.byref(tot), self.ops._stream_ptr(None)), "wfb_mg_stats")
+        return tot.value
+
+    def results_to_host(self, out, out_ts, n_out):
+        n = int(n_out.item())
+        return self.ops.to_host(out, self.res_dtype)[:n].copy(), self.ops.ts_to_host(out_ts)[:n].copy()
+
+    def timing(self, enable=True):
+        return 0.0, 0.0, 0.0, 0.0, 0
+
+    def close(self):
+        if self.h:
+            self.L.wfb_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _NoLaunches:
+    launches = 0
