@@ -116,6 +116,23 @@ template <class T> struct ChainStages { // both the "map" and the "filter" slot 
 };
 template <class X> struct is_chain : std::false_type {};
 template <class T> struct is_chain<ChainStages<T>> : std::true_type {};
+// The same run with the functor TYPES known where the program is instantiated (a fluent pipe.chain(map).chain(filter).add(ffat):
+// FusedPipe below): the functors are called directly and inlined into the tile pass -- no thunks, no tuple in local memory.
+template <class F, bool IS_FILTER> struct TypedStage { F f; };
+template <class T, class... S> struct TypedChain { __host__ __device__ bool operator()(T &) const { return true; } };
+template <class T, class F, bool IS_FILTER, class... Rest>
+struct TypedChain<T, TypedStage<F, IS_FILTER>, Rest...> {
+    F f; TypedChain<T, Rest...> rest;
+    __host__ __device__ bool operator()(T &t) const
+    {
+        F fn(f);
+        if constexpr (IS_FILTER) { if (!fn(t)) return false; } else fn(t);
+        return rest(t);
+    }
+};
+template <class T> inline TypedChain<T> make_typed_chain() { return {}; }
+template <class T, class F, bool IS_FILTER, class... Rest>
+inline TypedChain<T, TypedStage<F, IS_FILTER>, Rest...> make_typed_chain(TypedStage<F, IS_FILTER> s, Rest... rest) { return {s.f, make_typed_chain<T>(rest...)}; }
 
 // ---- default functors of the slots an operator does not use -------------------------------------------------------------
 template <class T> struct NoKey { __host__ __device__ uint64_t operator()(const T &) const { return 0; } };
@@ -125,10 +142,10 @@ template <class T> struct NoReduce { __host__ __device__ T operator()(const T &a
 
 // The program the kernels are instantiated for: the user's functor objects travel by value in params_t; the map / filter slots
 // hold the fused chain that runs in front of the operator.
-template <class T, class R, class KeyF, class LiftF, class CombF, class RedF, bool KEYED>
+template <class T, class R, class KeyF, class LiftF, class CombF, class RedF, bool KEYED, class PreF = ChainStages<T>>
 struct FacadeProgram {
     using tuple_t = T; using result_t = R; using key_t = uint64_t;
-    struct params_t { ChainStages<T> map; ChainStages<T> filt; KeyF key; LiftF lift; CombF comb; RedF red; };
+    struct params_t { ChainStages<T> map; PreF filt; KeyF key; LiftF lift; CombF comb; RedF red; };
     static_assert(std::is_trivially_copyable<T>::value && std::is_trivially_copyable<R>::value, "tuple_t / result_t must be trivially copyable");
     static_assert(sizeof(T) % 8 == 0 && sizeof(R) % 8 == 0, "tuple_t / result_t sizes must be multiples of 8 bytes");
     __host__ __device__ static void map(tuple_t &t, const params_t &p) { p.map(t); }
@@ -801,18 +818,25 @@ public:
 // Ffat_Windows_GPU, count-based and time-based (wf/ffat_windows_gpu.hpp:59-274, wf/ffat_replica_gpu.hpp:707-1047). svc(): the K
 // batches found queued go to ONE wfb_ffat_process_cb call, with the fused run of stateless operators in front of it as `pre`;
 // the results of the call form one output batch whose size stays on the device.
-template <class lift_func_gpu_t, class comb_func_gpu_t, class keyextr_func_gpu_t>
+template <class lift_func_gpu_t, class comb_func_gpu_t, class keyextr_func_gpu_t, class pre_t = ChainStages<fn_arg_t<lift_func_gpu_t, 0>>>
 class Ffat_Windows_GPU: public Basic_Operator {
 public:
     using tuple_t = fn_arg_t<lift_func_gpu_t, 0>;
     using result_t = fn_arg_t<lift_func_gpu_t, 1>;
     static constexpr bool isKeyed = !std::is_same<keyextr_func_gpu_t, NoKey<tuple_t>>::value;
-    using prog_t = FacadeProgram<tuple_t, result_t, keyextr_func_gpu_t, lift_func_gpu_t, comb_func_gpu_t, NoReduce<tuple_t>, isKeyed>;
+    static constexpr bool typed_pre = !is_chain<pre_t>::value; // the run in front is part of the program's type (FusedPipe)
+    using prog_t = FacadeProgram<tuple_t, result_t, keyextr_func_gpu_t, lift_func_gpu_t, comb_func_gpu_t, NoReduce<tuple_t>, isKeyed, pre_t>;
     static constexpr op_type_t op_type = op_type_t::WIN_GPU;
     lift_func_gpu_t lift; comb_func_gpu_t comb; keyextr_func_gpu_t key_extr;
     uint64_t win_len, slide_len, lateness; Win_Type_t winType; size_t numWinPerBatch; uint32_t max_keys; bool dense_keys;
     size_t maxk = WF_MAX_BATCHES_PER_CALL;
-    StageChain pre{}; // the fused run of stateless operators chained in front of this operator (MultiPipe fills it)
+    pre_t pre{}; // the fused run of stateless operators chained in front of this operator (MultiPipe / FusedPipe fill it)
+    bool has_pre() const { if constexpr (typed_pre) return true; else return pre.c.n != 0; }
+    // the same operator with the typed run `p` in front (FusedPipe)
+    template <class other_pre_t>
+    Ffat_Windows_GPU(const Ffat_Windows_GPU<lift_func_gpu_t, comb_func_gpu_t, keyextr_func_gpu_t, other_pre_t> &o, pre_t p):
+        Basic_Operator(o), lift(o.lift), comb(o.comb), key_extr(o.key_extr), win_len(o.win_len), slide_len(o.slide_len), lateness(o.lateness), winType(o.winType),
+        numWinPerBatch(o.numWinPerBatch), max_keys(o.max_keys), dense_keys(o.dense_keys), maxk(o.maxk), pre(p) {}
     Ffat_Windows_GPU(lift_func_gpu_t l, comb_func_gpu_t c, keyextr_func_gpu_t k, std::string n, uint64_t w, uint64_t s, uint64_t late,
                      Win_Type_t wt, size_t nwb, uint32_t mk, bool dense, size_t mbpc):
         Basic_Operator(std::move(n), 1 /* forced to 1, wf/ffat_windows_gpu.hpp:197 */, isKeyed ? Routing_Mode_t::KEYBY : Routing_Mode_t::FORWARD, nwb), lift(l), comb(c), key_extr(k),
@@ -834,7 +858,7 @@ public:
         std::vector<batch_t *> in;
         std::vector<wfb_batch_t> bi;
     public:
-        explicit Replica(const Ffat_Windows_GPU &o): Basic_Replica(o.name), op(o), prm{{}, {o.pre}, o.key_extr, o.lift, o.comb, {}}, tb(o.winType == Win_Type_t::TB) {}
+        explicit Replica(const Ffat_Windows_GPU &o): Basic_Replica(o.name), op(o), prm{{}, o.pre, o.key_extr, o.lift, o.comb, {}}, tb(o.winType == Win_Type_t::TB) {}
         ~Replica() override { if (ffat) wfb_ffat_destroy(ffat); cudaFree(counts_d); cudaFreeHost(counts_h); }
         int svc_init() override
         {
@@ -869,7 +893,7 @@ public:
             Batch_GPU_t<result_t> *out = pool.get(cap);
             if (out->reuse_after) gpuErrChk(cudaStreamWaitEvent(stream, out->reuse_after, 0));
             if (ring == RING) ring = 0;
-            const wfb_functors_t *pre = op.pre.n ? reinterpret_cast<const wfb_functors_t *>(&prm) : nullptr;
+            const wfb_functors_t *pre = op.has_pre() ? reinterpret_cast<const wfb_functors_t *>(&prm) : nullptr;
             if (tb) { wfbErrChk(wfb_ffat_process_tb(ffat, pre, bi.data(), static_cast<uint32_t>(k), out->tuples_gpu, out->ts_gpu, static_cast<uint32_t>(cap), counts_d + ring, stream)); }
             else { wfbErrChk(wfb_ffat_process_cb(ffat, pre, bi.data(), static_cast<uint32_t>(k), out->tuples_gpu, out->ts_gpu, static_cast<uint32_t>(cap), counts_d + ring, stream)); }
             if (tb) check_errors(); // (the time-based path synchronises per batch anyway: a result that did not fit is reported, not lost silently)
@@ -1025,8 +1049,10 @@ public:
 // operator arrives: a Ffat_Windows_GPU over the same tuple type absorbs it as its `pre` stage, anything else turns it into ONE
 // replica group running one fused streaming pass.
 class PipeGraph;
+template <class... Ops> class FusedPipe;
 class MultiPipe {
     friend class PipeGraph;
+    template <class... Ops> friend class FusedPipe;
     ff::ff_pipeline pipe;
     std::vector<std::string> op_names;
     bool has_sink = false, tail_is_gpu = false; size_t prevOutputBatchSize = 0;
@@ -1074,8 +1100,8 @@ class MultiPipe {
 public:
     // chain == add here: an operator that cannot be fused into its neighbour runs on its own thread, so that its input queue
     // can fill while it works (the replica then takes everything queued in one call)
-    template <class F> MultiPipe &chain(Map_GPU<F> op) { return chain_stateless(op); }
-    template <class F> MultiPipe &chain(Filter_GPU<F> op) { return chain_stateless(op); }
+    // (stateless operators return a proxy that remembers the functor types while the expression goes on: FusedPipe below)
+    template <class F, bool IS> FusedPipe<Stateless_GPU<F, IS>> chain(Stateless_GPU<F, IS> op);
     template <class F, class K> MultiPipe &chain(Map_GPU_KB<F, K> op) { return add_replicated(op); }
     template <class F, class K> MultiPipe &chain(Filter_GPU_KB<F, K> op) { return add_replicated(op); }
     template <class F, class K> MultiPipe &chain(Reduce_GPU<F, K> op) { return add_replicated(op); }
@@ -1083,12 +1109,12 @@ public:
     {
         using T = typename Ffat_Windows_GPU<L, C, K>::tuple_t;
         if (pending.n && pending_type == std::type_index(typeid(T))) { // the run in front becomes the window operator's own ingest stage
-            op.pre = pending;
+            op.pre.c = pending;
             pending = StageChain{}; pending_type = std::type_index(typeid(void)); materialize_pending = nullptr;
         }
         return add_replicated(op);
     }
-    template <class op_t> MultiPipe &add(op_t op) { return chain(op); }
+    template <class op_t> auto add(op_t op) -> decltype(this->chain(op)) { return chain(op); }
     template <class sink_f> MultiPipe &chain_sink(Sink<sink_f> op)
     {
         if (has_sink) wf_fatal("MultiPipe is already terminated by a Sink");
@@ -1104,6 +1130,59 @@ public:
     size_t getNumThreads() const { return static_cast<size_t>(pipe.cardinality()); }
     const std::vector<std::string> &getOperatorNames() const { return op_names; }
 };
+
+// What pipe.chain(map_or_filter) returns: the MultiPipe plus the stateless operators of the expression so far, with their types.
+//   .chain(another Map_GPU / Filter_GPU)   -> a longer FusedPipe
+//   .chain / .add(Ffat_Windows_GPU)        -> the run becomes part of the window operator's PROGRAM TYPE (TypedChain): its functors are
+//                                             inlined into the tile pass -- the pipeline of BASELINE.json is one kernel with no indirect call
+//   anything else, conversion to MultiPipe &, or the end of the statement -> the operators are handed to the MultiPipe as usual (the
+//                                             run stays open there: a window operator chained by a later statement still absorbs it, through thunks)
+template <class... Ops>
+class FusedPipe {
+    MultiPipe *mp; std::tuple<Ops...> ops; bool done = false;
+    template <class... O> friend class FusedPipe;
+public:
+    FusedPipe(MultiPipe &m, std::tuple<Ops...> o): mp(&m), ops(std::move(o)) {}
+    FusedPipe(FusedPipe &&o) noexcept: mp(o.mp), ops(std::move(o.ops)), done(o.done) { o.done = true; }
+    FusedPipe(const FusedPipe &) = delete;
+    ~FusedPipe() { if (!done) materialize(); }
+    MultiPipe &materialize()
+    {
+        if (!done) { done = true; std::apply([this](auto &...op) { (mp->chain_stateless(op), ...); }, ops); }
+        return *mp;
+    }
+    operator MultiPipe &() { return materialize(); }
+    template <class F, bool IS> FusedPipe<Ops..., Stateless_GPU<F, IS>> chain(Stateless_GPU<F, IS> op)
+    {
+        if (done) wf_fatal("FusedPipe used after it was handed over");
+        done = true;
+        return FusedPipe<Ops..., Stateless_GPU<F, IS>>(*mp, std::tuple_cat(std::move(ops), std::make_tuple(op)));
+    }
+    template <class L, class C, class K> MultiPipe &chain(Ffat_Windows_GPU<L, C, K> op)
+    {
+        using T = typename Ffat_Windows_GPU<L, C, K>::tuple_t;
+        constexpr bool same_type = (std::is_same<typename Ops::tuple_t, T>::value && ...);
+        if constexpr (!same_type) return materialize().chain(op);
+        else {
+            if (done) wf_fatal("FusedPipe used after it was handed over");
+            if (mp->pending.n) return materialize().chain(op); // (an open run of earlier statements goes first: thunks for all of it)
+            done = true;
+            std::apply([this](auto &...o) { (mp->attach(o), ...); }, ops);
+            using pre_t = TypedChain<T, TypedStage<decltype(std::declval<Ops>().func), Ops::is_filter>...>;
+            pre_t pre = std::apply([](auto &...o) { return make_typed_chain<T>(TypedStage<decltype(o.func), std::decay_t<decltype(o)>::is_filter>{o.func}...); }, ops);
+            Ffat_Windows_GPU<L, C, K, pre_t> fop(op, pre);
+            mp->tail_is_gpu = true;
+            return mp->add_replicated(fop);
+        }
+    }
+    template <class Op> decltype(auto) chain(Op op) { return materialize().chain(op); }
+    template <class Op> decltype(auto) add(Op op) { return this->chain(op); }
+    template <class sink_f> MultiPipe &chain_sink(Sink<sink_f> op) { return materialize().chain_sink(op); }
+    template <class sink_f> MultiPipe &add_sink(Sink<sink_f> op) { return materialize().chain_sink(op); }
+    size_t getNumThreads() { return materialize().getNumThreads(); }
+    const std::vector<std::string> &getOperatorNames() { return materialize().getOperatorNames(); }
+};
+template <class F, bool IS> FusedPipe<Stateless_GPU<F, IS>> MultiPipe::chain(Stateless_GPU<F, IS> op) { return FusedPipe<Stateless_GPU<F, IS>>(*this, std::make_tuple(op)); }
 
 class PipeGraph {
     std::string name; Execution_Mode_t mode; Time_Policy_t policy;

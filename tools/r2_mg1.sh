@@ -1,9 +1,9 @@
 #!/bin/bash
-# one-GPU look at the N>1 step (bench.py --mg-path) and at the facade's pipeline: tests, timings, launch lists
+# one-GPU look at the N>1 step (bench.py --mg-path, one rank): tests, timing of the bucketed and the two-partition exchange, launch list
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_keyed.py tests/test_multi_gpu.py tests/test_gpu_ffat.py -m gpu -q -x > gpurun_out/mg1_pytest.log 2>&1; echo "pytest rc=$? $(grep -E 'passed|failed' gpurun_out/mg1_pytest.log | tail -1)"
+timeout 900 python -m pytest tests/test_gpu_keyed.py tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/mg1_pytest.log 2>&1; echo "pytest rc=$? $(grep -E 'passed|failed' gpurun_out/mg1_pytest.log | tail -1)"
 R() { tag=$1; shift
-timeout 600 python bench.py "$@" --steps 65 --warmup 3 --cpu-seconds 0.2 --e2e-steps 2 --no-extras > gpurun_out/mg1_$tag.json 2> gpurun_out/mg1_$tag.err
+env $ENVV timeout 600 python bench.py "$@" --steps 65 --warmup 3 --cpu-seconds 0.2 --e2e-steps 2 --no-extras > gpurun_out/mg1_$tag.json 2> gpurun_out/mg1_$tag.err
 python -c "
 import json
 for l in open('gpurun_out/mg1_$tag.json'):
@@ -11,9 +11,7 @@ for l in open('gpurun_out/mg1_$tag.json'):
         d=json.loads(l); print('$tag', round(d['value']/1e9,2),'GT/s ms/step', round(d['ms_per_step'],4), 'host', round(d.get('host_issue_ms_per_step'),3), [round(x['avg_us'],1) for x in (d['roofline'].get('kernels') or [])], 'check', d['check'] and d['check']['windows_compared'])
 " || tail -5 gpurun_out/mg1_$tag.err
 }
-R default
 R mgpath --mg-path
+ENVV="WFB_MG_BUCKETED=0" R mgpath_twopart --mg-path
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/mg1_launches_raw.csv python bench.py --mg-path --steps 2 --warmup 3 --prime-steps 2 --cpu-seconds 0.05 --e2e-steps 2 --no-check --no-extras > gpurun_out/mg1_launches.log 2>&1
 python tools/launch_summary.py gpurun_out/mg1_launches_raw.csv > gpurun_out/mg1_launches.txt; cat gpurun_out/mg1_launches.txt
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_tile|k_wide|k_ffat|k_slots' -c 300 --csv --log-file gpurun_out/facade_launches_raw.csv windflow_b200/apps/pipeline_bench.bin 128 512 > gpurun_out/facade_launches.log 2>&1
-python tools/launch_summary.py gpurun_out/facade_launches_raw.csv > gpurun_out/facade_launches.txt; cat gpurun_out/facade_launches.txt

@@ -133,6 +133,11 @@ struct TileArgs {
     uint32_t l2_hints;         // 1: input tiles are loaded evict-first, lifted records stored evict-last (they are re-read by the update)
     // MODE_INGEST with nshards != 0 (wfb_shard_lift): the "slot" of a tuple is its destination key % nshards
     uint32_t nshards, region_cap;
+    // ... and with shard_slots != 0 (bucketed exchange, wfb_mg_*): the "slot" is the VIRTUAL slot dest * shard_slots + key / nshards
+    // (shard_slots a power of two, nshards * shard_slots <= 65536), so that ONE wide partition at the source leaves the records
+    // grouped by (destination, bucket of the destination's slot space); keys at or above shard_keys * nshards raise *shard_err
+    uint32_t shard_slots, shard_keys;
+    uint32_t *shard_err;
     // MODE_INGEST: digit histograms of the slot sort that follows (RadixSorter ctl), accumulated per CTA in shared memory
     uint32_t *sort_ctl; uint32_t sort_passes, sort_shift, sort_dbits; // sort_dbits: digit width of a pass (8, or 10 for the wide pass)
     // MODE_INGEST outputs (compacted over the whole segment, arrival order)
@@ -468,7 +473,11 @@ __global__ void __launch_bounds__(TP_THREADS) k_tile_pass(const __grid_constant_
             if constexpr (MODE == MODE_INGEST) {
                 if (keep) {
                     P::lift(tup, res, prm);
-                    if (a.nshards) slot = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); // keyby across GPUs: the "slot" is the destination
+                    if (a.nshards && a.shard_slots) { // keyby across GPUs, bucketed: destination-major virtual slot
+                        const uint64_t key = P::key(tup, prm), q = key / a.nshards;
+                        if (q < a.shard_keys) slot = static_cast<uint32_t>(key - q * a.nshards) * a.shard_slots + static_cast<uint32_t>(q);
+                        else atomicOr(a.shard_err, 2u); // (a key outside the declared key space: the record is dropped, the step fails)
+                    } else if (a.nshards) slot = static_cast<uint32_t>(P::key(tup, prm) % a.nshards); // keyby across GPUs: the "slot" is the destination
                     else {
                         if (a.ext_slots != nullptr) { slot = a.ext_slots[m.tile * TILE + ctid]; if (slot >= a.ff.max_keys) slot = INVALID_SLOT; }
                         else slot = slot_of_key(a.ff, P::key(tup, prm));
@@ -1069,9 +1078,13 @@ static __global__ void __launch_bounds__(OSW_DIGITS) k_wide_chunk_scan(uint32_t 
 //      cell): an item's place = number of the cell's entries with a smaller position; a cell holds a few entries, read from shared memory,
 //   4. one write of (slot, position) per item to its final place.
 // Output: keys_out[i] = slot, vals_out[i] = arrival position, stable by (digit, position) -- what k_wide_scatter produces.
+// RBYTES != 0: the records travel (payload_in at the arrival positions -> payload_out at the final places; keys_out gets the slots,
+// vals_out is not written): the source side of the bucketed multi-GPU exchange.
+template <int RBYTES>
 static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(const uint32_t *__restrict__ packed, uint32_t *__restrict__ keys_out,
                                                                             uint32_t *__restrict__ vals_out, uint32_t n, uint32_t shift, uint32_t chunk_shift,
-                                                                            const uint16_t *__restrict__ H, const uint32_t *__restrict__ Cx)
+                                                                            const uint16_t *__restrict__ H, const uint32_t *__restrict__ Cx,
+                                                                            const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out)
 {
     constexpr uint32_t NW = OSW_THREADS / 32;
     __shared__ __align__(16) uint32_t bin_base[OSW_DIGITS];
@@ -1134,8 +1147,67 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
             for (uint32_t e = 0; e < cnt; e += 4) { const uint2 v = cell[e >> 2]; less += __popc((mm - v.x) & 0x80008000u) + __popc((mm - v.y) & 0x80008000u); }
             const uint32_t dst = bin_base[d] + less;
             keys_out[dst] = slot;
-            vals_out[dst] = start + mine;
+            if constexpr (RBYTES == 0) vals_out[dst] = start + mine;
+            else {
+                static_assert(RBYTES % 8 == 0, "record size");
+                using W = typename std::conditional<RBYTES % 16 == 0, uint4, uint2>::type;
+                const W *src = reinterpret_cast<const W *>(payload_in + static_cast<size_t>(start + mine) * RBYTES);
+                W *dstp = reinterpret_cast<W *>(payload_out + static_cast<size_t>(dst) * RBYTES);
+                W v[RBYTES / sizeof(W)];
+#pragma unroll
+                for (uint32_t q = 0; q < RBYTES / sizeof(W); q++) v[q] = src[q];
+#pragma unroll
+                for (uint32_t q = 0; q < RBYTES / sizeof(W); q++) dstp[q] = v[q];
+            }
         }
+    }
+}
+
+// bucketed exchange, source side: records per destination = sums of the bins [d * bps, (d + 1) * bps) of the partition
+static __global__ void k_shard_bin_counts(const uint32_t *__restrict__ bin_counts, uint32_t nshards, uint32_t bps, uint32_t *__restrict__ counts_out)
+{
+    const uint32_t d = threadIdx.x >> 5, lane = threadIdx.x & 31; // one warp per destination
+    uint32_t c = 0;
+    if (d < nshards) for (uint32_t b = lane; b < bps; b += 32) c += bin_counts[d * bps + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0 && d < MAX_SHARDS) counts_out[d] = d < nshards ? c : 0u; // ([MAX_SHARDS]: error flags, set by the tile pass)
+}
+
+// bucketed exchange, destination side: source s delivered, for every bucket b of this GPU's slot space, a run of cnt[s][b] records
+// (arrival order) -- the runs of one source back to back from recv position off[s]. Bucket b's items are its runs in source order
+// (= global stream order): write them as the (slot, position) lists k_ffat_update_buckets consumes + the bucket sizes. One CTA per bucket.
+struct MgRuns { uint32_t off[MAX_SHARDS + 1]; };
+static __global__ void __launch_bounds__(256) k_mg_lists(const uint32_t *__restrict__ cnt, uint32_t nsrc, uint32_t bps, const MgRuns runs,
+                                                         const uint32_t *__restrict__ recv_slots, uint32_t slot_mask, uint32_t *__restrict__ out_slots,
+                                                         uint32_t *__restrict__ out_pos, uint32_t *__restrict__ digit_counts,
+                                                         uint32_t *__restrict__ n_trig, uint32_t *__restrict__ n_heavy)
+{
+    __shared__ uint32_t part[8][MAX_SHARDS];
+    __shared__ uint32_t run_start[MAX_SHARDS], own[MAX_SHARDS];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (b == 0 && tid == 0) { *n_trig = 0; *n_heavy = 0; } // per-segment lists filled by the update kernel
+    for (uint32_t s = 0; s < nsrc; s++) { // records of source s in the buckets before b
+        uint32_t c = 0;
+        for (uint32_t q = tid; q < b; q += 256) c += cnt[s * bps + q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (lane == 0) part[warp][s] = c;
+    }
+    __syncthreads();
+    if (tid < nsrc) {
+        uint32_t c = 0;
+        for (uint32_t w = 0; w < 8; w++) c += part[w][tid];
+        run_start[tid] = c; own[tid] = cnt[tid * bps + b];
+    }
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (uint32_t s = 0; s < nsrc; s++) { base += run_start[s]; total += own[s]; }
+    if (tid == 0) digit_counts[b] = total;
+    for (uint32_t s = 0; s < nsrc; s++) {
+        const uint32_t src0 = runs.off[s] + run_start[s], m = own[s];
+        for (uint32_t i = tid; i < m; i += 256) { out_slots[base + i] = recv_slots[src0 + i] & slot_mask; out_pos[base + i] = src0 + i; }
+        base += m;
     }
 }
 

@@ -283,8 +283,21 @@ struct RadixSorter {
             }
         }
         if (prefix && ranked && sizeof(K) == 4 && !payload_in && keys_out_ok(kout, vout)) {
-            k_wide_scatter_ranked<<<tiles, OSW_THREADS, 0, s>>>(reinterpret_cast<const uint32_t *>(kin), reinterpret_cast<uint32_t *>(kout), vout, n_host, shift, chunk_shift,
-                                                                h16_rows ? h16_rows : wideH, wideC);
+            k_wide_scatter_ranked<0><<<tiles, OSW_THREADS, 0, s>>>(reinterpret_cast<const uint32_t *>(kin), reinterpret_cast<uint32_t *>(kout), vout, n_host, shift, chunk_shift,
+                                                                   h16_rows ? h16_rows : wideH, wideC, nullptr, nullptr);
+            CK(cudaGetLastError());
+            launches += 2;
+            *counts = c;
+            return 0;
+        }
+        if (prefix && ranked && sizeof(K) == 4 && payload_in && payload_out && kout && !region_stride) { // the records travel with their slots (bucketed exchange)
+#define WFB_WSR(RB_) k_wide_scatter_ranked<RB_><<<tiles, OSW_THREADS, 0, s>>>(reinterpret_cast<const uint32_t *>(kin), reinterpret_cast<uint32_t *>(kout), nullptr, n_host, shift, \
+                                                                             chunk_shift, h16_rows ? h16_rows : wideH, wideC, payload_in, payload_out)
+            switch (payload_bytes) {
+                case 16: WFB_WSR(16); break; case 24: WFB_WSR(24); break; case 32: WFB_WSR(32); break; case 48: WFB_WSR(48); break; case 64: WFB_WSR(64); break;
+                default: return WFB_E_UNSUPPORTED;
+            }
+#undef WFB_WSR
             CK(cudaGetLastError());
             launches += 2;
             *counts = c;
@@ -797,12 +810,29 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
     return 0;
 }
 
+// bucketed mode (wfb_mg_*): shard_slots != 0 -- the partition is the full 1024-bin one on the destination-major virtual slot
+// (dest * shard_slots + key / num_shards) >> shift: out_regions gets the records bin after bin (capacity: the segment's positions),
+// out_slots their virtual slots, bins_ctl (OSW_DIGITS + 1 words, the caller's) the bin sizes, counts_dev the records per destination
+static int shard_lift_impl(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
+                           void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream,
+                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl);
+
 int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
                    void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream)
+{
+    return shard_lift_impl(e, pre, batches_h, nbatches, num_shards, out_regions, region_capacity, counts_dev, stream, 0, 0, 0, nullptr, nullptr);
+}
+
+static int shard_lift_impl(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
+                           void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream,
+                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl)
 {
     // Map -> Filter -> lift in one streaming pass (no compaction chain: tile t owns positions [t*TILE, +TILE)), then one
     // stable partition pass on the destination (key % num_shards) that moves the lifted records into the shard regions.
     if (!e || !counts_dev || !out_regions || num_shards == 0 || num_shards > MAX_SHARDS || (nbatches && !batches_h)) return WFB_E_BADARG;
+    const bool bucketed = shard_slots != 0;
+    if (bucketed && (!out_slots || !bins_ctl || (shard_slots & (shard_slots - 1)) || static_cast<uint64_t>(num_shards) * shard_slots > 65536u ||
+                     shard_keys > shard_slots || (shard_slots >> shift) == 0)) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = e->ts.enter(s); if (rc) return rc;
     CK(cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * (MAX_SHARDS + 1), s));
@@ -819,9 +849,9 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
         span_begin = std::min(span_begin, p0); span_end = std::max(span_end, p0 + static_cast<uint64_t>(b.n) * e->ops->tuple_bytes);
         hb.push_back(b);
     }
-    if (total == 0) return 0;
+    if (total == 0) { if (bucketed) CK(cudaMemsetAsync(bins_ctl, 0, sizeof(uint32_t) * (OSW_DIGITS + 1), s)); return 0; }
     const uint64_t positions = static_cast<uint64_t>(tiles) * TILE;
-    if (positions > 0x7fffffffull) return WFB_E_BADARG;
+    if (positions > 0x7fffffffull || (bucketed && positions > region_capacity)) return WFB_E_BADARG;
     nbatches = static_cast<uint32_t>(hb.size());
     const size_t RB = e->ops->result_bytes;
     if (positions > e->sh_cap) {
@@ -835,13 +865,16 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
     rc = e->ts.ensure_tiles(tiles); if (rc) return rc;
     rc = e->ts.ensure_batches(nbatches); if (rc) return rc;
     { int rc_ = e->ts.stage.h2d(e->ts.d_batches, hb.data(), sizeof(DevBatch) * nbatches, s); if (rc_) return rc_; }
-    rc = RadixSorter::prepare_wide(e->sh_ctl, s); if (rc) return rc;
+    uint32_t *ctl = bucketed ? bins_ctl : e->sh_ctl;
+    rc = RadixSorter::prepare_wide(ctl, s); if (rc) return rc;
     TileArgs a; std::memset(&a, 0, sizeof(a));
     a.batches = e->ts.d_batches; a.nbatches = nbatches; a.num_tiles = tiles;
     a.lifted = e->sh_lifted; a.slots = e->sh_dest; a.nshards = num_shards; a.sparse = 1; a.l2_hints = 1;
-    a.sort_ctl = e->sh_ctl; a.sort_passes = 1; a.sort_shift = 0; a.sort_dbits = OSW_BITS;
+    a.sort_ctl = ctl; a.sort_passes = 1; a.sort_shift = 0; a.sort_dbits = OSW_BITS;
+    if (bucketed) { a.shard_slots = shard_slots; a.shard_keys = shard_keys; a.shard_err = counts_dev + MAX_SHARDS; a.sort_shift = shift; a.pack_rank = 1; }
     // the tile pass claims whole wide tiles and files the per-tile destination counts itself (no counting pass in the partition)
-    static const bool h16 = !(std::getenv("WFB_TILE_H16") && std::atoi(std::getenv("WFB_TILE_H16")) == 0);
+    static const bool h16_env = !(std::getenv("WFB_TILE_H16") && std::atoi(std::getenv("WFB_TILE_H16")) == 0);
+    const bool h16 = h16_env || bucketed;
     uint32_t claims = tiles;
     if (h16) {
         rc = e->sorter.ensure_wide(static_cast<uint32_t>(positions), s, &a.wide_h16); if (rc) return rc;
@@ -855,11 +888,19 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
     e->launches++;
     const uint32_t *counts = nullptr;
     const uint64_t before = e->sorter.launches;
-    rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, nullptr, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), 0, s,
-                                       e->sh_ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
-                                       region_capacity, num_shards, false, h16);
-    if (rc) return rc;
-    k_shard_counts<<<1, 32, 0, s>>>(counts, num_shards, region_capacity, counts_dev);
+    if (bucketed) {
+        rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, out_slots, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), shift, s,
+                                           ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
+                                           0, 0, false, true, nullptr, true);
+        if (rc) return rc;
+        k_shard_bin_counts<<<1, 32 * MAX_SHARDS, 0, s>>>(counts, num_shards, shard_slots >> shift, counts_dev);
+    } else {
+        rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, nullptr, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), 0, s,
+                                           e->sh_ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
+                                           region_capacity, num_shards, false, h16);
+        if (rc) return rc;
+        k_shard_counts<<<1, 32, 0, s>>>(counts, num_shards, region_capacity, counts_dev);
+    }
     CK(cudaGetLastError());
     e->launches += e->sorter.launches - before + 1;
     return 0;
@@ -1622,6 +1663,52 @@ static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch
     return 0;
 }
 
+// Window update on records that arrive grouped by bucket (destination side of the bucketed multi-GPU exchange): source s delivered
+// offs_h[s+1] - offs_h[s] records from position offs_h[s] of `records`, bucket after bucket of this handle's slot space (buckets of
+// 2^shift slots, bps of them; bins = the run lengths [nsrc][bps], recv_slots = the records' slots before masking). No partition pass:
+// the runs of a bucket, in source order, ARE its items in stream order.
+static int ffat_process_prebucketed(wfb_ffat *h, const unsigned char *records, const uint32_t *recv_slots, const uint32_t *bins, uint32_t nsrc,
+                                    uint32_t bps, const uint32_t *offs_h, const uint64_t *wms_h, uint32_t slot_mask, uint32_t shift,
+                                    void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, cudaStream_t s)
+{
+    if (!h || !n_out_dev || nsrc == 0 || nsrc > MAX_SHARDS || bps == 0 || bps > OSW_DIGITS || (1u << shift) > BK_KEYS) return WFB_E_BADARG;
+    if (h->win_type != 0 || h->pipelined || !h->buckets) return WFB_E_UNSUPPORTED;
+    int rc = h->ts.enter(s); if (rc) return rc;
+    SegScratch &g = h->seg[0];
+    const uint32_t total = offs_h[nsrc];
+    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+    if (total == 0) return 0;
+    rc = ffat_ensure_segment(h, g, total, nsrc, s); if (rc) return rc;
+    std::vector<DevBatch> hb(nsrc);
+    for (uint32_t i = 0; i < nsrc; i++) {
+        std::memset(&hb[i], 0, sizeof(DevBatch));
+        hb[i].tuples = records + static_cast<size_t>(offs_h[i]) * h->ops->result_bytes; hb[i].n = offs_h[i + 1] - offs_h[i]; hb[i].watermark = wms_h[i];
+    }
+    { int rc_ = h->ts.stage.h2d(g.d_batches, hb.data(), sizeof(DevBatch) * nsrc, s); if (rc_) return rc_; }
+    { int rc_ = h->ts.stage.h2d(g.batch_off, offs_h, sizeof(uint32_t) * (nsrc + 1), s); if (rc_) return rc_; }
+    g.nbatches = nsrc; g.total = total; g.sparse = true; g.lifted_src = records;
+    FfatDev ff = h->ff;
+    ff.seg_cnt = g.seg_cnt; ff.trig = g.trig; ff.n_trig = g.n_trig; ff.trig_cap = g.trig_cap; ff.n_heavy = g.n_heavy;
+    rc = RadixSorter::prepare_wide(g.sort_ctl, s); if (rc) return rc; // (buckets at or above bps stay empty)
+    h->mark(0, s); h->mark(1, s);
+    MgRuns runs;
+    for (uint32_t i = 0; i <= MAX_SHARDS; i++) runs.off[i] = offs_h[std::min(i, nsrc)];
+    k_mg_lists<<<bps, 256, 0, s>>>(bins, nsrc, bps, runs, recv_slots, slot_mask, g.slotsB, g.posB, g.sort_ctl, g.n_trig, g.n_heavy);
+    CK(cudaGetLastError());
+    h->mark(2, s);
+    rc = h->ops->ffat_buckets(ff, records, g.slotsB, g.posB, g.sort_ctl, shift, 0u, g.batch_off, g.d_batches, nsrc, static_cast<unsigned char *>(out_results), out_ts,
+                              out_capacity, n_out_dev, s, h->pp());
+    if (rc) return rc;
+    rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, nsrc, static_cast<unsigned char *>(out_results), out_ts, out_capacity, static_cast<uint32_t>(g_num_sms) * 4u, s,
+                              h->pp(), n_out_dev);
+    if (rc) return rc;
+    h->mark(3, s);
+    h->launches += 3;
+    if (h->timing && h->tev_used < wfb_ffat::TEV_MAX) h->tev_used++;
+    h->call_no++;
+    return 0;
+}
+
 int wfb_ffat_flush(wfb_ffat_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
 {
     if (!h || !n_out_dev || (out_capacity && !out_results)) return WFB_E_BADARG;
@@ -1727,7 +1814,10 @@ __global__ void k_mg_meta(const uint32_t *__restrict__ counts, uint64_t watermar
 }
 
 struct MgSlot { // buffers of one step in flight (two: the exchange of step i-1 overlaps the source pass of step i)
-    unsigned char *regions = nullptr; uint32_t region_cap = 0;
+    unsigned char *regions = nullptr; uint32_t region_cap = 0; // records by destination (bucketed: bin after bin, region_cap = the segment's positions)
+    uint32_t *vslots = nullptr;                // bucketed: virtual slot of every record of `regions`
+    uint32_t *bins = nullptr;                  // bucketed: OSW_DIGITS + 1 words, the bin sizes of this step's partition
+    uint32_t *recv_slots = nullptr, *recv_bins = nullptr; size_t recv_slots_cap = 0; // bucketed: what the sources delivered ([nranks][bps] run lengths)
     uint32_t *counts = nullptr;                // MAX_SHARDS + 1 (device)
     uint64_t *send_meta = nullptr, *recv_meta = nullptr; // [nranks][2] (device)
     uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
@@ -1748,6 +1838,9 @@ struct wfb_mg {
     uint64_t step_no = 0;
     MgSlot *pending = nullptr;
     std::vector<wfb_batch_t> chunks;
+    // bucketed exchange: the source partitions by (destination, bucket of the destination's slot space), the destination only concatenates runs
+    bool bucketed = false;
+    uint32_t shard_slots = 0, shard_keys = 0, shift = 0, bps = 0; // slots per destination (power of two), keys per destination, bucket = slot >> shift, buckets per destination
 };
 
 extern "C" {
@@ -1769,6 +1862,7 @@ int wfb_mg_destroy(wfb_mg_t *h)
     if (h->ffat) wfb_ffat_destroy(h->ffat);
     for (MgSlot &sl : h->slot) {
         cudaFree(sl.regions); cudaFree(sl.counts); cudaFree(sl.send_meta); cudaFree(sl.recv_meta); cudaFree(sl.recv);
+        cudaFree(sl.vslots); cudaFree(sl.bins); cudaFree(sl.recv_slots); cudaFree(sl.recv_bins);
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
         if (sl.h_recv) cudaFreeHost(sl.h_recv);
         for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done}) if (e) cudaEventDestroy(e);
@@ -1798,7 +1892,22 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
     MGCK(wfb_ffat_create(&h->ffat, lp, win, slide, wins_per_batch, (max_keys_total + nranks - 1) / nranks, 0, 0, WFB_FFAT_DENSE_KEYS));
     if (nranks > 1) MGCK(wfb_ffat_set_key_shard(h->ffat, static_cast<uint32_t>(nranks), static_cast<uint32_t>(rank)));
     MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)));
+    {   // bucketed exchange when the destination-major virtual slots fit 16 bits (they travel packed with a 16-bit rank)
+        const uint32_t keys = (max_keys_total + nranks - 1) / nranks;
+        uint32_t L = 1; while (L < keys) L <<= 1;
+        static const bool off = std::getenv("WFB_MG_BUCKETED") && std::atoi(std::getenv("WFB_MG_BUCKETED")) == 0;
+        const size_t rb = o->result_bytes;
+        if (!off && static_cast<uint64_t>(L) * nranks <= 65536u && h->ffat->buckets && (rb == 16 || rb == 24 || rb == 32 || rb == 48 || rb == 64)) {
+            uint32_t span = 1; while (span < L * static_cast<uint32_t>(nranks)) span <<= 1; // virtual slot space, rounded up
+            uint32_t sh = 0; while ((span >> sh) > OSW_DIGITS) sh++;
+            if ((L >> sh) >= 1) { h->bucketed = true; h->shard_slots = L; h->shard_keys = keys; h->shift = sh; h->bps = L >> sh; }
+        }
+    }
     for (MgSlot &sl : h->slot) {
+        if (h->bucketed) {
+            MGCK(static_cast<int>(cudaMalloc(&sl.bins, sizeof(uint32_t) * (OSW_DIGITS + 1))));
+            MGCK(static_cast<int>(cudaMalloc(&sl.recv_bins, sizeof(uint32_t) * MAX_SHARDS * OSW_DIGITS)));
+        }
         MGCK(static_cast<int>(cudaMalloc(&sl.counts, sizeof(uint32_t) * (MAX_SHARDS + 1))));
         MGCK(static_cast<int>(cudaMalloc(&sl.send_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
         MGCK(static_cast<int>(cudaMalloc(&sl.recv_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
@@ -1822,13 +1931,28 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
     uint64_t n = 0;
     for (uint32_t i = 0; i < nbatches; i++) n += batches_h[i].n;
     if (n > 0x7fffffffull) return WFB_E_BADARG;
-    if (sl.region_cap < n) { // worst case: every item of the segment survives and goes to one shard
-        if (sl.used) CK(cudaDeviceSynchronize());
-        cudaFree(sl.regions);
-        sl.region_cap = static_cast<uint32_t>(n);
-        CK(cudaMalloc(&sl.regions, static_cast<size_t>(h->nranks) * sl.region_cap * h->rb));
+    int rc;
+    if (h->bucketed) {
+        uint64_t positions = 0;
+        for (uint32_t i = 0; i < nbatches; i++) positions += static_cast<uint64_t>(tiles_of(batches_h[i].n)) * TILE;
+        if (sl.region_cap < positions) {
+            if (sl.used) CK(cudaDeviceSynchronize());
+            cudaFree(sl.regions); cudaFree(sl.vslots);
+            sl.region_cap = static_cast<uint32_t>(positions);
+            CK(cudaMalloc(&sl.regions, static_cast<size_t>(sl.region_cap) * h->rb));
+            CK(cudaMalloc(&sl.vslots, sizeof(uint32_t) * sl.region_cap));
+        }
+        rc = shard_lift_impl(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s,
+                             h->shard_slots, h->shard_keys, h->shift, sl.vslots, sl.bins);
+    } else {
+        if (sl.region_cap < n) { // worst case: every item of the segment survives and goes to one shard
+            if (sl.used) CK(cudaDeviceSynchronize());
+            cudaFree(sl.regions);
+            sl.region_cap = static_cast<uint32_t>(n);
+            CK(cudaMalloc(&sl.regions, static_cast<size_t>(h->nranks) * sl.region_cap * h->rb));
+        }
+        rc = wfb_shard_lift(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s);
     }
-    int rc = wfb_shard_lift(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s);
     if (rc) return rc;
     k_mg_meta<<<1, 32, 0, s>>>(sl.counts, watermark, static_cast<uint32_t>(h->nranks), sl.send_meta);
     CK(cudaGetLastError());
@@ -1853,8 +1977,51 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
 static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out_dev, cudaStream_t s)
 {
     CK(cudaEventSynchronize(sl.ev_meta)); // the sizes of this step on the host (a step old: no stall)
-    if (sl.h_counts[MAX_SHARDS]) return WFB_E_CAPACITY; // a shard region overflowed
+    if (sl.h_counts[MAX_SHARDS]) return WFB_E_CAPACITY; // a shard region overflowed / a key outside the declared key space
     const int n = h->nranks;
+    if (h->bucketed) {
+        // records, their slots and the run lengths of every source; source-rank order = global stream order
+        uint32_t offs[MAX_SHARDS + 1]; uint64_t wms[MAX_SHARDS]; uint64_t tot = 0;
+        for (int p = 0; p < n; p++) { offs[p] = static_cast<uint32_t>(tot); tot += sl.h_recv[2 * p]; wms[p] = sl.h_recv[2 * p + 1]; }
+        if (tot > 0x7fffffffull) return WFB_E_CAPACITY;
+        offs[n] = static_cast<uint32_t>(tot);
+        const size_t need = std::max<size_t>(1, tot);
+        if (sl.recv_bytes < need * h->rb || sl.recv_slots_cap < need) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(sl.recv); cudaFree(sl.recv_slots);
+            sl.recv_slots_cap = need * 5 / 4; sl.recv_bytes = sl.recv_slots_cap * h->rb;
+            CK(cudaMalloc(&sl.recv, sl.recv_bytes));
+            CK(cudaMalloc(&sl.recv_slots, sizeof(uint32_t) * sl.recv_slots_cap));
+        }
+        if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs, sl.ev_done, 0)); // the window update that read these receive buffers two steps ago
+        size_t send_off[MAX_SHARDS + 1]; send_off[0] = 0;
+        for (int p = 0; p < n; p++) send_off[p + 1] = send_off[p] + sl.h_counts[p];
+        const size_t bin_bytes = sizeof(uint32_t) * h->bps;
+        if (n > 1) {
+            NK(nccl().GroupStart());
+            for (int p = 0; p < n; p++) {
+                NK(nccl().Send(sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(sl.recv + static_cast<size_t>(offs[p]) * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Send(sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(sl.recv_slots + offs[p], static_cast<size_t>(sl.h_recv[2 * p]) * 4, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Send(sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(sl.recv_bins + static_cast<size_t>(p) * h->bps, bin_bytes, NCCL_UINT8, p, h->comm, h->cs));
+            }
+            NK(nccl().GroupEnd());
+        } else {
+            CK(cudaMemcpyAsync(sl.recv, sl.regions, static_cast<size_t>(sl.h_counts[0]) * h->rb, cudaMemcpyDeviceToDevice, h->cs));
+            CK(cudaMemcpyAsync(sl.recv_slots, sl.vslots, static_cast<size_t>(sl.h_counts[0]) * 4, cudaMemcpyDeviceToDevice, h->cs));
+            CK(cudaMemcpyAsync(sl.recv_bins, sl.bins, bin_bytes, cudaMemcpyDeviceToDevice, h->cs));
+        }
+        CK(cudaEventRecord(sl.ev_a2a, h->cs));
+        CK(cudaStreamWaitEvent(s, sl.ev_a2a, 0));
+        int rc = ffat_process_prebucketed(h->ffat, sl.recv, sl.recv_slots, sl.recv_bins, static_cast<uint32_t>(n), h->bps, offs, wms, h->shard_slots - 1u, h->shift,
+                                          out, out_ts, out_cap, n_out_dev, s);
+        if (rc) return rc;
+        CK(cudaEventRecord(sl.ev_done, s));
+        sl.done_recorded = true;
+        return 0;
+    }
     size_t offs[MAX_SHARDS + 1]; size_t tiles = 0; // every source's chunk at its tile position of the receive buffer (read in place)
     for (int p = 0; p < n; p++) { offs[p] = tiles * TILE; tiles += (static_cast<size_t>(sl.h_recv[2 * p]) + TILE - 1) / TILE; }
     const size_t need = std::max<size_t>(1, tiles * TILE) * h->rb;
