@@ -339,7 +339,7 @@ def run_ours(args):
         else:                                        # the whole step under the C ABI (wfb_mg_step: NCCL send/recv groups issued from C)
             pipe = multigpu.KeyShardedPipelineC(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev)
         ff = pipe.ff
-    cap = ff.max_results(seg_tuples * (2 if world > 1 else 1))
+    cap = ff.max_results(seg_tuples * (3 if pipe is not None else 1))  # (a flush of the multi-GPU pipeline delivers two steps at once)
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
     out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -589,18 +589,21 @@ def facade_sweep(nb):
     if not os.path.exists(FACADE_APP):
         return {"unavailable": "windflow_b200/apps/pipeline_bench.bin not built"}
     rows = []
-    for k, timed in ((1, 2048), (4, 8192), (16, 16384), (64, 24576), (128, 32768)):
+    for k, timed, style in ((1, 2048, "fluent"), (4, 8192, "fluent"), (16, 16384, "fluent"), (64, 24576, "fluent"), (128, 32768, "fluent"), (128, 32768, "statements")):
         try:
-            p = subprocess.run([FACADE_APP, str(k), str(timed), str(NKEYS), str(nb)], capture_output=True, text=True, timeout=300)
+            p = subprocess.run([FACADE_APP, str(k), str(timed), str(NKEYS), str(nb), "512", "2", style], capture_output=True, text=True, timeout=300)
             if p.returncode != 0:
-                rows.append({"max_batches_per_call": k, "error": (p.stdout + p.stderr)[-300:]})
+                rows.append({"max_batches_per_call": k, "style": style, "error": (p.stdout + p.stderr)[-300:]})
                 continue
             r = json.loads(p.stdout.strip().splitlines()[-1])
-            rows.append({"max_batches_per_call": k, "value": r["tuples_per_s"], "unit": "tuples/s", "tuples": r["tuples"], "threads": r["threads"], "windows": r["windows"]})
+            rows.append({"max_batches_per_call": k, "style": style, "value": r["tuples_per_s"], "unit": "tuples/s", "tuples": r["tuples"], "threads": r["threads"],
+                         "windows": r["windows"]})
         except Exception as e:  # pragma: no cover
-            rows.append({"max_batches_per_call": k, "error": repr(e)})
+            rows.append({"max_batches_per_call": k, "style": style, "error": repr(e)})
     return {"api": "facade", "what": "SourceGPU (ring of batches in HBM) -> Map_GPU -> Filter_GPU -> Ffat_Windows_GPU -> Sink built with the builders and "
-                                     "MultiPipe; Map and Filter are fused into the window operator's ingest pass; wall clock over the timed batches after priming",
+                                     "MultiPipe; Map and Filter are fused into the window operator's ingest pass -- style fluent: one chain expression, the functor types reach the "
+                                     "program (inlined); style statements: one chain call per statement, fused through device function pointers; wall clock over the timed "
+                                     "batches after priming",
             "rows": rows}
 
 

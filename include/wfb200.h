@@ -251,14 +251,19 @@ int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream);
  * NVLink), and the rank's Ffat_Windows_GPU replica on the keys with key % nranks == rank, fed the received chunks in source-rank
  * order = global stream order (every count window equals the single-GPU one). Stands in for KeyBy_Emitter_GPU between the
  * replicas of different devices. NCCL is looked up at run time (dlopen "libnccl.so.2"): WFB_E_UNSUPPORTED when it is missing.
- * The exchange and the window update of step t are issued behind the source pass of step t+1, so results arrive one step late
- * (wfb_mg_flush delivers the last ones) and the host never waits for the GPU: the sizes NCCL needs on the host are a step old. */
+ * Exchange: when every rank's slots fit 16 bits together (max_keys_total, rounded up per rank to a power of two, times nranks <= 65536)
+ * the SOURCE partitions its surviving records by (destination, bucket of the destination's slot space) in its one partition pass, and
+ * the destination only concatenates the runs it receives, source after source, bucket by bucket -- it runs no partition of its own;
+ * otherwise the source partitions by destination and the destination partitions what it received (WFB_MG_BUCKETED=0 forces this).
+ * The exchange and the window update of step t are issued behind the source pass of step t+2, so results arrive TWO steps late
+ * (wfb_mg_flush delivers the rest, appended in step order) and the host never waits for the GPU: the sizes NCCL needs on the host
+ * are a step old when it reads them. */
 typedef struct wfb_mg wfb_mg_t;
 int wfb_mg_unique_id(void *id128_h);   /* rank 0: an ncclUniqueId (128 bytes) to hand to the other ranks (broadcast it with the launcher's means) */
 int wfb_mg_create(wfb_mg_t **h, int prog, int nranks, int rank, const void *id128_h, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
                   uint32_t max_keys_total /* keys 0 .. max_keys_total-1 over all ranks */);
 int wfb_mg_destroy(wfb_mg_t *h);
-/* this rank's K batches of the next global step; the window results of the PREVIOUS step go to out_results / out_ts (none on the first call).
+/* this rank's K batches of the next global step; the window results of the step two calls back go to out_results / out_ts (none on the first two calls).
  * `watermark`: the watermark of the segment (result timestamps carry the watermark of the source segment that held the triggering item). */
 int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark,
                 void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);

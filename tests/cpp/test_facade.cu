@@ -113,6 +113,27 @@ int main()
         check("ffat cb windows sum", global_sum, exp * static_cast<long>(keys));
         check("ffat cb windows count", received, static_cast<long>(groups * nwb * keys));
     }
+    // ---- test 2b: the same pipeline written as ONE expression: the Map/Filter functor types become part of the window operator's
+    // program (FusedPipe / TypedChain: no thunks); a filter that keeps everything rides along. Same expected sums.
+    {
+        global_sum = 0; received = 0;
+        const uint64_t win = 64, slide = 16; const size_t nwb = 3;
+        PipeGraph graph("test_win_fat_gpu_cb_fluent", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
+        Source_Positive_Functor sf{len, keys};
+        graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(batch).build())
+            .chain(MapGPU_Builder(Map_Functor_GPU()).withName("mapgpu").build())
+            .chain(FilterGPU_Builder(Filter_Functor_GPU{1}).withName("filtergpu_all").build())
+            .add(Ffat_WindowsGPU_Builder(Lift_Functor_GPU(), Comb_Functor_GPU()).withName("ffat_agg").withKeyBy(Key_Functor())
+                     .withCBWindows(win, slide).withNumWinPerBatch(nwb).withMaxKeys(16).build())
+            .chain_sink(Sink_Builder(Sink_Functor()).withName("sink").build());
+        graph.run();
+        const uint64_t B = (nwb - 1) * slide + win;
+        const uint64_t groups = 1 + (len - B) / (slide * nwb);
+        long exp = 0;
+        for (uint64_t g = 0; g < groups * nwb; g++) { const long a = g * slide + 1 + 2, b = g * slide + win + 2; exp += (a + b) * static_cast<long>(win) / 2; }
+        check("ffat cb windows sum (fluent, typed fusion)", global_sum, exp * static_cast<long>(keys));
+        check("ffat cb windows count (fluent, typed fusion)", received, static_cast<long>(groups * nwb * keys));
+    }
     // ---- test 3: Source -> Reduce_GPU (keyed) -> Sink (test_graph_gpu_4 shape) -----------------------------------------------
     {
         global_sum = 0; received = 0;

@@ -7,13 +7,17 @@
 // built with the builders, wired with MultiPipe, every replica a thread of the runtime with a queue in front of it. The window
 // replica takes up to K queued batches per svc() (withMaxBatchesPerCall): K = 1 is the reference's one-batch-per-svc behaviour,
 // larger K is what a replica finds queued when the source is faster than one launch sequence.
-//   usage: pipeline_bench.bin [K=128] [timed_batches=40960] [keys=65536] [nb=65] [ring_batches=512] [sink_replicas=2]
+//   usage: pipeline_bench.bin [K=128] [timed_batches=40960] [keys=65536] [nb=65] [ring_batches=512] [sink_replicas=2] [style=fluent]
+// style: "fluent" = source.chain(map).chain(filter).add(ffat) in ONE expression -- the functor types reach the window operator's
+// program and are inlined into its tile pass; "statements" = one mp.chain(...) per statement -- the same fusion through per-stage
+// device function pointers (the types are gone by the time the window operator arrives).
 // prints one JSON line. Build: nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr
 //        --expt-extended-lambda -I include windflow_b200/apps/pipeline_bench.cu -L windflow_b200 -lwfb200
 #include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <optional>
 #include <thread>
 #include <wf/windflow_gpu.hpp>
@@ -53,6 +57,7 @@ int main(int argc, char **argv)
     const size_t nb = argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 65;
     const uint64_t ring = argc > 5 ? std::strtoull(argv[5], nullptr, 10) : 512; // 512 x 4 MiB = 2 GiB of input, far larger than L2
     const size_t sinks = argc > 6 ? std::strtoull(argv[6], nullptr, 10) : 2;
+    const bool fluent = !(argc > 7 && std::strcmp(argv[7], "statements") == 0);
     const uint64_t BATCH = 65536, WIN = 4096, SLIDE = 64;
     const uint64_t B = (nb - 1) * SLIDE + WIN;
     // every key past its first trigger before the clock starts: B surviving tuples per key at selectivity 0.5
@@ -82,10 +87,14 @@ int main(int argc, char **argv)
     {
         PipeGraph graph("pipeline_bench", Execution_Mode_t::DEFAULT, Time_Policy_t::EVENT_TIME);
         MultiPipe &mp = graph.add_source(SourceGPU_Builder(source).withName("source").build());
-        mp.chain(MapGPU_Builder(MapF()).withName("map").build());
-        mp.chain(FilterGPU_Builder(FiltF()).withName("filter").build());
-        mp.add(Ffat_WindowsGPU_Builder(LiftF(), CombF()).withName("ffat").withKeyBy(KeyF()).withCBWindows(WIN, SLIDE).withNumWinPerBatch(nb)
-                   .withMaxKeys(static_cast<uint32_t>(nkeys)).withDenseKeys().withMaxBatchesPerCall(K).build());
+        auto ffat = Ffat_WindowsGPU_Builder(LiftF(), CombF()).withName("ffat").withKeyBy(KeyF()).withCBWindows(WIN, SLIDE).withNumWinPerBatch(nb)
+                        .withMaxKeys(static_cast<uint32_t>(nkeys)).withDenseKeys().withMaxBatchesPerCall(K).build();
+        if (fluent) mp.chain(MapGPU_Builder(MapF()).withName("map").build()).chain(FilterGPU_Builder(FiltF()).withName("filter").build()).add(ffat);
+        else {
+            mp.chain(MapGPU_Builder(MapF()).withName("map").build());
+            mp.chain(FilterGPU_Builder(FiltF()).withName("filter").build());
+            mp.add(ffat);
+        }
         // the sink also publishes how far the stream has been processed (the watermark of every result batch = its last input batch)
         mp.chain_sink(Sink_Builder(SinkF()).withName("sink").withParallelism(sinks).withWatermarkProbe(&g_seen_wm).build());
         threads = graph.getNumThreads();
@@ -93,9 +102,9 @@ int main(int argc, char **argv)
     }
     const double sec = std::chrono::duration<double>(t1 - t0).count();
     std::printf("{\"api\": \"facade\", \"max_batches_per_call\": %zu, \"tuples\": %llu, \"seconds\": %.6f, \"tuples_per_s\": %.1f, \"windows\": %llu, \"isum\": %lld, "
-                "\"threads\": %zu, \"keys\": %llu, \"nb\": %zu, \"primed_batches\": %llu}\n",
+                "\"threads\": %zu, \"keys\": %llu, \"nb\": %zu, \"primed_batches\": %llu, \"style\": \"%s\"}\n",
                 K, static_cast<unsigned long long>(timed * BATCH), sec, timed * BATCH / sec, static_cast<unsigned long long>(g_windows.load()),
-                g_isum.load(), threads, static_cast<unsigned long long>(nkeys), nb, static_cast<unsigned long long>(prime));
+                g_isum.load(), threads, static_cast<unsigned long long>(nkeys), nb, static_cast<unsigned long long>(prime), fluent ? "fluent" : "statements");
     cudaFree(d_tuples); cudaFree(d_ts);
     return 0;
 }

@@ -71,6 +71,8 @@ struct FfatDev {
     uint32_t *n_slots;         // number of keys inserted so far
     uint32_t *err_flags;       // bit0: key table full, bit1: output capacity exceeded
     unsigned long long *results_total; // window results delivered so far (added by the last kernel of every call)
+    uint64_t defer_items;              // a fired group may wait for the deferred pass (k_ffat_windows*) while fewer than this many further items of
+                                       // its key follow in the call: (spare ring leaves + 1) panes -- later panes then do not overwrite leaves it reads
     uint32_t dense;            // 1: slot = key (keys < max_keys), or key / key_div for one shard of a keyby
     uint32_t key_div, key_rem; // dense: the handle owns the keys with key % key_div == key_rem (key_div <= 1: all keys)
     // per-slot state
@@ -1100,6 +1102,11 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
     uint32_t w[OSW_ITEMS];
 #pragma unroll
     for (uint32_t r = 0; r < OSW_ITEMS; r++) { const uint32_t idx = start + r * OSW_THREADS + tid; w[r] = idx < n ? packed[idx] : INVALID_SLOT; }
+    if constexpr (RBYTES != 0) { // the records this CTA will move: on their way to L2 while the offsets are worked out below
+#pragma unroll
+        for (uint32_t r = 0; r < OSW_ITEMS; r++)
+            if (w[r] != INVALID_SLOT) asm volatile("prefetch.global.L2 [%0];" ::"l"(payload_in + static_cast<size_t>(start + r * OSW_THREADS + tid) * RBYTES));
+    }
     {
         const uint32_t chunk = tile >> chunk_shift;
         uint4 acc = reinterpret_cast<const uint4 *>(Cx)[static_cast<size_t>(chunk) * (OSW_DIGITS / 4) + tid];
@@ -1174,40 +1181,103 @@ static __global__ void k_shard_bin_counts(const uint32_t *__restrict__ bin_count
     if (lane == 0 && d < MAX_SHARDS) counts_out[d] = d < nshards ? c : 0u; // ([MAX_SHARDS]: error flags, set by the tile pass)
 }
 
-// bucketed exchange, destination side: source s delivered, for every bucket b of this GPU's slot space, a run of cnt[s][b] records
-// (arrival order) -- the runs of one source back to back from recv position off[s]. Bucket b's items are its runs in source order
-// (= global stream order): write them as the (slot, position) lists k_ffat_update_buckets consumes + the bucket sizes. One CTA per bucket.
+// bucketed exchange, destination side: source s delivered, for every COARSE bucket b of this GPU's slot space (bps of them: the
+// source's 1024 bins are shared by all destinations), a run of cnt[s][b] records in arrival order -- the runs of one source back to
+// back from recv position off[s]. The update kernel wants all 1024 CTAs busy, so every coarse bucket is split into nsub = 1024 / bps
+// sub-buckets by slot: the items of sub-bucket (b, j) are, source after source (= global stream order), the items of run (s, b) whose
+// slot falls into j, in arrival order. Three small kernels write them as the (slot, position) lists + sizes k_ffat_update_buckets
+// consumes: count per (b, j, s) | exclusive scan in that order | stable split of every run.
 struct MgRuns { uint32_t off[MAX_SHARDS + 1]; };
-static __global__ void __launch_bounds__(256) k_mg_lists(const uint32_t *__restrict__ cnt, uint32_t nsrc, uint32_t bps, const MgRuns runs,
-                                                         const uint32_t *__restrict__ recv_slots, uint32_t slot_mask, uint32_t *__restrict__ out_slots,
-                                                         uint32_t *__restrict__ out_pos, uint32_t *__restrict__ digit_counts,
-                                                         uint32_t *__restrict__ n_trig, uint32_t *__restrict__ n_heavy)
-{
-    __shared__ uint32_t part[8][MAX_SHARDS];
-    __shared__ uint32_t run_start[MAX_SHARDS], own[MAX_SHARDS];
-    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (b == 0 && tid == 0) { *n_trig = 0; *n_heavy = 0; } // per-segment lists filled by the update kernel
-    for (uint32_t s = 0; s < nsrc; s++) { // records of source s in the buckets before b
-        uint32_t c = 0;
-        for (uint32_t q = tid; q < b; q += 256) c += cnt[s * bps + q];
+constexpr uint32_t MG_THREADS = 256;
+__device__ __forceinline__ uint32_t mg_run_start(const uint32_t *__restrict__ cnt, uint32_t s, uint32_t bps, uint32_t b, uint32_t *sh)
+{   // records of source s in the coarse buckets before b (block-wide sum; sh: 8 words of shared memory)
+    uint32_t c = 0;
+    for (uint32_t q = threadIdx.x; q < b; q += MG_THREADS) c += cnt[s * bps + q];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-        if (lane == 0) part[warp][s] = c;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < MG_THREADS / 32; w++) t += sh[w];
+    __syncthreads();
+    return t;
+}
+static __global__ void __launch_bounds__(MG_THREADS) k_mg_count(const uint32_t *__restrict__ cnt, uint32_t nsrc, uint32_t bps, const MgRuns runs,
+                                                                const uint32_t *__restrict__ recv_slots, uint32_t slot_mask, uint32_t shift2, uint32_t nsub,
+                                                                uint32_t *__restrict__ cnt3, uint32_t *__restrict__ run_starts,
+                                                                uint32_t *__restrict__ n_trig, uint32_t *__restrict__ n_heavy)
+{
+    __shared__ uint32_t sh[8], c[MAX_SHARDS];
+    const uint32_t b = blockIdx.x, s = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    if (b == 0 && s == 0 && tid == 0) { *n_trig = 0; *n_heavy = 0; } // per-segment lists filled by the update kernel
+    if (tid < MAX_SHARDS) c[tid] = 0;
+    const uint32_t rs = mg_run_start(cnt, s, bps, b, sh), m = cnt[s * bps + b];
+    if (tid == 0) run_starts[s * bps + b] = rs;
+    const uint32_t *sl = recv_slots + runs.off[s] + rs;
+    for (uint32_t i0 = 0; i0 < m; i0 += MG_THREADS) {
+        const uint32_t i = i0 + tid;
+        const uint32_t j = i < m ? ((sl[i] & slot_mask) >> shift2) & (nsub - 1u) : nsub;
+        for (uint32_t jj = 0; jj < nsub; jj++) { const uint32_t bal = __ballot_sync(FULL, j == jj); if (lane == 0 && bal) atomicAdd(&c[jj], __popc(bal)); }
     }
     __syncthreads();
-    if (tid < nsrc) {
-        uint32_t c = 0;
-        for (uint32_t w = 0; w < 8; w++) c += part[w][tid];
-        run_start[tid] = c; own[tid] = cnt[tid * bps + b];
+    if (tid < nsub) cnt3[(b * nsub + tid) * nsrc + s] = c[tid];
+}
+// exclusive scan of cnt3 in (bucket, sub-bucket, source) order + the sub-bucket sizes (one CTA of 1024 threads; n <= 1024 * MAX_SHARDS)
+static __global__ void __launch_bounds__(1024) k_mg_scan(const uint32_t *__restrict__ cnt3, uint32_t n, uint32_t nsrc, uint32_t *__restrict__ off3,
+                                                         uint32_t *__restrict__ digit_counts)
+{
+    __shared__ uint32_t wsum[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (n + 1023u) / 1024u, lo = tid * per;
+    uint32_t v[MAX_SHARDS], sum = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < MAX_SHARDS; q++) { v[q] = (q < per && lo + q < n) ? cnt3[lo + q] : 0u; sum += v[q]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(FULL, incl, o); if (lane >= static_cast<uint32_t>(o)) incl += x; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(FULL, wi, o); if (lane >= static_cast<uint32_t>(o)) wi += x; }
+        wsum[lane] = wi - w;
     }
     __syncthreads();
-    uint32_t base = 0, total = 0;
-    for (uint32_t s = 0; s < nsrc; s++) { base += run_start[s]; total += own[s]; }
-    if (tid == 0) digit_counts[b] = total;
-    for (uint32_t s = 0; s < nsrc; s++) {
-        const uint32_t src0 = runs.off[s] + run_start[s], m = own[s];
-        for (uint32_t i = tid; i < m; i += 256) { out_slots[base + i] = recv_slots[src0 + i] & slot_mask; out_pos[base + i] = src0 + i; }
-        base += m;
+    uint32_t run = wsum[warp] + incl - sum;
+#pragma unroll
+    for (uint32_t q = 0; q < MAX_SHARDS; q++) if (q < per && lo + q < n) { off3[lo + q] = run; run += v[q]; }
+    for (uint32_t d = tid; d * nsrc < n; d += 1024) { uint32_t t = 0; for (uint32_t q = 0; q < nsrc; q++) t += cnt3[d * nsrc + q]; digit_counts[d] = t; }
+}
+static __global__ void __launch_bounds__(MG_THREADS) k_mg_split(const uint32_t *__restrict__ cnt, uint32_t nsrc, uint32_t bps, const MgRuns runs,
+                                                                const uint32_t *__restrict__ recv_slots, uint32_t slot_mask, uint32_t shift2, uint32_t nsub,
+                                                                const uint32_t *__restrict__ off3, const uint32_t *__restrict__ run_starts,
+                                                                uint32_t *__restrict__ out_slots, uint32_t *__restrict__ out_pos)
+{
+    __shared__ uint32_t wc[MG_THREADS / 32][MAX_SHARDS], fill[MAX_SHARDS];
+    const uint32_t b = blockIdx.x, s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t m = cnt[s * bps + b], src0 = runs.off[s] + run_starts[s * bps + b];
+    if (tid < nsub) fill[tid] = off3[(b * nsub + tid) * nsrc + s];
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < m; i0 += MG_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint32_t slot = 0, j = nsub, before = 0;
+        if (i < m) { slot = recv_slots[src0 + i] & slot_mask; j = (slot >> shift2) & (nsub - 1u); }
+        for (uint32_t jj = 0; jj < nsub; jj++) {
+            const uint32_t bal = __ballot_sync(FULL, j == jj);
+            if (lane == 0) wc[warp][jj] = __popc(bal);
+            if (j == jj) before = __popc(bal & lanemask_lt());
+        }
+        __syncthreads();
+        if (i < m) {
+            uint32_t dst = fill[j] + before;
+            for (uint32_t w = 0; w < warp; w++) dst += wc[w][j];
+            out_slots[dst] = slot; out_pos[dst] = src0 + i;
+        }
+        __syncthreads();
+        if (tid < nsub) { uint32_t t = 0; for (uint32_t w = 0; w < MG_THREADS / 32; w++) t += wc[w][tid]; fill[tid] += t; }
+        __syncthreads();
     }
 }
 
@@ -1526,7 +1596,7 @@ __global__ void __launch_bounds__(128) k_ffat_update_lanes(const FfatDev ff, con
                 if (c == trig) {
                     const uint32_t last_pos = sorted_pos[off + j - 1]; // arrival position of the triggering item
                     const uint32_t obase = atomicAdd(n_out, ff.nb);
-                    bool deferred = (m - j) < P_; // no further pane of this key can complete in this segment
+                    bool deferred = (m - j) < ff.defer_items; // the panes this key still completes in this segment fit the spare ring leaves
                     if (deferred) {
                         const uint32_t ti = atomicAdd(ff.n_trig, 1u);
                         if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
@@ -1880,7 +1950,7 @@ __global__ void __launch_bounds__(BK_THREADS, LAZY ? WFB_BK_MINBLOCKS_LAZY : WFB
                             const uint32_t lp = s_idx[koff[k] + consumed - 1];
                             const uint32_t last_pos = moved ? bk_pos[lp] : lp; // arrival position of the triggering item
                             const uint32_t obase = atomicAdd(n_out, ff.nb);
-                            bool deferred = (left0 - consumed) < P32; // no further pane of this key can complete in this segment
+                            bool deferred = (left0 - consumed) < ff.defer_items; // the panes this key still completes in this segment fit the spare ring leaves
                             if (deferred) {
                                 const uint32_t ti = atomicAdd(ff.n_trig, 1u);
                                 if (ti < ff.trig_cap) { Trigger tr; tr.key = key; tr.g = g; tr.slot = slot; tr.last_pos = last_pos; tr.obase = obase; tr.pad = 0; ff.trig[ti] = tr; }
@@ -1963,7 +2033,7 @@ __global__ void __launch_bounds__(BK_THREADS, LAZY ? WFB_BK_MINBLOCKS_LAZY : WFB
                                 uint32_t obase = 0;
                                 if (lane == 0) obase = atomicAdd(n_out, ff.nb);
                                 obase = __shfl_sync(FULL, obase, 0);
-                                bool deferred = left < P32; // no further pane of this key can complete in this segment
+                                bool deferred = left < ff.defer_items; // the panes this key still completes in this segment fit the spare ring leaves
                                 if (deferred) {
                                     uint32_t ti = 0;
                                     if (lane == 0) ti = atomicAdd(ff.n_trig, 1u);
@@ -2502,7 +2572,7 @@ __global__ void __launch_bounds__(256) k_ffat_update(const FfatDev ff, const uns
                     obase = __shfl_sync(FULL, obase, 0);
                     // No further pane of this key can complete in this segment => the tree stays as it is now and the
                     // queries can run later, thread-per-window, in k_ffat_windows; otherwise evaluate them here.
-                    bool deferred = (m - j) < P_;
+                    bool deferred = (m - j) < ff.defer_items;
                     if (deferred) {
                         uint32_t ti = 0;
                         if (lane == 0) ti = atomicAdd(ff.n_trig, 1u);

@@ -481,6 +481,8 @@ struct wfb_ffat {
     bool shares_slot_key = false;                   // back end of a time-based handle: ff.slot_key / ff.n_slots belong to the front end
     uint32_t *own_n_slots = nullptr;                // the allocation behind ff.n_slots / ff.err_flags of this handle
     uint32_t *tb_head = nullptr, *tb_seg = nullptr, *tb_misc = nullptr; // misc: [0] n_segs [1] first_seg dummy [2] n_present [3] popped total [4] ignored [5] ring capacity needed
+    uint32_t *mg_scratch = nullptr; // (internal, ffat_process_prebucketed) per-(bucket, sub-bucket, source) counts, their scan, run starts
+    bool append_results = false;  // (internal, wfb_mg_flush) the next call's results follow the ones already in the output buffer
     bool buckets = true;          // one wide radix pass + per-bucket CTAs (<= 65536 keys); WFB_UPDATE=lanes selects the
                                   // full sort + thread-per-key update instead
     uint32_t bucket_shift = 0;    // the wide pass partitions on (slot >> bucket_shift) & 1023
@@ -1254,8 +1256,14 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
     const uint64_t bp = ff.B / pane;
     if (pane > 0xffffffffull || bp > (1ull << 30)) { delete h; return WFB_E_BADARG; }
     ff.pane = static_cast<uint32_t>(pane); ff.wp = static_cast<uint32_t>(win / pane); ff.sp = static_cast<uint32_t>(slide / pane);
-    uint32_t n = 1, lg = 0; while (n < bp) { n <<= 1; lg++; }
+    // ring of n leaves (a power of two) for the bp panes a group reads + spare leaves: a key that completes up to `spare` further panes in
+    // the call that fires a group leaves the group's leaves alone, so the group can wait for the deferred pass (one warp per group, levels
+    // built on chip) instead of being evaluated inside the update kernel. WFB_RING_SPARE: minimum spare leaves (default min(bp, 32)).
+    static const int spare_env = std::getenv("WFB_RING_SPARE") ? std::atoi(std::getenv("WFB_RING_SPARE")) : -1;
+    const uint64_t spare_min = spare_env >= 0 ? static_cast<uint64_t>(spare_env) : std::min<uint64_t>(bp, 32);
+    uint32_t n = 1, lg = 0; while (n < bp + spare_min) { n <<= 1; lg++; }
     ff.n_leaves = n; ff.log_leaves = lg;
+    ff.defer_items = (static_cast<uint64_t>(n) - bp + 1) * pane;
     ff.max_keys = max_keys; ff.dense = (flags & WFB_FFAT_DENSE_KEYS) ? 1u : 0u;
     uint32_t cap = 1; while (cap < 2ull * max_keys) cap <<= 1;
     ff.ht_mask = cap - 1;
@@ -1347,7 +1355,7 @@ int wfb_ffat_destroy(wfb_ffat_t *h)
     cudaDeviceSynchronize();
     FfatDev &ff = h->ff;
     cudaFree(ff.ht_keys); cudaFree(ff.ht_slots); cudaFree(h->own_n_slots); if (!h->shares_slot_key) cudaFree(ff.slot_key); cudaFree(ff.cnt);
-    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off); cudaFree(ff.heavy);
+    cudaFree(ff.acc); cudaFree(ff.tree); cudaFree(ff.seg_off); cudaFree(ff.heavy); cudaFree(h->mg_scratch);
     for (int p = 0; p < 2; p++) h->seg[p].destroy();
     h->sorter.destroy();
     if (h->cb) wfb_ffat_destroy(h->cb);
@@ -1543,7 +1551,7 @@ static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch
     if (total > 0x7fffffffull) return WFB_E_BADARG;
     if (total == 0) { // nothing to ingest: (pipelined) still deliver what is pending
         if (h->pipelined) return ffat_deliver(h, prev, out, out_ts, out_capacity, n_out_dev, s);
-        CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+        if (!h->append_results) CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
         return 0;
     }
     nbatches = static_cast<uint32_t>(hb.size());
@@ -1642,7 +1650,7 @@ static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch
     SEC(2);
 
     if (!h->pipelined) {
-        CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+        if (!h->append_results) CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
         rc = ffat_window_phase(h, g, ff, out, out_ts, out_capacity, n_out_dev, s); if (rc) return rc;
         h->mark(3, s);
         SEC(5);
@@ -1669,14 +1677,14 @@ static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch
 // the runs of a bucket, in source order, ARE its items in stream order.
 static int ffat_process_prebucketed(wfb_ffat *h, const unsigned char *records, const uint32_t *recv_slots, const uint32_t *bins, uint32_t nsrc,
                                     uint32_t bps, const uint32_t *offs_h, const uint64_t *wms_h, uint32_t slot_mask, uint32_t shift,
-                                    void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, cudaStream_t s)
+                                    void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, cudaStream_t s, bool append)
 {
     if (!h || !n_out_dev || nsrc == 0 || nsrc > MAX_SHARDS || bps == 0 || bps > OSW_DIGITS || (1u << shift) > BK_KEYS) return WFB_E_BADARG;
     if (h->win_type != 0 || h->pipelined || !h->buckets) return WFB_E_UNSUPPORTED;
     int rc = h->ts.enter(s); if (rc) return rc;
     SegScratch &g = h->seg[0];
     const uint32_t total = offs_h[nsrc];
-    CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s));
+    if (!append) CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); // (append: the results follow the ones already in the buffer)
     if (total == 0) return 0;
     rc = ffat_ensure_segment(h, g, total, nsrc, s); if (rc) return rc;
     std::vector<DevBatch> hb(nsrc);
@@ -1693,17 +1701,25 @@ static int ffat_process_prebucketed(wfb_ffat *h, const unsigned char *records, c
     h->mark(0, s); h->mark(1, s);
     MgRuns runs;
     for (uint32_t i = 0; i <= MAX_SHARDS; i++) runs.off[i] = offs_h[std::min(i, nsrc)];
-    k_mg_lists<<<bps, 256, 0, s>>>(bins, nsrc, bps, runs, recv_slots, slot_mask, g.slotsB, g.posB, g.sort_ctl, g.n_trig, g.n_heavy);
+    // the sources' 1024 bins are shared by all destinations: split every coarse bucket so that the update kernel gets (up to) 1024 buckets
+    uint32_t nsub = 1, shift2 = shift;
+    while (nsub * 2 * bps <= OSW_DIGITS && nsub * 2 <= MAX_SHARDS && shift2 > 0) { nsub *= 2; shift2--; }
+    if (!h->mg_scratch) CK(cudaMalloc(&h->mg_scratch, sizeof(uint32_t) * 3 * OSW_DIGITS * MAX_SHARDS));
+    uint32_t *cnt3 = h->mg_scratch, *off3 = cnt3 + OSW_DIGITS * MAX_SHARDS, *run_starts = off3 + OSW_DIGITS * MAX_SHARDS;
+    const dim3 grid(bps, nsrc);
+    k_mg_count<<<grid, MG_THREADS, 0, s>>>(bins, nsrc, bps, runs, recv_slots, slot_mask, shift2, nsub, cnt3, run_starts, g.n_trig, g.n_heavy);
+    k_mg_scan<<<1, 1024, 0, s>>>(cnt3, bps * nsub * nsrc, nsrc, off3, g.sort_ctl);
+    k_mg_split<<<grid, MG_THREADS, 0, s>>>(bins, nsrc, bps, runs, recv_slots, slot_mask, shift2, nsub, off3, run_starts, g.slotsB, g.posB);
     CK(cudaGetLastError());
     h->mark(2, s);
-    rc = h->ops->ffat_buckets(ff, records, g.slotsB, g.posB, g.sort_ctl, shift, 0u, g.batch_off, g.d_batches, nsrc, static_cast<unsigned char *>(out_results), out_ts,
+    rc = h->ops->ffat_buckets(ff, records, g.slotsB, g.posB, g.sort_ctl, shift2, 0u, g.batch_off, g.d_batches, nsrc, static_cast<unsigned char *>(out_results), out_ts,
                               out_capacity, n_out_dev, s, h->pp());
     if (rc) return rc;
     rc = h->ops->ffat_windows(ff, g.batch_off, g.d_batches, nsrc, static_cast<unsigned char *>(out_results), out_ts, out_capacity, static_cast<uint32_t>(g_num_sms) * 4u, s,
                               h->pp(), n_out_dev);
     if (rc) return rc;
     h->mark(3, s);
-    h->launches += 3;
+    h->launches += 5;
     if (h->timing && h->tev_used < wfb_ffat::TEV_MAX) h->tev_used++;
     h->call_no++;
     return 0;
@@ -1813,17 +1829,22 @@ __global__ void k_mg_meta(const uint32_t *__restrict__ counts, uint64_t watermar
     if (d < nranks) { send_meta[2 * d] = counts[d]; send_meta[2 * d + 1] = watermark; }
 }
 
-struct MgSlot { // buffers of one step in flight (two: the exchange of step i-1 overlaps the source pass of step i)
+// appended results (wfb_mg_flush): the call about to run adds the WHOLE count of the output buffer to the handle's total
+__global__ void k_mg_pre_append(unsigned long long *results_total, const uint32_t *n_out) { if (results_total) *results_total -= *n_out; }
+
+struct MgSlot { // buffers of one step in flight (three: the exchange of step i-2 overlaps the source pass of step i)
     unsigned char *regions = nullptr; uint32_t region_cap = 0; // records by destination (bucketed: bin after bin, region_cap = the segment's positions)
     uint32_t *vslots = nullptr;                // bucketed: virtual slot of every record of `regions`
     uint32_t *bins = nullptr;                  // bucketed: OSW_DIGITS + 1 words, the bin sizes of this step's partition
     uint32_t *recv_slots = nullptr, *recv_bins = nullptr; size_t recv_slots_cap = 0; // bucketed: what the sources delivered ([nranks][bps] run lengths)
+    uint32_t offs[MAX_SHARDS + 1] = {}; uint64_t wms[MAX_SHARDS] = {}; // where every source's records start in `recv` / their watermarks (host, set by the exchange)
     uint32_t *counts = nullptr;                // MAX_SHARDS + 1 (device)
     uint64_t *send_meta = nullptr, *recv_meta = nullptr; // [nranks][2] (device)
     uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
     unsigned char *recv = nullptr; size_t recv_bytes = 0;
-    cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr, ev_self = nullptr;
     bool used = false, done_recorded = false;
+    cudaEvent_t tr[8] = {}; bool tr_valid = false; // WFB_MG_TRACE: source begin/end, update begin/end (caller's stream); exchange begin/end, sizes begin/end (communication stream)
 };
 } // namespace
 
@@ -1833,12 +1854,14 @@ struct wfb_mg {
     wfb_engine_t *eng = nullptr;
     wfb_ffat_t *ffat = nullptr;
     size_t rb = 0;
-    MgSlot slot[2];
+    MgSlot slot[3];            // three steps in flight: the host reads the sizes of step i while the GPU is two steps further
     cudaStream_t cs = nullptr; // communication stream
+    cudaStream_t cs2 = nullptr; // the rank's own share of an exchange: device-to-device copies (copy engine), next to the NCCL group
     uint64_t step_no = 0;
-    MgSlot *pending = nullptr;
+    MgSlot *pend[2] = {nullptr, nullptr}; int npend = 0; // steps whose records have not been exchanged yet, oldest first
     std::vector<wfb_batch_t> chunks;
     // bucketed exchange: the source partitions by (destination, bucket of the destination's slot space), the destination only concatenates runs
+    bool trace = false; double tr_acc[8] = {}; uint64_t tr_n = 0; // WFB_MG_TRACE=1: device timeline of a step, printed every 64 steps (tuning aid)
     bool bucketed = false;
     uint32_t shard_slots = 0, shard_keys = 0, shift = 0, bps = 0; // slots per destination (power of two), keys per destination, bucket = slot >> shift, buckets per destination
 };
@@ -1865,9 +1888,11 @@ int wfb_mg_destroy(wfb_mg_t *h)
         cudaFree(sl.vslots); cudaFree(sl.bins); cudaFree(sl.recv_slots); cudaFree(sl.recv_bins);
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
         if (sl.h_recv) cudaFreeHost(sl.h_recv);
-        for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done, sl.ev_self}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : sl.tr) if (e) cudaEventDestroy(e);
     }
     if (h->cs) cudaStreamDestroy(h->cs);
+    if (h->cs2) cudaStreamDestroy(h->cs2);
     delete h;
     cudaGetLastError();
     return 0;
@@ -1886,12 +1911,14 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
     wfb_mg *h = new (std::nothrow) wfb_mg();
     if (!h) return WFB_E_BADARG;
     h->nranks = nranks; h->rank = rank; h->rb = o->result_bytes;
+    h->trace = std::getenv("WFB_MG_TRACE") && std::atoi(std::getenv("WFB_MG_TRACE")) != 0;
 #define MGCK(call) do { int r__ = (call); if (r__) { wfb_mg_destroy(h); return r__; } } while (0)
     MGCK(wfb_engine_create(&h->eng, prog));
     // the rank's replica owns the keys with key % nranks == rank: compact slots key / nranks, records read in place
     MGCK(wfb_ffat_create(&h->ffat, lp, win, slide, wins_per_batch, (max_keys_total + nranks - 1) / nranks, 0, 0, WFB_FFAT_DENSE_KEYS));
     if (nranks > 1) MGCK(wfb_ffat_set_key_shard(h->ffat, static_cast<uint32_t>(nranks), static_cast<uint32_t>(rank)));
     MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)));
+    MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs2, cudaStreamNonBlocking)));
     {   // bucketed exchange when the destination-major virtual slots fit 16 bits (they travel packed with a 16-bit rank)
         const uint32_t keys = (max_keys_total + nranks - 1) / nranks;
         uint32_t L = 1; while (L < keys) L <<= 1;
@@ -1913,7 +1940,8 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
         MGCK(static_cast<int>(cudaMalloc(&sl.recv_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
         MGCK(static_cast<int>(cudaMallocHost(&sl.h_counts, sizeof(uint32_t) * (MAX_SHARDS + 1))));
         MGCK(static_cast<int>(cudaMallocHost(&sl.h_recv, sizeof(uint64_t) * 2 * MAX_SHARDS)));
-        for (cudaEvent_t *e : {&sl.ev_src, &sl.ev_meta, &sl.ev_a2a, &sl.ev_done}) MGCK(static_cast<int>(cudaEventCreateWithFlags(e, cudaEventDisableTiming)));
+        for (cudaEvent_t *e : {&sl.ev_src, &sl.ev_meta, &sl.ev_a2a, &sl.ev_done, &sl.ev_self}) MGCK(static_cast<int>(cudaEventCreateWithFlags(e, cudaEventDisableTiming)));
+        if (h->trace) for (cudaEvent_t &e : sl.tr) MGCK(static_cast<int>(cudaEventCreate(&e)));
     }
     if (nranks > 1) {
         Nccl::Id id; std::memcpy(id.b, id128_h, sizeof(id.b));
@@ -1932,6 +1960,20 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
     for (uint32_t i = 0; i < nbatches; i++) n += batches_h[i].n;
     if (n > 0x7fffffffull) return WFB_E_BADARG;
     int rc;
+    if (h->trace) {
+        if (sl.tr_valid) { // this slot's previous step (three calls ago) is complete: add its timeline
+            CK(cudaEventSynchronize(sl.tr[3]));
+            float ms; const int pairs[6][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}, {4, 2}, {5, 2}};
+            for (int i = 0; i < 6; i++) if (cudaEventElapsedTime(&ms, sl.tr[pairs[i][0]], sl.tr[pairs[i][1]]) == cudaSuccess) h->tr_acc[i] += ms;
+            if (++h->tr_n % 64 == 0) {
+                std::fprintf(stderr, "[wfb_mg rank %d] us/step over 64 steps: source %.0f | update %.0f | exchange %.0f | sizes %.0f | exchange begin -> update begin %.0f | exchange end -> update begin %.0f\n",
+                             h->rank, h->tr_acc[0] / 64 * 1e3, h->tr_acc[1] / 64 * 1e3, h->tr_acc[2] / 64 * 1e3, h->tr_acc[3] / 64 * 1e3, h->tr_acc[4] / 64 * 1e3, h->tr_acc[5] / 64 * 1e3);
+                for (double &a : h->tr_acc) a = 0;
+            }
+            sl.tr_valid = false;
+        }
+        CK(cudaEventRecord(sl.tr[0], s));
+    }
     if (h->bucketed) {
         uint64_t positions = 0;
         for (uint32_t i = 0; i < nbatches; i++) positions += static_cast<uint64_t>(tiles_of(batches_h[i].n)) * TILE;
@@ -1957,7 +1999,9 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
     k_mg_meta<<<1, 32, 0, s>>>(sl.counts, watermark, static_cast<uint32_t>(h->nranks), sl.send_meta);
     CK(cudaGetLastError());
     CK(cudaEventRecord(sl.ev_src, s));
+    if (h->trace) CK(cudaEventRecord(sl.tr[1], s));
     CK(cudaStreamWaitEvent(h->cs, sl.ev_src, 0));
+    if (h->trace) CK(cudaEventRecord(sl.tr[6], h->cs));
     if (h->nranks > 1) {
         NK(nccl().GroupStart());
         for (int p = 0; p < h->nranks; p++) {
@@ -1969,22 +2013,23 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
     CK(cudaMemcpyAsync(sl.h_counts, sl.counts, sizeof(uint32_t) * (MAX_SHARDS + 1), cudaMemcpyDeviceToHost, h->cs));
     CK(cudaMemcpyAsync(sl.h_recv, sl.recv_meta, sizeof(uint64_t) * 2 * h->nranks, cudaMemcpyDeviceToHost, h->cs));
     CK(cudaEventRecord(sl.ev_meta, h->cs));
+    if (h->trace) CK(cudaEventRecord(sl.tr[7], h->cs));
     sl.used = true;
     return 0;
 }
 
-// exchange of the records of a step (communication stream), then the window update on the received chunks (caller's stream)
-static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out_dev, cudaStream_t s)
+// exchange of the records of a step, on the communication stream (issued BEFORE the next step's source pass so that it runs next to it)
+static int mg_exchange(wfb_mg *h, MgSlot &sl)
 {
     CK(cudaEventSynchronize(sl.ev_meta)); // the sizes of this step on the host (a step old: no stall)
     if (sl.h_counts[MAX_SHARDS]) return WFB_E_CAPACITY; // a shard region overflowed / a key outside the declared key space
     const int n = h->nranks;
     if (h->bucketed) {
         // records, their slots and the run lengths of every source; source-rank order = global stream order
-        uint32_t offs[MAX_SHARDS + 1]; uint64_t wms[MAX_SHARDS]; uint64_t tot = 0;
-        for (int p = 0; p < n; p++) { offs[p] = static_cast<uint32_t>(tot); tot += sl.h_recv[2 * p]; wms[p] = sl.h_recv[2 * p + 1]; }
+        uint64_t tot = 0;
+        for (int p = 0; p < n; p++) { sl.offs[p] = static_cast<uint32_t>(tot); tot += sl.h_recv[2 * p]; sl.wms[p] = sl.h_recv[2 * p + 1]; }
         if (tot > 0x7fffffffull) return WFB_E_CAPACITY;
-        offs[n] = static_cast<uint32_t>(tot);
+        sl.offs[n] = static_cast<uint32_t>(tot);
         const size_t need = std::max<size_t>(1, tot);
         if (sl.recv_bytes < need * h->rb || sl.recv_slots_cap < need) {
             CK(cudaDeviceSynchronize());
@@ -1994,16 +2039,27 @@ static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts
             CK(cudaMalloc(&sl.recv_slots, sizeof(uint32_t) * sl.recv_slots_cap));
         }
         if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs, sl.ev_done, 0)); // the window update that read these receive buffers two steps ago
+        if (h->trace) CK(cudaEventRecord(sl.tr[4], h->cs));
         size_t send_off[MAX_SHARDS + 1]; send_off[0] = 0;
         for (int p = 0; p < n; p++) send_off[p + 1] = send_off[p] + sl.h_counts[p];
         const size_t bin_bytes = sizeof(uint32_t) * h->bps;
         if (n > 1) {
+            {   // this rank's own share does not go through NCCL: plain copies on the copy engine, next to the group
+                const int p = h->rank;
+                CK(cudaStreamWaitEvent(h->cs2, sl.ev_src, 0));
+                if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs2, sl.ev_done, 0));
+                CK(cudaMemcpyAsync(sl.recv + static_cast<size_t>(sl.offs[p]) * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaMemcpyAsync(sl.recv_slots + sl.offs[p], sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaMemcpyAsync(sl.recv_bins + static_cast<size_t>(p) * h->bps, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaEventRecord(sl.ev_self, h->cs2));
+            }
             NK(nccl().GroupStart());
             for (int p = 0; p < n; p++) {
+                if (p == h->rank) continue;
                 NK(nccl().Send(sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
-                NK(nccl().Recv(sl.recv + static_cast<size_t>(offs[p]) * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(sl.recv + static_cast<size_t>(sl.offs[p]) * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
                 NK(nccl().Send(sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, NCCL_UINT8, p, h->comm, h->cs));
-                NK(nccl().Recv(sl.recv_slots + offs[p], static_cast<size_t>(sl.h_recv[2 * p]) * 4, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(sl.recv_slots + sl.offs[p], static_cast<size_t>(sl.h_recv[2 * p]) * 4, NCCL_UINT8, p, h->comm, h->cs));
                 NK(nccl().Send(sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, NCCL_UINT8, p, h->comm, h->cs));
                 NK(nccl().Recv(sl.recv_bins + static_cast<size_t>(p) * h->bps, bin_bytes, NCCL_UINT8, p, h->comm, h->cs));
             }
@@ -2014,16 +2070,12 @@ static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts
             CK(cudaMemcpyAsync(sl.recv_bins, sl.bins, bin_bytes, cudaMemcpyDeviceToDevice, h->cs));
         }
         CK(cudaEventRecord(sl.ev_a2a, h->cs));
-        CK(cudaStreamWaitEvent(s, sl.ev_a2a, 0));
-        int rc = ffat_process_prebucketed(h->ffat, sl.recv, sl.recv_slots, sl.recv_bins, static_cast<uint32_t>(n), h->bps, offs, wms, h->shard_slots - 1u, h->shift,
-                                          out, out_ts, out_cap, n_out_dev, s);
-        if (rc) return rc;
-        CK(cudaEventRecord(sl.ev_done, s));
-        sl.done_recorded = true;
+        if (h->trace) CK(cudaEventRecord(sl.tr[5], h->cs));
         return 0;
     }
-    size_t offs[MAX_SHARDS + 1]; size_t tiles = 0; // every source's chunk at its tile position of the receive buffer (read in place)
-    for (int p = 0; p < n; p++) { offs[p] = tiles * TILE; tiles += (static_cast<size_t>(sl.h_recv[2 * p]) + TILE - 1) / TILE; }
+    size_t tiles = 0; // every source's chunk at its tile position of the receive buffer (read in place)
+    for (int p = 0; p < n; p++) { sl.offs[p] = static_cast<uint32_t>(tiles * TILE); tiles += (static_cast<size_t>(sl.h_recv[2 * p]) + TILE - 1) / TILE; sl.wms[p] = sl.h_recv[2 * p + 1]; }
+    if (tiles * TILE > 0x7fffffffull) return WFB_E_CAPACITY;
     const size_t need = std::max<size_t>(1, tiles * TILE) * h->rb;
     if (sl.recv_bytes < need) {
         CK(cudaDeviceSynchronize());
@@ -2032,24 +2084,47 @@ static int mg_exchange_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts
         CK(cudaMalloc(&sl.recv, sl.recv_bytes));
     }
     if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs, sl.ev_done, 0)); // the window update that read this receive buffer two steps ago
+    if (h->trace) CK(cudaEventRecord(sl.tr[4], h->cs));
     if (n > 1) {
         NK(nccl().GroupStart());
         for (int p = 0; p < n; p++) {
             NK(nccl().Send(sl.regions + static_cast<size_t>(p) * sl.region_cap * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
-            NK(nccl().Recv(sl.recv + offs[p] * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
+            NK(nccl().Recv(sl.recv + static_cast<size_t>(sl.offs[p]) * h->rb, static_cast<size_t>(sl.h_recv[2 * p]) * h->rb, NCCL_UINT8, p, h->comm, h->cs));
         }
         NK(nccl().GroupEnd());
     } else CK(cudaMemcpyAsync(sl.recv, sl.regions, static_cast<size_t>(sl.h_counts[0]) * h->rb, cudaMemcpyDeviceToDevice, h->cs));
     CK(cudaEventRecord(sl.ev_a2a, h->cs));
+    if (h->trace) CK(cudaEventRecord(sl.tr[5], h->cs));
+    return 0;
+}
+
+// window update on what mg_exchange delivered (caller's stream)
+static int mg_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_t out_cap, uint32_t *n_out_dev, cudaStream_t s, bool append = false)
+{
+    const int n = h->nranks;
     CK(cudaStreamWaitEvent(s, sl.ev_a2a, 0));
-    h->chunks.resize(n);
-    for (int p = 0; p < n; p++) { // source-rank order = global stream order
-        wfb_batch_t &b = h->chunks[p];
-        b.tuples = sl.recv + offs[p] * h->rb; b.ts = nullptr; b.watermark = sl.h_recv[2 * p + 1]; b.n = static_cast<uint32_t>(sl.h_recv[2 * p]); b.reserved = 0;
+    if (h->bucketed && n > 1) CK(cudaStreamWaitEvent(s, sl.ev_self, 0));
+    if (h->trace) CK(cudaEventRecord(sl.tr[2], s));
+    uint64_t items = 0;
+    for (int p = 0; p < n; p++) items += sl.h_recv[2 * p];
+    if (append && items != 0) { k_mg_pre_append<<<1, 1, 0, s>>>(h->ffat->ff.results_total, n_out_dev); CK(cudaGetLastError()); }
+    int rc;
+    if (h->bucketed) {
+        rc = ffat_process_prebucketed(h->ffat, sl.recv, sl.recv_slots, sl.recv_bins, static_cast<uint32_t>(n), h->bps, sl.offs, sl.wms, h->shard_slots - 1u, h->shift,
+                                      out, out_ts, out_cap, n_out_dev, s, append);
+    } else {
+        h->chunks.resize(n);
+        for (int p = 0; p < n; p++) { // source-rank order = global stream order
+            wfb_batch_t &b = h->chunks[p];
+            b.tuples = sl.recv + static_cast<size_t>(sl.offs[p]) * h->rb; b.ts = nullptr; b.watermark = sl.wms[p]; b.n = static_cast<uint32_t>(sl.h_recv[2 * p]); b.reserved = 0;
+        }
+        h->ffat->append_results = append;
+        rc = wfb_ffat_process_cb(h->ffat, nullptr, h->chunks.data(), static_cast<uint32_t>(n), out, out_ts, out_cap, n_out_dev, s);
+        h->ffat->append_results = false;
     }
-    int rc = wfb_ffat_process_cb(h->ffat, nullptr, h->chunks.data(), static_cast<uint32_t>(n), out, out_ts, out_cap, n_out_dev, s);
     if (rc) return rc;
     CK(cudaEventRecord(sl.ev_done, s));
+    if (h->trace) { CK(cudaEventRecord(sl.tr[3], s)); sl.tr_valid = true; }
     sl.done_recorded = true;
     return 0;
 }
@@ -2059,23 +2134,31 @@ int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batch
 {
     if (!h || !n_out_dev || (nbatches && !batches_h)) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    MgSlot &cur = h->slot[h->step_no & 1];
+    MgSlot &cur = h->slot[h->step_no % 3];
     h->step_no++;
-    MgSlot *prev = h->pending;
-    // the source pass of this step is issued first; the exchange of the previous step runs on the communication stream next to it
-    int rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
-    h->pending = &cur;
-    if (prev == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
-    return mg_exchange_update(h, *prev, out_results, out_ts, out_capacity, n_out_dev, s);
+    // step i: the records of step i-2 start travelling (communication stream; their sizes reached the host a step ago, so the host
+    // never waits for the GPU), the source pass of step i runs next to them, then the window update of step i-2
+    MgSlot *upd = nullptr;
+    int rc;
+    if (h->npend == 2) { upd = h->pend[0]; rc = mg_exchange(h, *upd); if (rc) return rc; }
+    rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
+    if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = &cur; } else h->pend[h->npend++] = &cur;
+    if (upd == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    return mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
 }
 
 int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
 {
     if (!h || !n_out_dev) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    MgSlot *prev = h->pending; h->pending = nullptr;
-    if (prev == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
-    return mg_exchange_update(h, *prev, out_results, out_ts, out_capacity, n_out_dev, s);
+    if (h->npend == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
+    const int n = h->npend; h->npend = 0;
+    for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
+        int rc = mg_exchange(h, *h->pend[i]); if (rc) return rc;
+        rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
+        h->pend[i] = nullptr;
+    }
+    return 0;
 }
 
 uint64_t wfb_mg_launches(const wfb_mg_t *h) { return h ? wfb_engine_launches(h->eng) + wfb_ffat_launches(h->ffat) : 0; }
