@@ -485,7 +485,10 @@ def run_ours(args):
                        "state_primed_steps": prime, "phase_stagger_rounds": 65 if args.prime_steps < 0 else 0,
                        "windows_in_timed_region": windows_timed, "windows_expected_steady_state": windows_expected,
                        "pipelined": args.pipeline if world == 1 else (not args.sync_exchange),
-                       "parallelism": f"keyby{world}" + ("" if world == 1 else " (Map->Filter->lift + partition by key % N | NCCL all-to-all of 32-B results | Ffat on the key shard, records read in place)")},
+                       "parallelism": f"keyby{world}" + ("" if world == 1 else (" (torch.distributed step: Map->Filter->lift + partition by key % N | NCCL all-to-all of 32-B results | Ffat on the key shard)"
+                                                                                  if (args.py_exchange or args.sync_exchange) else
+                                                                                  " (wfb_mg_step: Map->Filter->lift + ONE partition by (destination, bucket) at the source | 32-B results pushed over NVLink "
+                                                                                  "(copy engine; NCCL when cudaIpc is unavailable) | run concatenation + window update on the key shard)"))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,

@@ -1677,13 +1677,13 @@ static int ffat_process_cb_impl2(wfb_ffat_t *h, const void *pre, const wfb_batch
 // the runs of a bucket, in source order, ARE its items in stream order.
 static int ffat_process_prebucketed(wfb_ffat *h, const unsigned char *records, const uint32_t *recv_slots, const uint32_t *bins, uint32_t nsrc,
                                     uint32_t bps, const uint32_t *offs_h, const uint64_t *wms_h, uint32_t slot_mask, uint32_t shift,
-                                    void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, cudaStream_t s, bool append)
-{
+                                    void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, cudaStream_t s, bool append, uint32_t items)
+{   // items: records delivered in all (the runs of a source need not be back to back with the next source's: offs_h[nsrc] only bounds the positions)
     if (!h || !n_out_dev || nsrc == 0 || nsrc > MAX_SHARDS || bps == 0 || bps > OSW_DIGITS || (1u << shift) > BK_KEYS) return WFB_E_BADARG;
     if (h->win_type != 0 || h->pipelined || !h->buckets) return WFB_E_UNSUPPORTED;
     int rc = h->ts.enter(s); if (rc) return rc;
     SegScratch &g = h->seg[0];
-    const uint32_t total = offs_h[nsrc];
+    const uint32_t total = items;
     if (!append) CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); // (append: the results follow the ones already in the buffer)
     if (total == 0) return 0;
     rc = ffat_ensure_segment(h, g, total, nsrc, s); if (rc) return rc;
@@ -1837,13 +1837,16 @@ struct MgSlot { // buffers of one step in flight (three: the exchange of step i-
     uint32_t *vslots = nullptr;                // bucketed: virtual slot of every record of `regions`
     uint32_t *bins = nullptr;                  // bucketed: OSW_DIGITS + 1 words, the bin sizes of this step's partition
     uint32_t *recv_slots = nullptr, *recv_bins = nullptr; size_t recv_slots_cap = 0; // bucketed: what the sources delivered ([nranks][bps] run lengths)
+    unsigned char *ce_buf = nullptr;           // copy-engine exchange: the receive buffers of this slot in ONE allocation other ranks map (cudaIpc):
+                                               // [records n x cap][slots n x cap][run lengths n x bps], source s at stride cap
+    unsigned char *peer[MAX_SHARDS] = {};      // every rank's ce_buf of this slot, mapped here
     uint32_t offs[MAX_SHARDS + 1] = {}; uint64_t wms[MAX_SHARDS] = {}; // where every source's records start in `recv` / their watermarks (host, set by the exchange)
     uint32_t *counts = nullptr;                // MAX_SHARDS + 1 (device)
     uint64_t *send_meta = nullptr, *recv_meta = nullptr; // [nranks][2] (device)
     uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
     unsigned char *recv = nullptr; size_t recv_bytes = 0;
     cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr, ev_self = nullptr;
-    bool used = false, done_recorded = false;
+    bool used = false, done_recorded = false, ce_wait_token = false;
     cudaEvent_t tr[8] = {}; bool tr_valid = false; // WFB_MG_TRACE: source begin/end, update begin/end (caller's stream); exchange begin/end, sizes begin/end (communication stream)
 };
 } // namespace
@@ -1861,6 +1864,11 @@ struct wfb_mg {
     MgSlot *pend[2] = {nullptr, nullptr}; int npend = 0; // steps whose records have not been exchanged yet, oldest first
     std::vector<wfb_batch_t> chunks;
     // bucketed exchange: the source partitions by (destination, bucket of the destination's slot space), the destination only concatenates runs
+    // copy-engine exchange (bucketed mode, all ranks on one node): records are PUSHED into the peers' receive buffers with plain
+    // device-to-device copies over NVLink (no SM, no NCCL channel limit); the next step's size exchange is the completion signal
+    bool ce = false, ce_tried = false; uint64_t ce_cap = 0, peer_cap[MAX_SHARDS] = {};
+    unsigned char *ce_msg = nullptr; // device staging of the handle exchange
+    cudaEvent_t ev_flush = nullptr;
     bool trace = false; double tr_acc[8] = {}; uint64_t tr_n = 0; // WFB_MG_TRACE=1: device timeline of a step, printed every 64 steps (tuning aid)
     bool bucketed = false;
     uint32_t shard_slots = 0, shard_keys = 0, shift = 0, bps = 0; // slots per destination (power of two), keys per destination, bucket = slot >> shift, buckets per destination
@@ -1884,8 +1892,12 @@ int wfb_mg_destroy(wfb_mg_t *h)
     if (h->eng) wfb_engine_destroy(h->eng);
     if (h->ffat) wfb_ffat_destroy(h->ffat);
     for (MgSlot &sl : h->slot) {
-        cudaFree(sl.regions); cudaFree(sl.counts); cudaFree(sl.send_meta); cudaFree(sl.recv_meta); cudaFree(sl.recv);
-        cudaFree(sl.vslots); cudaFree(sl.bins); cudaFree(sl.recv_slots); cudaFree(sl.recv_bins);
+        cudaFree(sl.regions); cudaFree(sl.counts); cudaFree(sl.send_meta); cudaFree(sl.recv_meta); if (!sl.ce_buf) cudaFree(sl.recv);
+        cudaFree(sl.vslots); cudaFree(sl.bins);
+        if (sl.ce_buf) { // (recv / recv_slots / recv_bins point into ce_buf)
+            for (int p = 0; p < h->nranks; p++) if (p != h->rank && sl.peer[p]) cudaIpcCloseMemHandle(sl.peer[p]);
+            cudaFree(sl.ce_buf); sl.recv = nullptr;
+        } else { cudaFree(sl.recv_slots); cudaFree(sl.recv_bins); }
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
         if (sl.h_recv) cudaFreeHost(sl.h_recv);
         for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done, sl.ev_self}) if (e) cudaEventDestroy(e);
@@ -1893,6 +1905,8 @@ int wfb_mg_destroy(wfb_mg_t *h)
     }
     if (h->cs) cudaStreamDestroy(h->cs);
     if (h->cs2) cudaStreamDestroy(h->cs2);
+    cudaFree(h->ce_msg);
+    if (h->ev_flush) cudaEventDestroy(h->ev_flush);
     delete h;
     cudaGetLastError();
     return 0;
@@ -1919,6 +1933,7 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
     if (nranks > 1) MGCK(wfb_ffat_set_key_shard(h->ffat, static_cast<uint32_t>(nranks), static_cast<uint32_t>(rank)));
     MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)));
     MGCK(static_cast<int>(cudaStreamCreateWithFlags(&h->cs2, cudaStreamNonBlocking)));
+    MGCK(static_cast<int>(cudaEventCreateWithFlags(&h->ev_flush, cudaEventDisableTiming)));
     {   // bucketed exchange when the destination-major virtual slots fit 16 bits (they travel packed with a 16-bit rank)
         const uint32_t keys = (max_keys_total + nranks - 1) / nranks;
         uint32_t L = 1; while (L < keys) L <<= 1;
@@ -1953,6 +1968,85 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
     return 0;
 }
 
+// ---- copy-engine exchange: setup (collective, at the first step) ---------------------------------------------------------------
+struct CeLayout { size_t slots_off, bins_off, bytes; };
+static CeLayout ce_layout(uint64_t cap, int n, size_t rb, uint32_t bps)
+{
+    CeLayout l; l.slots_off = static_cast<size_t>(n) * cap * rb; l.bins_off = (l.slots_off + static_cast<size_t>(n) * cap * 4 + 255) & ~static_cast<size_t>(255);
+    l.bytes = l.bins_off + static_cast<size_t>(n) * bps * 4; return l;
+}
+struct CeMsg { cudaIpcMemHandle_t h[3]; uint64_t cap; uint64_t ok; };
+// one small message to / from every other rank (communication stream, synchronous)
+static int mg_all_exchange(wfb_mg *h, const void *mine_h, void *all_h, size_t bytes)
+{
+    const int n = h->nranks;
+    if (!h->ce_msg) CK(cudaMalloc(&h->ce_msg, sizeof(CeMsg) * (MAX_SHARDS + 1)));
+    if (bytes > sizeof(CeMsg)) return WFB_E_BADARG;
+    unsigned char *snd = h->ce_msg, *rcv = h->ce_msg + sizeof(CeMsg);
+    CK(cudaMemcpyAsync(snd, mine_h, bytes, cudaMemcpyHostToDevice, h->cs));
+    NK(nccl().GroupStart());
+    for (int p = 0; p < n; p++) {
+        if (p == h->rank) continue;
+        NK(nccl().Send(snd, bytes, NCCL_UINT8, p, h->comm, h->cs));
+        NK(nccl().Recv(rcv + static_cast<size_t>(p) * bytes, bytes, NCCL_UINT8, p, h->comm, h->cs));
+    }
+    NK(nccl().GroupEnd());
+    CK(cudaMemcpyAsync(all_h, rcv, bytes * n, cudaMemcpyDeviceToHost, h->cs));
+    CK(cudaStreamSynchronize(h->cs));
+    std::memcpy(static_cast<unsigned char *>(all_h) + static_cast<size_t>(h->rank) * bytes, mine_h, bytes);
+    return 0;
+}
+static int mg_ce_setup(wfb_mg *h, uint64_t positions)
+{
+    h->ce_tried = true;
+    static const bool off = std::getenv("WFB_MG_CE") && std::atoi(std::getenv("WFB_MG_CE")) == 0;
+    if (off || !h->bucketed || h->nranks < 2) return 0;
+    const int n = h->nranks;
+    const uint64_t cap = (positions + 1023) & ~1023ull; // worst case: every survivor of a source's step goes to one destination
+    const CeLayout l = ce_layout(cap, n, h->rb, h->bps);
+    CeMsg mine; std::memset(&mine, 0, sizeof(mine)); mine.cap = cap; mine.ok = 1;
+    for (int i = 0; i < 3 && mine.ok; i++) {
+        if (cudaMalloc(&h->slot[i].ce_buf, l.bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine.h[i], h->slot[i].ce_buf) != cudaSuccess) mine.ok = 0;
+    }
+    cudaGetLastError();
+    CeMsg all[MAX_SHARDS];
+    int rc = mg_all_exchange(h, &mine, all, sizeof(CeMsg)); if (rc) return rc;
+    uint64_t ok = 1;
+    for (int p = 0; p < n; p++) ok &= all[p].ok;
+    if (ok) {
+        for (int p = 0; p < n && ok; p++) {
+            h->peer_cap[p] = all[p].cap;
+            for (int i = 0; i < 3 && ok; i++) {
+                if (p == h->rank) { h->slot[i].peer[p] = h->slot[i].ce_buf; continue; }
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[p].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+                else h->slot[i].peer[p] = static_cast<unsigned char *>(ptr);
+            }
+        }
+    }
+    // second round: every rank could map every buffer, or nobody uses the path
+    uint64_t st_mine = ok, st_all[MAX_SHARDS];
+    rc = mg_all_exchange(h, &st_mine, st_all, sizeof(uint64_t)); if (rc) return rc;
+    for (int p = 0; p < n; p++) ok &= st_all[p];
+    if (!ok) {
+        for (MgSlot &sl : h->slot) {
+            for (int p = 0; p < n; p++) { if (p != h->rank && sl.peer[p]) cudaIpcCloseMemHandle(sl.peer[p]); sl.peer[p] = nullptr; }
+            cudaFree(sl.ce_buf); sl.ce_buf = nullptr;
+        }
+        cudaGetLastError();
+        if (h->trace) std::fprintf(stderr, "[wfb_mg rank %d] copy-engine exchange not available (cudaIpc): NCCL exchange\n", h->rank);
+        return 0; // (the NCCL exchange stays in use)
+    }
+    h->ce = true; h->ce_cap = cap;
+    if (h->trace) std::fprintf(stderr, "[wfb_mg rank %d] copy-engine exchange enabled (capacity %llu records per source)\n", h->rank, static_cast<unsigned long long>(cap));
+    for (MgSlot &sl : h->slot) {
+        cudaFree(sl.recv); cudaFree(sl.recv_slots); cudaFree(sl.recv_bins);
+        sl.recv = sl.ce_buf; sl.recv_slots = reinterpret_cast<uint32_t *>(sl.ce_buf + l.slots_off); sl.recv_bins = reinterpret_cast<uint32_t *>(sl.ce_buf + l.bins_off);
+        sl.recv_bytes = l.slots_off; sl.recv_slots_cap = static_cast<size_t>(n) * cap;
+    }
+    return 0;
+}
+
 // source side of a step: fused pass + partition by destination; the sizes travel (and reach the host a step later)
 static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark, cudaStream_t s)
 {
@@ -1977,6 +2071,7 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
     if (h->bucketed) {
         uint64_t positions = 0;
         for (uint32_t i = 0; i < nbatches; i++) positions += static_cast<uint64_t>(tiles_of(batches_h[i].n)) * TILE;
+        if (!h->ce_tried) { rc = mg_ce_setup(h, std::max<uint64_t>(positions, 1)); if (rc) return rc; } // (collective: every rank is in its first step)
         if (sl.region_cap < positions) {
             if (sl.used) CK(cudaDeviceSynchronize());
             cudaFree(sl.regions); cudaFree(sl.vslots);
@@ -2030,6 +2125,35 @@ static int mg_exchange(wfb_mg *h, MgSlot &sl)
         for (int p = 0; p < n; p++) { sl.offs[p] = static_cast<uint32_t>(tot); tot += sl.h_recv[2 * p]; sl.wms[p] = sl.h_recv[2 * p + 1]; }
         if (tot > 0x7fffffffull) return WFB_E_CAPACITY;
         sl.offs[n] = static_cast<uint32_t>(tot);
+        if (h->ce) {
+            // push: this rank's records for peer p go straight into p's receive buffer of this slot, at the stride-cap region of source `rank`
+            const uint64_t cap = h->ce_cap;
+            if (static_cast<uint64_t>(n) * cap > 0x7fffffffull) return WFB_E_CAPACITY;
+            for (int p = 0; p <= n; p++) sl.offs[p] = static_cast<uint32_t>(p * cap);
+            size_t send_off[MAX_SHARDS + 1]; send_off[0] = 0;
+            for (int p = 0; p < n; p++) {
+                send_off[p + 1] = send_off[p] + sl.h_counts[p];
+                if (sl.h_recv[2 * p] > cap || sl.h_counts[p] > h->peer_cap[p]) return WFB_E_CAPACITY; // (a step larger than the first one: WFB_MG_CE=0)
+            }
+            const int slot_idx = static_cast<int>(&sl - h->slot);
+            const size_t bin_bytes = sizeof(uint32_t) * h->bps;
+            if (h->trace) CK(cudaEventRecord(sl.tr[4], h->cs));
+            CK(cudaStreamWaitEvent(h->cs2, sl.ev_src, 0));
+            if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs2, sl.ev_done, 0));
+            for (int p = 0; p < n; p++) {
+                const CeLayout l = ce_layout(h->peer_cap[p], n, h->rb, h->bps);
+                unsigned char *dst = h->slot[slot_idx].peer[p];
+                const uint64_t me = static_cast<uint64_t>(h->rank), pc = h->peer_cap[p];
+                cudaStream_t st = (p == h->rank) ? h->cs2 : h->cs;
+                CK(cudaMemcpyAsync(dst + me * pc * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(dst + l.slots_off + me * pc * 4, sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(dst + l.bins_off + me * bin_bytes, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, st));
+            }
+            CK(cudaEventRecord(sl.ev_self, h->cs2));
+            if (h->trace) CK(cudaEventRecord(sl.tr[5], h->cs));
+            sl.ce_wait_token = true; // ev_a2a: after the next exchange of sizes (wfb_mg_step) / a token exchange (wfb_mg_flush)
+            return 0;
+        }
         const size_t need = std::max<size_t>(1, tot);
         if (sl.recv_bytes < need * h->rb || sl.recv_slots_cap < need) {
             CK(cudaDeviceSynchronize());
@@ -2111,7 +2235,7 @@ static int mg_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_
     int rc;
     if (h->bucketed) {
         rc = ffat_process_prebucketed(h->ffat, sl.recv, sl.recv_slots, sl.recv_bins, static_cast<uint32_t>(n), h->bps, sl.offs, sl.wms, h->shard_slots - 1u, h->shift,
-                                      out, out_ts, out_cap, n_out_dev, s, append);
+                                      out, out_ts, out_cap, n_out_dev, s, append, static_cast<uint32_t>(items));
     } else {
         h->chunks.resize(n);
         for (int p = 0; p < n; p++) { // source-rank order = global stream order
@@ -2142,6 +2266,12 @@ int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batch
     int rc;
     if (h->npend == 2) { upd = h->pend[0]; rc = mg_exchange(h, *upd); if (rc) return rc; }
     rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
+    if (upd != nullptr && upd->ce_wait_token) {
+        // copy-engine exchange: a peer's sizes of THIS step arrive after its copies of the step being updated (its communication stream runs
+        // them in that order), and it only sent them after its source pass, i.e. after the update that last read the buffers we are about to reuse
+        CK(cudaEventRecord(upd->ev_a2a, h->cs));
+        upd->ce_wait_token = false;
+    }
     if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = &cur; } else h->pend[h->npend++] = &cur;
     if (upd == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     return mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
@@ -2153,8 +2283,25 @@ int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (h->npend == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     const int n = h->npend; h->npend = 0;
+    int rc;
+    if (h->ce) {
+        // no further step whose sizes could carry the signals: two explicit token rounds (synchronous, flush is rare) --
+        // 1. every rank's window updates issued so far are complete (the receive buffers may be overwritten), 2. every rank's copies have landed
+        uint64_t tok = 1, all[MAX_SHARDS];
+        CK(cudaEventRecord(h->ev_flush, s));
+        CK(cudaStreamWaitEvent(h->cs, h->ev_flush, 0));
+        rc = mg_all_exchange(h, &tok, all, sizeof(uint64_t)); if (rc) return rc;
+        for (int i = 0; i < n; i++) { rc = mg_exchange(h, *h->pend[i]); if (rc) return rc; }
+        rc = mg_all_exchange(h, &tok, all, sizeof(uint64_t)); if (rc) return rc;
+        for (int i = 0; i < n; i++) { CK(cudaEventRecord(h->pend[i]->ev_a2a, h->cs)); h->pend[i]->ce_wait_token = false; }
+        for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
+            rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
+            h->pend[i] = nullptr;
+        }
+        return 0;
+    }
     for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
-        int rc = mg_exchange(h, *h->pend[i]); if (rc) return rc;
+        rc = mg_exchange(h, *h->pend[i]); if (rc) return rc;
         rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
         h->pend[i] = nullptr;
     }
