@@ -145,7 +145,9 @@ template <class T> struct NoReduce { __host__ __device__ T operator()(const T &a
 template <class T, class R, class KeyF, class LiftF, class CombF, class RedF, bool KEYED, class PreF = ChainStages<T>>
 struct FacadeProgram {
     using tuple_t = T; using result_t = R; using key_t = uint64_t;
-    struct params_t { ChainStages<T> map; PreF filt; KeyF key; LiftF lift; CombF comb; RedF red; };
+    // (a typed run leaves no stage that is called through a pointer: the tuple then stays in registers)
+    using map_slot_t = std::conditional_t<is_chain<PreF>::value, ChainStages<T>, TypedChain<T>>;
+    struct params_t { map_slot_t map; PreF filt; KeyF key; LiftF lift; CombF comb; RedF red; };
     static_assert(std::is_trivially_copyable<T>::value && std::is_trivially_copyable<R>::value, "tuple_t / result_t must be trivially copyable");
     static_assert(sizeof(T) % 8 == 0 && sizeof(R) % 8 == 0, "tuple_t / result_t sizes must be multiples of 8 bytes");
     __host__ __device__ static void map(tuple_t &t, const params_t &p) { p.map(t); }

@@ -1082,8 +1082,11 @@ static __global__ void __launch_bounds__(OSW_DIGITS) k_wide_chunk_scan(uint32_t 
 // Output: keys_out[i] = slot, vals_out[i] = arrival position, stable by (digit, position) -- what k_wide_scatter produces.
 // RBYTES != 0: the records travel (payload_in at the arrival positions -> payload_out at the final places; keys_out gets the slots,
 // vals_out is not written): the source side of the bucketed multi-GPU exchange.
+#ifndef WFB_OSR_MINBLOCKS
+#define WFB_OSR_MINBLOCKS 1   // (resident CTAs per SM the pair version is compiled for: 2048 tiles of the bench step are 2 full waves at 7)
+#endif
 template <int RBYTES>
-static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(const uint32_t *__restrict__ packed, uint32_t *__restrict__ keys_out,
+static __global__ void __launch_bounds__(OSW_THREADS, RBYTES == 0 ? WFB_OSR_MINBLOCKS : 1) k_wide_scatter_ranked(const uint32_t *__restrict__ packed, uint32_t *__restrict__ keys_out,
                                                                             uint32_t *__restrict__ vals_out, uint32_t n, uint32_t shift, uint32_t chunk_shift,
                                                                             const uint16_t *__restrict__ H, const uint32_t *__restrict__ Cx,
                                                                             const unsigned char *__restrict__ payload_in, unsigned char *__restrict__ payload_out)
@@ -1171,7 +1174,9 @@ static __global__ void __launch_bounds__(OSW_THREADS) k_wide_scatter_ranked(cons
 }
 
 // bucketed exchange, source side: records per destination = sums of the bins [d * bps, (d + 1) * bps) of the partition
-static __global__ void k_shard_bin_counts(const uint32_t *__restrict__ bin_counts, uint32_t nshards, uint32_t bps, uint32_t *__restrict__ counts_out)
+// (send_meta != nullptr: also the (count, watermark) pair every destination is sent ahead of the records)
+static __global__ void k_shard_bin_counts(const uint32_t *__restrict__ bin_counts, uint32_t nshards, uint32_t bps, uint32_t *__restrict__ counts_out,
+                                          uint64_t *__restrict__ send_meta, uint64_t watermark)
 {
     const uint32_t d = threadIdx.x >> 5, lane = threadIdx.x & 31; // one warp per destination
     uint32_t c = 0;
@@ -1179,6 +1184,7 @@ static __global__ void k_shard_bin_counts(const uint32_t *__restrict__ bin_count
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
     if (lane == 0 && d < MAX_SHARDS) counts_out[d] = d < nshards ? c : 0u; // ([MAX_SHARDS]: error flags, set by the tile pass)
+    if (lane == 0 && d < nshards && send_meta != nullptr) { send_meta[2 * d] = c; send_meta[2 * d + 1] = watermark; }
 }
 
 // bucketed exchange, destination side: source s delivered, for every COARSE bucket b of this GPU's slot space (bps of them: the

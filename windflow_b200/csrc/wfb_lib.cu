@@ -817,7 +817,8 @@ int wfb_shard_by_key(wfb_engine_t *e, const void *tuples, const uint64_t *ts, ui
 // out_slots their virtual slots, bins_ctl (OSW_DIGITS + 1 words, the caller's) the bin sizes, counts_dev the records per destination
 static int shard_lift_impl(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
                            void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream,
-                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl);
+                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl,
+                           uint64_t *send_meta = nullptr, uint64_t watermark = 0);
 
 int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
                    void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream)
@@ -827,7 +828,8 @@ int wfb_shard_lift(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t
 
 static int shard_lift_impl(wfb_engine_t *e, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint32_t num_shards,
                            void *out_regions, uint32_t region_capacity, uint32_t *counts_dev, void *stream,
-                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl)
+                           uint32_t shard_slots, uint32_t shard_keys, uint32_t shift, uint32_t *out_slots, uint32_t *bins_ctl,
+                           uint64_t *send_meta, uint64_t watermark)
 {
     // Map -> Filter -> lift in one streaming pass (no compaction chain: tile t owns positions [t*TILE, +TILE)), then one
     // stable partition pass on the destination (key % num_shards) that moves the lifted records into the shard regions.
@@ -895,7 +897,7 @@ static int shard_lift_impl(wfb_engine_t *e, const wfb_functors_t *pre, const wfb
                                            ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
                                            0, 0, false, true, nullptr, true);
         if (rc) return rc;
-        k_shard_bin_counts<<<1, 32 * MAX_SHARDS, 0, s>>>(counts, num_shards, shard_slots >> shift, counts_dev);
+        k_shard_bin_counts<<<1, 32 * MAX_SHARDS, 0, s>>>(counts, num_shards, shard_slots >> shift, counts_dev, send_meta, watermark);
     } else {
         rc = e->sorter.sort_wide<uint32_t>(e->sh_dest, nullptr, nullptr, nullptr, static_cast<uint32_t>(positions), static_cast<uint32_t>(positions), 0, s,
                                            e->sh_ctl, &counts, e->sh_lifted, static_cast<unsigned char *>(out_regions), static_cast<uint32_t>(RB), true,
@@ -1845,8 +1847,8 @@ struct MgSlot { // buffers of one step in flight (three: the exchange of step i-
     uint64_t *send_meta = nullptr, *recv_meta = nullptr; // [nranks][2] (device)
     uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
     unsigned char *recv = nullptr; size_t recv_bytes = 0;
-    cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr, ev_self = nullptr;
-    bool used = false, done_recorded = false, ce_wait_token = false;
+    cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr, ev_self = nullptr, ev_fork = nullptr;
+    bool used = false, done_recorded = false;
     cudaEvent_t tr[8] = {}; bool tr_valid = false; // WFB_MG_TRACE: source begin/end, update begin/end (caller's stream); exchange begin/end, sizes begin/end (communication stream)
 };
 } // namespace
@@ -1869,6 +1871,10 @@ struct wfb_mg {
     bool ce = false, ce_tried = false; uint64_t ce_cap = 0, peer_cap[MAX_SHARDS] = {};
     unsigned char *ce_msg = nullptr; // device staging of the handle exchange
     cudaEvent_t ev_flush = nullptr;
+    static constexpr int CE_STREAMS = 4;
+    cudaStream_t ce_s[CE_STREAMS] = {}; cudaEvent_t ce_ev[CE_STREAMS] = {}; // peer copies of one exchange are spread over these (several copy engines)
+    uint32_t *tok = nullptr;            // device words of the completion tokens: [0] sent, [1 + p] received from p
+    cudaEvent_t last_done = nullptr;    // end of the most recently issued window update (caller's stream)
     bool trace = false; double tr_acc[8] = {}; uint64_t tr_n = 0; // WFB_MG_TRACE=1: device timeline of a step, printed every 64 steps (tuning aid)
     bool bucketed = false;
     uint32_t shard_slots = 0, shard_keys = 0, shift = 0, bps = 0; // slots per destination (power of two), keys per destination, bucket = slot >> shift, buckets per destination
@@ -1900,13 +1906,15 @@ int wfb_mg_destroy(wfb_mg_t *h)
         } else { cudaFree(sl.recv_slots); cudaFree(sl.recv_bins); }
         if (sl.h_counts) cudaFreeHost(sl.h_counts);
         if (sl.h_recv) cudaFreeHost(sl.h_recv);
-        for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done, sl.ev_self}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {sl.ev_src, sl.ev_meta, sl.ev_a2a, sl.ev_done, sl.ev_self, sl.ev_fork}) if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : sl.tr) if (e) cudaEventDestroy(e);
     }
     if (h->cs) cudaStreamDestroy(h->cs);
     if (h->cs2) cudaStreamDestroy(h->cs2);
-    cudaFree(h->ce_msg);
+    cudaFree(h->ce_msg); cudaFree(h->tok);
     if (h->ev_flush) cudaEventDestroy(h->ev_flush);
+    for (cudaStream_t st : h->ce_s) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : h->ce_ev) if (e) cudaEventDestroy(e);
     delete h;
     cudaGetLastError();
     return 0;
@@ -1955,7 +1963,7 @@ int wfb_mg_create(wfb_mg_t **hh, int prog, int nranks, int rank, const void *id1
         MGCK(static_cast<int>(cudaMalloc(&sl.recv_meta, sizeof(uint64_t) * 2 * MAX_SHARDS)));
         MGCK(static_cast<int>(cudaMallocHost(&sl.h_counts, sizeof(uint32_t) * (MAX_SHARDS + 1))));
         MGCK(static_cast<int>(cudaMallocHost(&sl.h_recv, sizeof(uint64_t) * 2 * MAX_SHARDS)));
-        for (cudaEvent_t *e : {&sl.ev_src, &sl.ev_meta, &sl.ev_a2a, &sl.ev_done, &sl.ev_self}) MGCK(static_cast<int>(cudaEventCreateWithFlags(e, cudaEventDisableTiming)));
+        for (cudaEvent_t *e : {&sl.ev_src, &sl.ev_meta, &sl.ev_a2a, &sl.ev_done, &sl.ev_self, &sl.ev_fork}) MGCK(static_cast<int>(cudaEventCreateWithFlags(e, cudaEventDisableTiming)));
         if (h->trace) for (cudaEvent_t &e : sl.tr) MGCK(static_cast<int>(cudaEventCreate(&e)));
     }
     if (nranks > 1) {
@@ -2037,6 +2045,9 @@ static int mg_ce_setup(wfb_mg *h, uint64_t positions)
         if (h->trace) std::fprintf(stderr, "[wfb_mg rank %d] copy-engine exchange not available (cudaIpc): NCCL exchange\n", h->rank);
         return 0; // (the NCCL exchange stays in use)
     }
+    for (int i = 0; i < wfb_mg::CE_STREAMS; i++) { CK(cudaStreamCreateWithFlags(&h->ce_s[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&h->ce_ev[i], cudaEventDisableTiming)); }
+    CK(cudaMalloc(&h->tok, sizeof(uint32_t) * (MAX_SHARDS + 1)));
+    CK(cudaMemset(h->tok, 0, sizeof(uint32_t) * (MAX_SHARDS + 1)));
     h->ce = true; h->ce_cap = cap;
     if (h->trace) std::fprintf(stderr, "[wfb_mg rank %d] copy-engine exchange enabled (capacity %llu records per source)\n", h->rank, static_cast<unsigned long long>(cap));
     for (MgSlot &sl : h->slot) {
@@ -2080,7 +2091,7 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
             CK(cudaMalloc(&sl.vslots, sizeof(uint32_t) * sl.region_cap));
         }
         rc = shard_lift_impl(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s,
-                             h->shard_slots, h->shard_keys, h->shift, sl.vslots, sl.bins);
+                             h->shard_slots, h->shard_keys, h->shift, sl.vslots, sl.bins, n ? sl.send_meta : nullptr, watermark);
     } else {
         if (sl.region_cap < n) { // worst case: every item of the segment survives and goes to one shard
             if (sl.used) CK(cudaDeviceSynchronize());
@@ -2091,8 +2102,10 @@ static int mg_source(wfb_mg *h, MgSlot &sl, const wfb_functors_t *pre, const wfb
         rc = wfb_shard_lift(h->eng, pre, batches_h, nbatches, static_cast<uint32_t>(h->nranks), sl.regions, sl.region_cap, sl.counts, s);
     }
     if (rc) return rc;
-    k_mg_meta<<<1, 32, 0, s>>>(sl.counts, watermark, static_cast<uint32_t>(h->nranks), sl.send_meta);
-    CK(cudaGetLastError());
+    if (!(h->bucketed && n)) { // (bucketed: the kernel that sums the bins per destination wrote the pairs)
+        k_mg_meta<<<1, 32, 0, s>>>(sl.counts, watermark, static_cast<uint32_t>(h->nranks), sl.send_meta);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(sl.ev_src, s));
     if (h->trace) CK(cudaEventRecord(sl.tr[1], s));
     CK(cudaStreamWaitEvent(h->cs, sl.ev_src, 0));
@@ -2140,18 +2153,35 @@ static int mg_exchange(wfb_mg *h, MgSlot &sl)
             if (h->trace) CK(cudaEventRecord(sl.tr[4], h->cs));
             CK(cudaStreamWaitEvent(h->cs2, sl.ev_src, 0));
             if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs2, sl.ev_done, 0));
+            // the peers' shares go out on several streams (several copy engines, different NVLink destinations); the communication stream
+            // has seen everything the copies depend on (this step's source pass, the sizes received so far): fork from it, join back
+            CK(cudaEventRecord(sl.ev_fork, h->cs));
+            const int nst = std::min(wfb_mg::CE_STREAMS, n - 1);
+            for (int i = 0; i < nst; i++) CK(cudaStreamWaitEvent(h->ce_s[i], sl.ev_fork, 0));
+            int k = 0;
             for (int p = 0; p < n; p++) {
                 const CeLayout l = ce_layout(h->peer_cap[p], n, h->rb, h->bps);
                 unsigned char *dst = h->slot[slot_idx].peer[p];
                 const uint64_t me = static_cast<uint64_t>(h->rank), pc = h->peer_cap[p];
-                cudaStream_t st = (p == h->rank) ? h->cs2 : h->cs;
+                cudaStream_t st = (p == h->rank) ? h->cs2 : h->ce_s[k++ % nst];
                 CK(cudaMemcpyAsync(dst + me * pc * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, st));
                 CK(cudaMemcpyAsync(dst + l.slots_off + me * pc * 4, sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, st));
                 CK(cudaMemcpyAsync(dst + l.bins_off + me * bin_bytes, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, st));
             }
             CK(cudaEventRecord(sl.ev_self, h->cs2));
+            for (int i = 0; i < nst; i++) { CK(cudaEventRecord(h->ce_ev[i], h->ce_s[i])); CK(cudaStreamWaitEvent(h->cs, h->ce_ev[i], 0)); }
             if (h->trace) CK(cudaEventRecord(sl.tr[5], h->cs));
-            sl.ce_wait_token = true; // ev_a2a: after the next exchange of sizes (wfb_mg_step) / a token exchange (wfb_mg_flush)
+            // completion tokens: a peer's token arrives after its copies (its stream order) and after the window update it issued last
+            // (so that what this rank pushes NEXT into that peer's buffers overwrites nothing still being read)
+            if (h->last_done) CK(cudaStreamWaitEvent(h->cs, h->last_done, 0));
+            NK(nccl().GroupStart());
+            for (int p = 0; p < n; p++) {
+                if (p == h->rank) continue;
+                NK(nccl().Send(h->tok, 4, NCCL_UINT8, p, h->comm, h->cs));
+                NK(nccl().Recv(h->tok + 1 + p, 4, NCCL_UINT8, p, h->comm, h->cs));
+            }
+            NK(nccl().GroupEnd());
+            CK(cudaEventRecord(sl.ev_a2a, h->cs));
             return 0;
         }
         const size_t need = std::max<size_t>(1, tot);
@@ -2248,6 +2278,7 @@ static int mg_update(wfb_mg *h, MgSlot &sl, void *out, uint64_t *out_ts, uint32_
     }
     if (rc) return rc;
     CK(cudaEventRecord(sl.ev_done, s));
+    h->last_done = sl.ev_done;
     if (h->trace) { CK(cudaEventRecord(sl.tr[3], s)); sl.tr_valid = true; }
     sl.done_recorded = true;
     return 0;
@@ -2266,12 +2297,6 @@ int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batch
     int rc;
     if (h->npend == 2) { upd = h->pend[0]; rc = mg_exchange(h, *upd); if (rc) return rc; }
     rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
-    if (upd != nullptr && upd->ce_wait_token) {
-        // copy-engine exchange: a peer's sizes of THIS step arrive after its copies of the step being updated (its communication stream runs
-        // them in that order), and it only sent them after its source pass, i.e. after the update that last read the buffers we are about to reuse
-        CK(cudaEventRecord(upd->ev_a2a, h->cs));
-        upd->ce_wait_token = false;
-    }
     if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = &cur; } else h->pend[h->npend++] = &cur;
     if (upd == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     return mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
@@ -2284,22 +2309,6 @@ int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_
     if (h->npend == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     const int n = h->npend; h->npend = 0;
     int rc;
-    if (h->ce) {
-        // no further step whose sizes could carry the signals: two explicit token rounds (synchronous, flush is rare) --
-        // 1. every rank's window updates issued so far are complete (the receive buffers may be overwritten), 2. every rank's copies have landed
-        uint64_t tok = 1, all[MAX_SHARDS];
-        CK(cudaEventRecord(h->ev_flush, s));
-        CK(cudaStreamWaitEvent(h->cs, h->ev_flush, 0));
-        rc = mg_all_exchange(h, &tok, all, sizeof(uint64_t)); if (rc) return rc;
-        for (int i = 0; i < n; i++) { rc = mg_exchange(h, *h->pend[i]); if (rc) return rc; }
-        rc = mg_all_exchange(h, &tok, all, sizeof(uint64_t)); if (rc) return rc;
-        for (int i = 0; i < n; i++) { CK(cudaEventRecord(h->pend[i]->ev_a2a, h->cs)); h->pend[i]->ce_wait_token = false; }
-        for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
-            rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
-            h->pend[i] = nullptr;
-        }
-        return 0;
-    }
     for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
         rc = mg_exchange(h, *h->pend[i]); if (rc) return rc;
         rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;

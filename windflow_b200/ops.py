@@ -30,7 +30,6 @@ KEY_RR, KEY_UNIFORM, KEY_ZIPF = 0, 1, 2
 SEED = 0x5EED5EED
 
 
-_PROF = [0.0, 0.0, 0] if os.environ.get("WFB_BENCH_VERBOSE") else None  # host-side timing of the window call (args, C call, calls)
 
 
 def functors(map_kind=0, iadd=0, fscale=1.0, filt_kind=0, mod=1):
@@ -305,16 +304,6 @@ class FfatWindowsGPU:
         if self.win_type == 1:
             check(self.L.wfb_ffat_process_tb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                              _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)), "wfb_ffat_process_tb")
-            return out, out_ts, n_out
-        if _PROF is not None:
-            import time
-            t0 = time.perf_counter()
-            a = (self.h, C.byref(pre) if pre is not None else None, arr, len(batches), _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream))
-            t1 = time.perf_counter()
-            rc = self.L.wfb_ffat_process_cb(*a)
-            t2 = time.perf_counter()
-            _PROF[0] += t1 - t0; _PROF[1] += t2 - t1; _PROF[2] += 1
-            check(rc, "wfb_ffat_process_cb")
             return out, out_ts, n_out
         check(self.L.wfb_ffat_process_cb(self.h, C.byref(pre) if pre is not None else None, arr, len(batches),
                                          _ptr(out), _ptr(out_ts), cap, _ptr(n_out), _stream_ptr(stream)),
