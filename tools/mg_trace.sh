@@ -13,5 +13,5 @@ for l in open('gpurun_out/mg_${N}_$tag.json'):
         d=json.loads(l); print('N=$N $tag', round(d['value']/1e9,2),'GT/s ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']/1e9,3), 'win', d['config']['windows_in_timed_region'], d['config']['windows_expected_steady_state'], 'check', d['check'] and (d['check']['passed'], d['check']['windows_compared']))
 " || tail -5 gpurun_out/mg_${N}_$tag.err | cut -c1-300
 }
-run ce
+run ${TAG:-ce} ${EXTRA_ENV}
 if [ "$2" == "nccl" ]; then run nccl WFB_MG_CE=0; fi

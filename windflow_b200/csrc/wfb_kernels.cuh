@@ -1499,6 +1499,37 @@ __global__ void __launch_bounds__(OSW_THREADS) k_shard_scatter(const uint32_t *_
     }
 }
 
+// multi-GPU exchange, push with SMs: every peer's slice of records (16-byte words), slots and run lengths (4-byte words) is
+// stored straight into that peer's mapped receive buffer over NVLink. MG_PUSH_CTAS CTAs per peer share a slice.
+constexpr uint32_t MG_PUSH_CTAS = 16, MG_PUSH_THREADS = 256; // (one CTA moves ~10 GB/s over NVLink: stores to a peer are latency-bound)
+struct MgPush {
+    const uint4 *rec_src[MAX_SHARDS]; uint4 *rec_dst[MAX_SHARDS]; uint32_t rec_n16[MAX_SHARDS];
+    const uint32_t *slot_src[MAX_SHARDS]; uint32_t *slot_dst[MAX_SHARDS]; uint32_t slot_n[MAX_SHARDS];
+    const uint32_t *bin_src[MAX_SHARDS]; uint32_t *bin_dst[MAX_SHARDS]; uint32_t bin_n;
+};
+static __global__ void __launch_bounds__(MG_PUSH_THREADS) k_mg_push(const __grid_constant__ MgPush a)
+{
+    const uint32_t peer = blockIdx.x / MG_PUSH_CTAS, part = blockIdx.x % MG_PUSH_CTAS;
+    const uint32_t t = part * MG_PUSH_THREADS + threadIdx.x, stride = MG_PUSH_CTAS * MG_PUSH_THREADS;
+    {
+        const uint4 *src = a.rec_src[peer]; uint4 *dst = a.rec_dst[peer]; const uint32_t n = a.rec_n16[peer];
+        uint32_t i = t;
+        for (; i + 7 * stride < n; i += 8 * stride) { // eight independent 16-byte loads, then eight stores in flight per thread
+            uint4 v[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) v[q] = src[i + q * stride];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) dst[i + q * stride] = v[q];
+        }
+        for (; i < n; i += stride) dst[i] = src[i];
+    }
+    {
+        const uint32_t *src = a.slot_src[peer]; uint32_t *dst = a.slot_dst[peer]; const uint32_t n = a.slot_n[peer];
+        for (uint32_t i = t; i < n; i += stride) dst[i] = src[i];
+    }
+    if (part == 0) for (uint32_t i = threadIdx.x; i < a.bin_n; i += MG_PUSH_THREADS) a.bin_dst[peer][i] = a.bin_src[peer][i];
+}
+
 // counts of the destination partition (wfb_shard_lift): counts_out[0 .. nshards) + overflow flag at [MAX_SHARDS]
 static __global__ void k_shard_counts(const uint32_t *__restrict__ digit_counts, uint32_t nshards, uint32_t region_cap, uint32_t *__restrict__ counts_out)
 {

@@ -2153,23 +2153,54 @@ static int mg_exchange(wfb_mg *h, MgSlot &sl)
             if (h->trace) CK(cudaEventRecord(sl.tr[4], h->cs));
             CK(cudaStreamWaitEvent(h->cs2, sl.ev_src, 0));
             if (sl.done_recorded) CK(cudaStreamWaitEvent(h->cs2, sl.ev_done, 0));
-            // the peers' shares go out on several streams (several copy engines, different NVLink destinations); the communication stream
-            // has seen everything the copies depend on (this step's source pass, the sizes received so far): fork from it, join back
-            CK(cudaEventRecord(sl.ev_fork, h->cs));
-            const int nst = std::min(wfb_mg::CE_STREAMS, n - 1);
-            for (int i = 0; i < nst; i++) CK(cudaStreamWaitEvent(h->ce_s[i], sl.ev_fork, 0));
-            int k = 0;
-            for (int p = 0; p < n; p++) {
+            // the peers' shares: with few peers plain copies (copy engines: 450 GB/s to one peer, no SM); with many, one kernel that stores
+            // into the mapped buffers (the copy engines fall to ~250 GB/s aggregate with 7 peers x 3 pieces each). WFB_MG_PUSH=ce|sm overrides.
+            static const char *push_env = std::getenv("WFB_MG_PUSH");
+            const bool use_sm = (push_env ? (std::strcmp(push_env, "sm") == 0) : (n > 2)) && h->rb % 16 == 0;
+            {   // own share: a local copy next to the rest
+                const int p = h->rank;
                 const CeLayout l = ce_layout(h->peer_cap[p], n, h->rb, h->bps);
                 unsigned char *dst = h->slot[slot_idx].peer[p];
                 const uint64_t me = static_cast<uint64_t>(h->rank), pc = h->peer_cap[p];
-                cudaStream_t st = (p == h->rank) ? h->cs2 : h->ce_s[k++ % nst];
-                CK(cudaMemcpyAsync(dst + me * pc * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(dst + l.slots_off + me * pc * 4, sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(dst + l.bins_off + me * bin_bytes, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(dst + me * pc * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaMemcpyAsync(dst + l.slots_off + me * pc * 4, sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaMemcpyAsync(dst + l.bins_off + me * bin_bytes, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, h->cs2));
+                CK(cudaEventRecord(sl.ev_self, h->cs2));
             }
-            CK(cudaEventRecord(sl.ev_self, h->cs2));
-            for (int i = 0; i < nst; i++) { CK(cudaEventRecord(h->ce_ev[i], h->ce_s[i])); CK(cudaStreamWaitEvent(h->cs, h->ce_ev[i], 0)); }
+            if (use_sm) {
+                MgPush a; std::memset(&a, 0, sizeof(a));
+                int k = 0;
+                for (int p = 0; p < n; p++) {
+                    if (p == h->rank) continue;
+                    const CeLayout l = ce_layout(h->peer_cap[p], n, h->rb, h->bps);
+                    unsigned char *dst = h->slot[slot_idx].peer[p];
+                    const uint64_t me = static_cast<uint64_t>(h->rank), pc = h->peer_cap[p];
+                    a.rec_src[k] = reinterpret_cast<const uint4 *>(sl.regions + send_off[p] * h->rb); a.rec_dst[k] = reinterpret_cast<uint4 *>(dst + me * pc * h->rb);
+                    a.rec_n16[k] = static_cast<uint32_t>(static_cast<size_t>(sl.h_counts[p]) * h->rb / 16);
+                    a.slot_src[k] = sl.vslots + send_off[p]; a.slot_dst[k] = reinterpret_cast<uint32_t *>(dst + l.slots_off + me * pc * 4); a.slot_n[k] = sl.h_counts[p];
+                    a.bin_src[k] = sl.bins + static_cast<size_t>(p) * h->bps; a.bin_dst[k] = reinterpret_cast<uint32_t *>(dst + l.bins_off + me * bin_bytes);
+                    k++;
+                }
+                a.bin_n = h->bps;
+                k_mg_push<<<static_cast<uint32_t>(k) * MG_PUSH_CTAS, MG_PUSH_THREADS, 0, h->cs>>>(a);
+                CK(cudaGetLastError());
+            } else { // several streams (copy engines, different NVLink destinations), forked from the communication stream and joined back
+                CK(cudaEventRecord(sl.ev_fork, h->cs));
+                const int nst = std::min(wfb_mg::CE_STREAMS, n - 1);
+                for (int i = 0; i < nst; i++) CK(cudaStreamWaitEvent(h->ce_s[i], sl.ev_fork, 0));
+                int k = 0;
+                for (int p = 0; p < n; p++) {
+                    if (p == h->rank) continue;
+                    const CeLayout l = ce_layout(h->peer_cap[p], n, h->rb, h->bps);
+                    unsigned char *dst = h->slot[slot_idx].peer[p];
+                    const uint64_t me = static_cast<uint64_t>(h->rank), pc = h->peer_cap[p];
+                    cudaStream_t st = h->ce_s[k++ % nst];
+                    CK(cudaMemcpyAsync(dst + me * pc * h->rb, sl.regions + send_off[p] * h->rb, static_cast<size_t>(sl.h_counts[p]) * h->rb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(dst + l.slots_off + me * pc * 4, sl.vslots + send_off[p], static_cast<size_t>(sl.h_counts[p]) * 4, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(dst + l.bins_off + me * bin_bytes, sl.bins + static_cast<size_t>(p) * h->bps, bin_bytes, cudaMemcpyDeviceToDevice, st));
+                }
+                for (int i = 0; i < nst; i++) { CK(cudaEventRecord(h->ce_ev[i], h->ce_s[i])); CK(cudaStreamWaitEvent(h->cs, h->ce_ev[i], 0)); }
+            }
             if (h->trace) CK(cudaEventRecord(sl.tr[5], h->cs));
             // completion tokens: a peer's token arrives after its copies (its stream order) and after the window update it issued last
             // (so that what this rank pushes NEXT into that peer's buffers overwrites nothing still being read)
