@@ -1337,9 +1337,13 @@ int wfb_ffat_create(wfb_ffat_t **hh, int prog, uint64_t win, uint64_t slide, uin
         const char *e = std::getenv("WFB_UPDATE");
         h->buckets = !(e && std::strcmp(e, "lanes") == 0) && (1u << h->bucket_shift) <= BK_KEYS && ff.pane < (1ull << 32);
         // streaming update: one path update per completed pane inside the item loop, so panes of a few items at least
-        // lazy FlatFAT levels (FfatDev::lazy): bucket path, and the on-chip tree of one group must fit 32 KB
+        // lazy FlatFAT levels (FfatDev::lazy): bucket path, the on-chip tree of one group must fit 32 KB, and building the n - 1 internal
+        // nodes once per fired group must be cheaper than a root path (log n nodes) per completed pane: a group fires every sp * Nb panes.
+        // (Nb = 1 with slide = pane fires on every pane: eager levels there. WFB_LAZY_TREE=0 / 1 forces either.)
         { const char *lz = std::getenv("WFB_LAZY_TREE");
-          ff.lazy = (h->buckets && !(lz && std::atoi(lz) == 0) && static_cast<size_t>(2) * ff.n_leaves * RB <= (32u << 10)) ? 1u : 0u; }
+          const bool fits = h->buckets && static_cast<size_t>(2) * ff.n_leaves * RB <= (32u << 10);
+          const bool pays = static_cast<uint64_t>(ff.n_leaves) <= 2ull * std::max(1u, ff.log_leaves) * ff.sp * ff.nb;
+          ff.lazy = (fits && (lz ? std::atoi(lz) != 0 : pays)) ? 1u : 0u; }
         h->stream_update = h->buckets && !h->bucket_move && e && std::strcmp(e, "stream") == 0; // (measured: 173 us against 153 us for the bucket kernel at the bench configuration)
         const char *t = std::getenv("WFB_TILE_H16");
         h->tile_h16 = h->buckets && !(t && std::atoi(t) == 0);
@@ -1875,6 +1879,7 @@ struct wfb_mg {
     cudaStream_t ce_s[CE_STREAMS] = {}; cudaEvent_t ce_ev[CE_STREAMS] = {}; // peer copies of one exchange are spread over these (several copy engines)
     uint32_t *tok = nullptr;            // device words of the completion tokens: [0] sent, [1 + p] received from p
     cudaEvent_t last_done = nullptr;    // end of the most recently issued window update (caller's stream)
+    double host_acc[3] = {}; uint64_t host_n = 0;
     bool trace = false; double tr_acc[8] = {}; uint64_t tr_n = 0; // WFB_MG_TRACE=1: device timeline of a step, printed every 64 steps (tuning aid)
     bool bucketed = false;
     uint32_t shard_slots = 0, shard_keys = 0, shift = 0, bps = 0; // slots per destination (power of two), keys per destination, bucket = slot >> shift, buckets per destination
@@ -2327,11 +2332,24 @@ int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batch
     // never waits for the GPU), the source pass of step i runs next to them, then the window update of step i-2
     MgSlot *upd = nullptr;
     int rc;
+    const double t0 = h->trace ? host_now_us() : 0;
     if (h->npend == 2) { upd = h->pend[0]; rc = mg_exchange(h, *upd); if (rc) return rc; }
+    const double t1 = h->trace ? host_now_us() : 0;
     rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
+    const double t2 = h->trace ? host_now_us() : 0;
     if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = &cur; } else h->pend[h->npend++] = &cur;
     if (upd == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
-    return mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
+    rc = mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
+    if (h->trace) { // host time spent ISSUING the three parts of a step (includes any wait for a pinned staging slot)
+        const double t3 = host_now_us();
+        h->host_acc[0] += t1 - t0; h->host_acc[1] += t2 - t1; h->host_acc[2] += t3 - t2;
+        if (++h->host_n % 64 == 0) {
+            std::fprintf(stderr, "[wfb_mg rank %d] host us/step over 64 steps: issue exchange %.0f | issue source + sizes %.0f | issue update %.0f\n", h->rank,
+                         h->host_acc[0] / 64, h->host_acc[1] / 64, h->host_acc[2] / 64);
+            h->host_acc[0] = h->host_acc[1] = h->host_acc[2] = 0;
+        }
+    }
+    return rc;
 }
 
 int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream)
