@@ -255,6 +255,11 @@ int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream);
  * the SOURCE partitions its surviving records by (destination, bucket of the destination's slot space) in its one partition pass, and
  * the destination only concatenates the runs it receives, source after source, bucket by bucket -- it runs no partition of its own;
  * otherwise the source partitions by destination and the destination partitions what it received (WFB_MG_BUCKETED=0 forces this).
+ * Transport: at the first step every rank allocates its receive buffers (sized for the worst case of THAT step: a later step may not
+ * carry more tuples than the first one, WFB_E_CAPACITY) and maps its peers' buffers (cudaIpc: the ranks are processes of one node);
+ * the records are then pushed with device-to-device copies over NVLink and a 4-byte NCCL token round signals completion. When the
+ * buffers cannot be mapped, or with WFB_MG_CE=0, an NCCL send/recv group carries the records instead (buffers then grow on demand).
+ * WFB_MG_TRACE=1 prints the device timeline of a step and the host time spent issuing it, per rank, every 64 steps (stderr).
  * The exchange and the window update of step t are issued behind the source pass of step t+2, so results arrive TWO steps late
  * (wfb_mg_flush delivers the rest, appended in step order) and the host never waits for the GPU: the sizes NCCL needs on the host
  * are a step old when it reads them. */

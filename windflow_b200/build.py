@@ -11,6 +11,7 @@ HEADERS = ["wfb_kernels.cuh", "wfb_launch.cuh", "wfb_programs.cuh", "wfb_ptx.cuh
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+    "-diag-suppress", "186",  # "pointless comparison of unsigned integer with zero": loops whose bound is a template constant 0 (lazy FlatFAT levels)
 ]
 
 
@@ -46,7 +47,7 @@ def build_apps(force=False):
         deps = [os.path.join(APPS, src), LIB] + FACADE_HEADERS + [os.path.join(CSRC, h) for h in HEADERS if not h.startswith("..")]
         if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
             cmd = [os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
-                   "--expt-extended-lambda", "-I" + INCLUDE, "-o", exe, os.path.join(APPS, src), "-L" + HERE, "-lwfb200", "-lpthread",
+                   "--expt-extended-lambda", "-diag-suppress", "186", "-I" + INCLUDE, "-o", exe, os.path.join(APPS, src), "-L" + HERE, "-lwfb200", "-lpthread",
                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/.."]
             subprocess.check_call(cmd)
         out.append(exe)
