@@ -339,7 +339,7 @@ def run_ours(args):
         else:                                        # the whole step under the C ABI (wfb_mg_step: NCCL send/recv groups issued from C)
             pipe = multigpu.KeyShardedPipelineC(ops, f, WIN, SLIDE, nb, NKEYS, rank, world, dev)
         ff = pipe.ff
-    cap = ff.max_results(seg_tuples * (3 if pipe is not None else 1))  # (a flush of the multi-GPU pipeline delivers two steps at once)
+    cap = ff.max_results(seg_tuples * (4 if pipe is not None else 1))  # (a flush of the multi-GPU pipeline delivers three steps at once)
     out = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
     out_ts = torch.empty(cap, dtype=torch.int64, device=dev)
     n_out = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -260,15 +260,15 @@ int wfb_ffat_results_total(wfb_ffat_t *h, uint64_t *total_h, void *stream);
  * the records are then pushed with device-to-device copies over NVLink and a 4-byte NCCL token round signals completion. When the
  * buffers cannot be mapped, or with WFB_MG_CE=0, an NCCL send/recv group carries the records instead (buffers then grow on demand).
  * WFB_MG_TRACE=1 prints the device timeline of a step and the host time spent issuing it, per rank, every 64 steps (stderr).
- * The exchange and the window update of step t are issued behind the source pass of step t+2, so results arrive TWO steps late
- * (wfb_mg_flush delivers the rest, appended in step order) and the host never waits for the GPU: the sizes NCCL needs on the host
- * are a step old when it reads them. */
+ * The exchange of step t is issued behind the source pass of step t+2 and its window update behind that of step t+3, so results arrive THREE steps late
+ * (wfb_mg_flush delivers the rest, appended in step order). Neither the host nor the compute stream ever waits for an exchange: the sizes
+ * the host needs are a step old when it reads them, and a step's records have a whole step to arrive before they are read. */
 typedef struct wfb_mg wfb_mg_t;
 int wfb_mg_unique_id(void *id128_h);   /* rank 0: an ncclUniqueId (128 bytes) to hand to the other ranks (broadcast it with the launcher's means) */
 int wfb_mg_create(wfb_mg_t **h, int prog, int nranks, int rank, const void *id128_h, uint64_t win, uint64_t slide, uint32_t wins_per_batch,
                   uint32_t max_keys_total /* keys 0 .. max_keys_total-1 over all ranks */);
 int wfb_mg_destroy(wfb_mg_t *h);
-/* this rank's K batches of the next global step; the window results of the step two calls back go to out_results / out_ts (none on the first two calls).
+/* this rank's K batches of the next global step; the window results of the step three calls back go to out_results / out_ts (none on the first three calls).
  * `watermark`: the watermark of the segment (result timestamps carry the watermark of the source segment that held the triggering item). */
 int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batches_h, uint32_t nbatches, uint64_t watermark,
                 void *out_results, uint64_t *out_ts, uint32_t out_capacity, uint32_t *n_out_dev, void *stream);

@@ -1852,7 +1852,7 @@ struct MgSlot { // buffers of one step in flight (three: the exchange of step i-
     uint32_t *h_counts = nullptr; uint64_t *h_recv = nullptr; // pinned copies
     unsigned char *recv = nullptr; size_t recv_bytes = 0;
     cudaEvent_t ev_src = nullptr, ev_meta = nullptr, ev_a2a = nullptr, ev_done = nullptr, ev_self = nullptr, ev_fork = nullptr;
-    bool used = false, done_recorded = false;
+    bool used = false, done_recorded = false, exchanged = false;
     cudaEvent_t tr[8] = {}; bool tr_valid = false; // WFB_MG_TRACE: source begin/end, update begin/end (caller's stream); exchange begin/end, sizes begin/end (communication stream)
 };
 } // namespace
@@ -1863,11 +1863,11 @@ struct wfb_mg {
     wfb_engine_t *eng = nullptr;
     wfb_ffat_t *ffat = nullptr;
     size_t rb = 0;
-    MgSlot slot[3];            // three steps in flight: the host reads the sizes of step i while the GPU is two steps further
+    MgSlot slot[4];            // four steps in flight: step i's source pass, step i-1 waiting, step i-2 travelling, step i-3 being updated
     cudaStream_t cs = nullptr; // communication stream
     cudaStream_t cs2 = nullptr; // the rank's own share of an exchange: device-to-device copies (copy engine), next to the NCCL group
     uint64_t step_no = 0;
-    MgSlot *pend[2] = {nullptr, nullptr}; int npend = 0; // steps whose records have not been exchanged yet, oldest first
+    MgSlot *pend[3] = {nullptr, nullptr, nullptr}; int npend = 0; // steps not yet updated, oldest first (the oldest of three has been exchanged)
     std::vector<wfb_batch_t> chunks;
     // bucketed exchange: the source partitions by (destination, bucket of the destination's slot space), the destination only concatenates runs
     // copy-engine exchange (bucketed mode, all ranks on one node): records are PUSHED into the peers' receive buffers with plain
@@ -1988,7 +1988,8 @@ static CeLayout ce_layout(uint64_t cap, int n, size_t rb, uint32_t bps)
     CeLayout l; l.slots_off = static_cast<size_t>(n) * cap * rb; l.bins_off = (l.slots_off + static_cast<size_t>(n) * cap * 4 + 255) & ~static_cast<size_t>(255);
     l.bytes = l.bins_off + static_cast<size_t>(n) * bps * 4; return l;
 }
-struct CeMsg { cudaIpcMemHandle_t h[3]; uint64_t cap; uint64_t ok; };
+constexpr int MG_SLOTS = 4;
+struct CeMsg { cudaIpcMemHandle_t h[MG_SLOTS]; uint64_t cap; uint64_t ok; };
 // one small message to / from every other rank (communication stream, synchronous)
 static int mg_all_exchange(wfb_mg *h, const void *mine_h, void *all_h, size_t bytes)
 {
@@ -2018,7 +2019,7 @@ static int mg_ce_setup(wfb_mg *h, uint64_t positions)
     const uint64_t cap = (positions + 1023) & ~1023ull; // worst case: every survivor of a source's step goes to one destination
     const CeLayout l = ce_layout(cap, n, h->rb, h->bps);
     CeMsg mine; std::memset(&mine, 0, sizeof(mine)); mine.cap = cap; mine.ok = 1;
-    for (int i = 0; i < 3 && mine.ok; i++) {
+    for (int i = 0; i < MG_SLOTS && mine.ok; i++) {
         if (cudaMalloc(&h->slot[i].ce_buf, l.bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine.h[i], h->slot[i].ce_buf) != cudaSuccess) mine.ok = 0;
     }
     cudaGetLastError();
@@ -2029,7 +2030,7 @@ static int mg_ce_setup(wfb_mg *h, uint64_t positions)
     if (ok) {
         for (int p = 0; p < n && ok; p++) {
             h->peer_cap[p] = all[p].cap;
-            for (int i = 0; i < 3 && ok; i++) {
+            for (int i = 0; i < MG_SLOTS && ok; i++) {
                 if (p == h->rank) { h->slot[i].peer[p] = h->slot[i].ce_buf; continue; }
                 void *ptr = nullptr;
                 if (cudaIpcOpenMemHandle(&ptr, all[p].h[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
@@ -2326,20 +2327,23 @@ int wfb_mg_step(wfb_mg_t *h, const wfb_functors_t *pre, const wfb_batch_t *batch
 {
     if (!h || !n_out_dev || (nbatches && !batches_h)) return WFB_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    MgSlot &cur = h->slot[h->step_no % 3];
+    MgSlot &cur = h->slot[h->step_no % 4];
     h->step_no++;
-    // step i: the records of step i-2 start travelling (communication stream; their sizes reached the host a step ago, so the host
-    // never waits for the GPU), the source pass of step i runs next to them, then the window update of step i-2
-    MgSlot *upd = nullptr;
+    // call i: the records of step i-2 start travelling (communication stream; their sizes reached the host a step ago), the source pass
+    // of step i runs next to them, then the window update of step i-3 -- whose records arrived during the previous call, so the compute
+    // stream never waits for an exchange, and no rank waits for the slowest peer of the step in flight
+    MgSlot *ex = h->npend >= 2 ? h->pend[h->npend - 2] : nullptr, *upd = h->npend == 3 ? h->pend[0] : nullptr;
     int rc;
     const double t0 = h->trace ? host_now_us() : 0;
-    if (h->npend == 2) { upd = h->pend[0]; rc = mg_exchange(h, *upd); if (rc) return rc; }
+    if (ex != nullptr && !ex->exchanged) { rc = mg_exchange(h, *ex); if (rc) return rc; ex->exchanged = true; }
     const double t1 = h->trace ? host_now_us() : 0;
     rc = mg_source(h, cur, pre, batches_h, nbatches, watermark, s); if (rc) return rc;
     const double t2 = h->trace ? host_now_us() : 0;
-    if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = &cur; } else h->pend[h->npend++] = &cur;
+    cur.exchanged = false;
+    if (upd != nullptr) { h->pend[0] = h->pend[1]; h->pend[1] = h->pend[2]; h->pend[2] = &cur; } else h->pend[h->npend++] = &cur;
     if (upd == nullptr) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     rc = mg_update(h, *upd, out_results, out_ts, out_capacity, n_out_dev, s);
+    upd->exchanged = false;
     if (h->trace) { // host time spent ISSUING the three parts of a step (includes any wait for a pinned staging slot)
         const double t3 = host_now_us();
         h->host_acc[0] += t1 - t0; h->host_acc[1] += t2 - t1; h->host_acc[2] += t3 - t2;
@@ -2359,9 +2363,11 @@ int wfb_mg_flush(wfb_mg_t *h, void *out_results, uint64_t *out_ts, uint32_t out_
     if (h->npend == 0) { CK(cudaMemsetAsync(n_out_dev, 0, sizeof(uint32_t), s)); return 0; }
     const int n = h->npend; h->npend = 0;
     int rc;
-    for (int i = 0; i < n; i++) { // oldest first; the results of the second step follow the first one's in the buffer
-        rc = mg_exchange(h, *h->pend[i]); if (rc) return rc;
-        rc = mg_update(h, *h->pend[i], out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
+    for (int i = 0; i < n; i++) { // oldest first; the results of the later steps follow the first one's in the buffer
+        MgSlot &sl = *h->pend[i];
+        if (!sl.exchanged) { rc = mg_exchange(h, sl); if (rc) return rc; }
+        rc = mg_update(h, sl, out_results, out_ts, out_capacity, n_out_dev, s, i != 0); if (rc) return rc;
+        sl.exchanged = false;
         h->pend[i] = nullptr;
     }
     return 0;

@@ -210,7 +210,7 @@ class KeyShardedPipelineC:
     """The same pipeline with the whole step under the C ABI (wfb_mg_*): source pass, size exchange, NCCL all-to-all and window update
     are issued by ONE library call per step (NCCL send/recv groups from C on a communication stream; nothing of torch on the per-step
     path). Only the communicator's unique id travels through torch.distributed, once. Same interface as KeyShardedPipeline (always
-    pipelined: results arrive TWO steps late, flush() delivers the rest, in step order). With at most 65536 slots over all ranks the
+    pipelined: results arrive THREE steps late, flush() delivers the rest, in step order). With at most 65536 slots over all ranks the
     exchange is the bucketed one (include/wfb200.h): the destination side runs no partition."""
 
     def __init__(self, ops, functors, win, slide, nb, max_keys, rank, world, device, prog=None):
