@@ -241,7 +241,7 @@ def test_key_sharded_pipeline_world1_nccl(wfb, oracle, pipelined):
 
 def test_mg_pipeline_c_abi_world1(wfb, oracle):
     """The same pipeline with the whole step under the C ABI (wfb_mg_step / wfb_mg_flush): one rank, so the all-to-all is a device copy,
-    everything else -- source-side partition by (destination, bucket), size bookkeeping on the communication stream, results two steps late -- is the
+    everything else -- source-side partition by (destination, bucket), size bookkeeping on the communication stream, results three steps late -- is the
     code every rank runs. (bench.py's check covers the NCCL exchange itself at N > 1.)"""
     import torch
     from windflow_b200 import multigpu
