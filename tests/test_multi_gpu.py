@@ -80,3 +80,57 @@ def test_tile_layout():
     offs, total = M.tile_layout([0, 1, 256, 257, 0, 1000])
     assert offs == [0, 0, 256, 512, 1024, 1024] and total == 1024 + 1024
     assert M.tile_layout([]) == ([], 0)
+
+
+def test_bucketed_exchange_model_keeps_per_key_stream_order():
+    """numpy model of the bucketed exchange of wfb_mg_step: every source partitions its survivors, stably, on the
+    destination-major virtual slot (key % n) * L + key // n shifted to at most 1024 bins; a destination concatenates, bucket after bucket,
+    the runs of the sources in rank order and splits every coarse bucket into sub-buckets, stably. Claim the CUDA path relies on: for
+    every key the resulting item order is the global stream order (source rank major, arrival order inside a source), and the bucket of
+    an item is a function of its slot alone. (The kernels themselves are checked on the GPU: tests/test_gpu_keyed.py, bench.py --check.)"""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for n, nkeys, per_src in ((2, 65536, 40000), (4, 5000, 30000), (8, 65536, 20000), (3, 1000, 9000)):
+        keys_per = (nkeys + n - 1) // n
+        L = 1
+        while L < keys_per:
+            L <<= 1
+        span = 1
+        while span < L * n:
+            span <<= 1
+        shift = 0
+        while (span >> shift) > 1024:
+            shift += 1
+        bps = L >> shift
+        assert bps >= 1 and n * L <= 65536
+        nsub, shift2 = 1, shift
+        while nsub * 2 * bps <= 1024 and nsub * 2 <= 8 and shift2 > 0:
+            nsub, shift2 = nsub * 2, shift2 - 1
+        srcs = [rng.integers(0, nkeys, per_src) for _ in range(n)]                     # surviving keys of every source, arrival order
+        glob = [(int(k), s, i) for s in range(n) for i, k in enumerate(srcs[s])]       # global stream order: source rank major
+        delivered = {d: [] for d in range(n)}                                          # per destination: runs [(source, bucket, items)]
+        for s in range(n):
+            k = srcs[s]
+            v = (k % n) * L + k // n
+            order = np.argsort(v >> shift, kind="stable")                              # the source's ONE stable partition pass
+            bins = (v >> shift)[order]
+            for d in range(n):
+                sel = (bins >= d * bps) & (bins < (d + 1) * bps)
+                delivered[d].append((s, bins[sel] - d * bps, v[order][sel] & (L - 1), order[sel]))
+        for d in range(n):
+            # destination: bucket-major, sub-bucket, source rank, arrival order
+            rows = []
+            for s, b, slot, idx in delivered[d]:
+                assert (np.diff(b) >= 0).all()                                         # a source's runs arrive bucket after bucket
+                sub = (slot >> shift2) & (nsub - 1)
+                assert ((slot >> shift) == b).all()
+                rows.append(np.stack([b * nsub + sub, np.full_like(b, s), np.arange(len(b)), slot, idx], axis=1))
+            allr = np.concatenate(rows)
+            allr = allr[np.lexsort((allr[:, 2], allr[:, 1], allr[:, 0]))]              # what k_mg_count / scan / split produce
+            assert ((allr[:, 3] >> shift2) == allr[:, 0]).all()                        # bucket of the update kernel = slot >> shift2
+            assert (1 << shift2) <= 64                                                 # at most 64 slots per bucket (BK_KEYS)
+            for slot in np.unique(allr[:, 3])[:200]:
+                mine = allr[allr[:, 3] == slot]
+                key = int(slot) * n + d
+                want = [(s, i) for (k, s, i) in glob if k == key]
+                assert [(int(r[1]), int(r[4])) for r in mine] == want
