@@ -75,6 +75,20 @@ static void check(const char *what, long got, long exp)
     std::printf("%s OK (%ld)\n", what, got);
 }
 
+// compile-time only (never called): the ways an application may hold on to what chain() returns keep compiling now that the
+// chain() of a stateless operator returns a proxy (FusedPipe) instead of MultiPipe &
+[[maybe_unused]] static void api_shapes(PipeGraph &graph, Source_Positive_Functor sf)
+{
+    MultiPipe &mp = graph.add_source(Source_Builder(sf).withName("source").withOutputBatchSize(64).build());
+    MultiPipe &same = mp.chain(MapGPU_Builder(Map_Functor_GPU()).withName("m").build());                      // reference bound to the proxy's MultiPipe
+    same.chain(FilterGPU_Builder(Filter_Functor_GPU{2}).withName("f").build()).chain_sink(Sink_Builder(Sink_Functor_T()).withName("s").build()); // fluent into a sink
+    MultiPipe &mp2 = graph.add_source(Source_Builder(sf).withName("source2").withOutputBatchSize(64).build());
+    mp2.add(MapGPU_Builder(Map_Functor_GPU()).withName("m2").build())
+       .add(ReduceGPU_Builder(Reduce_Functor_GPU()).withName("r2").withKeyBy(Key_Functor()).build())                // stateless run, then an operator that is not fused
+       .add_sink(Sink_Builder(Sink_Functor_T()).withName("s2").build());
+    (void) mp2.getNumThreads();
+}
+
 int main()
 {
     const size_t len = 3000, keys = 7, batch = 1000;
